@@ -1,0 +1,142 @@
+"""Parity of the CUDA extractor (through the C ABI) with the CPU oracle on seeded inputs and weights.
+
+Tolerance (BASELINE.json north_star): cosine similarity >= 0.9999 per utterance.  fp16 operands meet it on all
+three networks; bf16 operands are checked against the looser bound their 8-bit mantissa allows.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import net_oracle
+from voxsrc2020_speaker_verification_b200 import arch
+
+pytestmark = pytest.mark.gpu
+
+COS_TOL = 0.9999
+
+
+def cosines(a, b):
+    return (a * b).sum(1) / np.linalg.norm(a, axis=1) / np.linalg.norm(b, axis=1)
+
+
+_cache = {}
+
+
+def model(model_id, feat_dim, precision="fp16"):
+    from voxsrc2020_speaker_verification_b200.extractor import Extractor
+    key = (model_id, feat_dim, precision)
+    if key not in _cache:
+        cfg = arch.get_config(model_id)
+        pkey = (model_id, feat_dim)
+        if pkey not in _cache:
+            _cache[pkey] = net_oracle.init_params(cfg, feat_dim, seed=4321)
+        ex = Extractor(model_id, feat_dim, precision=precision).load_params(_cache[pkey])
+        _cache[key] = (cfg, _cache[pkey], ex)
+    return _cache[key]
+
+
+def oracle_segments(cfg, params, utts):
+    return np.stack([net_oracle.forward(cfg, params, u[None])[0] for u in utts])
+
+
+def run_segments(ex, utts):
+    feats = torch.from_numpy(np.concatenate(utts, 0)).cuda()
+    offs = np.zeros(len(utts) + 1, np.int32)
+    offs[1:] = np.cumsum([u.shape[0] for u in utts])
+    out = ex.run_segments(feats, offs)
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+CASES = [
+    ("tdnn", 40, [61, 25, 320, 100]),
+    ("tdnn", 80, [47, 200]),
+    ("res2net50_w24_s4_c32", 80, [200, 57, 25, 26]),
+    ("res2net50_w24_s4_c32", 40, [64, 33]),
+    ("res2net50_w8_s6_c16", 80, [40, 121]),
+    ("res2net50_w24_s4_c64", 40, [48]),
+    ("dpn68", 80, [64, 57, 25, 26, 200]),
+    ("dpn68", 40, [50, 31]),
+]
+
+
+@pytest.mark.parametrize("model_id,feat_dim,lens", CASES)
+@pytest.mark.parametrize("path", ["umma", "simple"])
+def test_segments_match_oracle(model_id, feat_dim, lens, path):
+    cfg, params, ex = model(model_id, feat_dim)
+    ex.set_option("force_simple", 1 if path == "simple" else 0)
+    rng = np.random.default_rng(1234)
+    utts = [net_oracle.synth_feats(rng, 1, t, feat_dim)[0] for t in lens]
+    got = run_segments(ex, utts)
+    ex.set_option("force_simple", 0)
+    want = oracle_segments(cfg, params, utts)
+    assert np.isfinite(got).all()
+    cos = cosines(got, want)
+    assert cos.min() >= COS_TOL, (cos, np.abs(got - want).max())
+    assert ex.last_launches > 0
+
+
+def test_batch_independence():
+    """A segment's embedding must not depend on its neighbours in the tall image (zero rows isolate them)."""
+    cfg, params, ex = model("res2net50_w24_s4_c32", 80)
+    rng = np.random.default_rng(7)
+    utts = [net_oracle.synth_feats(rng, 1, t, 80)[0] for t in (90, 41, 200, 33)]
+    together = run_segments(ex, utts)
+    alone = np.concatenate([run_segments(ex, [u]) for u in utts])
+    np.testing.assert_allclose(together, alone, rtol=0, atol=1e-5)
+
+
+@pytest.mark.parametrize("model_id,feat_dim", [("tdnn", 40), ("res2net50_w8_s6_c16", 80)])
+def test_chunk_rule(model_id, feat_dim):
+    """tf_extract.py:96-111: 1000-frame chunks, tail < 25 dropped, length-weighted mean; T=1024 vs 1025."""
+    cfg, params, ex = model(model_id, feat_dim)
+    rng = np.random.default_rng(99)
+    utts = [net_oracle.synth_feats(rng, 1, t, feat_dim)[0] for t in (1024, 1025, 300, 2030)]
+    got = ex.extract(utts)
+    want = np.stack([net_oracle.extract_utterance(cfg, params, u) for u in utts])
+    cos = cosines(got, want)
+    assert cos.min() >= COS_TOL, cos
+    # the 24-frame tail of the 1024-frame utterance is dropped: identical to its first 1000 frames
+    first = ex.extract([utts[0][:1000]])
+    np.testing.assert_allclose(got[0], first[0], atol=1e-5)
+
+
+def test_short_utterance_fails_loudly():
+    _, _, ex = model("tdnn", 40)
+    from voxsrc2020_speaker_verification_b200.lib import SvxError
+    with pytest.raises(SvxError):
+        ex.extract([np.zeros((24, 40), np.float32)])
+
+
+def test_bf16_precision_mode():
+    cfg, params, ex = model("tdnn", 40, "bf16")
+    rng = np.random.default_rng(5)
+    utts = [net_oracle.synth_feats(rng, 1, t, 40)[0] for t in (80, 200)]
+    cos = cosines(run_segments(ex, utts), oracle_segments(cfg, params, utts))
+    assert cos.min() >= 0.9995, cos
+
+
+def test_extract_bucketed_order():
+    cfg, params, ex = model("tdnn", 40)
+    rng = np.random.default_rng(3)
+    utts = [net_oracle.synth_feats(rng, 1, t, 40)[0] for t in (200, 30, 120, 55, 400)]
+    a = ex.extract_bucketed(utts, max_frames=300)
+    b = ex.extract(utts)
+    np.testing.assert_allclose(a, b, atol=1e-5)
+
+
+def test_full_size_properties():
+    """BASELINE config 2 shape (batch 256 x 200 frames x 80-d): finite, deterministic, and equal to the
+    same utterances run in smaller groups."""
+    cfg, params, ex = model("res2net50_w24_s4_c32", 80)
+    rng = np.random.default_rng(11)
+    feats = net_oracle.synth_feats(rng, 256, 200, 80)
+    utts = [feats[i] for i in range(256)]
+    a = run_segments(ex, utts)
+    b = run_segments(ex, utts)
+    assert np.isfinite(a).all()
+    np.testing.assert_array_equal(a, b)
+    c = run_segments(ex, utts[:7])
+    np.testing.assert_allclose(a[:7], c, atol=1e-5)
+    want = oracle_segments(cfg, params, utts[:2])
+    assert cosines(a[:2], want).min() >= COS_TOL

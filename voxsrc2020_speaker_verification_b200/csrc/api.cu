@@ -1,0 +1,271 @@
+// C ABI (include/svx.h): handle management, error reporting, and the scorer that strings the scoring kernels
+// together (cohort GEMM on tcgen05 → exact top-k statistics → trial gather).
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "kernels.cuh"
+#include "model.h"
+#include "umma.cuh"
+
+namespace svx {
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+}  // namespace svx
+
+using namespace svx;
+
+struct svx_extractor { Model* model; };
+
+struct svx_scorer {
+  int device = 0;
+  long long launches = 0;
+  // workspaces
+  __nv_bfloat16* d_a = nullptr; size_t a_bytes = 0;     // split test block [block_rows, 3d]
+  __nv_bfloat16* d_b = nullptr; size_t b_bytes = 0;     // split cohort [c_pad, 3d]
+  float* d_s = nullptr; size_t s_bytes = 0;             // score block [block_rows, c_pad]
+};
+
+#define API_CUDA(expr)                                                                           \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) {                                                                     \
+      set_last_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e));                 \
+      return 1;                                                                                  \
+    }                                                                                            \
+  } while (0)
+
+static int require_device(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    set_last_error(std::string("no CUDA device available: ") + cudaGetErrorString(e) + " — libsvx has no CPU fallback");
+    return 1;
+  }
+  if (device < 0 || device >= n) { set_last_error("invalid device index"); return 1; }
+  cudaDeviceProp p;
+  if (cudaGetDeviceProperties(&p, device) != cudaSuccess) { set_last_error("cudaGetDeviceProperties failed"); return 1; }
+  if (p.major != 10) {
+    set_last_error("libsvx is built for sm_100a (B200); device is sm_" + std::to_string(p.major) + std::to_string(p.minor));
+    return 1;
+  }
+  return 0;
+}
+
+template <typename P>
+static int grow_buf(P** p, size_t* have, size_t need) {
+  if (need <= *have) return 0;
+  cudaDeviceSynchronize();
+  cudaFree(*p);
+  *p = nullptr;
+  if (cudaMalloc(p, need) != cudaSuccess) { set_last_error("cudaMalloc failed in scorer"); return 1; }
+  *have = need;
+  return 0;
+}
+
+extern "C" {
+
+int svx_version(void) { return 100; }
+
+const char* svx_last_error(void) { return g_last_error.c_str(); }
+
+int svx_extractor_create(const svx_model_config* cfg, int device, int precision, svx_extractor** out) {
+  if (!cfg || !out) { set_last_error("null argument"); return 1; }
+  *out = nullptr;
+  if (precision != SVX_PRECISION_FP16 && precision != SVX_PRECISION_BF16) { set_last_error("unknown precision"); return 1; }
+  if (require_device(device)) return 1;
+  Model* m = new (std::nothrow) Model(*cfg, device, precision);
+  if (!m) { set_last_error("out of host memory"); return 1; }
+  if (m->build()) { delete m; return 1; }
+  svx_extractor* h = new svx_extractor{m};
+  *out = h;
+  return 0;
+}
+
+int svx_extractor_destroy(svx_extractor* h) {
+  if (!h) return 0;
+  delete h->model;
+  delete h;
+  return 0;
+}
+
+int svx_extractor_num_tensors(svx_extractor* h) { return h ? static_cast<int>(h->model->vars().size()) : -1; }
+
+int svx_extractor_tensor_info(svx_extractor* h, int index, const char** name, int* ndim, int64_t shape[4]) {
+  if (!h || index < 0 || index >= static_cast<int>(h->model->vars().size())) { set_last_error("bad tensor index"); return 1; }
+  const VarSpec& v = h->model->vars()[index];
+  if (name) *name = v.name.c_str();
+  if (ndim) *ndim = static_cast<int>(v.shape.size());
+  if (shape) for (size_t i = 0; i < v.shape.size() && i < 4; ++i) shape[i] = v.shape[i];
+  return 0;
+}
+
+int svx_extractor_set_tensor(svx_extractor* h, const char* name, const float* data, int ndim, const int64_t* shape) {
+  if (!h || !name || !data || !shape) { set_last_error("null argument"); return 1; }
+  return h->model->set_tensor(name, data, ndim, shape);
+}
+
+int svx_extractor_finalize(svx_extractor* h) { if (!h) { set_last_error("null handle"); return 1; } return h->model->finalize(); }
+int svx_extractor_embed_dim(svx_extractor* h) { return h ? h->model->embed_dim() : -1; }
+int svx_extractor_set_option(svx_extractor* h, const char* key, int value) {
+  if (!h || !key) { set_last_error("null argument"); return 1; }
+  return h->model->set_option(key, value);
+}
+
+int svx_extractor_run_segments(svx_extractor* h, const float* feats_dev, const int32_t* frame_offsets_host, int n_segments,
+                               float* out_dev, void* cuda_stream) {
+  if (!h || !feats_dev || !frame_offsets_host || !out_dev) { set_last_error("null argument"); return 1; }
+  return h->model->run_segments(feats_dev, frame_offsets_host, n_segments, out_dev, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int svx_extractor_extract(svx_extractor* h, const float* feats, int feats_on_device, const int32_t* frame_offsets_host, int n_utts,
+                          float* out, int out_on_device, void* cuda_stream) {
+  if (!h || !feats || !frame_offsets_host || !out) { set_last_error("null argument"); return 1; }
+  return h->model->extract(feats, feats_on_device, frame_offsets_host, n_utts, out, out_on_device,
+                           static_cast<cudaStream_t>(cuda_stream));
+}
+
+long long svx_extractor_last_launches(svx_extractor* h) { return h ? h->model->last_launches() : -1; }
+
+int svx_extractor_conv_time(svx_extractor* h, double* ms, double* flops) {
+  if (!h || !ms || !flops) { set_last_error("null argument"); return 1; }
+  return h->model->conv_time(ms, flops);
+}
+
+// ------------------------------------------------------------------------------------------------ scoring
+int svx_scorer_create(int device, svx_scorer** out) {
+  if (!out) { set_last_error("null argument"); return 1; }
+  *out = nullptr;
+  if (require_device(device)) return 1;
+  API_CUDA(cudaSetDevice(device));
+  API_CUDA(conv_umma_init());
+  svx_scorer* s = new svx_scorer();
+  s->device = device;
+  *out = s;
+  return 0;
+}
+
+int svx_scorer_destroy(svx_scorer* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaFree(h->d_a); cudaFree(h->d_b); cudaFree(h->d_s);
+  delete h;
+  return 0;
+}
+
+int svx_l2norm_rows(const float* in_dev, float* out_dev, int64_t n, int d, void* cuda_stream) {
+  if (!in_dev || !out_dev) { set_last_error("null argument"); return 1; }
+  API_CUDA(launch_l2norm_rows(in_dev, out_dev, n, d, static_cast<cudaStream_t>(cuda_stream)));
+  return 0;
+}
+
+int svx_group_means(const float* unit_rows_dev, int64_t n, int d, const int32_t* group_dev, const float* inv_count_dev,
+                    float* out_dev, int n_groups, void* cuda_stream) {
+  if (!unit_rows_dev || !group_dev || !inv_count_dev || !out_dev) { set_last_error("null argument"); return 1; }
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  API_CUDA(cudaMemsetAsync(out_dev, 0, static_cast<size_t>(n_groups) * d * 4, st));
+  API_CUDA(launch_segment_mean(unit_rows_dev, n, d, group_dev, inv_count_dev, out_dev, n_groups, st));
+  return 0;
+}
+
+static int cohort_pass(svx_scorer* h, const float* test_dev, int64_t n, const float* cohort_dev, int c, int d, int topk,
+                       float* mean_dev, float* std_dev, float* vals_dev, void* cuda_stream);
+
+int svx_asnorm_stats(svx_scorer* h, const float* test_dev, int64_t n, const float* cohort_dev, int c, int d, int topk,
+                     float* mean_dev, float* std_dev, void* cuda_stream) {
+  if (!h || !test_dev || !cohort_dev || !mean_dev || !std_dev) { set_last_error("null argument"); return 1; }
+  return cohort_pass(h, test_dev, n, cohort_dev, c, d, topk, mean_dev, std_dev, nullptr, cuda_stream);
+}
+
+int svx_cohort_topk_values(svx_scorer* h, const float* test_dev, int64_t n, const float* cohort_dev, int c, int d, int topk,
+                           float* vals_dev, void* cuda_stream) {
+  if (!h || !test_dev || !cohort_dev || !vals_dev) { set_last_error("null argument"); return 1; }
+  return cohort_pass(h, test_dev, n, cohort_dev, c, d, topk, nullptr, nullptr, vals_dev, cuda_stream);
+}
+
+int svx_topk_stats(const float* vals_dev, int ld, int64_t n, int m, int topk, float* mean_dev, float* std_dev, void* cuda_stream) {
+  if (!vals_dev || !mean_dev || !std_dev) { set_last_error("null argument"); return 1; }
+  if (m <= 0 || topk <= 0 || ld < m) { set_last_error("bad top-k merge shape"); return 1; }
+  API_CUDA(launch_topk_stats(vals_dev, ld, n, m, topk, mean_dev, std_dev, nullptr, 0, static_cast<cudaStream_t>(cuda_stream)));
+  return 0;
+}
+
+}  // extern "C"
+
+static int cohort_pass(svx_scorer* h, const float* test_dev, int64_t n, const float* cohort_dev, int c, int d, int topk,
+                       float* mean_dev, float* std_dev, float* vals_dev, void* cuda_stream) {
+  if (c <= 0 || d <= 0 || topk <= 0) { set_last_error("cohort size, dimension and topk must be positive"); return 1; }
+  if (d % 8 != 0) { set_last_error("embedding dimension must be a multiple of 8"); return 1; }
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  API_CUDA(cudaSetDevice(h->device));
+  h->launches = 0;
+  if (n <= 0) return 0;
+  const int K = 3 * d;
+  const int kbox = (K % 64 == 0) ? 64 : (K % 32 == 0 ? 32 : 16);
+  const int nkc = (K + kbox - 1) / kbox;
+  int n_tile = 256;
+  while (n_tile > 16 && n_tile / 2 >= c) n_tile /= 2;
+  const int c_pad = (c + n_tile - 1) / n_tile * n_tile;
+  const int block_rows = 4096;
+  if (grow_buf(&h->d_a, &h->a_bytes, static_cast<size_t>(block_rows) * K * 2)) return 1;
+  if (grow_buf(&h->d_b, &h->b_bytes, static_cast<size_t>(c_pad) * K * 2)) return 1;
+  if (grow_buf(&h->d_s, &h->s_bytes, static_cast<size_t>(block_rows) * c_pad * 4)) return 1;
+  API_CUDA(launch_split3(cohort_dev, h->d_b, c, c_pad, d, 1, st));
+  ++h->launches;
+
+  UmmaConvParams up;
+  memset(&up, 0, sizeof up);
+  up.out_W = 1; up.w_box = 1; up.h_box = 128; up.w_tiles = 1;
+  up.taps = 1; up.nkc = nkc; up.kbox = kbox; up.n_tile = n_tile;
+  const int sw_bytes = kbox * 2;
+  up.layout_type = sw_bytes == 128 ? 2u : sw_bytes == 64 ? 4u : 6u;
+  up.sbo = 8u * sw_bytes;
+  up.idesc = ptx::make_idesc_f16(1u, 128u, static_cast<uint32_t>(n_tile));
+  up.a_stage_bytes = 128u * sw_bytes;
+  up.b_stage_bytes = static_cast<uint32_t>((n_tile * sw_bytes + 1023) / 1024 * 1024);
+  int stages = static_cast<int>((96 * 1024) / (up.a_stage_bytes + up.b_stage_bytes));
+  up.stages = stages < 2 ? 2 : (stages > 8 ? 8 : stages);
+  if (up.stages > nkc && nkc >= 2) up.stages = nkc;
+  int tc = 32;
+  while (tc < n_tile) tc *= 2;
+  up.tmem_cols = tc;
+  up.epi.n_valid = c_pad; up.epi.n_split = c_pad; up.epi.out_f32 = h->d_s; up.epi.ldf = c_pad;
+  AMaps am; CUtensorMap bm;
+  {
+    const uint64_t dims[3] = {static_cast<uint64_t>(K), 1, static_cast<uint64_t>(block_rows)};
+    const uint64_t str[2] = {static_cast<uint64_t>(K) * 2, static_cast<uint64_t>(K) * 2};
+    const uint32_t box[3] = {static_cast<uint32_t>(kbox), 1, 128};
+    if (encode_tmap(&am.m[0], 1, h->d_a, 3, dims, str, box, sw_bytes)) return 1;
+    for (int i = 1; i < 4; ++i) am.m[i] = am.m[0];
+    const uint64_t bdims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(c_pad)};
+    const uint64_t bstr[1] = {static_cast<uint64_t>(K) * 2};
+    const uint32_t bbox[2] = {static_cast<uint32_t>(kbox), static_cast<uint32_t>(n_tile)};
+    if (encode_tmap(&bm, 1, h->d_b, 2, bdims, bstr, bbox, sw_bytes)) return 1;
+  }
+  for (int64_t r0 = 0; r0 < n; r0 += block_rows) {
+    const int rows = static_cast<int>(n - r0 < block_rows ? n - r0 : block_rows);
+    const int rows_pad = (rows + 127) / 128 * 128;
+    API_CUDA(launch_split3(test_dev + r0 * d, h->d_a, rows, rows_pad, d, 0, st));
+    up.out_rows = rows;
+    API_CUDA(launch_conv_umma(up, am, bm, c_pad / n_tile, 1, st));
+    API_CUDA(launch_topk_stats(h->d_s, c_pad, rows, c, topk, mean_dev ? mean_dev + r0 : nullptr, std_dev ? std_dev + r0 : nullptr,
+                               vals_dev ? vals_dev + r0 * topk : nullptr, topk, st));
+    h->launches += 3;
+  }
+  return 0;
+}
+
+extern "C" {
+
+int svx_trial_scores(const float* emb_dev, int d, const int32_t* idx1_dev, const int32_t* idx2_dev, int64_t n_trials,
+                     const float* mean_dev, const float* std_dev, float* cos_dev, float* snorm_dev, void* cuda_stream) {
+  if (!emb_dev || !idx1_dev || !idx2_dev || !cos_dev) { set_last_error("null argument"); return 1; }
+  if (snorm_dev && (!mean_dev || !std_dev)) { set_last_error("snorm requested without cohort statistics"); return 1; }
+  API_CUDA(launch_trial_scores(emb_dev, d, idx1_dev, idx2_dev, n_trials, mean_dev, std_dev, cos_dev, snorm_dev,
+                               static_cast<cudaStream_t>(cuda_stream)));
+  return 0;
+}
+
+long long svx_scorer_last_launches(svx_scorer* h) { return h ? h->launches : -1; }
+
+}  // extern "C"

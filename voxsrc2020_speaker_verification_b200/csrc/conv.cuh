@@ -1,0 +1,135 @@
+// Shared parameter blocks for the convolution kernels (tcgen05 implicit-GEMM and the plain CUDA-core form).
+//
+// Activation layout ("tall image"): all segments (≤1000-frame chunks of utterances) of one call are stacked
+// along the time axis into one [rows, W, C] NHWC image per resolution stage, with at least one all-zero row
+// between consecutive segments.  The zero rows are the convolution's time padding, so one uniform tiling of
+// the tall image is exact for every segment, whatever its length.  seg_of_row[row] >= 0 marks rows that
+// belong to a segment; every epilogue writes zeros to the other rows it covers.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace svx {
+
+constexpr int kMaxTaps = 9;
+
+// Where a conv's output goes and what is fused on the way (BN as scale/shift, ReLU, residual, concat).
+struct Epilogue {
+  const float* scale;   // [n_total] or nullptr (=1)
+  const float* shift;   // [n_total] or nullptr (=0)
+  int pre_relu;         // relu(acc) before scale/shift   (TDNN: conv → ReLU → BN, tdnn_model.py:25-29)
+  int post_relu;        // relu after scale/shift/residual (Res2Net: conv → BN → ReLU)
+  int n_valid;          // real output channels (the MMA N may be padded up)
+  // primary destination: channels [0, n_split) → out[(row*W + col)*out_C + out_coff + c]
+  void* out; int out_C; int out_coff;
+  // optional residual added before post_relu, same channel range
+  const void* res; int res_C; int res_coff;
+  // channels [n_split, n_valid) → outb[... outb_coff + (c - n_split)], no residual
+  int n_split;
+  void* outb; int outb_C; int outb_coff;
+  // optional second output for channels [0, n_split): out2 = v + add2   (Res2Net x_{i+1} + o_i, res2net_model.py:65-66)
+  void* out2; int out2_C; int out2_coff;
+  const void* add2; int add2_C; int add2_coff;
+  // fp32 row-major output instead of 16-bit NHWC (scoring GEMM): out_f32[row*ldf + c]
+  float* out_f32; int ldf;
+  const int32_t* seg_of_row;   // nullptr → every row valid
+};
+
+// Geometry for the plain CUDA-core kernel (any stride / dilation / groups).
+struct SimpleConvParams {
+  const void* in; int in_C; int in_coff; int in_rows; int in_W;
+  const void* wgt;      // [n_pad][taps*kpad] K-major, same buffer the UMMA path uses
+  int kpad;             // padded input channels per tap
+  int cin_g;            // input channels per group
+  int cout_g;           // output channels per group
+  int grp_ntile;        // grouped weights: K positions of row n are relative to input channel
+  int grp_cstep;        //   (n / grp_ntile) * grp_cstep   (0/0 for dense: relative to channel 0)
+  int kh, kw, sh, sw, dh, dw, ph, pw;
+  int out_rows, out_W;
+  Epilogue epi;
+};
+
+// Geometry for the tcgen05 kernel.  One CTA = one 128-pixel (h_box x w_box) x n_tile output tile.
+struct UmmaConvParams {
+  int out_rows, out_W;
+  int w_box, h_box, w_tiles;
+  int taps;
+  int8_t tap_map[kMaxTaps];    // which of the (up to 4) A tensor maps the tap reads (stride-2 parity views)
+  int8_t tap_dh[kMaxTaps];     // row / col displacement of the tap in that map's coordinates
+  int8_t tap_dw[kMaxTaps];
+  int nkc;                     // k-boxes per tap
+  int kbox;                    // elements per k-box: 64 / 32 / 16 (= swizzle span / 2)
+  int a_c_step;                // grouped conv: input-channel offset per n-tile (0 for dense)
+  int n_tile;                  // UMMA N (multiple of 16, ≤ 256)
+  int stages;
+  uint32_t idesc, sbo, layout_type;
+  uint32_t a_stage_bytes, b_stage_bytes, tmem_cols;
+  Epilogue epi;
+};
+
+struct AMaps { CUtensorMap m[4]; };
+
+template <typename T> struct TypeOps;
+template <> struct TypeOps<__half> {
+  static __device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
+  static __device__ __forceinline__ __half from_f(float v) {
+    return __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+  }
+  static __device__ __forceinline__ uint32_t pack2(float a, float b) {
+    __half2 h = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  static __device__ __forceinline__ float2 unpack2(uint32_t u) {
+    return __half22float2(*reinterpret_cast<__half2*>(&u));
+  }
+};
+template <> struct TypeOps<__nv_bfloat16> {
+  static __device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+  static __device__ __forceinline__ __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
+  static __device__ __forceinline__ uint32_t pack2(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  static __device__ __forceinline__ float2 unpack2(uint32_t u) {
+    return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+  }
+};
+
+// Scalar epilogue used by the CUDA-core kernel (and as the semantic definition of the fused one).
+template <typename T>
+__device__ __forceinline__ void epilogue_scalar(const Epilogue& e, float acc, int row, int col, int W, int c, bool valid) {
+  if (c >= e.n_valid) return;
+  float v = acc;
+  if (e.pre_relu) v = fmaxf(v, 0.f);
+  if (e.scale) v *= e.scale[c];
+  if (e.shift) v += e.shift[c];
+  const size_t pix = static_cast<size_t>(row) * W + col;
+  if (e.out_f32) {
+    e.out_f32[static_cast<size_t>(row) * e.ldf + c] = valid ? v : 0.f;
+    return;
+  }
+  if (c < e.n_split) {
+    if (e.res) v += TypeOps<T>::to_f(static_cast<const T*>(e.res)[pix * e.res_C + e.res_coff + c]);
+    if (e.post_relu) v = fmaxf(v, 0.f);
+    if (!valid) v = 0.f;
+    static_cast<T*>(e.out)[pix * e.out_C + e.out_coff + c] = TypeOps<T>::from_f(v);
+    if (e.out2) {
+      float s = valid ? v + TypeOps<T>::to_f(static_cast<const T*>(e.add2)[pix * e.add2_C + e.add2_coff + c]) : 0.f;
+      static_cast<T*>(e.out2)[pix * e.out2_C + e.out2_coff + c] = TypeOps<T>::from_f(s);
+    }
+  } else {
+    if (e.post_relu) v = fmaxf(v, 0.f);
+    if (!valid) v = 0.f;
+    static_cast<T*>(e.outb)[pix * e.outb_C + e.outb_coff + (c - e.n_split)] = TypeOps<T>::from_f(v);
+  }
+}
+
+cudaError_t launch_conv_simple(const SimpleConvParams& p, int is_bf16, cudaStream_t stream);
+cudaError_t launch_conv_umma(const UmmaConvParams& p, const AMaps& amaps, const CUtensorMap& bmap, int n_total_tiles,
+                             int is_bf16, cudaStream_t stream);
+size_t conv_umma_smem_bytes(const UmmaConvParams& p);
+cudaError_t conv_umma_init();   // sets max dynamic smem attribute
+
+}  // namespace svx

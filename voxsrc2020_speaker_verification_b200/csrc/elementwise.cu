@@ -1,0 +1,375 @@
+// Bandwidth-bound kernels around the convolutions: input packing, Cin=1 stem conv, DPN pre-activation,
+// Res2Net stride-2 average pool, statistics pooling, the embedding FC and the chunk combine.
+// All use 128-bit accesses along the channel axis (NHWC, channels fastest).
+#include "kernels.cuh"
+
+namespace svx {
+
+// ---------------------------------------------------------------------------------------------------------
+// seg_of_row: mark which tall-image rows belong to which segment (-1 = zero padding row).
+__global__ void fill_seg_of_row_kernel(int32_t* seg_of_row, int rows_cap, const int32_t* seg_row_off, const int32_t* seg_h,
+                                       int n_seg) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows_cap) return;
+  // binary search: last segment whose offset <= i
+  int lo = 0, hi = n_seg - 1, ans = -1;
+  while (lo <= hi) {
+    const int mid = (lo + hi) >> 1;
+    if (seg_row_off[mid] <= i) { ans = mid; lo = mid + 1; } else { hi = mid - 1; }
+  }
+  int v = -1;
+  if (ans >= 0 && i < seg_row_off[ans] + seg_h[ans]) v = ans;
+  seg_of_row[i] = v;
+}
+
+cudaError_t launch_fill_seg_of_row(int32_t* seg_of_row, int rows, const int32_t* seg_row_off, const int32_t* seg_h, int n_seg,
+                                   cudaStream_t st) {
+  if (rows <= 0) return cudaSuccess;
+  fill_seg_of_row_kernel<<<(rows + 255) / 256, 256, 0, st>>>(seg_of_row, rows, seg_row_off, seg_h, n_seg);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// TDNN input: fp32 [frames, F] per segment → tall image [rows, 1, Cpad] 16-bit (reference tf_extract.py:32 with
+// expand_dim=2: the feature axis is the channel axis).  Padding rows and channels F..Cpad-1 are zero.
+template <typename T>
+__global__ void pack_input_kernel(const float* feats, const int32_t* seg_frame_off, const int32_t* seg_row_off,
+                                  const int32_t* seg_of_row, T* out, int rows, int F, int Cpad) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(rows) * Cpad;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % Cpad);
+  const int row = static_cast<int>(idx / Cpad);
+  const int seg = seg_of_row[row];
+  float v = 0.f;
+  if (seg >= 0 && c < F) v = feats[(static_cast<size_t>(seg_frame_off[seg]) + (row - seg_row_off[seg])) * F + c];
+  out[idx] = TypeOps<T>::from_f(v);
+}
+
+cudaError_t launch_pack_input(const float* feats, const int32_t* seg_frame_off, const int32_t* seg_row_off,
+                              const int32_t* seg_of_row, void* out, int rows, int F, int Cpad, int is_bf16, cudaStream_t st) {
+  const long long total = static_cast<long long>(rows) * Cpad;
+  if (total <= 0) return cudaSuccess;
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  if (is_bf16)
+    pack_input_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(feats, seg_frame_off, seg_row_off, seg_of_row,
+                                                              static_cast<__nv_bfloat16*>(out), rows, F, Cpad);
+  else
+    pack_input_kernel<__half><<<blocks, 256, 0, st>>>(feats, seg_frame_off, seg_row_off, seg_of_row,
+                                                       static_cast<__half*>(out), rows, F, Cpad);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Stem: 3x3 conv, Cin = 1, stride 1, zero padding (1,1) in time and feature, then BN and ReLU
+// (res2net_model.py:192-203, dpn_model.py:32-37).  Reads the fp32 features directly ([N,T,F,1] with expand_dim=3),
+// writes the stage-0 tall image [rows, F, Cpad].  One thread = one pixel x 8 output channels.
+template <typename T>
+__global__ void __launch_bounds__(256) stem_conv_kernel(const float* feats, const int32_t* seg_frame_off, const int32_t* seg_row_off,
+                                                        const int32_t* seg_h, const int32_t* seg_of_row, const float* w9,
+                                                        const float* scale, const float* shift, T* out, int rows, int F,
+                                                        int C, int Cpad) {
+  extern __shared__ float sw[];   // [9][Cpad] weights, then scale[Cpad], shift[Cpad]
+  for (int i = threadIdx.x; i < 9 * Cpad; i += blockDim.x) {
+    const int c = i % Cpad;
+    sw[i] = c < C ? w9[(i / Cpad) * C + c] : 0.f;
+  }
+  for (int i = threadIdx.x; i < Cpad; i += blockDim.x) {
+    sw[9 * Cpad + i] = i < C ? scale[i] : 0.f;
+    sw[10 * Cpad + i] = i < C ? shift[i] : 0.f;
+  }
+  __syncthreads();
+  const int groups = Cpad >> 3;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(rows) * F * groups;
+  if (idx >= total) return;
+  const int g = static_cast<int>(idx % groups);
+  const long long pix = idx / groups;
+  const int f = static_cast<int>(pix % F);
+  const int row = static_cast<int>(pix / F);
+  const int seg = seg_of_row[row];
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = 0.f;
+  if (seg >= 0) {
+    const int t = row - seg_row_off[seg];
+    const int T_ = seg_h[seg];
+    const float* base = feats + static_cast<size_t>(seg_frame_off[seg]) * F;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int tt = t + r - 1;
+      if (tt < 0 || tt >= T_) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int ff = f + s - 1;
+        if (ff < 0 || ff >= F) continue;
+        const float x = base[static_cast<size_t>(tt) * F + ff];
+        const float* wk = sw + (r * 3 + s) * Cpad + g * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += x * wk[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j] * sw[9 * Cpad + g * 8 + j] + sw[10 * Cpad + g * 8 + j], 0.f);
+  }
+  uint4 o;
+  o.x = TypeOps<T>::pack2(v[0], v[1]); o.y = TypeOps<T>::pack2(v[2], v[3]);
+  o.z = TypeOps<T>::pack2(v[4], v[5]); o.w = TypeOps<T>::pack2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(out + pix * Cpad + g * 8) = o;
+}
+
+cudaError_t launch_stem_conv(const float* feats, const int32_t* seg_frame_off, const int32_t* seg_row_off, const int32_t* seg_h,
+                             const int32_t* seg_of_row, const float* w9, const float* scale, const float* shift, void* out,
+                             int rows, int F, int C, int Cpad, int is_bf16, cudaStream_t st) {
+  const long long total = static_cast<long long>(rows) * F * (Cpad / 8);
+  if (total <= 0) return cudaSuccess;
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  const size_t smem = 11 * Cpad * sizeof(float);
+  if (is_bf16)
+    stem_conv_kernel<__nv_bfloat16><<<blocks, 256, smem, st>>>(feats, seg_frame_off, seg_row_off, seg_h, seg_of_row, w9, scale,
+                                                                shift, static_cast<__nv_bfloat16*>(out), rows, F, C, Cpad);
+  else
+    stem_conv_kernel<__half><<<blocks, 256, smem, st>>>(feats, seg_frame_off, seg_row_off, seg_h, seg_of_row, w9, scale, shift,
+                                                         static_cast<__half*>(out), rows, F, C, Cpad);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// y = relu(x*scale + shift) over a channel slice, optionally sub-sampled by 2 in time and feature
+// (DPN pre-activation BN→ReLU, dpn_model.py:41-42, for the block input that several convs normalise differently;
+// the stride-2 1x1 projection, dpn_model.py:75, samples even positions of each segment [ext: TF SAME, k=1]).
+template <typename T>
+__global__ void __launch_bounds__(256) bn_relu_kernel(const T* in, int in_C, int in_coff, int in_W, const float* scale,
+                                                      const float* shift, T* out, int out_C, int out_rows, int out_W, int C,
+                                                      int stride, const int32_t* out_seg_of_row, const int32_t* out_seg_row_off,
+                                                      const int32_t* in_seg_row_off) {
+  const int groups = C >> 3;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(out_rows) * out_W * groups;
+  if (idx >= total) return;
+  const int g = static_cast<int>(idx % groups);
+  const long long pix = idx / groups;
+  const int col = static_cast<int>(pix % out_W);
+  const int row = static_cast<int>(pix / out_W);
+  const int seg = out_seg_of_row[row];
+  uint4 o = make_uint4(0, 0, 0, 0);
+  if (seg >= 0) {
+    const int in_row = stride == 1 ? row : in_seg_row_off[seg] + (row - out_seg_row_off[seg]) * stride;
+    const int in_col = col * stride;
+    const uint4 x = *reinterpret_cast<const uint4*>(in + (static_cast<size_t>(in_row) * in_W + in_col) * in_C + in_coff + g * 8);
+    const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+    uint32_t os[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 f = TypeOps<T>::unpack2(xs[j]);
+      const int c = g * 8 + j * 2;
+      f.x = fmaxf(f.x * scale[c] + shift[c], 0.f);
+      f.y = fmaxf(f.y * scale[c + 1] + shift[c + 1], 0.f);
+      os[j] = TypeOps<T>::pack2(f.x, f.y);
+    }
+    o = make_uint4(os[0], os[1], os[2], os[3]);
+  }
+  *reinterpret_cast<uint4*>(out + pix * out_C + g * 8) = o;
+}
+
+cudaError_t launch_bn_relu(const void* in, int in_C, int in_coff, int in_W, const float* scale, const float* shift, void* out,
+                           int out_C, int out_rows, int out_W, int C, int stride, const int32_t* out_seg_of_row,
+                           const int32_t* out_seg_row_off, const int32_t* in_seg_row_off, int is_bf16, cudaStream_t st) {
+  const long long total = static_cast<long long>(out_rows) * out_W * (C / 8);
+  if (total <= 0) return cudaSuccess;
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  if (is_bf16)
+    bn_relu_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), in_C, in_coff, in_W, scale, shift,
+                                                           static_cast<__nv_bfloat16*>(out), out_C, out_rows, out_W, C, stride,
+                                                           out_seg_of_row, out_seg_row_off, in_seg_row_off);
+  else
+    bn_relu_kernel<__half><<<blocks, 256, 0, st>>>(static_cast<const __half*>(in), in_C, in_coff, in_W, scale, shift,
+                                                    static_cast<__half*>(out), out_C, out_rows, out_W, C, stride, out_seg_of_row,
+                                                    out_seg_row_off, in_seg_row_off);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Res2Net stride-2 last split: avg_pool 3x3 / 2, VALID over the (1,1) zero-padded tensor → divisor always 9
+// (res2net_model.py:76-77).  Uniform row map in_row = 2*out_row + r - 1 (layout guarantees it per segment).
+template <typename T>
+__global__ void __launch_bounds__(256) avgpool3x3s2_kernel(const T* in, int in_C, int in_coff, int in_rows, int in_W, T* out,
+                                                           int out_C, int out_coff, int out_rows, int out_W, int C,
+                                                           const int32_t* out_seg_of_row) {
+  const int groups = C >> 3;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(out_rows) * out_W * groups;
+  if (idx >= total) return;
+  const int g = static_cast<int>(idx % groups);
+  const long long pix = idx / groups;
+  const int col = static_cast<int>(pix % out_W);
+  const int row = static_cast<int>(pix / out_W);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (out_seg_of_row[row] >= 0) {
+    for (int r = 0; r < 3; ++r) {
+      const int ir = 2 * row + r - 1;
+      if (ir < 0 || ir >= in_rows) continue;
+      for (int s = 0; s < 3; ++s) {
+        const int ic = 2 * col + s - 1;
+        if (ic < 0 || ic >= in_W) continue;
+        const uint4 x = *reinterpret_cast<const uint4*>(in + (static_cast<size_t>(ir) * in_W + ic) * in_C + in_coff + g * 8);
+        const float2 a = TypeOps<T>::unpack2(x.x), b = TypeOps<T>::unpack2(x.y), c = TypeOps<T>::unpack2(x.z),
+                     d = TypeOps<T>::unpack2(x.w);
+        acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+      }
+    }
+  }
+  const float k = 1.f / 9.f;
+  uint4 o;
+  o.x = TypeOps<T>::pack2(acc[0] * k, acc[1] * k); o.y = TypeOps<T>::pack2(acc[2] * k, acc[3] * k);
+  o.z = TypeOps<T>::pack2(acc[4] * k, acc[5] * k); o.w = TypeOps<T>::pack2(acc[6] * k, acc[7] * k);
+  *reinterpret_cast<uint4*>(out + pix * out_C + out_coff + g * 8) = o;
+}
+
+cudaError_t launch_avgpool3x3s2(const void* in, int in_C, int in_coff, int in_rows, int in_W, void* out, int out_C, int out_coff,
+                                int out_rows, int out_W, int C, const int32_t* out_seg_of_row, int is_bf16, cudaStream_t st) {
+  const long long total = static_cast<long long>(out_rows) * out_W * (C / 8);
+  if (total <= 0) return cudaSuccess;
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  if (is_bf16)
+    avgpool3x3s2_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), in_C, in_coff, in_rows, in_W,
+                                                                static_cast<__nv_bfloat16*>(out), out_C, out_coff, out_rows,
+                                                                out_W, C, out_seg_of_row);
+  else
+    avgpool3x3s2_kernel<__half><<<blocks, 256, 0, st>>>(static_cast<const __half*>(in), in_C, in_coff, in_rows, in_W,
+                                                         static_cast<__half*>(out), out_C, out_coff, out_rows, out_W, C,
+                                                         out_seg_of_row);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Statistics pooling (models.py:262-269): per segment, per (w, c): mean over time and sqrt(population var + eps).
+// Two passes over the segment's rows (they sit in L2), fp32.  Optional fused pre-activation relu(x*scale+shift)
+// (DPN concat_bn_relu, dpn_model.py:24-29).  Output fp32 [n_seg, W*2C], index w*2C + {c | C + c}.
+// One thread = 2 adjacent channels of one (segment, w); lanes run along channels → coalesced 4-byte loads.
+template <typename T>
+__global__ void __launch_bounds__(256) stats_pool_kernel(const T* in, int C_tot, int C, int W, const int32_t* seg_row_off,
+                                                         const int32_t* seg_h, const float* scale, const float* shift, float* out,
+                                                         float eps) {
+  const int seg = blockIdx.y;
+  const int half_c = C >> 1;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= W * half_c) return;
+  const int w = idx / half_c;
+  const int c = (idx - w * half_c) * 2;
+  const int r0 = seg_row_off[seg];
+  const int H = seg_h[seg];
+  float s0 = 1.f, s1 = 1.f, b0 = 0.f, b1 = 0.f;
+  const bool act = scale != nullptr;
+  if (act) { s0 = scale[c]; s1 = scale[c + 1]; b0 = shift[c]; b1 = shift[c + 1]; }
+  const T* base = in + (static_cast<size_t>(r0) * W + w) * C_tot + c;
+  const size_t rstride = static_cast<size_t>(W) * C_tot;
+  float m0 = 0.f, m1 = 0.f;
+  for (int h = 0; h < H; ++h) {
+    float2 f = TypeOps<T>::unpack2(*reinterpret_cast<const uint32_t*>(base + h * rstride));
+    if (act) { f.x = fmaxf(f.x * s0 + b0, 0.f); f.y = fmaxf(f.y * s1 + b1, 0.f); }
+    m0 += f.x; m1 += f.y;
+  }
+  const float inv = 1.f / static_cast<float>(H);
+  m0 *= inv; m1 *= inv;
+  float v0 = 0.f, v1 = 0.f;
+  for (int h = 0; h < H; ++h) {
+    float2 f = TypeOps<T>::unpack2(*reinterpret_cast<const uint32_t*>(base + h * rstride));
+    if (act) { f.x = fmaxf(f.x * s0 + b0, 0.f); f.y = fmaxf(f.y * s1 + b1, 0.f); }
+    const float d0 = f.x - m0, d1 = f.y - m1;
+    v0 += d0 * d0; v1 += d1 * d1;
+  }
+  float* o = out + static_cast<size_t>(seg) * W * 2 * C + static_cast<size_t>(w) * 2 * C;
+  *reinterpret_cast<float2*>(o + c) = make_float2(m0, m1);
+  *reinterpret_cast<float2*>(o + C + c) = make_float2(sqrtf(v0 * inv + eps), sqrtf(v1 * inv + eps));
+}
+
+cudaError_t launch_stats_pool(const void* in, int C_tot, int C, int W, const int32_t* seg_row_off, const int32_t* seg_h, int n_seg,
+                              const float* scale, const float* shift, float* out, float eps, int is_bf16, cudaStream_t st) {
+  if (n_seg <= 0) return cudaSuccess;
+  dim3 grid((W * (C / 2) + 255) / 256, n_seg);
+  if (is_bf16)
+    stats_pool_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), C_tot, C, W, seg_row_off, seg_h,
+                                                            scale, shift, out, eps);
+  else
+    stats_pool_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(in), C_tot, C, W, seg_row_off, seg_h, scale, shift,
+                                                     out, eps);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Embedding FC with both 2-D batch norms folded in (BN → dense → BN, res2net_model.py:240-242):
+//   out[n, e] = bias[e] + sum_d pooled[n, d] * Wf[d, e]       Wf = diag(s1) W diag(s2), fp32.
+// Split-K: grid = (E/128, n-tiles of 8, K-splits); each thread owns one output column for 8 segments and
+// streams its slice of Wf with coalesced loads; partial sums are combined with fp32 atomics on an output
+// that was pre-set to the bias.
+constexpr int kFcRows = 8;
+constexpr int kFcKChunk = 512;
+
+__global__ void fc_init_kernel(float* out, const float* bias, int n, int E) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n * E) out[i] = bias[i % E];
+}
+
+__global__ void __launch_bounds__(128) fc_kernel(const float* __restrict__ pooled, const float* __restrict__ Wf, float* out, int n,
+                                                 int D, int E) {
+  __shared__ float sp[kFcRows][kFcKChunk];
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n0 = blockIdx.y * kFcRows;
+  const int d0 = blockIdx.z * kFcKChunk;
+  const int dn = min(kFcKChunk, D - d0);
+  for (int i = threadIdx.x; i < kFcRows * kFcKChunk; i += blockDim.x) {
+    const int r = i / kFcKChunk, d = i % kFcKChunk;
+    sp[r][d] = (n0 + r < n && d < dn) ? pooled[static_cast<size_t>(n0 + r) * D + d0 + d] : 0.f;
+  }
+  __syncthreads();
+  if (e >= E) return;
+  float acc[kFcRows];
+#pragma unroll
+  for (int r = 0; r < kFcRows; ++r) acc[r] = 0.f;
+  const float* wp = Wf + static_cast<size_t>(d0) * E + e;
+  for (int d = 0; d < dn; ++d) {
+    const float w = wp[static_cast<size_t>(d) * E];
+#pragma unroll
+    for (int r = 0; r < kFcRows; ++r) acc[r] += sp[r][d] * w;
+  }
+#pragma unroll
+  for (int r = 0; r < kFcRows; ++r)
+    if (n0 + r < n) atomicAdd(out + static_cast<size_t>(n0 + r) * E + e, acc[r]);
+}
+
+cudaError_t launch_fc(const float* pooled, const float* Wf, const float* bias, float* out, int n, int D, int E, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  fc_init_kernel<<<(n * E + 255) / 256, 256, 0, st>>>(out, bias, n, E);
+  dim3 grid((E + 127) / 128, (n + kFcRows - 1) / kFcRows, (D + kFcKChunk - 1) / kFcKChunk);
+  fc_kernel<<<grid, 128, 0, st>>>(pooled, Wf, out, n, D, E);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Chunk combine (tf_extract.py:104-111): utterance embedding = sum_i y_i * len_i / sum_i len_i over its chunks.
+__global__ void chunk_combine_kernel(const float* seg_emb, const int32_t* utt_seg_off, const int32_t* seg_len, float* out, int n_utt,
+                                     int E) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_utt * E) return;
+  const int u = i / E, e = i % E;
+  const int s0 = utt_seg_off[u], s1 = utt_seg_off[u + 1];
+  float acc = 0.f, tot = 0.f;
+  for (int s = s0; s < s1; ++s) {
+    const float l = static_cast<float>(seg_len[s]);
+    acc += seg_emb[static_cast<size_t>(s) * E + e] * l;
+    tot += l;
+  }
+  out[i] = acc / tot;
+}
+
+cudaError_t launch_chunk_combine(const float* seg_emb, const int32_t* utt_seg_off, const int32_t* seg_len, float* out, int n_utt,
+                                 int E, cudaStream_t st) {
+  if (n_utt <= 0) return cudaSuccess;
+  chunk_combine_kernel<<<(n_utt * E + 255) / 256, 256, 0, st>>>(seg_emb, utt_seg_off, seg_len, out, n_utt, E);
+  return cudaGetLastError();
+}
+
+}  // namespace svx

@@ -1,0 +1,35 @@
+// Launchers for the non-GEMM kernels (elementwise.cu, scoring.cu).
+#pragma once
+#include "conv.cuh"
+
+namespace svx {
+
+cudaError_t launch_fill_seg_of_row(int32_t* seg_of_row, int rows, const int32_t* seg_row_off, const int32_t* seg_h, int n_seg,
+                                   cudaStream_t st);
+cudaError_t launch_pack_input(const float* feats, const int32_t* seg_frame_off, const int32_t* seg_row_off,
+                              const int32_t* seg_of_row, void* out, int rows, int F, int Cpad, int is_bf16, cudaStream_t st);
+cudaError_t launch_stem_conv(const float* feats, const int32_t* seg_frame_off, const int32_t* seg_row_off, const int32_t* seg_h,
+                             const int32_t* seg_of_row, const float* w9, const float* scale, const float* shift, void* out,
+                             int rows, int F, int C, int Cpad, int is_bf16, cudaStream_t st);
+cudaError_t launch_bn_relu(const void* in, int in_C, int in_coff, int in_W, const float* scale, const float* shift, void* out,
+                           int out_C, int out_rows, int out_W, int C, int stride, const int32_t* out_seg_of_row,
+                           const int32_t* out_seg_row_off, const int32_t* in_seg_row_off, int is_bf16, cudaStream_t st);
+cudaError_t launch_avgpool3x3s2(const void* in, int in_C, int in_coff, int in_rows, int in_W, void* out, int out_C, int out_coff,
+                                int out_rows, int out_W, int C, const int32_t* out_seg_of_row, int is_bf16, cudaStream_t st);
+cudaError_t launch_stats_pool(const void* in, int C_tot, int C, int W, const int32_t* seg_row_off, const int32_t* seg_h, int n_seg,
+                              const float* scale, const float* shift, float* out, float eps, int is_bf16, cudaStream_t st);
+cudaError_t launch_fc(const float* pooled, const float* Wf, const float* bias, float* out, int n, int D, int E, cudaStream_t st);
+cudaError_t launch_chunk_combine(const float* seg_emb, const int32_t* utt_seg_off, const int32_t* seg_len, float* out, int n_utt,
+                                 int E, cudaStream_t st);
+
+// scoring
+cudaError_t launch_l2norm_rows(const float* in, float* out, long long n, int d, cudaStream_t st);
+cudaError_t launch_split3(const float* in, __nv_bfloat16* out, long long n, long long n_pad, int d, int cohort_side, cudaStream_t st);
+cudaError_t launch_topk_stats(const float* scores, int ld, long long n_rows, int c, int topk, float* mean, float* stdv,
+                              float* vals_out, int vals_ld, cudaStream_t st);
+cudaError_t launch_trial_scores(const float* emb, int d, const int32_t* idx1, const int32_t* idx2, long long t, const float* mean,
+                                const float* stdv, float* cos_out, float* snorm_out, cudaStream_t st);
+cudaError_t launch_segment_mean(const float* unit_rows, long long n, int d, const int32_t* group, const float* inv_count,
+                                float* out, int n_groups, cudaStream_t st);
+
+}  // namespace svx

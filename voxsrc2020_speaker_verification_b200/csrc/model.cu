@@ -1,0 +1,901 @@
+// Extractor model: layer plans that restate the reference graph builders as fused GPU ops.
+//   TDNN    reference tensorflow/models/tdnn_model.py:24-30,128-161
+//   Res2Net reference tensorflow/models/res2net_model.py:26-136,185-262
+//   DPN     reference tensorflow/models/dpn_model.py:24-171
+//   ops     reference tensorflow/models/models.py:62-67 (BN), :107-203 (conv, padding), :262-269 (stats pool), :306-309 (dense)
+#include "model.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "kernels.cuh"
+#include "umma.cuh"
+
+namespace svx {
+
+#define SVX_CUDA(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) {                                                                    \
+      set_last_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
+      return 1;                                                                                 \
+    }                                                                                           \
+  } while (0)
+
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+static inline int ceil_half(int a) { return (a + 1) / 2; }
+
+constexpr float kBnEps4d = 1.001e-5f;   // TF fused batch norm clamps epsilon for 4-D inputs [ext]
+constexpr float kBnEps2d = 1e-5f;       // models.py:20
+constexpr float kPoolEps = 1e-5f;       // models.py:262
+constexpr int kMaxChunk = 1000;         // tf_extract.py:96
+constexpr int kMinFrames = 25;          // tf_extract.py:101-102
+
+// ------------------------------------------------------------------------------------------------ TMA encode
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+int encode_tmap(CUtensorMap* m, int is_bf16, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                const uint32_t* box, int swizzle_bytes) {
+  PFN_encodeTiled fn = get_encode();
+  if (!fn) { set_last_error("cuTensorMapEncodeTiled entry point not available"); return 1; }
+  cuuint64_t gdim[5]; cuuint64_t gstr[5]; cuuint32_t bdim[5]; cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                        : swizzle_bytes == 64  ? CU_TENSOR_MAP_SWIZZLE_64B
+                        : swizzle_bytes == 32  ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(m, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, base, gdim, gstr, bdim,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu box %u %u %u stride0 %llu", (int)r, rank,
+             (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0), (unsigned long long)(rank > 2 ? dims[2] : 0),
+             box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, (unsigned long long)(rank > 1 ? strides_bytes[0] : 0));
+    set_last_error(buf);
+    return 1;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ construction
+Model::Model(const svx_model_config& cfg, int device, int precision) : cfg_(cfg), device_(device), is_bf16_(precision == SVX_PRECISION_BF16) {
+  const char* fs = getenv("SVX_FORCE_SIMPLE");
+  if (fs && fs[0] == '1') force_simple_ = 1;
+}
+
+Model::~Model() {
+  cudaSetDevice(device_);
+  for (void* p : owned_) cudaFree(p);
+  for (void* p : act_bufs_) cudaFree(p);
+  for (auto p : d_seg_row_off_) cudaFree(p);
+  for (auto p : d_seg_h_) cudaFree(p);
+  for (auto p : d_seg_of_row_) cudaFree(p);
+  cudaFree(d_seg_frame_off_); cudaFree(d_seg_len_); cudaFree(d_utt_seg_off_);
+  cudaFree(d_pooled_); cudaFree(d_seg_emb_); cudaFree(d_feats_); cudaFree(d_out_);
+  if (h_stage_) cudaFreeHost(h_stage_);
+  for (auto e : events_) cudaEventDestroy(e);
+}
+
+int Model::new_tensor(int stage, int C) {
+  ActTensor t; t.stage = stage; t.C = C;
+  tensors_.push_back(t);
+  return static_cast<int>(tensors_.size()) - 1;
+}
+
+std::string Model::next_name(std::map<std::string, int>& counts, const std::string& prefix, const std::string& base) {
+  int k = counts[base]++;
+  return prefix + (k == 0 ? base : base + "_" + std::to_string(k));
+}
+
+void Model::add_var(const std::string& name, std::vector<int64_t> shape) { vars_.push_back({name, std::move(shape)}); }
+
+int Model::build() {
+  if (cfg_.feat_dim <= 0 || cfg_.embed_dim <= 0) { set_last_error("bad feat_dim/embed_dim"); return 1; }
+  switch (cfg_.family) {
+    case SVX_FAMILY_TDNN: build_tdnn(); break;
+    case SVX_FAMILY_RES2NET: build_res2net(); break;
+    case SVX_FAMILY_DPN: build_dpn(); break;
+    default: set_last_error("unknown model family"); return 1;
+  }
+  return 0;
+}
+
+void Model::build_tdnn() {
+  std::map<std::string, int> root;
+  n_stages_ = 1; gap_ = 3; stage_W_ = {1};
+  const int F = cfg_.feat_dim;
+  int cur = new_tensor(0, round_up(F, 8));
+  { Op op; op.kind = OP_PACK_INPUT; op.out = {cur, 0}; ops_.push_back(op); }
+  int cin = F;
+  for (int l = 0; l < cfg_.tdnn_layers; ++l) {
+    const int f = cfg_.tdnn_filters[l], k = cfg_.tdnn_kernels[l], d = cfg_.tdnn_dilations[l];
+    Op op; op.kind = OP_CONV;
+    ConvDesc& c = op.conv;
+    c.kernel_name = next_name(root, "", "conv2d") + "/kernel";            // tdnn_model.py:25-27
+    add_var(c.kernel_name, {k, 1, cin, f});
+    c.bn_name = next_name(root, "", "batch_normalization");               // tdnn_model.py:29
+    add_var(c.bn_name + "/moving_mean", {f}); add_var(c.bn_name + "/moving_variance", {f});
+    c.in = {cur, 0}; c.cin = cin; c.kh = k; c.kw = 1; c.dil = d; c.ph = d * (k - 1) / 2; c.pw = 0; c.cout = f;
+    c.pre_relu = 1;                                                       // conv → ReLU → BN (tdnn_model.py:25-29)
+    cur = new_tensor(0, f);
+    c.out = {cur, 0};
+    ops_.push_back(op);
+    cin = f;
+  }
+  pool_tensor_ = cur; pool_C_ = cin; flat_dim_ = 2 * cin;
+  tail_bn1_ = next_name(root, "", "batch_normalization");
+  add_var(tail_bn1_ + "/moving_mean", {flat_dim_}); add_var(tail_bn1_ + "/moving_variance", {flat_dim_});
+  add_var("dense/kernel", {flat_dim_, cfg_.embed_dim});
+  tail_bn2_ = next_name(root, "", "batch_normalization");
+  add_var(tail_bn2_ + "/moving_mean", {cfg_.embed_dim}); add_var(tail_bn2_ + "/moving_variance", {cfg_.embed_dim});
+}
+
+void Model::build_res2net() {
+  std::map<std::string, int> root;
+  const int F = cfg_.feat_dim, S = cfg_.split;
+  // stage s = resolution after the s-th stride-2 layer
+  n_stages_ = 1; gap_ = 1; stage_W_ = {F};
+  for (int li = 0; li < 4; ++li)
+    if (cfg_.block_strides[li] == 2) { stage_W_.push_back(ceil_half(stage_W_.back())); ++n_stages_; }
+  int stage = 0;
+  // stem (res2net_model.py:192-203)
+  const int c0 = cfg_.num_filters[0];
+  int cur = new_tensor(0, round_up(c0, 8));
+  {
+    Op op; op.kind = OP_STEM; op.out = {cur, 0}; op.C = c0;
+    op.conv.kernel_name = next_name(root, "", "conv2d") + "/kernel";
+    add_var(op.conv.kernel_name, {3, 3, 1, c0});
+    op.bn_name = next_name(root, "", "batch_normalization");
+    add_var(op.bn_name + "/moving_mean", {c0}); add_var(op.bn_name + "/moving_variance", {c0});
+    ops_.push_back(op);
+  }
+  int cin = c0;
+  for (int li = 0; li < 4; ++li) {
+    const int filt = cfg_.num_filters[li], w = cfg_.width[li], cout = filt * 4, mid = S * w;
+    const int st = cfg_.block_strides[li];
+    const int in_stage = stage;
+    if (st == 2) ++stage;
+    const int xa = new_tensor(stage, cout), xb = new_tensor(stage, cout), sc = new_tensor(stage, cout);
+    const int m = new_tensor(stage, mid), z = new_tensor(stage, mid), y = new_tensor(stage, mid);
+    const int mp = st == 2 ? new_tensor(in_stage, mid) : -1;
+    int out_t = xa;
+    for (int b = 0; b < cfg_.block_sizes[li]; ++b) {
+      const bool first = b == 0;
+      const int bstride = first ? st : 1;
+      int shortcut = cur;
+      if (first) {   // projection shortcut: 1x1 conv stride s + BN (res2net_model.py:85-87,119-127)
+        Op op; op.kind = OP_CONV; ConvDesc& c = op.conv;
+        c.kernel_name = next_name(root, "", "conv2d") + "/kernel"; add_var(c.kernel_name, {1, 1, cin, cout});
+        c.bn_name = next_name(root, "", "batch_normalization");
+        add_var(c.bn_name + "/moving_mean", {cout}); add_var(c.bn_name + "/moving_variance", {cout});
+        c.in = {cur, 0}; c.cin = cin; c.stride = bstride; c.cout = cout; c.out = {sc, 0};
+        ops_.push_back(op);
+        shortcut = sc;
+      }
+      {   // conv1 1x1 + BN + ReLU (res2net_model.py:89-91)
+        Op op; op.kind = OP_CONV; ConvDesc& c = op.conv;
+        c.kernel_name = next_name(root, "", "conv2d") + "/kernel"; add_var(c.kernel_name, {1, 1, cin, mid});
+        c.bn_name = next_name(root, "", "batch_normalization");
+        add_var(c.bn_name + "/moving_mean", {mid}); add_var(c.bn_name + "/moving_variance", {mid});
+        c.in = {cur, 0}; c.cin = cin; c.cout = mid; c.post_relu = 1;
+        if (bstride == 1) { c.out = {m, 0}; c.n_split = (S - 1) * w; c.outb = {y, (S - 1) * w}; }   // last split passes through (:74-75)
+        else { c.out = {mp, 0}; }
+        ops_.push_back(op);
+      }
+      {   // hierarchical 3x3 (res2net_model.py:26-78)
+        std::map<std::string, int> inner;
+        const std::string hscope = next_name(root, "", "conv2d");
+        add_var(hscope + "/kernel", {3, 3, w, w * (S - 1)});
+        for (int i = 0; i < S - 1; ++i) {
+          Op op; op.kind = OP_CONV; ConvDesc& c = op.conv;
+          c.kernel_name = hscope + "/kernel"; c.kernel_out_off = i * w;
+          c.bn_name = next_name(inner, hscope + "/", "batch_normalization");
+          add_var(c.bn_name + "/moving_mean", {w}); add_var(c.bn_name + "/moving_variance", {w});
+          c.kh = c.kw = 3; c.stride = bstride; c.ph = c.pw = 1; c.cin = w; c.cout = w; c.post_relu = 1;
+          c.out = {y, i * w};
+          if (bstride == 1) {
+            c.in = {i == 0 ? m : z, i * w};
+            if (i < S - 2) { c.out2 = {z, (i + 1) * w}; c.add2 = {m, (i + 1) * w}; }   // x_{i+1} + o_i (:65-66)
+          } else {
+            c.in = {mp, i * w};                                                        // no cross-split add when strided
+          }
+          ops_.push_back(op);
+        }
+        if (bstride == 2) {   // last split: avg_pool 3x3/2 over the padded tensor (:76-77)
+          Op op; op.kind = OP_AVGPOOL; op.in = {mp, (S - 1) * w}; op.out = {y, (S - 1) * w}; op.C = w;
+          ops_.push_back(op);
+        }
+      }
+      {   // conv3 1x1 + BN + shortcut + ReLU (res2net_model.py:98-101)
+        Op op; op.kind = OP_CONV; ConvDesc& c = op.conv;
+        c.kernel_name = next_name(root, "", "conv2d") + "/kernel"; add_var(c.kernel_name, {1, 1, mid, cout});
+        c.bn_name = next_name(root, "", "batch_normalization");
+        add_var(c.bn_name + "/moving_mean", {cout}); add_var(c.bn_name + "/moving_variance", {cout});
+        c.in = {y, 0}; c.cin = mid; c.cout = cout; c.res = {shortcut, 0}; c.post_relu = 1; c.out = {out_t, 0};
+        ops_.push_back(op);
+      }
+      cur = out_t; out_t = (out_t == xa) ? xb : xa; cin = cout;
+    }
+  }
+  pool_tensor_ = cur; pool_C_ = cin; flat_dim_ = stage_W_.back() * 2 * cin;
+  tail_bn1_ = next_name(root, "", "batch_normalization");
+  add_var(tail_bn1_ + "/moving_mean", {flat_dim_}); add_var(tail_bn1_ + "/moving_variance", {flat_dim_});
+  add_var("dense/kernel", {flat_dim_, cfg_.embed_dim});
+  tail_bn2_ = next_name(root, "", "batch_normalization");
+  add_var(tail_bn2_ + "/moving_mean", {cfg_.embed_dim}); add_var(tail_bn2_ + "/moving_variance", {cfg_.embed_dim});
+}
+
+void Model::build_dpn() {
+  std::map<std::string, int> root;
+  const int F = cfg_.feat_dim;
+  n_stages_ = 4; gap_ = 1; stage_W_ = {F, ceil_half(F), ceil_half(ceil_half(F)), ceil_half(ceil_half(ceil_half(F)))};
+  const int c0 = cfg_.init_features;
+  int cur = new_tensor(0, round_up(c0, 8));   // raw block input of the next stage (S0 first, then X[s])
+  {
+    Op op; op.kind = OP_STEM; op.out = {cur, 0}; op.C = c0;                 // dpn_model.py:32-37
+    op.conv.kernel_name = next_name(root, "", "conv2d") + "/kernel"; add_var(op.conv.kernel_name, {3, 3, 1, c0});
+    op.bn_name = next_name(root, "", "batch_normalization");
+    add_var(op.bn_name + "/moving_mean", {c0}); add_var(op.bn_name + "/moving_variance", {c0});
+    ops_.push_back(op);
+  }
+  int c_in = c0;
+  auto bn_vars = [&](const std::string& n, int C) { add_var(n + "/moving_mean", {C}); add_var(n + "/moving_variance", {C}); };
+  for (int s = 0; s < 4; ++s) {
+    const int bw = cfg_.bw << s, inc = cfg_.inc_sec[s], r = cfg_.k_r * bw / cfg_.bw, card = cfg_.cardinality;
+    const int c_out = bw + (cfg_.k_sec[s] + 2) * inc;
+    const int st = s == 0 ? 1 : 2;
+    const int in_stage = s == 0 ? 0 : s - 1;
+    const int X = new_tensor(s, c_out);
+    const int XA = new_tensor(s, c_out), Y1 = new_tensor(s, r), Y2 = new_tensor(s, r);
+    const int XP = new_tensor(s, round_up(c_in, 8)), XAP = new_tensor(in_stage, round_up(c_in, 8)), Y1P = new_tensor(in_stage, r);
+    int c = c_in;
+    for (int b = 0; b < cfg_.k_sec[s]; ++b) {
+      const bool first = b == 0;
+      const int bstride = first ? st : 1;
+      int a_in, y1;
+      if (first) {
+        {   // projection: BN → ReLU → 1x1 conv stride s (dpn_model.py:75), split into res0 | dense0 (:76-79)
+          Op e; e.kind = OP_BN_RELU; e.bn_name = next_name(root, "", "batch_normalization"); bn_vars(e.bn_name, c_in);
+          e.in = {cur, 0}; e.out = {XP, 0}; e.C = c_in; e.stride = bstride; ops_.push_back(e);
+          Op op; op.kind = OP_CONV; ConvDesc& cv = op.conv;
+          cv.kernel_name = next_name(root, "", "conv2d") + "/kernel"; add_var(cv.kernel_name, {1, 1, c_in, bw + 2 * inc});
+          cv.in = {XP, 0}; cv.cin = c_in; cv.cout = bw + 2 * inc; cv.out = {X, 0};
+          ops_.push_back(op);
+        }
+        {   // conv_a input: BN → ReLU of the un-projected block input at its own resolution (dpn_model.py:49,81)
+          Op e; e.kind = OP_BN_RELU; e.bn_name = next_name(root, "", "batch_normalization"); bn_vars(e.bn_name, c_in);
+          e.in = {cur, 0}; e.out = {XAP, 0}; e.C = c_in; e.stride = 1; ops_.push_back(e);
+        }
+        a_in = XAP; y1 = Y1P;
+      } else {
+        Op e; e.kind = OP_BN_RELU; e.bn_name = next_name(root, "", "batch_normalization"); bn_vars(e.bn_name, c);
+        e.in = {X, 0}; e.out = {XA, 0}; e.C = c; e.stride = 1; ops_.push_back(e);
+        a_in = XA; y1 = Y1;
+      }
+      const int ca = first ? c_in : c;
+      // conv_a 1x1 → r, fused with the next BN → ReLU (dpn_model.py:49-50)
+      const std::string ka = next_name(root, "", "conv2d") + "/kernel"; add_var(ka, {1, 1, ca, r});
+      const std::string bnb = next_name(root, "", "batch_normalization"); bn_vars(bnb, r);
+      {
+        Op op; op.kind = OP_CONV; ConvDesc& cv = op.conv;
+        cv.kernel_name = ka; cv.bn_name = bnb; cv.in = {a_in, 0}; cv.cin = ca; cv.cout = r; cv.post_relu = 1; cv.out = {y1, 0};
+        ops_.push_back(op);
+      }
+      // conv_b 3x3 grouped, stride s, TF SAME, fused with the next BN → ReLU (dpn_model.py:50,53)
+      const std::string kb = next_name(root, "", "conv2d") + "/kernel"; add_var(kb, {3, 3, r / card, r});
+      const std::string bnc = next_name(root, "", "batch_normalization"); bn_vars(bnc, r);
+      {
+        Op op; op.kind = OP_CONV; ConvDesc& cv = op.conv;
+        cv.kernel_name = kb; cv.bn_name = bnc; cv.in = {y1, 0}; cv.cin = r; cv.cout = r; cv.groups = card;
+        cv.kh = cv.kw = 3; cv.stride = bstride; cv.post_relu = 1; cv.out = {Y2, 0};
+        cv.ph = 1;   // rows: the segment layout makes in_row = stride*out_row + r - 1 hold for even and odd lengths
+        cv.pw = bstride == 1 ? 1 : ((stage_W_[in_stage] % 2 == 0) ? 0 : 1);   // TF SAME, stride 2: pad_left = 0 for even extents [ext]
+        ops_.push_back(op);
+      }
+      // conv_c 1x1 → bw+inc, raw: first bw channels add into the residual path, the rest append to the dense path (:83-87)
+      {
+        Op op; op.kind = OP_CONV; ConvDesc& cv = op.conv;
+        cv.kernel_name = next_name(root, "", "conv2d") + "/kernel"; add_var(cv.kernel_name, {1, 1, r, bw + inc});
+        const int c_now = first ? bw + 2 * inc : c;
+        cv.in = {Y2, 0}; cv.cin = r; cv.cout = bw + inc; cv.n_split = bw;
+        cv.out = {X, 0}; cv.res = {X, 0}; cv.outb = {X, c_now};
+        ops_.push_back(op);
+        c = c_now + inc;
+      }
+    }
+    cur = X; c_in = c_out;
+  }
+  pool_tensor_ = cur; pool_C_ = c_in; flat_dim_ = stage_W_.back() * 2 * c_in;
+  pool_bn_ = next_name(root, "", "batch_normalization"); bn_vars(pool_bn_, c_in);   // dpn_model.py:24-29
+  tail_bn1_ = next_name(root, "", "batch_normalization"); bn_vars(tail_bn1_, flat_dim_);
+  add_var("dense/kernel", {flat_dim_, cfg_.embed_dim});
+  tail_bn2_ = next_name(root, "", "batch_normalization"); bn_vars(tail_bn2_, cfg_.embed_dim);
+}
+
+// ------------------------------------------------------------------------------------------------ weights
+int Model::set_tensor(const char* name, const float* data, int ndim, const int64_t* shape) {
+  for (const auto& v : vars_) {
+    if (v.name != name) continue;
+    if (static_cast<int>(v.shape.size()) != ndim) { set_last_error(std::string("rank mismatch for ") + name); return 1; }
+    size_t n = 1;
+    for (int i = 0; i < ndim; ++i) {
+      if (v.shape[i] != shape[i]) {
+        set_last_error(std::string("shape mismatch for ") + name + ": expected dim " + std::to_string(i) + " = " +
+                       std::to_string(v.shape[i]) + ", got " + std::to_string(shape[i]));
+        return 1;
+      }
+      n *= static_cast<size_t>(shape[i]);
+    }
+    HostTensor& t = host_[name];
+    t.shape.assign(shape, shape + ndim);
+    t.data.assign(data, data + n);
+    t.set = true;
+    return 0;
+  }
+  set_last_error(std::string("unknown tensor name: ") + name);
+  return 1;
+}
+
+int Model::fold_bn(const std::string& bn, int C, bool four_d, std::vector<float>& scale, std::vector<float>& shift) {
+  const HostTensor& m = host_[bn + "/moving_mean"];
+  const HostTensor& v = host_[bn + "/moving_variance"];
+  const float eps = four_d ? kBnEps4d : kBnEps2d;
+  scale.resize(C); shift.resize(C);
+  for (int i = 0; i < C; ++i) {
+    const float s = 1.0f / std::sqrt(v.data[i] + eps);
+    scale[i] = s;
+    shift[i] = -m.data[i] * s;
+  }
+  return 0;
+}
+
+template <typename T> static T host_cvt(float v);
+template <> __half host_cvt<__half>(float v) { return __float2half_rn(std::min(std::max(v, -65504.f), 65504.f)); }
+template <> __nv_bfloat16 host_cvt<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+static int pick_kbox(int cin) {
+  if (cin % 64 == 0) return 64;
+  if (cin % 32 == 0) return 32;
+  if (cin <= 16) return 16;
+  if (cin <= 32) return 32;
+  return 64;
+}
+
+static int pick_ntile(int cout) {
+  const int n = round_up(cout, 16);
+  if (n <= 256) return n;
+  for (int parts = 2; parts <= 16; ++parts)
+    if (n % parts == 0 && (n / parts) % 16 == 0 && n / parts <= 256) return n / parts;
+  return 128;
+}
+
+int Model::upload_conv_weights(ConvDesc& c) {
+  const HostTensor& k = host_[c.kernel_name];   // [kh,kw,cin_g,cout_total]
+  const int taps = c.kh * c.kw;
+  const int cin_g = c.cin / c.groups, cout_g = c.cout / c.groups;
+  const int cout_total = static_cast<int>(k.shape[3]);
+  const bool grouped = c.groups > 1;
+  int grp_ntile = 0, grp_cstep = 0;
+  if (grouped) {
+    if (cin_g != cout_g || 32 % cin_g != 0) { set_last_error("unsupported grouped conv shape"); return 1; }
+    grp_ntile = 32; grp_cstep = 32;
+    c.kbox = 32; c.nkc = 1; c.kpad = 32; c.n_tile = 32;
+  } else {
+    c.kbox = pick_kbox(c.cin);
+    c.nkc = (c.cin + c.kbox - 1) / c.kbox;
+    c.kpad = c.nkc * c.kbox;
+    c.n_tile = pick_ntile(c.cout);
+  }
+  c.n_pad = round_up(c.cout, c.n_tile);
+  c.n_tiles = c.n_pad / c.n_tile;
+  const size_t K = static_cast<size_t>(taps) * c.kpad;
+  std::vector<float> w(static_cast<size_t>(c.n_pad) * K, 0.f);
+  for (int n = 0; n < c.cout; ++n) {
+    const int g = n / cout_g;
+    const int abase = grouped ? (n / grp_ntile) * grp_cstep : 0;
+    for (int t = 0; t < taps; ++t)
+      for (int ci = 0; ci < cin_g; ++ci) {
+        const int j = g * cin_g + ci - abase;     // position inside the k-box row
+        w[static_cast<size_t>(n) * K + static_cast<size_t>(t) * c.kpad + j] =
+            k.data[(static_cast<size_t>(t) * cin_g + ci) * cout_total + c.kernel_out_off + n];
+      }
+  }
+  void* d = nullptr;
+  SVX_CUDA(cudaMalloc(&d, w.size() * 2));
+  owned_.push_back(d);
+  if (is_bf16_) {
+    std::vector<__nv_bfloat16> h(w.size());
+    for (size_t i = 0; i < w.size(); ++i) h[i] = host_cvt<__nv_bfloat16>(w[i]);
+    SVX_CUDA(cudaMemcpy(d, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+  } else {
+    std::vector<__half> h(w.size());
+    for (size_t i = 0; i < w.size(); ++i) h[i] = host_cvt<__half>(w[i]);
+    SVX_CUDA(cudaMemcpy(d, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+  }
+  c.d_wgt = d;
+  c.sp.grp_ntile = grp_ntile; c.sp.grp_cstep = grp_cstep;
+  if (!c.bn_name.empty()) {
+    std::vector<float> sc, sh;
+    fold_bn(c.bn_name, c.cout, true, sc, sh);
+    sc.resize(c.n_pad, 0.f); sh.resize(c.n_pad, 0.f);
+    float* ds = nullptr; float* dh = nullptr;
+    SVX_CUDA(cudaMalloc(&ds, c.n_pad * 4)); owned_.push_back(ds);
+    SVX_CUDA(cudaMalloc(&dh, c.n_pad * 4)); owned_.push_back(dh);
+    SVX_CUDA(cudaMemcpy(ds, sc.data(), c.n_pad * 4, cudaMemcpyHostToDevice));
+    SVX_CUDA(cudaMemcpy(dh, sh.data(), c.n_pad * 4, cudaMemcpyHostToDevice));
+    c.d_scale = ds; c.d_shift = dh;
+  }
+  return 0;
+}
+
+static int upload_floats(std::vector<void*>& owned, const std::vector<float>& v, float** out) {
+  float* d = nullptr;
+  if (cudaMalloc(&d, std::max<size_t>(v.size(), 1) * 4) != cudaSuccess) { set_last_error("cudaMalloc failed"); return 1; }
+  owned.push_back(d);
+  if (cudaMemcpy(d, v.data(), v.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) { set_last_error("cudaMemcpy failed"); return 1; }
+  *out = d;
+  return 0;
+}
+
+int Model::finalize() {
+  SVX_CUDA(cudaSetDevice(device_));
+  for (const auto& v : vars_)
+    if (!host_.count(v.name) || !host_[v.name].set) { set_last_error("tensor not set: " + v.name); return 1; }
+  SVX_CUDA(conv_umma_init());
+  for (Op& op : ops_) {
+    if (op.kind == OP_CONV) {
+      if (upload_conv_weights(op.conv)) return 1;
+    } else if (op.kind == OP_STEM) {
+      const HostTensor& k = host_[op.conv.kernel_name];   // [3,3,1,C] → [9][C]
+      if (upload_floats(owned_, k.data, &op.d_w9)) return 1;
+      std::vector<float> sc, sh;
+      fold_bn(op.bn_name, op.C, true, sc, sh);
+      if (upload_floats(owned_, sc, &op.d_scale) || upload_floats(owned_, sh, &op.d_shift)) return 1;
+    } else if (op.kind == OP_BN_RELU) {
+      std::vector<float> sc, sh;
+      fold_bn(op.bn_name, op.C, true, sc, sh);
+      const int cp = round_up(op.C, 8);
+      sc.resize(cp, 0.f); sh.resize(cp, 0.f);
+      if (upload_floats(owned_, sc, &op.d_scale) || upload_floats(owned_, sh, &op.d_shift)) return 1;
+    }
+  }
+  if (!pool_bn_.empty()) {
+    std::vector<float> sc, sh;
+    fold_bn(pool_bn_, pool_C_, true, sc, sh);
+    if (upload_floats(owned_, sc, &d_pool_scale_) || upload_floats(owned_, sh, &d_pool_shift_)) return 1;
+  }
+  {   // BN → dense → BN folded into one fp32 affine map (models.py:306-309 between two 2-D batch norms)
+    std::vector<float> s1, b1, s2, b2;
+    fold_bn(tail_bn1_, flat_dim_, false, s1, b1);
+    fold_bn(tail_bn2_, cfg_.embed_dim, false, s2, b2);
+    const HostTensor& W = host_["dense/kernel"];
+    const int D = flat_dim_, E = cfg_.embed_dim;
+    std::vector<float> Wf(static_cast<size_t>(D) * E);
+    std::vector<double> bias(E, 0.0);
+    for (int d = 0; d < D; ++d)
+      for (int e = 0; e < E; ++e) {
+        const float w = W.data[static_cast<size_t>(d) * E + e];
+        Wf[static_cast<size_t>(d) * E + e] = s1[d] * w * s2[e];
+        bias[e] += static_cast<double>(b1[d]) * w;
+      }
+    std::vector<float> bf(E);
+    for (int e = 0; e < E; ++e) bf[e] = static_cast<float>(bias[e] * s2[e] + b2[e]);
+    if (upload_floats(owned_, Wf, &d_Wf_) || upload_floats(owned_, bf, &d_bias_)) return 1;
+  }
+  host_.clear();
+  finalized_ = true;
+  return 0;
+}
+
+int Model::set_option(const char* key, int value) {
+  if (!strcmp(key, "force_simple")) { force_simple_ = value; return 0; }
+  if (!strcmp(key, "time_convs")) { time_convs_ = value; return 0; }
+  set_last_error(std::string("unknown option: ") + key);
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------------ workspace
+int Model::plan_conv(ConvDesc& c) {
+  const ActTensor& tin = tensors_[c.in.id];
+  const ActTensor& tout = tensors_[c.out.id];
+  const int in_W = stage_W_[tin.stage], out_W = stage_W_[tout.stage];
+  const int in_rows = rows_cap_[tin.stage];
+  auto tptr = [&](const TensorRef& r) -> void* { return r.id >= 0 ? tensors_[r.id].ptr : nullptr; };
+  auto tC = [&](const TensorRef& r) -> int { return r.id >= 0 ? tensors_[r.id].C : 0; };
+  Epilogue e;
+  memset(&e, 0, sizeof e);
+  e.scale = c.d_scale; e.shift = c.d_shift; e.pre_relu = c.pre_relu; e.post_relu = c.post_relu; e.n_valid = c.cout;
+  e.out = tptr(c.out); e.out_C = tC(c.out); e.out_coff = c.out.coff;
+  e.res = tptr(c.res); e.res_C = tC(c.res); e.res_coff = c.res.coff;
+  e.n_split = c.n_split < 0 ? c.cout : c.n_split;
+  e.outb = tptr(c.outb); e.outb_C = tC(c.outb); e.outb_coff = c.outb.coff;
+  e.out2 = tptr(c.out2); e.out2_C = tC(c.out2); e.out2_coff = c.out2.coff;
+  e.add2 = tptr(c.add2); e.add2_C = tC(c.add2); e.add2_coff = c.add2.coff;
+  e.seg_of_row = d_seg_of_row_[tout.stage];
+  // ---- CUDA-core form
+  SimpleConvParams& sp = c.sp;
+  sp.in = tin.ptr; sp.in_C = tin.C; sp.in_coff = c.in.coff; sp.in_rows = in_rows; sp.in_W = in_W;
+  sp.wgt = c.d_wgt; sp.kpad = c.kpad; sp.cin_g = c.cin / c.groups; sp.cout_g = c.cout / c.groups;
+  sp.kh = c.kh; sp.kw = c.kw; sp.sh = c.stride; sp.sw = c.stride; sp.dh = c.dil; sp.dw = 1; sp.ph = c.ph; sp.pw = c.pw;
+  sp.out_rows = 0; sp.out_W = out_W; sp.epi = e;
+  // ---- tcgen05 form
+  c.use_umma = false;
+  const int taps = c.kh * c.kw;
+  auto mult8 = [](int v) { return v % 8 == 0; };
+  bool ok = c.groups == 1 && taps <= kMaxTaps && (c.stride == 1 || (c.stride == 2 && c.dil == 1)) && mult8(tin.C) && mult8(c.in.coff) &&
+            mult8(c.cout) && mult8(e.out_C) && mult8(e.out_coff) && mult8(e.n_split) &&
+            (!e.res || (mult8(e.res_C) && mult8(e.res_coff))) && (!e.outb || (mult8(e.outb_C) && mult8(e.outb_coff))) &&
+            (!e.out2 || (mult8(e.out2_C) && mult8(e.out2_coff) && mult8(e.add2_C) && mult8(e.add2_coff)));
+  if (!ok) return 0;
+  UmmaConvParams& up = c.up;
+  memset(&up, 0, sizeof up);
+  int w_box = 1;
+  while (w_box < 128 && out_W % (w_box * 2) == 0) w_box *= 2;
+  up.out_rows = 0; up.out_W = out_W; up.w_box = w_box; up.h_box = 128 / w_box; up.w_tiles = out_W / w_box;
+  up.taps = taps; up.nkc = c.nkc; up.kbox = c.kbox; up.a_c_step = 0; up.n_tile = c.n_tile;
+  const int sw_bytes = c.kbox * 2;
+  up.layout_type = sw_bytes == 128 ? 2u : sw_bytes == 64 ? 4u : 6u;
+  up.sbo = 8u * sw_bytes;
+  up.idesc = ptx::make_idesc_f16(is_bf16_ ? 1u : 0u, 128u, static_cast<uint32_t>(c.n_tile));
+  up.a_stage_bytes = 128u * sw_bytes;
+  up.b_stage_bytes = static_cast<uint32_t>(round_up(c.n_tile * sw_bytes, 1024));
+  const int total_it = taps * c.nkc;
+  int stages = static_cast<int>((96 * 1024) / (up.a_stage_bytes + up.b_stage_bytes));
+  stages = std::max(2, std::min(std::min(stages, 8), std::max(total_it, 2)));
+  up.stages = stages;
+  int tc = 32;
+  while (tc < c.n_tile) tc *= 2;
+  up.tmem_cols = tc;
+  up.epi = e;
+  const size_t esz = 2;
+  uint8_t* base = static_cast<uint8_t*>(tin.ptr);
+  for (int t = 0; t < taps; ++t) {
+    const int r = t / c.kw, s = t % c.kw;
+    if (c.stride == 1) {
+      up.tap_map[t] = 0; up.tap_dh[t] = static_cast<int8_t>(r * c.dil - c.ph); up.tap_dw[t] = static_cast<int8_t>(s - c.pw);
+    } else {
+      const int a = r - c.ph, b = s - c.pw;
+      const int p = ((a % 2) + 2) % 2, q = ((b % 2) + 2) % 2;
+      up.tap_map[t] = static_cast<int8_t>(p * 2 + q);
+      up.tap_dh[t] = static_cast<int8_t>((a - p) / 2); up.tap_dw[t] = static_cast<int8_t>((b - q) / 2);
+    }
+  }
+  const uint32_t box[3] = {static_cast<uint32_t>(c.kbox), static_cast<uint32_t>(w_box), static_cast<uint32_t>(128 / w_box)};
+  if (c.stride == 1) {
+    const uint64_t dims[3] = {static_cast<uint64_t>(c.cin), static_cast<uint64_t>(in_W), static_cast<uint64_t>(in_rows)};
+    const uint64_t str[2] = {static_cast<uint64_t>(tin.C) * esz, static_cast<uint64_t>(in_W) * tin.C * esz};
+    if (encode_tmap(&c.amaps.m[0], is_bf16_, base + static_cast<size_t>(c.in.coff) * esz, 3, dims, str, box, sw_bytes)) return 1;
+    for (int i = 1; i < 4; ++i) c.amaps.m[i] = c.amaps.m[0];
+  } else {
+    for (int p = 0; p < 2; ++p)
+      for (int q = 0; q < 2; ++q) {
+        const int wv = (in_W - q + 1) / 2, rv = (in_rows - p + 1) / 2;
+        if (wv <= 0 || rv <= 0) { c.amaps.m[p * 2 + q] = c.amaps.m[0]; continue; }
+        const uint64_t dims[3] = {static_cast<uint64_t>(c.cin), static_cast<uint64_t>(wv), static_cast<uint64_t>(rv)};
+        const uint64_t str[2] = {2ull * tin.C * esz, 2ull * in_W * tin.C * esz};
+        uint8_t* b = base + (static_cast<size_t>(p) * in_W + q) * tin.C * esz + static_cast<size_t>(c.in.coff) * esz;
+        if (encode_tmap(&c.amaps.m[p * 2 + q], is_bf16_, b, 3, dims, str, box, sw_bytes)) return 1;
+      }
+  }
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(taps) * c.kpad, static_cast<uint64_t>(c.n_pad)};
+    const uint64_t str[1] = {static_cast<uint64_t>(taps) * c.kpad * esz};
+    const uint32_t bbox[2] = {static_cast<uint32_t>(c.kbox), static_cast<uint32_t>(c.n_tile)};
+    if (encode_tmap(&c.bmap, is_bf16_, c.d_wgt, 2, dims, str, bbox, sw_bytes)) return 1;
+  }
+  c.use_umma = true;
+  return 0;
+}
+
+int Model::ensure_capacity(int rows0) {
+  if (!rows_cap_.empty() && rows0 <= rows_cap_[0]) return 0;
+  SVX_CUDA(cudaDeviceSynchronize());
+  for (void* p : act_bufs_) cudaFree(p);
+  act_bufs_.clear();
+  for (auto p : d_seg_of_row_) cudaFree(p);
+  d_seg_of_row_.assign(n_stages_, nullptr);
+  rows_cap_.assign(n_stages_, 0);
+  int rows = round_up(std::max(rows0, 256), 256);
+  for (int s = 0; s < n_stages_; ++s) {
+    rows_cap_[s] = rows;
+    SVX_CUDA(cudaMalloc(&d_seg_of_row_[s], static_cast<size_t>(rows) * 4));
+    rows = rows / 2 + 8;
+  }
+  for (ActTensor& t : tensors_) {
+    const size_t bytes = static_cast<size_t>(rows_cap_[t.stage]) * stage_W_[t.stage] * t.C * 2;
+    SVX_CUDA(cudaMalloc(&t.ptr, bytes));
+    SVX_CUDA(cudaMemset(t.ptr, 0, bytes));
+    act_bufs_.push_back(t.ptr);
+  }
+  for (Op& op : ops_)
+    if (op.kind == OP_CONV && plan_conv(op.conv)) return 1;
+  return 0;
+}
+
+// Tall-image layout of one call: per stage, where each segment starts and how tall it is.
+//   Res2Net: stride-2 layers pad (1,1) regardless of the extent (models.py:121-134) → in_row = 2*out_row + r - 1 holds
+//            for every segment when row_off[s] = 2*row_off[s+1].
+//   DPN:     TF SAME pads (0,1) on even and (1,1) on odd extents [ext] → row_off[s] = 2*row_off[s+1] - 1 + (H odd).
+int Model::layout_segments(const std::vector<int>& seg_len) {
+  const int n = static_cast<int>(seg_len.size());
+  seg_h_host_.assign(n_stages_, std::vector<int>(n));
+  seg_off_host_.assign(n_stages_, std::vector<int>(n));
+  for (int i = 0; i < n; ++i) {
+    int h = seg_len[i];
+    for (int s = 0; s < n_stages_; ++s) { seg_h_host_[s][i] = h; h = ceil_half(h); }
+  }
+  const int last = n_stages_ - 1;
+  int off = 1;
+  for (int i = 0; i < n; ++i) { seg_off_host_[last][i] = off; off += seg_h_host_[last][i] + gap_; }
+  for (int s = last - 1; s >= 0; --s)
+    for (int i = 0; i < n; ++i) {
+      if (cfg_.family == SVX_FAMILY_DPN)
+        seg_off_host_[s][i] = 2 * seg_off_host_[s + 1][i] - 1 + (seg_h_host_[s][i] & 1);
+      else
+        seg_off_host_[s][i] = 2 * seg_off_host_[s + 1][i];
+    }
+  rows_used_.assign(n_stages_, 0);
+  for (int s = 0; s < n_stages_; ++s) rows_used_[s] = n ? seg_off_host_[s][n - 1] + seg_h_host_[s][n - 1] + gap_ : 0;
+  // every finer stage must still cover 2*rows of the coarser one (stride-2 reads) — guaranteed by the capacity rule
+  if (ensure_capacity(rows_used_[0])) return 1;
+  for (int s = 0; s < n_stages_; ++s)
+    if (rows_used_[s] > rows_cap_[s]) { set_last_error("internal: stage capacity too small"); return 1; }
+  return 0;
+}
+
+// Device time of the tensor-core conv launches of the last call (option "time_convs"): CUDA events bracket every
+// launch on the launching stream; bench.py divides the algorithmic FLOPs of those launches by this.
+int Model::conv_time(double* ms, double* flops) {
+  double total = 0.0;
+  for (size_t i = 0; i + 1 < ev_used_; i += 2) {
+    float t = 0.f;
+    SVX_CUDA(cudaEventSynchronize(events_[i + 1]));
+    SVX_CUDA(cudaEventElapsedTime(&t, events_[i], events_[i + 1]));
+    total += t;
+  }
+  *ms = total; *flops = conv_flops_;
+  return 0;
+}
+
+int Model::launch_conv(ConvDesc& c, cudaStream_t st) {
+  const int out_stage = tensors_[c.out.id].stage;
+  const int out_rows = rows_used_[out_stage];
+  if (c.use_umma && !force_simple_) {
+    c.up.out_rows = out_rows;
+    if (time_convs_) {
+      while (events_.size() < ev_used_ + 2) { cudaEvent_t e; SVX_CUDA(cudaEventCreate(&e)); events_.push_back(e); }
+      SVX_CUDA(cudaEventRecord(events_[ev_used_], st));
+    }
+    SVX_CUDA(launch_conv_umma(c.up, c.amaps, c.bmap, c.n_tiles, is_bf16_, st));
+    if (time_convs_) {
+      SVX_CUDA(cudaEventRecord(events_[ev_used_ + 1], st));
+      ev_used_ += 2;
+      // algorithmic FLOPs: 2 * valid output pixels * taps * cin * cout (no padding waste counted)
+      double pix = 0.0;
+      for (int h : seg_h_host_[out_stage]) pix += static_cast<double>(h) * stage_W_[out_stage];
+      conv_flops_ += 2.0 * pix * c.kh * c.kw * (c.cin / c.groups) * c.cout;
+    }
+  } else {
+    c.sp.out_rows = out_rows;
+    SVX_CUDA(launch_conv_simple(c.sp, is_bf16_, st));
+  }
+  ++launches_;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ execution
+int Model::ensure_seg_capacity(int n) {
+  if (n <= seg_cap_) return 0;
+  SVX_CUDA(cudaDeviceSynchronize());
+  const int cap = round_up(n, 1024);
+  for (auto p : d_seg_row_off_) cudaFree(p);
+  for (auto p : d_seg_h_) cudaFree(p);
+  cudaFree(d_seg_frame_off_); cudaFree(d_seg_len_); cudaFree(d_utt_seg_off_);
+  d_seg_row_off_.assign(n_stages_, nullptr); d_seg_h_.assign(n_stages_, nullptr);
+  for (int s = 0; s < n_stages_; ++s) {
+    SVX_CUDA(cudaMalloc(&d_seg_row_off_[s], cap * 4));
+    SVX_CUDA(cudaMalloc(&d_seg_h_[s], cap * 4));
+  }
+  SVX_CUDA(cudaMalloc(&d_seg_frame_off_, cap * 4));
+  SVX_CUDA(cudaMalloc(&d_seg_len_, cap * 4));
+  SVX_CUDA(cudaMalloc(&d_utt_seg_off_, (cap + 1) * 4));
+  seg_cap_ = cap;
+  return 0;
+}
+
+// Runs the network on segments given by (frame start, length) pairs → d_seg_emb_[n_seg, E].
+static int grow(float** p, size_t* have, size_t need) {
+  if (need <= *have) return 0;
+  cudaFree(*p);
+  *p = nullptr;
+  if (cudaMalloc(p, need) != cudaSuccess) return 1;
+  *have = need;
+  return 0;
+}
+
+int Model::run_segments(const float* d_feats, const int32_t* h_frame_off, int n_seg, float* d_out, cudaStream_t st) {
+  if (!finalized_) { set_last_error("extractor not finalized"); return 1; }
+  SVX_CUDA(cudaSetDevice(device_));
+  launches_ = 0;
+  if (!in_extract_) { ev_used_ = 0; conv_flops_ = 0.0; }
+  if (n_seg <= 0) return 0;
+  std::vector<int> starts(n_seg), lens(n_seg);
+  for (int i = 0; i < n_seg; ++i) {
+    starts[i] = h_frame_off[i]; lens[i] = h_frame_off[i + 1] - h_frame_off[i];
+    if (lens[i] <= 0) { set_last_error("empty segment"); return 1; }
+  }
+  // sub-batches bounded by workspace rows
+  const int max_rows0 = 1 << 17;
+  int i0 = 0;
+  while (i0 < n_seg) {
+    int i1 = i0; long long rows = 8;
+    while (i1 < n_seg && (i1 == i0 || rows + lens[i1] + 8 <= max_rows0)) { rows += lens[i1] + 8; ++i1; }
+    const int nb = i1 - i0;
+    std::vector<int> sl(lens.begin() + i0, lens.begin() + i1);
+    if (layout_segments(sl)) return 1;
+    if (ensure_seg_capacity(nb)) return 1;
+    // stage the tables through pinned memory
+    const size_t words = static_cast<size_t>(nb) * (2 * n_stages_ + 1);
+    if (words * 4 > h_stage_bytes_) {
+      SVX_CUDA(cudaStreamSynchronize(st));
+      if (h_stage_) cudaFreeHost(h_stage_);
+      h_stage_bytes_ = round_up(static_cast<int>(words * 4), 1 << 16);
+      SVX_CUDA(cudaMallocHost(&h_stage_, h_stage_bytes_));
+    } else {
+      SVX_CUDA(cudaStreamSynchronize(st));   // previous call's async table copies must have drained
+    }
+    int32_t* hp = h_stage_;
+    for (int s = 0; s < n_stages_; ++s) {
+      for (int i = 0; i < nb; ++i) hp[i] = seg_off_host_[s][i];
+      SVX_CUDA(cudaMemcpyAsync(d_seg_row_off_[s], hp, nb * 4, cudaMemcpyHostToDevice, st));
+      hp += nb;
+      for (int i = 0; i < nb; ++i) hp[i] = seg_h_host_[s][i];
+      SVX_CUDA(cudaMemcpyAsync(d_seg_h_[s], hp, nb * 4, cudaMemcpyHostToDevice, st));
+      hp += nb;
+    }
+    for (int i = 0; i < nb; ++i) hp[i] = starts[i0 + i];
+    SVX_CUDA(cudaMemcpyAsync(d_seg_frame_off_, hp, nb * 4, cudaMemcpyHostToDevice, st));
+    for (int s = 0; s < n_stages_; ++s) {
+      SVX_CUDA(launch_fill_seg_of_row(d_seg_of_row_[s], rows_used_[s], d_seg_row_off_[s], d_seg_h_[s], nb, st));
+      ++launches_;
+    }
+    if (grow(&d_pooled_, &pooled_bytes_, static_cast<size_t>(nb) * flat_dim_ * 4)) { set_last_error("allocation failed"); return 1; }
+    for (Op& op : ops_) {
+      switch (op.kind) {
+        case OP_PACK_INPUT: {
+          const ActTensor& t = tensors_[op.out.id];
+          SVX_CUDA(launch_pack_input(d_feats, d_seg_frame_off_, d_seg_row_off_[0], d_seg_of_row_[0], t.ptr, rows_used_[0], cfg_.feat_dim,
+                                     t.C, is_bf16_, st));
+          ++launches_;
+          break;
+        }
+        case OP_STEM: {
+          const ActTensor& t = tensors_[op.out.id];
+          SVX_CUDA(launch_stem_conv(d_feats, d_seg_frame_off_, d_seg_row_off_[0], d_seg_h_[0], d_seg_of_row_[0], op.d_w9, op.d_scale,
+                                    op.d_shift, t.ptr, rows_used_[0], cfg_.feat_dim, op.C, t.C, is_bf16_, st));
+          ++launches_;
+          break;
+        }
+        case OP_CONV:
+          if (launch_conv(op.conv, st)) return 1;
+          break;
+        case OP_BN_RELU: {
+          const ActTensor& ti = tensors_[op.in.id];
+          const ActTensor& to = tensors_[op.out.id];
+          SVX_CUDA(launch_bn_relu(ti.ptr, ti.C, op.in.coff, stage_W_[ti.stage], op.d_scale, op.d_shift, to.ptr, to.C,
+                                  rows_used_[to.stage], stage_W_[to.stage], round_up(op.C, 8), op.stride, d_seg_of_row_[to.stage],
+                                  d_seg_row_off_[to.stage], d_seg_row_off_[ti.stage], is_bf16_, st));
+          ++launches_;
+          break;
+        }
+        case OP_AVGPOOL: {
+          const ActTensor& ti = tensors_[op.in.id];
+          const ActTensor& to = tensors_[op.out.id];
+          SVX_CUDA(launch_avgpool3x3s2(ti.ptr, ti.C, op.in.coff, rows_cap_[ti.stage], stage_W_[ti.stage], to.ptr, to.C, op.out.coff,
+                                       rows_used_[to.stage], stage_W_[to.stage], op.C, d_seg_of_row_[to.stage], is_bf16_, st));
+          ++launches_;
+          break;
+        }
+        default: break;
+      }
+    }
+    const ActTensor& tp = tensors_[pool_tensor_];
+    SVX_CUDA(launch_stats_pool(tp.ptr, tp.C, pool_C_, stage_W_[tp.stage], d_seg_row_off_[tp.stage], d_seg_h_[tp.stage], nb,
+                               d_pool_scale_, d_pool_shift_, d_pooled_, kPoolEps, is_bf16_, st));
+    SVX_CUDA(launch_fc(d_pooled_, d_Wf_, d_bias_, d_out + static_cast<size_t>(i0) * cfg_.embed_dim, nb, flat_dim_, cfg_.embed_dim, st));
+    launches_ += 3;
+    i0 = i1;
+  }
+  return 0;
+}
+
+int Model::extract(const float* feats, int feats_on_device, const int32_t* h_frame_off, int n_utts, float* out, int out_on_device,
+                   cudaStream_t st) {
+  if (!finalized_) { set_last_error("extractor not finalized"); return 1; }
+  SVX_CUDA(cudaSetDevice(device_));
+  if (n_utts <= 0) return 0;
+  const int F = cfg_.feat_dim, E = cfg_.embed_dim;
+  // chunk rule (tf_extract.py:101-110)
+  std::vector<int32_t> starts, seg_len, utt_seg_off(n_utts + 1, 0);
+  for (int u = 0; u < n_utts; ++u) {
+    const int T = h_frame_off[u + 1] - h_frame_off[u];
+    if (T < kMinFrames) {
+      set_last_error("utterance " + std::to_string(u) + " has " + std::to_string(T) +
+                     " frames; fewer than 25 is a division by zero in the reference (tf_extract.py:102,111)");
+      return 2;
+    }
+    const int nch = 1 + (T - kMinFrames) / kMaxChunk;
+    for (int i = 0; i < nch; ++i) {
+      const int len = ((i + 1) * kMaxChunk <= T) ? kMaxChunk : T - i * kMaxChunk;
+      starts.push_back(h_frame_off[u] + i * kMaxChunk);
+      seg_len.push_back(len);
+    }
+    utt_seg_off[u + 1] = static_cast<int32_t>(starts.size());
+  }
+  const int n_seg = static_cast<int>(starts.size());
+  const size_t total_frames = static_cast<size_t>(h_frame_off[n_utts]);
+  const float* d_feats = feats;
+  if (!feats_on_device) {
+    if (grow(&d_feats_, &d_feats_bytes_, total_frames * F * 4)) { set_last_error("feature staging allocation failed"); return 1; }
+    SVX_CUDA(cudaMemcpyAsync(d_feats_, feats, total_frames * F * 4, cudaMemcpyHostToDevice, st));
+    d_feats = d_feats_;
+  }
+  if (grow(&d_seg_emb_, &seg_emb_bytes_, static_cast<size_t>(n_seg) * E * 4)) { set_last_error("allocation failed"); return 1; }
+  float* d_out = out;
+  if (!out_on_device) {
+    if (grow(&d_out_, &d_out_bytes_, static_cast<size_t>(n_utts) * E * 4)) { set_last_error("allocation failed"); return 1; }
+    d_out = d_out_;
+  }
+  // run_segments wants contiguous offsets; chunks of one utterance are contiguous except for dropped tails, so
+  // feed (start,len) pairs through a synthetic offset table per contiguous run.
+  long long total_launches = 0;
+  ev_used_ = 0; conv_flops_ = 0.0; in_extract_ = true;
+  struct Guard { bool& f; ~Guard() { f = false; } } guard{in_extract_};
+  int s0 = 0;
+  while (s0 < n_seg) {
+    int s1 = s0 + 1;
+    while (s1 < n_seg && starts[s1] == starts[s1 - 1] + seg_len[s1 - 1]) ++s1;
+    std::vector<int32_t> offs(s1 - s0 + 1);
+    for (int i = s0; i < s1; ++i) offs[i - s0] = starts[i];
+    offs[s1 - s0] = starts[s1 - 1] + seg_len[s1 - 1];
+    if (run_segments(d_feats, offs.data(), s1 - s0, d_seg_emb_ + static_cast<size_t>(s0) * E, st)) return 1;
+    total_launches += launches_;
+    s0 = s1;
+  }
+  bool single = true;
+  for (int u = 0; u < n_utts; ++u) if (utt_seg_off[u + 1] - utt_seg_off[u] != 1) { single = false; break; }
+  if (single) {
+    SVX_CUDA(cudaMemcpyAsync(d_out, d_seg_emb_, static_cast<size_t>(n_utts) * E * 4, cudaMemcpyDeviceToDevice, st));
+  } else {
+    if (ensure_seg_capacity(std::max(n_seg, n_utts + 1))) return 1;
+    SVX_CUDA(cudaStreamSynchronize(st));
+    SVX_CUDA(cudaMemcpyAsync(d_seg_len_, seg_len.data(), n_seg * 4, cudaMemcpyHostToDevice, st));
+    SVX_CUDA(cudaMemcpyAsync(d_utt_seg_off_, utt_seg_off.data(), (n_utts + 1) * 4, cudaMemcpyHostToDevice, st));
+    SVX_CUDA(launch_chunk_combine(d_seg_emb_, d_utt_seg_off_, d_seg_len_, d_out, n_utts, E, st));
+    SVX_CUDA(cudaStreamSynchronize(st));   // seg_len / utt_seg_off are stack-owned host vectors
+    ++total_launches;
+  }
+  launches_ = total_launches;
+  if (!out_on_device) {
+    SVX_CUDA(cudaMemcpyAsync(out, d_out, static_cast<size_t>(n_utts) * E * 4, cudaMemcpyDeviceToHost, st));
+    SVX_CUDA(cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
+}  // namespace svx

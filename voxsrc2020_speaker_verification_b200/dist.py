@@ -1,0 +1,86 @@
+"""Multi-GPU layout of the hot path: one process per GPU, torch.distributed (NCCL over NVLink) for the plumbing.
+
+* Extraction shards by utterance — the reference's own layout (eval_inference_model.sh:29-39: static contiguous
+  scp shards, one process per GPU, no communication).  ``balance_by_frames`` deals length-sorted utterances so
+  every rank gets the same number of frames; ``gather_embeddings`` is the only collective (all-gather of [n,E]).
+* AS-norm statistics shard the COHORT by rows (BASELINE.json north_star): every rank scores all test rows against
+  its cohort slice and keeps the per-row top-k candidates, one all-gather exchanges the candidate lists, and the
+  top-k of their union is reduced to mean/std.  The exchange is the path's only real collective.
+The helpers take the process group explicitly so the same code runs under gloo on CPU in the tests.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous near-equal split of n items (first n % world shards get one more), like utils/split_scp.pl:212-243."""
+    base, rem = divmod(n, world)
+    out, lo = [], 0
+    for r in range(world):
+        hi = lo + base + (1 if r < rem else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+def balance_by_frames(lengths: Sequence[int], world: int) -> List[List[int]]:
+    """Longest-processing-time greedy: utterance indices per rank with near-equal total frames; within a rank
+    indices stay sorted by length (descending) so that batches are length-homogeneous."""
+    order = np.argsort(-np.asarray(lengths, dtype=np.int64), kind="stable")
+    loads = [0] * world
+    parts: List[List[int]] = [[] for _ in range(world)]
+    for i in order:
+        r = int(np.argmin(loads))
+        parts[r].append(int(i))
+        loads[r] += int(lengths[i])
+    return parts
+
+
+def gather_embeddings(local: torch.Tensor, local_index: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """All-gather per-rank embeddings [n_r, E] with their global utterance indices → [n_total, E] on every rank."""
+    world = dist.get_world_size(group)
+    counts = [torch.zeros(1, dtype=torch.int64, device=local.device) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device), group=group)
+    n_max = int(max(int(c.item()) for c in counts))
+    e = local.shape[1]
+    pad = torch.zeros((n_max, e), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    idx = torch.full((n_max,), -1, dtype=torch.int64, device=local.device)
+    idx[: local.shape[0]] = local_index.to(torch.int64)
+    all_e = [torch.empty_like(pad) for _ in range(world)]
+    all_i = [torch.empty_like(idx) for _ in range(world)]
+    dist.all_gather(all_e, pad, group=group)
+    dist.all_gather(all_i, idx, group=group)
+    out = torch.zeros((n_total, e), dtype=local.dtype, device=local.device)
+    for ee, ii in zip(all_e, all_i):
+        keep = ii >= 0
+        out[ii[keep]] = ee[keep]
+    return out
+
+
+def merge_candidates(gathered: torch.Tensor) -> torch.Tensor:
+    """[world, n, k] per-rank candidate lists → [n, world*k] row-wise union."""
+    w, n, k = gathered.shape
+    return gathered.permute(1, 0, 2).reshape(n, w * k).contiguous()
+
+
+def sharded_cohort_mean_std(scorer, test: torch.Tensor, cohort: torch.Tensor, topk: int, group=None):
+    """get_cohort_mean_std (snorm.py:83-110) with the cohort row-sharded over the ranks of ``group``.
+
+    ``scorer`` provides cohort_topk_values(test, shard, k) → [n,k] and topk_stats(vals, k) → (mean, std);
+    every rank holds the full ``test`` and ``cohort`` (or at least its own slice of the cohort rows)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    c = cohort.shape[0]
+    k_eff = min(int(topk), c)
+    lo, hi = shard_bounds(c, world)[rank]
+    k_shard = max(1, min(k_eff, max(b - a for a, b in shard_bounds(c, world))))
+    vals = scorer.cohort_topk_values(test, cohort[lo:hi], k_shard)                 # [n, k_shard], padded with -1e30
+    gathered = torch.empty((world,) + tuple(vals.shape), dtype=vals.dtype, device=vals.device)
+    dist.all_gather_into_tensor(gathered, vals.contiguous(), group=group)
+    return scorer.topk_stats(merge_candidates(gathered), k_eff)

@@ -1,0 +1,77 @@
+"""Drop-in for the reference's ``tensorflow/tf_extract.py`` stage (same flags, same files in and out).
+
+    python -m voxsrc2020_speaker_verification_b200.tf_extract --pb-file M.pb --expand-dim {2,3} --rspec P --wspec Q
+
+reads ``P.scp`` (Kaldi script file of FBANK matrices, compressed or not), applies what the reference's pipe
+``apply-cmvn-sliding --norm-vars=false --center=true --cmn-window=300`` applies (tf_extract.py:63), extracts one
+embedding per utterance with the reference's chunk rule (tf_extract.py:96-111) and writes ``Q.ark`` + ``Q.scp``
+like ``copy-vector ark:- ark,scp:Q.ark,Q.scp`` (tf_extract.py:65).  One process per GPU, selected by
+CUDA_VISIBLE_DEVICES as in eval_inference_model.sh:29-36.
+"""
+from __future__ import annotations
+
+import argparse
+import sys
+
+import numpy as np
+
+from . import kaldi_ark
+from .extractor import Extractor
+
+
+def iter_features(rspec: str, cmvn: bool = True):
+    for key, mat in kaldi_ark.read_mat_scp(rspec + ".scp"):
+        mat = np.asarray(mat, dtype=np.float32)
+        yield key, (kaldi_ark.apply_cmvn_sliding(mat) if cmvn else mat)
+
+
+def run(pb_file: str, expand_dim: int, rspec: str, wspec: str, precision: str = "fp16", device: int = 0,
+        max_frames: int = 60000, cmvn: bool = True, model_id=None, feat_dim=None) -> int:
+    ex = Extractor.from_pb(pb_file, expand_dim, device=device, precision=precision, model_id=model_id, feat_dim=feat_dim)
+    n_done = 0
+    with kaldi_ark.VectorArkScpWriter(wspec) as writer:
+        keys, mats, frames = [], [], 0
+
+        def flush():
+            nonlocal keys, mats, frames, n_done
+            if not keys:
+                return
+            emb = ex.extract_bucketed(mats, max_frames=max_frames)
+            for k, e in zip(keys, emb):          # written in input order, like the reference
+                writer.write(k, e)
+            n_done += len(keys)
+            keys, mats, frames = [], [], 0
+
+        for key, mat in iter_features(rspec, cmvn):
+            if mat.shape[0] < 25:
+                # the reference divides by zero here (tf_extract.py:102,111); fail as loudly
+                raise ZeroDivisionError("utterance %s has %d frames (< 25)" % (key, mat.shape[0]))
+            keys.append(key)
+            mats.append(mat)
+            frames += mat.shape[0]
+            if frames >= 4 * max_frames:
+                flush()
+        flush()
+    return n_done
+
+
+def main(argv=None) -> int:
+    p = argparse.ArgumentParser()
+    p.add_argument("--pb-file", dest="pb_file", default="", help="protobuffer model file")
+    p.add_argument("--expand-dim", dest="expand_dim", default=2, type=int, help="expansion dimension of the input feature")
+    p.add_argument("--rspec", dest="rspec", default="/tmp/fbank", help='source fbank scp path specification, without ".scp" suffix')
+    p.add_argument("--wspec", dest="wspec", default="/tmp/xvector", help='destination xvector scp path specification, without ".scp" suffix')
+    # additions (all optional; defaults reproduce the reference)
+    p.add_argument("--precision", default="fp16", choices=["fp16", "bf16"])
+    p.add_argument("--no-cmvn", dest="cmvn", action="store_false", help="features are already mean-normalised")
+    p.add_argument("--max-frames", type=int, default=60000, help="frames per GPU launch sequence")
+    p.add_argument("--model-id", default=None)
+    p.add_argument("--feat-dim", type=int, default=None)
+    a = p.parse_args(argv)
+    n = run(a.pb_file, a.expand_dim, a.rspec, a.wspec, a.precision, 0, a.max_frames, a.cmvn, a.model_id, a.feat_dim)
+    print("extracted %d embeddings → %s.ark" % (n, a.wspec), file=sys.stderr)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
