@@ -303,17 +303,12 @@ cudaError_t launch_stats_pool(const void* in, int C_tot, int C, int W, const int
 // Embedding FC with both 2-D batch norms folded in (BN → dense → BN, res2net_model.py:240-242):
 //   out[n, e] = bias[e] + sum_d pooled[n, d] * Wf[d, e]       Wf = diag(s1) W diag(s2), fp32.
 // Split-K: grid = (E/128, n-tiles of 8, K-splits); each thread owns one output column for 8 segments and
-// streams its slice of Wf with coalesced loads; partial sums are combined with fp32 atomics on an output
-// that was pre-set to the bias.
+// streams its slice of Wf with coalesced loads into a partial-sum slab; a second kernel adds the slabs in a
+// fixed order (bit-reproducible, no atomics).
 constexpr int kFcRows = 8;
 constexpr int kFcKChunk = 512;
 
-__global__ void fc_init_kernel(float* out, const float* bias, int n, int E) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n * E) out[i] = bias[i % E];
-}
-
-__global__ void __launch_bounds__(128) fc_kernel(const float* __restrict__ pooled, const float* __restrict__ Wf, float* out, int n,
+__global__ void __launch_bounds__(128) fc_kernel(const float* __restrict__ pooled, const float* __restrict__ Wf, float* partial, int n,
                                                  int D, int E) {
   __shared__ float sp[kFcRows][kFcKChunk];
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -335,16 +330,29 @@ __global__ void __launch_bounds__(128) fc_kernel(const float* __restrict__ poole
 #pragma unroll
     for (int r = 0; r < kFcRows; ++r) acc[r] += sp[r][d] * w;
   }
+  float* po = partial + static_cast<size_t>(blockIdx.z) * n * E;
 #pragma unroll
   for (int r = 0; r < kFcRows; ++r)
-    if (n0 + r < n) atomicAdd(out + static_cast<size_t>(n0 + r) * E + e, acc[r]);
+    if (n0 + r < n) po[static_cast<size_t>(n0 + r) * E + e] = acc[r];
 }
 
-cudaError_t launch_fc(const float* pooled, const float* Wf, const float* bias, float* out, int n, int D, int E, cudaStream_t st) {
+__global__ void fc_reduce_kernel(const float* partial, const float* bias, float* out, int n, int E, int splits) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * E) return;
+  float acc = bias[i % E];
+  for (int z = 0; z < splits; ++z) acc += partial[static_cast<size_t>(z) * n * E + i];
+  out[i] = acc;
+}
+
+int fc_splits(int D) { return (D + kFcKChunk - 1) / kFcKChunk; }
+
+cudaError_t launch_fc(const float* pooled, const float* Wf, const float* bias, float* partial, float* out, int n, int D, int E,
+                      cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
-  fc_init_kernel<<<(n * E + 255) / 256, 256, 0, st>>>(out, bias, n, E);
-  dim3 grid((E + 127) / 128, (n + kFcRows - 1) / kFcRows, (D + kFcKChunk - 1) / kFcKChunk);
-  fc_kernel<<<grid, 128, 0, st>>>(pooled, Wf, out, n, D, E);
+  const int splits = fc_splits(D);
+  dim3 grid((E + 127) / 128, (n + kFcRows - 1) / kFcRows, splits);
+  fc_kernel<<<grid, 128, 0, st>>>(pooled, Wf, partial, n, D, E);
+  fc_reduce_kernel<<<(n * E + 255) / 256, 256, 0, st>>>(partial, bias, out, n, E, splits);
   return cudaGetLastError();
 }
 

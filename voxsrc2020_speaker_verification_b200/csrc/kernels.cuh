@@ -18,7 +18,9 @@ cudaError_t launch_avgpool3x3s2(const void* in, int in_C, int in_coff, int in_ro
                                 int out_rows, int out_W, int C, const int32_t* out_seg_of_row, int is_bf16, cudaStream_t st);
 cudaError_t launch_stats_pool(const void* in, int C_tot, int C, int W, const int32_t* seg_row_off, const int32_t* seg_h, int n_seg,
                               const float* scale, const float* shift, float* out, float eps, int is_bf16, cudaStream_t st);
-cudaError_t launch_fc(const float* pooled, const float* Wf, const float* bias, float* out, int n, int D, int E, cudaStream_t st);
+int fc_splits(int D);
+cudaError_t launch_fc(const float* pooled, const float* Wf, const float* bias, float* partial, float* out, int n, int D, int E,
+                      cudaStream_t st);
 cudaError_t launch_chunk_combine(const float* seg_emb, const int32_t* utt_seg_off, const int32_t* seg_len, float* out, int n_utt,
                                  int E, cudaStream_t st);
 

@@ -86,7 +86,7 @@ Model::~Model() {
   for (auto p : d_seg_h_) cudaFree(p);
   for (auto p : d_seg_of_row_) cudaFree(p);
   cudaFree(d_seg_frame_off_); cudaFree(d_seg_len_); cudaFree(d_utt_seg_off_);
-  cudaFree(d_pooled_); cudaFree(d_seg_emb_); cudaFree(d_feats_); cudaFree(d_out_);
+  cudaFree(d_pooled_); cudaFree(d_fc_partial_); cudaFree(d_seg_emb_); cudaFree(d_feats_); cudaFree(d_out_);
   if (h_stage_) cudaFreeHost(h_stage_);
   for (auto e : events_) cudaEventDestroy(e);
 }
@@ -774,7 +774,10 @@ int Model::run_segments(const float* d_feats, const int32_t* h_frame_off, int n_
       SVX_CUDA(launch_fill_seg_of_row(d_seg_of_row_[s], rows_used_[s], d_seg_row_off_[s], d_seg_h_[s], nb, st));
       ++launches_;
     }
-    if (grow(&d_pooled_, &pooled_bytes_, static_cast<size_t>(nb) * flat_dim_ * 4)) { set_last_error("allocation failed"); return 1; }
+    if (grow(&d_pooled_, &pooled_bytes_, static_cast<size_t>(nb) * flat_dim_ * 4) ||
+        grow(&d_fc_partial_, &fc_partial_bytes_, static_cast<size_t>(fc_splits(flat_dim_)) * nb * cfg_.embed_dim * 4)) {
+      set_last_error("allocation failed"); return 1;
+    }
     for (Op& op : ops_) {
       switch (op.kind) {
         case OP_PACK_INPUT: {
@@ -817,7 +820,8 @@ int Model::run_segments(const float* d_feats, const int32_t* h_frame_off, int n_
     const ActTensor& tp = tensors_[pool_tensor_];
     SVX_CUDA(launch_stats_pool(tp.ptr, tp.C, pool_C_, stage_W_[tp.stage], d_seg_row_off_[tp.stage], d_seg_h_[tp.stage], nb,
                                d_pool_scale_, d_pool_shift_, d_pooled_, kPoolEps, is_bf16_, st));
-    SVX_CUDA(launch_fc(d_pooled_, d_Wf_, d_bias_, d_out + static_cast<size_t>(i0) * cfg_.embed_dim, nb, flat_dim_, cfg_.embed_dim, st));
+    SVX_CUDA(launch_fc(d_pooled_, d_Wf_, d_bias_, d_fc_partial_, d_out + static_cast<size_t>(i0) * cfg_.embed_dim, nb, flat_dim_,
+                       cfg_.embed_dim, st));
     launches_ += 3;
     i0 = i1;
   }

@@ -127,7 +127,8 @@ class Model {
   int pool_tensor_ = -1, pool_C_ = 0, flat_dim_ = 0;
   std::string pool_bn_;
   float* d_pool_scale_ = nullptr; float* d_pool_shift_ = nullptr;
-  size_t pooled_bytes_ = 0, seg_emb_bytes_ = 0;
+  size_t pooled_bytes_ = 0, seg_emb_bytes_ = 0, fc_partial_bytes_ = 0;
+  float* d_fc_partial_ = nullptr;
   float* d_pooled_ = nullptr; float* d_Wf_ = nullptr; float* d_bias_ = nullptr; float* d_seg_emb_ = nullptr;
   std::string tail_bn1_, tail_bn2_;
   // io staging

@@ -81,6 +81,7 @@ def sharded_cohort_mean_std(scorer, test: torch.Tensor, cohort: torch.Tensor, to
     lo, hi = shard_bounds(c, world)[rank]
     k_shard = max(1, min(k_eff, max(b - a for a, b in shard_bounds(c, world))))
     vals = scorer.cohort_topk_values(test, cohort[lo:hi], k_shard)                 # [n, k_shard], padded with -1e30
-    gathered = torch.empty((world,) + tuple(vals.shape), dtype=vals.dtype, device=vals.device)
+    n, k = vals.shape
+    gathered = torch.empty((world * n, k), dtype=vals.dtype, device=vals.device)
     dist.all_gather_into_tensor(gathered, vals.contiguous(), group=group)
-    return scorer.topk_stats(merge_candidates(gathered), k_eff)
+    return scorer.topk_stats(merge_candidates(gathered.view(world, n, k)), k_eff)
