@@ -216,21 +216,17 @@ static int cohort_pass(svx_scorer* h, const float* test_dev, int64_t n, const fl
   UmmaConvParams up;
   memset(&up, 0, sizeof up);
   up.out_W = 1; up.w_box = 1; up.h_box = 128; up.w_tiles = 1;
-  up.taps = 1; up.nkc = nkc; up.kbox = kbox; up.n_tile = n_tile;
+  up.taps = 1; up.nkc = nkc; up.kbox = kbox; up.n_tile = n_tile; up.n_tiles = c_pad / n_tile;
   const int sw_bytes = kbox * 2;
   up.layout_type = sw_bytes == 128 ? 2u : sw_bytes == 64 ? 4u : 6u;
   up.sbo = 8u * sw_bytes;
   up.idesc = ptx::make_idesc_f16(1u, 128u, static_cast<uint32_t>(n_tile));
   up.a_stage_bytes = 128u * sw_bytes;
   up.b_stage_bytes = static_cast<uint32_t>((n_tile * sw_bytes + 1023) / 1024 * 1024);
-  int stages = static_cast<int>((96 * 1024) / (up.a_stage_bytes + up.b_stage_bytes));
-  up.stages = stages < 2 ? 2 : (stages > 8 ? 8 : stages);
-  if (up.stages > nkc && nkc >= 2) up.stages = nkc;
-  int tc = 32;
-  while (tc < n_tile) tc *= 2;
-  up.tmem_cols = tc;
+  if (!conv_umma_finish_params(up)) { set_last_error("scoring GEMM tile does not fit"); return 1; }
   up.epi.n_valid = c_pad; up.epi.n_split = c_pad; up.epi.out_f32 = h->d_s; up.epi.ldf = c_pad;
-  AMaps am; CUtensorMap bm;
+  AMaps am; CUtensorMap bm; CUtensorMap auxm;
+  memset(&auxm, 0, sizeof auxm);
   {
     const uint64_t dims[3] = {static_cast<uint64_t>(K), 1, static_cast<uint64_t>(block_rows)};
     const uint64_t str[2] = {static_cast<uint64_t>(K) * 2, static_cast<uint64_t>(K) * 2};
@@ -247,7 +243,7 @@ static int cohort_pass(svx_scorer* h, const float* test_dev, int64_t n, const fl
     const int rows_pad = (rows + 127) / 128 * 128;
     API_CUDA(launch_split3(test_dev + r0 * d, h->d_a, rows, rows_pad, d, 0, st));
     up.out_rows = rows;
-    API_CUDA(launch_conv_umma(up, am, bm, c_pad / n_tile, 1, st));
+    API_CUDA(launch_conv_umma(up, am, bm, auxm, 1, st));
     API_CUDA(launch_topk_stats(h->d_s, c_pad, rows, c, topk, mean_dev ? mean_dev + r0 : nullptr, std_dev ? std_dev + r0 : nullptr,
                                vals_dev ? vals_dev + r0 * topk : nullptr, topk, st));
     h->launches += 3;

@@ -63,7 +63,13 @@ struct UmmaConvParams {
   int kbox;                    // elements per k-box: 64 / 32 / 16 (= swizzle span / 2)
   int a_c_step;                // grouped conv: input-channel offset per n-tile (0 for dense)
   int n_tile;                  // UMMA N (multiple of 16, ≤ 256)
+  int n_tiles;                 // number of n-tiles (Cout padded / n_tile)
   int stages;
+  int aux_mode;                // 0 none, 1 residual added before post-ReLU, 2 second output = v + add2
+  int aux_boxes;               // 64-channel TMA boxes per tile (≤ ceil(n_tile/64))
+  int aux_width;               // channels of the aux slice (boxes past it are skipped)
+  uint32_t aux_bytes;          // bytes of one aux buffer
+  uint32_t ss_bytes;           // shared-memory bytes of the staged scale/shift vectors
   uint32_t idesc, sbo, layout_type;
   uint32_t a_stage_bytes, b_stage_bytes, tmem_cols;
   Epilogue epi;
@@ -127,8 +133,9 @@ __device__ __forceinline__ void epilogue_scalar(const Epilogue& e, float acc, in
 }
 
 cudaError_t launch_conv_simple(const SimpleConvParams& p, int is_bf16, cudaStream_t stream);
-cudaError_t launch_conv_umma(const UmmaConvParams& p, const AMaps& amaps, const CUtensorMap& bmap, int n_total_tiles,
+cudaError_t launch_conv_umma(const UmmaConvParams& p, const AMaps& amaps, const CUtensorMap& bmap, const CUtensorMap& auxmap,
                              int is_bf16, cudaStream_t stream);
+bool conv_umma_finish_params(UmmaConvParams& p);   // stages / tmem_cols / aux_bytes from the tile shape
 size_t conv_umma_smem_bytes(const UmmaConvParams& p);
 cudaError_t conv_umma_init();   // sets max dynamic smem attribute
 

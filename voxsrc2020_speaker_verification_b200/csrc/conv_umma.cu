@@ -9,9 +9,13 @@
 // the end of a channel slice) are zero-filled by the TMA unit.  Stride-2 convs read 4 parity-phase views of
 // the input through separate tensor maps.  B is the [Cout, taps*kpad] weight matrix, one 2-D box per k-step.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2-5 = epilogue (TMEM → registers → fused scale/shift/ReLU/residual/concat routing → 16-byte stores).
-// Shared memory is sized so that two CTAs share an SM: one CTA's epilogue overlaps the other's main loop.
+// Persistent, warp-specialised CTA (one per SM, 320 threads), tiles dealt round-robin:
+//   warp 0      TMA producer: runs ahead across tile boundaries through a shared-memory ring of (A,B) stages and
+//               prefetches the tile's residual / add2 operand ("aux", 64-channel SWIZZLE_128B boxes)
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer; two accumulator buffers in TMEM so the
+//               MMAs of tile i+1 overlap the epilogue of tile i
+//   warps 2-5   epilogue warpgroup 0 (even tiles), warps 6-9 epilogue warpgroup 1 (odd tiles):
+//               tcgen05.ld → scale/shift/ReLU/residual/concat routing → 16-byte stores
 #include "conv.cuh"
 #include "umma.cuh"
 
@@ -19,26 +23,48 @@ namespace svx {
 
 using namespace ptx;
 
-constexpr int kUmmaThreads = 192;
+constexpr int kUmmaThreads = 320;
 constexpr int kMaxStages = 8;
+constexpr int kAuxBoxBytes = 128 * 128;   // 128 rows x 64 channels x 2 B
+
+// 8 consecutive channels of one pixel from the aux tile in shared memory (SWIZZLE_128B: 16-byte unit u of row m
+// lives at unit u ^ (m & 7)).
+__device__ __forceinline__ uint4 aux_load8(const uint8_t* aux, int m, int c_local) {
+  const int box = c_local >> 6;
+  const int u = (c_local & 63) >> 3;
+  return *reinterpret_cast<const uint4*>(aux + box * kAuxBoxBytes + m * 128 + ((u ^ (m & 7)) << 4));
+}
 
 template <typename T>
-__device__ __forceinline__ void epilogue8(const Epilogue& e, float (&v)[8], int c, size_t pix, int row, bool valid) {
-  // c: first of 8 consecutive output channels (multiple of 8), all < n_valid
+__device__ __forceinline__ void add8(float (&v)[8], const uint4& r) {
+  const float2 a = TypeOps<T>::unpack2(r.x), b = TypeOps<T>::unpack2(r.y), c = TypeOps<T>::unpack2(r.z), d = TypeOps<T>::unpack2(r.w);
+  v[0] += a.x; v[1] += a.y; v[2] += b.x; v[3] += b.y; v[4] += c.x; v[5] += c.y; v[6] += d.x; v[7] += d.y;
+}
+
+template <typename T>
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  uint4 o;
+  o.x = TypeOps<T>::pack2(v[0], v[1]); o.y = TypeOps<T>::pack2(v[2], v[3]);
+  o.z = TypeOps<T>::pack2(v[4], v[5]); o.w = TypeOps<T>::pack2(v[6], v[7]);
+  return o;
+}
+
+// c: first of 8 consecutive output channels (multiple of 8, < n_valid); c_local = c - n0.
+template <typename T>
+__device__ __forceinline__ void epilogue8(const Epilogue& e, float (&v)[8], int c, int c_local, size_t pix, int row, int m,
+                                          bool valid, const uint8_t* aux, int aux_mode, const float* s_scale,
+                                          const float* s_shift) {
+  if (e.pre_relu) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
-    if (e.pre_relu) v[j] = fmaxf(v[j], 0.f);
-  if (e.scale) {
-    const float4 s0 = *reinterpret_cast<const float4*>(e.scale + c);
-    const float4 s1 = *reinterpret_cast<const float4*>(e.scale + c + 4);
-    v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w;
-    v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
+    for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
   }
-  if (e.shift) {
-    const float4 s0 = *reinterpret_cast<const float4*>(e.shift + c);
-    const float4 s1 = *reinterpret_cast<const float4*>(e.shift + c + 4);
-    v[0] += s0.x; v[1] += s0.y; v[2] += s0.z; v[3] += s0.w;
-    v[4] += s1.x; v[5] += s1.y; v[6] += s1.z; v[7] += s1.w;
+  {   // per-channel scale / shift staged in shared memory at kernel start (1 / 0 when the conv has no BN)
+    const float4 s0 = *reinterpret_cast<const float4*>(s_scale + c);
+    const float4 s1 = *reinterpret_cast<const float4*>(s_scale + c + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(s_shift + c);
+    const float4 b1 = *reinterpret_cast<const float4*>(s_shift + c + 4);
+    v[0] = fmaf(v[0], s0.x, b0.x); v[1] = fmaf(v[1], s0.y, b0.y); v[2] = fmaf(v[2], s0.z, b0.z); v[3] = fmaf(v[3], s0.w, b0.w);
+    v[4] = fmaf(v[4], s1.x, b1.x); v[5] = fmaf(v[5], s1.y, b1.y); v[6] = fmaf(v[6], s1.z, b1.z); v[7] = fmaf(v[7], s1.w, b1.w);
   }
   if (e.out_f32) {
     float* o = e.out_f32 + static_cast<size_t>(row) * e.ldf + c;
@@ -51,31 +77,16 @@ __device__ __forceinline__ void epilogue8(const Epilogue& e, float (&v)[8], int 
     return;
   }
   if (c < e.n_split) {
-    if (e.res) {
-      const uint4 r = *reinterpret_cast<const uint4*>(static_cast<const T*>(e.res) + pix * e.res_C + e.res_coff + c);
-      const float2 a = TypeOps<T>::unpack2(r.x), b = TypeOps<T>::unpack2(r.y), cc = TypeOps<T>::unpack2(r.z),
-                   d = TypeOps<T>::unpack2(r.w);
-      v[0] += a.x; v[1] += a.y; v[2] += b.x; v[3] += b.y; v[4] += cc.x; v[5] += cc.y; v[6] += d.x; v[7] += d.y;
-    }
+    if (aux_mode == 1) add8<T>(v, aux_load8(aux, m, c_local));
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       if (e.post_relu) v[j] = fmaxf(v[j], 0.f);
       if (!valid) v[j] = 0.f;
     }
-    uint4 o;
-    o.x = TypeOps<T>::pack2(v[0], v[1]); o.y = TypeOps<T>::pack2(v[2], v[3]);
-    o.z = TypeOps<T>::pack2(v[4], v[5]); o.w = TypeOps<T>::pack2(v[6], v[7]);
-    *reinterpret_cast<uint4*>(static_cast<T*>(e.out) + pix * e.out_C + e.out_coff + c) = o;
-    if (e.out2) {
-      if (valid) {
-        const uint4 r = *reinterpret_cast<const uint4*>(static_cast<const T*>(e.add2) + pix * e.add2_C + e.add2_coff + c);
-        const float2 a = TypeOps<T>::unpack2(r.x), b = TypeOps<T>::unpack2(r.y), cc = TypeOps<T>::unpack2(r.z),
-                     d = TypeOps<T>::unpack2(r.w);
-        v[0] += a.x; v[1] += a.y; v[2] += b.x; v[3] += b.y; v[4] += cc.x; v[5] += cc.y; v[6] += d.x; v[7] += d.y;
-      }
-      o.x = TypeOps<T>::pack2(v[0], v[1]); o.y = TypeOps<T>::pack2(v[2], v[3]);
-      o.z = TypeOps<T>::pack2(v[4], v[5]); o.w = TypeOps<T>::pack2(v[6], v[7]);
-      *reinterpret_cast<uint4*>(static_cast<T*>(e.out2) + pix * e.out2_C + e.out2_coff + c) = o;
+    *reinterpret_cast<uint4*>(static_cast<T*>(e.out) + pix * e.out_C + e.out_coff + c) = pack8<T>(v);
+    if (aux_mode == 2) {
+      if (valid) add8<T>(v, aux_load8(aux, m, c_local));
+      *reinterpret_cast<uint4*>(static_cast<T*>(e.out2) + pix * e.out2_C + e.out2_coff + c) = pack8<T>(v);
     }
   } else {
 #pragma unroll
@@ -83,124 +94,197 @@ __device__ __forceinline__ void epilogue8(const Epilogue& e, float (&v)[8], int 
       if (e.post_relu) v[j] = fmaxf(v[j], 0.f);
       if (!valid) v[j] = 0.f;
     }
-    uint4 o;
-    o.x = TypeOps<T>::pack2(v[0], v[1]); o.y = TypeOps<T>::pack2(v[2], v[3]);
-    o.z = TypeOps<T>::pack2(v[4], v[5]); o.w = TypeOps<T>::pack2(v[6], v[7]);
-    *reinterpret_cast<uint4*>(static_cast<T*>(e.outb) + pix * e.outb_C + e.outb_coff + (c - e.n_split)) = o;
+    *reinterpret_cast<uint4*>(static_cast<T*>(e.outb) + pix * e.outb_C + e.outb_coff + (c - e.n_split)) = pack8<T>(v);
   }
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kUmmaThreads)
+__global__ void __launch_bounds__(kUmmaThreads, 1)
 conv_umma_kernel(const __grid_constant__ UmmaConvParams p, const __grid_constant__ AMaps amaps,
-                 const __grid_constant__ CUtensorMap bmap) {
+                 const __grid_constant__ CUtensorMap bmap, const __grid_constant__ CUtensorMap auxmap) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
-  uint64_t* empty_bar = full_bar + kMaxStages;
-  uint64_t* tmem_full_bar = empty_bar + kMaxStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  uint8_t* tiles = smem + 1024;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);          // [kMaxStages]
+  uint64_t* empty_bar = full_bar + kMaxStages;                      // [kMaxStages]
+  uint64_t* tmem_full_bar = empty_bar + kMaxStages;                 // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;                     // [2]
+  uint64_t* aux_full_bar = tmem_empty_bar + 2;                      // [2]
+  uint64_t* aux_empty_bar = aux_full_bar + 2;                       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_empty_bar + 2);
+  float* s_scale = reinterpret_cast<float*>(smem + 1024);          // [n_pad]
+  float* s_shift = s_scale + p.n_tiles * p.n_tile;                  // [n_pad]
+  uint8_t* aux_smem = smem + 1024 + p.ss_bytes;                     // [2][aux_boxes][16 KB]
+  uint8_t* tiles = aux_smem + 2 * p.aux_bytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
+  const int aux_mode = p.aux_mode;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) prefetch_tmap(&amaps.m[i]);
     prefetch_tmap(&bmap);
+    if (aux_mode) prefetch_tmap(&auxmap);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], 4);     // one arrive per epilogue warp of the warpgroup
+      mbar_init(&aux_full_bar[b], 1);
+      mbar_init(&aux_empty_bar[b], 4);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, p.tmem_cols);
     tmem_relinquish();
   }
+  for (int i = threadIdx.x; i < p.n_tiles * p.n_tile; i += kUmmaThreads) {
+    s_scale[i] = (p.epi.scale && i < p.epi.n_valid) ? p.epi.scale[i] : 1.f;
+    s_shift[i] = (p.epi.shift && i < p.epi.n_valid) ? p.epi.shift[i] : 0.f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int mt = blockIdx.x;
-  const int row0 = (mt / p.w_tiles) * p.h_box;
-  const int w0 = (mt % p.w_tiles) * p.w_box;
-  const int n_blk = blockIdx.y;
-  const int n0 = n_blk * p.n_tile;
+  const int row_tiles = (p.out_rows + p.h_box - 1) / p.h_box;
+  const int total_tiles = row_tiles * p.w_tiles * p.n_tiles;
   const int total_it = p.taps * p.nkc;
 
   if (warp == 0) {
     if (lane == 0) {
       const uint32_t tx_bytes = static_cast<uint32_t>(128 + p.n_tile) * p.kbox * 2u;
-      const int a_c0 = n_blk * p.a_c_step;
-      int it = 0;
-      for (int tap = 0; tap < p.taps; ++tap) {
-        const CUtensorMap* am = &amaps.m[p.tap_map[tap]];
-        const int wc = w0 + p.tap_dw[tap];
-        const int rc = row0 + p.tap_dh[tap];
-        for (int kc = 0; kc < p.nkc; ++kc, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_expect_tx(&full_bar[s], tx_bytes);
-          uint8_t* a_dst = tiles + static_cast<size_t>(s) * stage_bytes;
-          tma_load_3d(a_dst, am, &full_bar[s], a_c0 + kc * p.kbox, wc, rc);
-          tma_load_2d(a_dst + p.a_stage_bytes, &bmap, &full_bar[s], (tap * p.nkc + kc) * p.kbox, n0);
+      uint32_t it = 0;
+      int local = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
+        const int n_blk = t % p.n_tiles;
+        const int mt = t / p.n_tiles;
+        const int row0 = (mt / p.w_tiles) * p.h_box;
+        const int w0 = (mt % p.w_tiles) * p.w_box;
+        const int n0 = n_blk * p.n_tile;
+        if (aux_mode) {
+          const int b = local & 1;
+          const int boxes = min(p.aux_boxes, (p.aux_width - n0 + 63) >> 6);
+          mbar_wait(&aux_empty_bar[b], ((local >> 1) & 1) ^ 1);
+          if (boxes > 0) {
+            mbar_expect_tx(&aux_full_bar[b], static_cast<uint32_t>(boxes) * kAuxBoxBytes);
+            for (int j = 0; j < boxes; ++j)
+              tma_load_3d(aux_smem + b * p.aux_bytes + j * kAuxBoxBytes, &auxmap, &aux_full_bar[b], n0 + j * 64, w0, row0);
+          } else {
+            mbar_arrive(&aux_full_bar[b]);
+          }
+        }
+        const int a_c0 = n_blk * p.a_c_step;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const CUtensorMap* am = &amaps.m[p.tap_map[tap]];
+          const int wc = w0 + p.tap_dw[tap];
+          const int rc = row0 + p.tap_dh[tap];
+          for (int kc = 0; kc < p.nkc; ++kc, ++it) {
+            const int s = it % p.stages;
+            const uint32_t ph = (it / p.stages) & 1;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            mbar_expect_tx(&full_bar[s], tx_bytes);
+            uint8_t* a_dst = tiles + static_cast<size_t>(s) * stage_bytes;
+            tma_load_3d(a_dst, am, &full_bar[s], a_c0 + kc * p.kbox, wc, rc);
+            tma_load_2d(a_dst + p.a_stage_bytes, &bmap, &full_bar[s], (tap * p.nkc + kc) * p.kbox, n0);
+          }
         }
       }
     }
   } else if (warp == 1) {
     const int ksteps = p.kbox >> 4;   // UMMA K = 16 elements = 32 bytes
-    for (int it = 0; it < total_it; ++it) {
-      const int s = it % p.stages;
-      const uint32_t ph = (it / p.stages) & 1;
-      mbar_wait(&full_bar[s], ph);
+    uint32_t it = 0;
+    int local = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
+      const int b = local & 1;
+      mbar_wait(&tmem_empty_bar[b], ((local >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t a_addr = smem_u32(tiles + static_cast<size_t>(s) * stage_bytes);
-        const uint32_t b_addr = a_addr + p.a_stage_bytes;
-        for (int k = 0; k < ksteps; ++k) {
-          const uint64_t adesc = make_kmajor_desc(a_addr + k * 32, p.sbo, p.layout_type);
-          const uint64_t bdesc = make_kmajor_desc(b_addr + k * 32, p.sbo, p.layout_type);
-          umma_f16(tmem_base, adesc, bdesc, p.idesc, (it | k) != 0 ? 1u : 0u);
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(b * p.n_tile);
+      for (int i = 0; i < total_it; ++i, ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(tiles + static_cast<size_t>(s) * stage_bytes);
+          const uint32_t b_addr = a_addr + p.a_stage_bytes;
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t adesc = make_kmajor_desc(a_addr + k * 32, p.sbo, p.layout_type);
+            const uint64_t bdesc = make_kmajor_desc(b_addr + k * 32, p.sbo, p.layout_type);
+            umma_f16(d_tmem, adesc, bdesc, p.idesc, (i | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);                       // frees the smem slot when these MMAs retire
+          if (i == total_it - 1) umma_commit(&tmem_full_bar[b]);
         }
-        umma_commit(&empty_bar[s]);                       // frees the smem slot when these MMAs retire
-        if (it == total_it - 1) umma_commit(tmem_full_bar);
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
-    const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int m = q * 32 + lane;            // accumulator row = pixel of the tile
+    const int wg = (warp - 2) >> 2;          // epilogue warpgroup: even / odd local tiles
+    const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    const int m = q * 32 + lane;             // accumulator row = pixel of the tile
     const int h = m / p.w_box;
     const int w = m - h * p.w_box;
-    const int row = row0 + h;
-    const int col = w0 + w;
-    const bool in_range = (row < p.out_rows) && (col < p.out_W);
-    bool valid = in_range;
-    if (in_range && p.epi.seg_of_row) valid = p.epi.seg_of_row[row] >= 0;
-    const size_t pix = static_cast<size_t>(row) * p.out_W + col;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
-      uint32_t r[16];
-      tmem_ld16(taddr + c0, r);
-      tmem_ld_wait();
-      if (in_range) {
+    int local = wg;
+    for (int t = blockIdx.x + wg * gridDim.x; t < total_tiles; t += 2 * gridDim.x, local += 2) {
+      const int n_blk = t % p.n_tiles;
+      const int mt = t / p.n_tiles;
+      const int row = (mt / p.w_tiles) * p.h_box + h;
+      const int col = (mt % p.w_tiles) * p.w_box + w;
+      const int n0 = n_blk * p.n_tile;
+      const bool in_range = (row < p.out_rows) && (col < p.out_W);
+      bool valid = in_range;
+      if (in_range && p.epi.seg_of_row) valid = p.epi.seg_of_row[row] >= 0;
+      const size_t pix = static_cast<size_t>(row) * p.out_W + col;
+      const uint32_t ph = (local >> 1) & 1;
+      const uint8_t* aux = aux_smem + wg * p.aux_bytes;
+      if (aux_mode) mbar_wait(&aux_full_bar[wg], ph);
+      mbar_wait(&tmem_full_bar[wg], ph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(wg * p.n_tile);
+      // two register buffers: the TMEM load of chunk i+1 is in flight while chunk i is converted and stored
+      uint32_t ra[16], rb[16];
+      tmem_ld16(taddr, ra);
+      for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
+        tmem_ld_wait();
+        if (c0 + 16 < p.n_tile) tmem_ld16(taddr + c0 + 16, rb);
+        if (in_range) {
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          const int c = n0 + c0 + g * 8;
-          if (c < p.epi.n_valid) {
-            float v[8];
+          for (int g = 0; g < 2; ++g) {
+            const int c = n0 + c0 + g * 8;
+            if (c < p.epi.n_valid) {
+              float v[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
-            epilogue8<T>(p.epi, v, c, pix, row, valid);
+              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(ra[g * 8 + j]);
+              epilogue8<T>(p.epi, v, c, c0 + g * 8, pix, row, m, valid, aux, aux_mode, s_scale, s_shift);
+            }
           }
         }
+        if (c0 + 16 < p.n_tile) {
+          tmem_ld_wait();
+          if (c0 + 32 < p.n_tile) tmem_ld16(taddr + c0 + 32, ra);
+          if (in_range) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              const int c = n0 + c0 + 16 + g * 8;
+              if (c < p.epi.n_valid) {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(rb[g * 8 + j]);
+                epilogue8<T>(p.epi, v, c, c0 + 16 + g * 8, pix, row, m, valid, aux, aux_mode, s_scale, s_shift);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&tmem_empty_bar[wg]);
+        if (aux_mode) mbar_arrive(&aux_empty_bar[wg]);
       }
     }
   }
@@ -210,25 +294,52 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p, const __grid_constant
 }
 
 size_t conv_umma_smem_bytes(const UmmaConvParams& p) {
-  return 2048 + static_cast<size_t>(p.stages) * (p.a_stage_bytes + p.b_stage_bytes);
+  return 2048 + p.ss_bytes + 2 * static_cast<size_t>(p.aux_bytes) + static_cast<size_t>(p.stages) * (p.a_stage_bytes + p.b_stage_bytes);
 }
+
+// Fills stages / tmem_cols / aux_bytes from the tile shape; returns false if the tile cannot be scheduled.
+bool conv_umma_finish_params(UmmaConvParams& p) {
+  const int total_it = p.taps * p.nkc;
+  p.aux_bytes = p.aux_mode ? static_cast<uint32_t>(p.aux_boxes) * kAuxBoxBytes : 0u;
+  p.ss_bytes = static_cast<uint32_t>((2 * p.n_tiles * p.n_tile * 4 + 1023) / 1024 * 1024);
+  const long long budget = 225 * 1024 - 2048 - p.ss_bytes - 2LL * p.aux_bytes;
+  long long stages = budget / (p.a_stage_bytes + p.b_stage_bytes);
+  if (stages < 2) return false;
+  if (stages > kMaxStages) stages = kMaxStages;
+  (void)total_it;
+  p.stages = static_cast<int>(stages);
+  uint32_t tc = 32;
+  while (tc < 2u * p.n_tile) tc *= 2;
+  if (tc > 512) return false;
+  p.tmem_cols = tc;
+  return true;
+}
+
+static int g_num_sms = 0;
 
 cudaError_t conv_umma_init() {
   cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(conv_umma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  e = cudaFuncSetAttribute(conv_umma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return e;
+  int dev = 0;
+  e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  return cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
 }
 
-cudaError_t launch_conv_umma(const UmmaConvParams& p, const AMaps& amaps, const CUtensorMap& bmap, int n_tiles,
+cudaError_t launch_conv_umma(const UmmaConvParams& p, const AMaps& amaps, const CUtensorMap& bmap, const CUtensorMap& auxmap,
                              int is_bf16, cudaStream_t stream) {
   const int row_tiles = (p.out_rows + p.h_box - 1) / p.h_box;
-  if (row_tiles <= 0) return cudaSuccess;
-  dim3 grid(static_cast<unsigned>(row_tiles * p.w_tiles), static_cast<unsigned>(n_tiles), 1);
+  const long long total = static_cast<long long>(row_tiles) * p.w_tiles * p.n_tiles;
+  if (total <= 0) return cudaSuccess;
+  const int sms = g_num_sms > 0 ? g_num_sms : 148;
+  dim3 grid(static_cast<unsigned>(total < sms ? total : sms), 1, 1);
   const size_t smem = conv_umma_smem_bytes(p);
   if (is_bf16)
-    conv_umma_kernel<__nv_bfloat16><<<grid, kUmmaThreads, smem, stream>>>(p, amaps, bmap);
+    conv_umma_kernel<__nv_bfloat16><<<grid, kUmmaThreads, smem, stream>>>(p, amaps, bmap, auxmap);
   else
-    conv_umma_kernel<__half><<<grid, kUmmaThreads, smem, stream>>>(p, amaps, bmap);
+    conv_umma_kernel<__half><<<grid, kUmmaThreads, smem, stream>>>(p, amaps, bmap, auxmap);
   return cudaGetLastError();
 }
 

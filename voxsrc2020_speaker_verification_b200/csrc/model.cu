@@ -376,12 +376,12 @@ static int pick_kbox(int cin) {
   return 64;
 }
 
-static int pick_ntile(int cout) {
+static int pick_ntile(int cout, int max_tile) {
   const int n = round_up(cout, 16);
-  if (n <= 256) return n;
-  for (int parts = 2; parts <= 16; ++parts)
-    if (n % parts == 0 && (n / parts) % 16 == 0 && n / parts <= 256) return n / parts;
-  return 128;
+  if (n <= max_tile) return n;
+  for (int parts = 2; parts <= 64; ++parts)
+    if (n % parts == 0 && (n / parts) % 16 == 0 && n / parts <= max_tile) return n / parts;
+  return 64;
 }
 
 int Model::upload_conv_weights(ConvDesc& c) {
@@ -399,7 +399,8 @@ int Model::upload_conv_weights(ConvDesc& c) {
     c.kbox = pick_kbox(c.cin);
     c.nkc = (c.cin + c.kbox - 1) / c.kbox;
     c.kpad = c.nkc * c.kbox;
-    c.n_tile = pick_ntile(c.cout);
+    // tiles that prefetch a residual / add2 operand keep n_tile ≤ 128 so two aux buffers and a deep ring fit in smem
+    c.n_tile = pick_ntile(c.cout, (c.res.id >= 0 || c.add2.id >= 0) ? 128 : 256);
   }
   c.n_pad = round_up(c.cout, c.n_tile);
   c.n_tiles = c.n_pad / c.n_tile;
@@ -547,20 +548,17 @@ int Model::plan_conv(ConvDesc& c) {
   int w_box = 1;
   while (w_box < 128 && out_W % (w_box * 2) == 0) w_box *= 2;
   up.out_rows = 0; up.out_W = out_W; up.w_box = w_box; up.h_box = 128 / w_box; up.w_tiles = out_W / w_box;
-  up.taps = taps; up.nkc = c.nkc; up.kbox = c.kbox; up.a_c_step = 0; up.n_tile = c.n_tile;
+  up.taps = taps; up.nkc = c.nkc; up.kbox = c.kbox; up.a_c_step = 0; up.n_tile = c.n_tile; up.n_tiles = c.n_tiles;
+  up.aux_mode = e.res ? 1 : (e.out2 ? 2 : 0);
+  up.aux_boxes = up.aux_mode ? (c.n_tile + 63) / 64 : 0;
+  up.aux_width = up.aux_mode == 1 ? e.n_split : (up.aux_mode == 2 ? c.cout : 0);
   const int sw_bytes = c.kbox * 2;
   up.layout_type = sw_bytes == 128 ? 2u : sw_bytes == 64 ? 4u : 6u;
   up.sbo = 8u * sw_bytes;
   up.idesc = ptx::make_idesc_f16(is_bf16_ ? 1u : 0u, 128u, static_cast<uint32_t>(c.n_tile));
   up.a_stage_bytes = 128u * sw_bytes;
   up.b_stage_bytes = static_cast<uint32_t>(round_up(c.n_tile * sw_bytes, 1024));
-  const int total_it = taps * c.nkc;
-  int stages = static_cast<int>((96 * 1024) / (up.a_stage_bytes + up.b_stage_bytes));
-  stages = std::max(2, std::min(std::min(stages, 8), std::max(total_it, 2)));
-  up.stages = stages;
-  int tc = 32;
-  while (tc < c.n_tile) tc *= 2;
-  up.tmem_cols = tc;
+  if (!conv_umma_finish_params(up)) return 0;
   up.epi = e;
   const size_t esz = 2;
   uint8_t* base = static_cast<uint8_t*>(tin.ptr);
@@ -576,6 +574,15 @@ int Model::plan_conv(ConvDesc& c) {
     }
   }
   const uint32_t box[3] = {static_cast<uint32_t>(c.kbox), static_cast<uint32_t>(w_box), static_cast<uint32_t>(128 / w_box)};
+  memset(&c.auxmap, 0, sizeof c.auxmap);
+  if (up.aux_mode) {   // residual / add2 tile: 64-channel SWIZZLE_128B boxes over the output-resolution tensor slice
+    const TensorRef& ar = up.aux_mode == 1 ? c.res : c.add2;
+    const ActTensor& ta = tensors_[ar.id];
+    const uint64_t dims[3] = {static_cast<uint64_t>(up.aux_width), static_cast<uint64_t>(out_W), static_cast<uint64_t>(rows_cap_[ta.stage])};
+    const uint64_t str[2] = {static_cast<uint64_t>(ta.C) * esz, static_cast<uint64_t>(out_W) * ta.C * esz};
+    const uint32_t abox[3] = {64u, static_cast<uint32_t>(w_box), static_cast<uint32_t>(128 / w_box)};
+    if (encode_tmap(&c.auxmap, is_bf16_, static_cast<uint8_t*>(ta.ptr) + static_cast<size_t>(ar.coff) * esz, 3, dims, str, abox, 128)) return 1;
+  }
   if (c.stride == 1) {
     const uint64_t dims[3] = {static_cast<uint64_t>(c.cin), static_cast<uint64_t>(in_W), static_cast<uint64_t>(in_rows)};
     const uint64_t str[2] = {static_cast<uint64_t>(tin.C) * esz, static_cast<uint64_t>(in_W) * tin.C * esz};
@@ -681,7 +688,7 @@ int Model::launch_conv(ConvDesc& c, cudaStream_t st) {
       while (events_.size() < ev_used_ + 2) { cudaEvent_t e; SVX_CUDA(cudaEventCreate(&e)); events_.push_back(e); }
       SVX_CUDA(cudaEventRecord(events_[ev_used_], st));
     }
-    SVX_CUDA(launch_conv_umma(c.up, c.amaps, c.bmap, c.n_tiles, is_bf16_, st));
+    SVX_CUDA(launch_conv_umma(c.up, c.amaps, c.bmap, c.auxmap, is_bf16_, st));
     if (time_convs_) {
       SVX_CUDA(cudaEventRecord(events_[ev_used_ + 1], st));
       ev_used_ += 2;
