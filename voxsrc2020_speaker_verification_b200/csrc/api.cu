@@ -225,8 +225,9 @@ static int cohort_pass(svx_scorer* h, const float* test_dev, int64_t n, const fl
   up.b_stage_bytes = static_cast<uint32_t>((n_tile * sw_bytes + 1023) / 1024 * 1024);
   if (!conv_umma_finish_params(up)) { set_last_error("scoring GEMM tile does not fit"); return 1; }
   up.epi.n_valid = c_pad; up.epi.n_split = c_pad; up.epi.out_f32 = h->d_s; up.epi.ldf = c_pad;
-  AMaps am; CUtensorMap bm; CUtensorMap auxm;
+  AMaps am; CUtensorMap bm; CUtensorMap auxm; OMaps om;
   memset(&auxm, 0, sizeof auxm);
+  memset(&om, 0, sizeof om);
   {
     const uint64_t dims[3] = {static_cast<uint64_t>(K), 1, static_cast<uint64_t>(block_rows)};
     const uint64_t str[2] = {static_cast<uint64_t>(K) * 2, static_cast<uint64_t>(K) * 2};
@@ -243,7 +244,7 @@ static int cohort_pass(svx_scorer* h, const float* test_dev, int64_t n, const fl
     const int rows_pad = (rows + 127) / 128 * 128;
     API_CUDA(launch_split3(test_dev + r0 * d, h->d_a, rows, rows_pad, d, 0, st));
     up.out_rows = rows;
-    API_CUDA(launch_conv_umma(up, am, bm, auxm, 1, st));
+    API_CUDA(launch_conv_umma(up, am, bm, auxm, om, 1, st));
     API_CUDA(launch_topk_stats(h->d_s, c_pad, rows, c, topk, mean_dev ? mean_dev + r0 : nullptr, std_dev ? std_dev + r0 : nullptr,
                                vals_dev ? vals_dev + r0 * topk : nullptr, topk, st));
     h->launches += 3;

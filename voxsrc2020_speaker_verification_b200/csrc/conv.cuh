@@ -70,12 +70,16 @@ struct UmmaConvParams {
   int aux_width;               // channels of the aux slice (boxes past it are skipped)
   uint32_t aux_bytes;          // bytes of one aux buffer
   uint32_t ss_bytes;           // shared-memory bytes of the staged scale/shift vectors
+  int store_mode;              // 0: direct 16-byte stores (fp32 output form); 1: swizzled smem boxes + TMA stores
+  uint32_t stage_bytes;        // bytes of one output staging buffer (0 when the residual tile is reused in place)
+  uint32_t bres_bytes;         // bytes of the resident weight region (0 → weights stream through the ring)
   uint32_t idesc, sbo, layout_type;
   uint32_t a_stage_bytes, b_stage_bytes, tmem_cols;
   Epilogue epi;
 };
 
 struct AMaps { CUtensorMap m[4]; };
+struct OMaps { CUtensorMap m[2]; };   // TMA-store maps: [0] primary destination slice, [1] out2 slice
 
 template <typename T> struct TypeOps;
 template <> struct TypeOps<__half> {
@@ -134,7 +138,7 @@ __device__ __forceinline__ void epilogue_scalar(const Epilogue& e, float acc, in
 
 cudaError_t launch_conv_simple(const SimpleConvParams& p, int is_bf16, cudaStream_t stream);
 cudaError_t launch_conv_umma(const UmmaConvParams& p, const AMaps& amaps, const CUtensorMap& bmap, const CUtensorMap& auxmap,
-                             int is_bf16, cudaStream_t stream);
+                             const OMaps& omaps, int is_bf16, cudaStream_t stream);
 bool conv_umma_finish_params(UmmaConvParams& p);   // stages / tmem_cols / aux_bytes from the tile shape
 size_t conv_umma_smem_bytes(const UmmaConvParams& p);
 cudaError_t conv_umma_init();   // sets max dynamic smem attribute

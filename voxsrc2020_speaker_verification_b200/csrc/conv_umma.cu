@@ -16,6 +16,8 @@
 //               MMAs of tile i+1 overlap the epilogue of tile i
 //   warps 2-5   epilogue warpgroup 0 (even tiles), warps 6-9 epilogue warpgroup 1 (odd tiles):
 //               tcgen05.ld → scale/shift/ReLU/residual/concat routing → 16-byte stores
+#include <cstdlib>
+
 #include "conv.cuh"
 #include "umma.cuh"
 
@@ -50,10 +52,31 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
 }
 
 // c: first of 8 consecutive output channels (multiple of 8, < n_valid); c_local = c - n0.
+// Swizzled (SWIZZLE_128B) address of the 16-byte unit that holds channels [c_local, c_local+8) of tile row m inside a
+// buffer of 64-channel boxes — the layout TMA loads produce and TMA stores consume.
+__device__ __forceinline__ uint8_t* box_unit(uint8_t* buf, int m, int c_local) {
+  const int box = c_local >> 6;
+  const int u = (c_local & 63) >> 3;
+  return buf + box * kAuxBoxBytes + m * 128 + ((u ^ (m & 7)) << 4);
+}
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+// One group of 8 consecutive output channels of one pixel: BN scale/shift, ReLUs, residual, routing.
+//   c: first channel (multiple of 8, < n_valid); c_local = c - n0; m = tile row.
+// Staged mode (stage != nullptr or aux in place): 16-bit results go to swizzled shared-memory boxes that one thread
+// later hands to TMA stores; secondary-destination channels and the fp32 form are stored directly.
 template <typename T>
 __device__ __forceinline__ void epilogue8(const Epilogue& e, float (&v)[8], int c, int c_local, size_t pix, int row, int m,
-                                          bool valid, const uint8_t* aux, int aux_mode, const float* s_scale,
-                                          const float* s_shift) {
+                                          bool in_range, bool valid, uint8_t* aux, int aux_mode, uint8_t* stage, bool staged,
+                                          const float* s_scale, const float* s_shift) {
   if (e.pre_relu) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -67,6 +90,7 @@ __device__ __forceinline__ void epilogue8(const Epilogue& e, float (&v)[8], int 
     v[4] = fmaf(v[4], s1.x, b1.x); v[5] = fmaf(v[5], s1.y, b1.y); v[6] = fmaf(v[6], s1.z, b1.z); v[7] = fmaf(v[7], s1.w, b1.w);
   }
   if (e.out_f32) {
+    if (!in_range) return;
     float* o = e.out_f32 + static_cast<size_t>(row) * e.ldf + c;
     if (!valid) {
 #pragma unroll
@@ -77,18 +101,31 @@ __device__ __forceinline__ void epilogue8(const Epilogue& e, float (&v)[8], int 
     return;
   }
   if (c < e.n_split) {
-    if (aux_mode == 1) add8<T>(v, aux_load8(aux, m, c_local));
+    uint4* ap = reinterpret_cast<uint4*>(box_unit(aux, m, c_local));
+    if (aux_mode == 1) add8<T>(v, *ap);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       if (e.post_relu) v[j] = fmaxf(v[j], 0.f);
       if (!valid) v[j] = 0.f;
     }
-    *reinterpret_cast<uint4*>(static_cast<T*>(e.out) + pix * e.out_C + e.out_coff + c) = pack8<T>(v);
-    if (aux_mode == 2) {
-      if (valid) add8<T>(v, aux_load8(aux, m, c_local));
-      *reinterpret_cast<uint4*>(static_cast<T*>(e.out2) + pix * e.out2_C + e.out2_coff + c) = pack8<T>(v);
+    if (!staged) {                                              // direct 16-byte stores (debug / fallback form)
+      if (!in_range) return;
+      *reinterpret_cast<uint4*>(static_cast<T*>(e.out) + pix * e.out_C + e.out_coff + c) = pack8<T>(v);
+      if (aux_mode == 2) {
+        if (valid) add8<T>(v, *ap);
+        *reinterpret_cast<uint4*>(static_cast<T*>(e.out2) + pix * e.out2_C + e.out2_coff + c) = pack8<T>(v);
+      }
+    } else if (aux_mode == 1) {
+      *ap = pack8<T>(v);                                        // residual tile is overwritten in place and stored from there
+    } else {
+      *reinterpret_cast<uint4*>(box_unit(stage, m, c_local)) = pack8<T>(v);
+      if (aux_mode == 2) {                                      // out2 = v + add2, in place on the add2 tile
+        if (valid) add8<T>(v, *ap);
+        *ap = pack8<T>(v);
+      }
     }
   } else {
+    if (!in_range) return;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       if (e.post_relu) v[j] = fmaxf(v[j], 0.f);
@@ -101,7 +138,8 @@ __device__ __forceinline__ void epilogue8(const Epilogue& e, float (&v)[8], int 
 template <typename T>
 __global__ void __launch_bounds__(kUmmaThreads, 1)
 conv_umma_kernel(const __grid_constant__ UmmaConvParams p, const __grid_constant__ AMaps amaps,
-                 const __grid_constant__ CUtensorMap bmap, const __grid_constant__ CUtensorMap auxmap) {
+                 const __grid_constant__ CUtensorMap bmap, const __grid_constant__ CUtensorMap auxmap,
+                 const __grid_constant__ OMaps omaps) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);          // [kMaxStages]
@@ -110,21 +148,28 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p, const __grid_constant
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;                     // [2]
   uint64_t* aux_full_bar = tmem_empty_bar + 2;                      // [2]
   uint64_t* aux_empty_bar = aux_full_bar + 2;                       // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_empty_bar + 2);
+  uint64_t* bres_bar = aux_empty_bar + 2;                           // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 1);
   float* s_scale = reinterpret_cast<float*>(smem + 1024);          // [n_pad]
   float* s_shift = s_scale + p.n_tiles * p.n_tile;                  // [n_pad]
-  uint8_t* aux_smem = smem + 1024 + p.ss_bytes;                     // [2][aux_boxes][16 KB]
-  uint8_t* tiles = aux_smem + 2 * p.aux_bytes;
+  uint8_t* bres = smem + 1024 + p.ss_bytes;                         // resident weights: [taps*nkc][b_stage_bytes]
+  uint8_t* aux_smem = bres + p.bres_bytes;                          // [2][aux_boxes][16 KB]
+  uint8_t* stage_smem = aux_smem + 2 * p.aux_bytes;                 // [2][stage_boxes][16 KB]
+  uint8_t* tiles = stage_smem + 2 * p.stage_bytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
+  const bool b_res = p.bres_bytes != 0;
+  const uint32_t ring_bytes = p.a_stage_bytes + (b_res ? 0u : p.b_stage_bytes);
   const int aux_mode = p.aux_mode;
+  const bool staged = p.store_mode == 1;
+  const int aux_arrivals = staged ? 1 : 4;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) prefetch_tmap(&amaps.m[i]);
     prefetch_tmap(&bmap);
     if (aux_mode) prefetch_tmap(&auxmap);
+    if (staged) { prefetch_tmap(&omaps.m[0]); prefetch_tmap(&omaps.m[1]); }
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -133,8 +178,9 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p, const __grid_constant
       mbar_init(&tmem_full_bar[b], 1);
       mbar_init(&tmem_empty_bar[b], 4);     // one arrive per epilogue warp of the warpgroup
       mbar_init(&aux_full_bar[b], 1);
-      mbar_init(&aux_empty_bar[b], 4);
+      mbar_init(&aux_empty_bar[b], aux_arrivals);
     }
+    mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -150,21 +196,35 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Tile schedule: CTA b owns n-tile (b % n_tiles) for its whole life (its weights can stay resident) and walks the
+  // m-tiles (b / n_tiles) + j * (gridDim.x / n_tiles).
   const int row_tiles = (p.out_rows + p.h_box - 1) / p.h_box;
-  const int total_tiles = row_tiles * p.w_tiles * p.n_tiles;
+  const int m_tiles = row_tiles * p.w_tiles;
+  const int groups = gridDim.x / p.n_tiles;
+  const int my_group = blockIdx.x / p.n_tiles;
+  const int n_blk = blockIdx.x % p.n_tiles;
+  const int n0 = n_blk * p.n_tile;
   const int total_it = p.taps * p.nkc;
+  const bool active = my_group < groups;     // CTAs past the last full group (never launched by the host) stay idle
 
   if (warp == 0) {
-    if (lane == 0) {
-      const uint32_t tx_bytes = static_cast<uint32_t>(128 + p.n_tile) * p.kbox * 2u;
+    if (lane == 0 && active) {
+      const uint32_t b_box_bytes = static_cast<uint32_t>(p.n_tile) * p.kbox * 2u;
+#ifdef SVX_ASHIFT
+      const uint32_t tx_bytes = 256u * p.kbox * 2u + (b_res ? 0u : b_box_bytes);
+#else
+      const uint32_t tx_bytes = 128u * p.kbox * 2u + (b_res ? 0u : b_box_bytes);
+#endif
+      if (b_res) {
+        mbar_expect_tx(bres_bar, b_box_bytes * total_it);
+        for (int i = 0; i < total_it; ++i) tma_load_2d(bres + static_cast<size_t>(i) * p.b_stage_bytes, &bmap, bres_bar, i * p.kbox, n0);
+      }
+      const int a_c0 = n_blk * p.a_c_step;
       uint32_t it = 0;
       int local = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
-        const int n_blk = t % p.n_tiles;
-        const int mt = t / p.n_tiles;
+      for (int mt = my_group; mt < m_tiles; mt += groups, ++local) {
         const int row0 = (mt / p.w_tiles) * p.h_box;
         const int w0 = (mt % p.w_tiles) * p.w_box;
-        const int n0 = n_blk * p.n_tile;
         if (aux_mode) {
           const int b = local & 1;
           const int boxes = min(p.aux_boxes, (p.aux_width - n0 + 63) >> 6);
@@ -177,7 +237,6 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p, const __grid_constant
             mbar_arrive(&aux_full_bar[b]);
           }
         }
-        const int a_c0 = n_blk * p.a_c_step;
         for (int tap = 0; tap < p.taps; ++tap) {
           const CUtensorMap* am = &amaps.m[p.tap_map[tap]];
           const int wc = w0 + p.tap_dw[tap];
@@ -187,60 +246,82 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p, const __grid_constant
             const uint32_t ph = (it / p.stages) & 1;
             mbar_wait(&empty_bar[s], ph ^ 1);
             mbar_expect_tx(&full_bar[s], tx_bytes);
-            uint8_t* a_dst = tiles + static_cast<size_t>(s) * stage_bytes;
+            uint8_t* a_dst = tiles + static_cast<size_t>(s) * ring_bytes;
+#ifdef SVX_ASHIFT
+            // experiment (W = 1 only): the stage holds rows [rc - SHIFT, rc - SHIFT + 256); the MMA reads a view that starts
+            // SHIFT rows into it
+            tma_load_3d(a_dst, am, &full_bar[s], a_c0 + kc * p.kbox, wc, rc - SVX_ASHIFT);
+            tma_load_3d(a_dst + 128 * p.kbox * 2, am, &full_bar[s], a_c0 + kc * p.kbox, wc, rc - SVX_ASHIFT + 128);
+#else
             tma_load_3d(a_dst, am, &full_bar[s], a_c0 + kc * p.kbox, wc, rc);
-            tma_load_2d(a_dst + p.a_stage_bytes, &bmap, &full_bar[s], (tap * p.nkc + kc) * p.kbox, n0);
+#endif
+            if (!b_res) tma_load_2d(a_dst + p.a_stage_bytes, &bmap, &full_bar[s], (tap * p.nkc + kc) * p.kbox, n0);
           }
         }
       }
     }
   } else if (warp == 1) {
-    const int ksteps = p.kbox >> 4;   // UMMA K = 16 elements = 32 bytes
-    uint32_t it = 0;
-    int local = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
-      const int b = local & 1;
-      mbar_wait(&tmem_empty_bar[b], ((local >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(b * p.n_tile);
-      for (int i = 0; i < total_it; ++i, ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
-        mbar_wait(&full_bar[s], ph);
+    if (active) {
+      const int ksteps = p.kbox >> 4;   // UMMA K = 16 elements = 32 bytes
+      if (b_res) mbar_wait(bres_bar, 0);
+      uint32_t it = 0;
+      int local = 0;
+      for (int mt = my_group; mt < m_tiles; mt += groups, ++local) {
+        const int b = local & 1;
+        mbar_wait(&tmem_empty_bar[b], ((local >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_addr = smem_u32(tiles + static_cast<size_t>(s) * stage_bytes);
-          const uint32_t b_addr = a_addr + p.a_stage_bytes;
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t adesc = make_kmajor_desc(a_addr + k * 32, p.sbo, p.layout_type);
-            const uint64_t bdesc = make_kmajor_desc(b_addr + k * 32, p.sbo, p.layout_type);
-            umma_f16(d_tmem, adesc, bdesc, p.idesc, (i | k) != 0 ? 1u : 0u);
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(b * p.n_tile);
+        for (int i = 0; i < total_it; ++i, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_addr0 = smem_u32(tiles + static_cast<size_t>(s) * ring_bytes);
+            const uint32_t b_addr = b_res ? smem_u32(bres + static_cast<size_t>(i) * p.b_stage_bytes) : a_addr0 + p.a_stage_bytes;
+#ifdef SVX_ASHIFT
+            const uint32_t a_addr = a_addr0 + SVX_ASHIFT * p.kbox * 2;
+            const uint32_t a_bo = SVX_BASEOFF_MODE == 0 ? 0u : ((a_addr >> 7) & 7u);
+#else
+            const uint32_t a_addr = a_addr0;
+            const uint32_t a_bo = 0u;
+#endif
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t adesc = make_kmajor_desc(a_addr + k * 32, p.sbo, p.layout_type, a_bo);
+              const uint64_t bdesc = make_kmajor_desc(b_addr + k * 32, p.sbo, p.layout_type);
+              umma_f16(d_tmem, adesc, bdesc, p.idesc, (i | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[s]);                       // frees the smem slot when these MMAs retire
+            if (i == total_it - 1) umma_commit(&tmem_full_bar[b]);
           }
-          umma_commit(&empty_bar[s]);                       // frees the smem slot when these MMAs retire
-          if (i == total_it - 1) umma_commit(&tmem_full_bar[b]);
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
-  } else {
+  } else if (active) {
     const int wg = (warp - 2) >> 2;          // epilogue warpgroup: even / odd local tiles
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
     const int m = q * 32 + lane;             // accumulator row = pixel of the tile
     const int h = m / p.w_box;
     const int w = m - h * p.w_box;
+    const bool leader = (warp - 2) == wg * 4 && lane == 0;
+    uint8_t* aux = aux_smem + wg * p.aux_bytes;
+    uint8_t* stage = stage_smem + wg * p.stage_bytes;
     int local = wg;
-    for (int t = blockIdx.x + wg * gridDim.x; t < total_tiles; t += 2 * gridDim.x, local += 2) {
-      const int n_blk = t % p.n_tiles;
-      const int mt = t / p.n_tiles;
-      const int row = (mt / p.w_tiles) * p.h_box + h;
-      const int col = (mt % p.w_tiles) * p.w_box + w;
-      const int n0 = n_blk * p.n_tile;
+    for (int mt = my_group + wg * groups; mt < m_tiles; mt += 2 * groups, local += 2) {
+      const int row0 = (mt / p.w_tiles) * p.h_box;
+      const int w0 = (mt % p.w_tiles) * p.w_box;
+      const int row = row0 + h;
+      const int col = w0 + w;
       const bool in_range = (row < p.out_rows) && (col < p.out_W);
       bool valid = in_range;
       if (in_range && p.epi.seg_of_row) valid = p.epi.seg_of_row[row] >= 0;
       const size_t pix = static_cast<size_t>(row) * p.out_W + col;
       const uint32_t ph = (local >> 1) & 1;
-      const uint8_t* aux = aux_smem + wg * p.aux_bytes;
+      if (staged && p.stage_bytes) {          // the previous tile's TMA store must have finished reading the staging boxes
+        if (leader) bulk_wait_read0();
+        named_bar(1 + wg, 128);
+      }
       if (aux_mode) mbar_wait(&aux_full_bar[wg], ph);
       mbar_wait(&tmem_full_bar[wg], ph);
       tc_fence_after();
@@ -251,7 +332,7 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p, const __grid_constant
       for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
         tmem_ld_wait();
         if (c0 + 16 < p.n_tile) tmem_ld16(taddr + c0 + 16, rb);
-        if (in_range) {
+        if (in_range || staged) {
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             const int c = n0 + c0 + g * 8;
@@ -259,14 +340,14 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p, const __grid_constant
               float v[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(ra[g * 8 + j]);
-              epilogue8<T>(p.epi, v, c, c0 + g * 8, pix, row, m, valid, aux, aux_mode, s_scale, s_shift);
+              epilogue8<T>(p.epi, v, c, c0 + g * 8, pix, row, m, in_range, valid, aux, aux_mode, stage, staged, s_scale, s_shift);
             }
           }
         }
         if (c0 + 16 < p.n_tile) {
           tmem_ld_wait();
           if (c0 + 32 < p.n_tile) tmem_ld16(taddr + c0 + 32, ra);
-          if (in_range) {
+          if (in_range || staged) {
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
               const int c = n0 + c0 + 16 + g * 8;
@@ -274,7 +355,7 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p, const __grid_constant
                 float v[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(rb[g * 8 + j]);
-                epilogue8<T>(p.epi, v, c, c0 + 16 + g * 8, pix, row, m, valid, aux, aux_mode, s_scale, s_shift);
+                epilogue8<T>(p.epi, v, c, c0 + 16 + g * 8, pix, row, m, in_range, valid, aux, aux_mode, stage, staged, s_scale, s_shift);
               }
             }
           }
@@ -282,31 +363,65 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&tmem_empty_bar[wg]);
-        if (aux_mode) mbar_arrive(&aux_empty_bar[wg]);
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[wg]);
+      if (staged) {
+        fence_proxy_async();                  // generic-proxy writes to the boxes → visible to the TMA (async proxy)
+        named_bar(1 + wg, 128);
+        if (leader) {
+          // primary destination: 64-channel boxes, clipped by the tensor map at the slice width (n_split)
+          const int prim_hi = min(p.epi.n_split, p.epi.n_valid);
+          uint8_t* src = aux_mode == 1 ? aux : stage;
+          for (int j = 0; n0 + j * 64 < min(prim_hi, n0 + p.n_tile); ++j)
+            tma_store_3d(&omaps.m[0], src + j * kAuxBoxBytes, n0 + j * 64, w0, row0);
+          if (aux_mode == 2)
+            for (int j = 0; n0 + j * 64 < min(prim_hi, n0 + p.n_tile); ++j)
+              tma_store_3d(&omaps.m[1], aux + j * kAuxBoxBytes, n0 + j * 64, w0, row0);
+          bulk_commit();
+          if (aux_mode) {                     // the producer may refill this aux buffer once the stores have read it
+            bulk_wait_read0();
+            mbar_arrive(&aux_empty_bar[wg]);
+          }
+        }
+      } else if (aux_mode && lane == 0) {
+        mbar_arrive(&aux_empty_bar[wg]);
       }
     }
+    if (staged && leader) bulk_wait0();
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
+static size_t ring_stage_bytes(const UmmaConvParams& p) { return p.a_stage_bytes + (p.bres_bytes ? 0u : p.b_stage_bytes); }
+
 size_t conv_umma_smem_bytes(const UmmaConvParams& p) {
-  return 2048 + p.ss_bytes + 2 * static_cast<size_t>(p.aux_bytes) + static_cast<size_t>(p.stages) * (p.a_stage_bytes + p.b_stage_bytes);
+  return 2048 + p.ss_bytes + p.bres_bytes + 2 * static_cast<size_t>(p.aux_bytes) + 2 * static_cast<size_t>(p.stage_bytes) +
+         static_cast<size_t>(p.stages) * ring_stage_bytes(p);
 }
 
-// Fills stages / tmem_cols / aux_bytes from the tile shape; returns false if the tile cannot be scheduled.
+// Fills the shared-memory plan (resident weights, aux / staging boxes, ring depth) and tmem_cols from the tile shape;
+// returns false if the tile cannot be scheduled.
 bool conv_umma_finish_params(UmmaConvParams& p) {
+#ifdef SVX_ASHIFT
+  p.a_stage_bytes *= 2;      // experiment: 256-row stage so a shifted 128-row view stays inside loaded data
+#endif
   const int total_it = p.taps * p.nkc;
+  const int boxes = (p.n_tile + 63) / 64;
   p.aux_bytes = p.aux_mode ? static_cast<uint32_t>(p.aux_boxes) * kAuxBoxBytes : 0u;
+  p.stage_bytes = (p.store_mode == 1 && p.aux_mode != 1) ? static_cast<uint32_t>(boxes) * kAuxBoxBytes : 0u;
   p.ss_bytes = static_cast<uint32_t>((2 * p.n_tiles * p.n_tile * 4 + 1023) / 1024 * 1024);
-  const long long budget = 225 * 1024 - 2048 - p.ss_bytes - 2LL * p.aux_bytes;
-  long long stages = budget / (p.a_stage_bytes + p.b_stage_bytes);
+  const long long fixed = 2048 + p.ss_bytes + 2LL * p.aux_bytes + 2LL * p.stage_bytes;
+  // weights stay resident in shared memory when they are small (every layer of the two high-resolution stages)
+  const long long b_total = static_cast<long long>(total_it) * p.b_stage_bytes;
+  p.bres_bytes = 0;
+  static const bool no_bres = getenv("SVX_NO_BRES") != nullptr;   // debug switch
+  if (!no_bres && b_total <= 64 * 1024 && 225 * 1024 - fixed - b_total >= 4LL * p.a_stage_bytes)
+    p.bres_bytes = static_cast<uint32_t>(b_total);
+  const long long budget = 225 * 1024 - fixed - p.bres_bytes;
+  long long stages = budget / static_cast<long long>(ring_stage_bytes(p));
   if (stages < 2) return false;
   if (stages > kMaxStages) stages = kMaxStages;
-  (void)total_it;
   p.stages = static_cast<int>(stages);
   uint32_t tc = 32;
   while (tc < 2u * p.n_tile) tc *= 2;
@@ -329,17 +444,20 @@ cudaError_t conv_umma_init() {
 }
 
 cudaError_t launch_conv_umma(const UmmaConvParams& p, const AMaps& amaps, const CUtensorMap& bmap, const CUtensorMap& auxmap,
-                             int is_bf16, cudaStream_t stream) {
+                             const OMaps& omaps, int is_bf16, cudaStream_t stream) {
   const int row_tiles = (p.out_rows + p.h_box - 1) / p.h_box;
-  const long long total = static_cast<long long>(row_tiles) * p.w_tiles * p.n_tiles;
-  if (total <= 0) return cudaSuccess;
+  const long long m_tiles = static_cast<long long>(row_tiles) * p.w_tiles;
+  if (m_tiles <= 0) return cudaSuccess;
   const int sms = g_num_sms > 0 ? g_num_sms : 148;
-  dim3 grid(static_cast<unsigned>(total < sms ? total : sms), 1, 1);
+  long long groups = sms / p.n_tiles;                  // CTAs come in groups of n_tiles (one per n-tile of an m-tile)
+  if (groups < 1) groups = 1;
+  if (groups > m_tiles) groups = m_tiles;
+  dim3 grid(static_cast<unsigned>(groups * p.n_tiles), 1, 1);
   const size_t smem = conv_umma_smem_bytes(p);
   if (is_bf16)
-    conv_umma_kernel<__nv_bfloat16><<<grid, kUmmaThreads, smem, stream>>>(p, amaps, bmap, auxmap);
+    conv_umma_kernel<__nv_bfloat16><<<grid, kUmmaThreads, smem, stream>>>(p, amaps, bmap, auxmap, omaps);
   else
-    conv_umma_kernel<__half><<<grid, kUmmaThreads, smem, stream>>>(p, amaps, bmap, auxmap);
+    conv_umma_kernel<__half><<<grid, kUmmaThreads, smem, stream>>>(p, amaps, bmap, auxmap, omaps);
   return cudaGetLastError();
 }
 

@@ -368,20 +368,27 @@ template <typename T> static T host_cvt(float v);
 template <> __half host_cvt<__half>(float v) { return __float2half_rn(std::min(std::max(v, -65504.f), 65504.f)); }
 template <> __nv_bfloat16 host_cvt<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
+// TMA issues one request per box row at a fixed ~1.75 ns whatever its width (profiles/r01_microbench_tma_rate.txt),
+// so the widest swizzle span that the slice fills at all is the cheapest; padded K only costs idle MMA cycles.
 static int pick_kbox(int cin) {
-  if (cin % 64 == 0) return 64;
-  if (cin % 32 == 0) return 32;
+  if (getenv("SVX_KBOX_OLD")) {   // debug switch: exact-fit boxes
+    if (cin % 64 == 0) return 64;
+    if (cin % 32 == 0) return 32;
+  }
   if (cin <= 16) return 16;
   if (cin <= 32) return 32;
   return 64;
 }
 
-static int pick_ntile(int cout, int max_tile) {
+// Output tiles are staged as 64-channel boxes for TMA stores, and a store box cannot be clipped at a tile boundary
+// (only at the end of the destination slice), so a conv is either one n-tile (≤ 128 channels) or several n-tiles whose
+// width is a multiple of 64.  Returns 0 when no such tiling exists (the caller then keeps direct stores).
+static int pick_ntile(int cout, int max_multi) {
   const int n = round_up(cout, 16);
-  if (n <= max_tile) return n;
-  for (int parts = 2; parts <= 64; ++parts)
-    if (n % parts == 0 && (n / parts) % 16 == 0 && n / parts <= max_tile) return n / parts;
-  return 64;
+  if (n <= 128) return n;
+  for (int t = max_multi; t >= 64; t -= 64)
+    if (cout % t == 0) return t;
+  return 0;
 }
 
 int Model::upload_conv_weights(ConvDesc& c) {
@@ -399,8 +406,10 @@ int Model::upload_conv_weights(ConvDesc& c) {
     c.kbox = pick_kbox(c.cin);
     c.nkc = (c.cin + c.kbox - 1) / c.kbox;
     c.kpad = c.nkc * c.kbox;
-    // tiles that prefetch a residual / add2 operand keep n_tile ≤ 128 so two aux buffers and a deep ring fit in smem
-    c.n_tile = pick_ntile(c.cout, (c.res.id >= 0 || c.add2.id >= 0) ? 128 : 256);
+    // outputs are staged in 64-channel shared-memory boxes for TMA stores: ≤ 2 boxes per tile, 1 when an add2 tile
+    // and an out2 tile are live as well
+    c.n_tile = pick_ntile(c.cout, c.add2.id >= 0 ? 64 : 128);
+    if (c.n_tile == 0) { c.n_tile = 128; c.no_staged = true; }
   }
   c.n_pad = round_up(c.cout, c.n_tile);
   c.n_tiles = c.n_pad / c.n_tile;
@@ -545,6 +554,7 @@ int Model::plan_conv(ConvDesc& c) {
   if (!ok) return 0;
   UmmaConvParams& up = c.up;
   memset(&up, 0, sizeof up);
+  const size_t esz = 2;
   int w_box = 1;
   while (w_box < 128 && out_W % (w_box * 2) == 0) w_box *= 2;
   up.out_rows = 0; up.out_W = out_W; up.w_box = w_box; up.h_box = 128 / w_box; up.w_tiles = out_W / w_box;
@@ -552,6 +562,13 @@ int Model::plan_conv(ConvDesc& c) {
   up.aux_mode = e.res ? 1 : (e.out2 ? 2 : 0);
   up.aux_boxes = up.aux_mode ? (c.n_tile + 63) / 64 : 0;
   up.aux_width = up.aux_mode == 1 ? e.n_split : (up.aux_mode == 2 ? c.cout : 0);
+  {   // debug switch: SVX_STAGED_MASK bit 1 plain, 2 split, 4 residual, 8 add2, 16 stride-2 (default all)
+    const char* mk = getenv("SVX_STAGED_MASK");
+    const int mask = mk ? atoi(mk) : 63;
+    int kind = up.aux_mode == 1 ? 4 : up.aux_mode == 2 ? 8 : (e.n_split < c.cout ? 2 : (c.cout % 64 == 0 ? 32 : 1));
+    if (c.stride == 2 && !(mask & 16)) kind = 0;
+    up.store_mode = ((mask & kind) && !c.no_staged) ? 1 : 0;
+  }
   const int sw_bytes = c.kbox * 2;
   up.layout_type = sw_bytes == 128 ? 2u : sw_bytes == 64 ? 4u : 6u;
   up.sbo = 8u * sw_bytes;
@@ -560,7 +577,6 @@ int Model::plan_conv(ConvDesc& c) {
   up.b_stage_bytes = static_cast<uint32_t>(round_up(c.n_tile * sw_bytes, 1024));
   if (!conv_umma_finish_params(up)) return 0;
   up.epi = e;
-  const size_t esz = 2;
   uint8_t* base = static_cast<uint8_t*>(tin.ptr);
   for (int t = 0; t < taps; ++t) {
     const int r = t / c.kw, s = t % c.kw;
@@ -575,6 +591,22 @@ int Model::plan_conv(ConvDesc& c) {
   }
   const uint32_t box[3] = {static_cast<uint32_t>(c.kbox), static_cast<uint32_t>(w_box), static_cast<uint32_t>(128 / w_box)};
   memset(&c.auxmap, 0, sizeof c.auxmap);
+  memset(&c.omaps, 0, sizeof c.omaps);
+  {   // TMA-store maps over the destination slices (64-channel boxes, clipped at the slice width)
+    const uint32_t obox[3] = {64u, static_cast<uint32_t>(w_box), static_cast<uint32_t>(128 / w_box)};
+    const uint64_t dims[3] = {static_cast<uint64_t>(e.n_split), static_cast<uint64_t>(out_W), static_cast<uint64_t>(rows_cap_[tout.stage])};
+    const uint64_t str[2] = {static_cast<uint64_t>(tout.C) * esz, static_cast<uint64_t>(out_W) * tout.C * esz};
+    if (encode_tmap(&c.omaps.m[0], is_bf16_, static_cast<uint8_t*>(tout.ptr) + static_cast<size_t>(c.out.coff) * esz, 3, dims, str, obox, 128))
+      return 1;
+    c.omaps.m[1] = c.omaps.m[0];
+    if (c.out2.id >= 0) {
+      const ActTensor& t2 = tensors_[c.out2.id];
+      const uint64_t d2[3] = {static_cast<uint64_t>(c.cout), static_cast<uint64_t>(out_W), static_cast<uint64_t>(rows_cap_[t2.stage])};
+      const uint64_t s2[2] = {static_cast<uint64_t>(t2.C) * esz, static_cast<uint64_t>(out_W) * t2.C * esz};
+      if (encode_tmap(&c.omaps.m[1], is_bf16_, static_cast<uint8_t*>(t2.ptr) + static_cast<size_t>(c.out2.coff) * esz, 3, d2, s2, obox, 128))
+        return 1;
+    }
+  }
   if (up.aux_mode) {   // residual / add2 tile: 64-channel SWIZZLE_128B boxes over the output-resolution tensor slice
     const TensorRef& ar = up.aux_mode == 1 ? c.res : c.add2;
     const ActTensor& ta = tensors_[ar.id];
@@ -688,7 +720,7 @@ int Model::launch_conv(ConvDesc& c, cudaStream_t st) {
       while (events_.size() < ev_used_ + 2) { cudaEvent_t e; SVX_CUDA(cudaEventCreate(&e)); events_.push_back(e); }
       SVX_CUDA(cudaEventRecord(events_[ev_used_], st));
     }
-    SVX_CUDA(launch_conv_umma(c.up, c.amaps, c.bmap, c.auxmap, is_bf16_, st));
+    SVX_CUDA(launch_conv_umma(c.up, c.amaps, c.bmap, c.auxmap, c.omaps, is_bf16_, st));
     if (time_convs_) {
       SVX_CUDA(cudaEventRecord(events_[ev_used_ + 1], st));
       ev_used_ += 2;
@@ -785,7 +817,27 @@ int Model::run_segments(const float* d_feats, const int32_t* h_frame_off, int n_
         grow(&d_fc_partial_, &fc_partial_bytes_, static_cast<size_t>(fc_splits(flat_dim_)) * nb * cfg_.embed_dim * 4)) {
       set_last_error("allocation failed"); return 1;
     }
+    int op_index = 0;
+    const char* dump_dir = getenv("SVX_DUMP_DIR");   // debug: raw dump of every op's destination tensor
     for (Op& op : ops_) {
+      struct Dump {
+        Model* m; Op& op; int idx; const char* dir; cudaStream_t st;
+        ~Dump() {
+          if (!dir) return;
+          const TensorRef& r = op.kind == OP_CONV ? op.conv.out : op.out;
+          if (r.id < 0) return;
+          cudaStreamSynchronize(st);
+          const ActTensor& t = m->tensors_[r.id];
+          const size_t bytes = static_cast<size_t>(m->rows_used_[t.stage]) * m->stage_W_[t.stage] * t.C * 2;
+          std::vector<char> h(bytes);
+          cudaMemcpy(h.data(), t.ptr, bytes, cudaMemcpyDeviceToHost);
+          char path[512];
+          snprintf(path, sizeof path, "%s/op%03d_k%d_t%d_r%d_w%d_c%d_off%d_n%d.bin", dir, idx, (int)op.kind, r.id, m->rows_used_[t.stage],
+                   m->stage_W_[t.stage], t.C, r.coff, op.kind == OP_CONV ? op.conv.cout : op.C);
+          FILE* f = fopen(path, "wb");
+          if (f) { fwrite(h.data(), 1, bytes, f); fclose(f); }
+        }
+      } dump{this, op, op_index++, dump_dir, st};
       switch (op.kind) {
         case OP_PACK_INPUT: {
           const ActTensor& t = tensors_[op.out.id];

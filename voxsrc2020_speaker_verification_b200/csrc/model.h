@@ -49,8 +49,8 @@ struct ConvDesc {
   // resolved
   void* d_wgt = nullptr; int kpad = 0, kbox = 0, nkc = 0, n_pad = 0, n_tile = 0, n_tiles = 0;
   float* d_scale = nullptr; float* d_shift = nullptr;
-  bool use_umma = false;
-  UmmaConvParams up; AMaps amaps; CUtensorMap bmap; CUtensorMap auxmap;
+  bool use_umma = false; bool no_staged = false;
+  UmmaConvParams up; AMaps amaps; CUtensorMap bmap; CUtensorMap auxmap; OMaps omaps;
   SimpleConvParams sp;
 };
 

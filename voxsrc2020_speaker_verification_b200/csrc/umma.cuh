@@ -116,8 +116,9 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // K-major shared-memory matrix descriptor (version 1 = Blackwell).  The tile is rows x kbox elements,
 // row pitch = swizzle span (kbox*2 bytes ∈ {128,64,32}), 8-row groups packed back to back (SBO = 8*pitch).
 //   layout_type: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B
-__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout_type) {
-  uint64_t d = 0;
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout_type,
+                                                     uint32_t base_offset = 0) {
+  uint64_t d = static_cast<uint64_t>(base_offset & 7) << 49;
   d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
   d |= static_cast<uint64_t>(1) << 16;                               // LBO (ignored for swizzled K-major)
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
