@@ -7,6 +7,9 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from voxsrc2020_speaker_verification_b200 import lib as _lib
+if os.environ.get("SVX_LIB"):
+    _lib.LIB_PATH = os.environ["SVX_LIB"]
 from oracle import net_oracle  # synthetic weights / features generator only
 from voxsrc2020_speaker_verification_b200 import arch
 from voxsrc2020_speaker_verification_b200.extractor import Extractor

@@ -14,6 +14,7 @@
 namespace svx {
 
 constexpr int kMaxTaps = 9;
+constexpr int kTraceEvents = 4096;
 
 // Where a conv's output goes and what is fused on the way (BN as scale/shift, ReLU, residual, concat).
 struct Epilogue {
@@ -73,6 +74,7 @@ struct UmmaConvParams {
   int store_mode;              // 0: direct 16-byte stores (fp32 output form); 1: swizzled smem boxes + TMA stores
   uint32_t stage_bytes;        // bytes of one output staging buffer (0 when the residual tile is reused in place)
   uint32_t bres_bytes;         // bytes of the resident weight region (0 → weights stream through the ring)
+  unsigned long long* trace;   // debug: per-role event timestamps of CTA 0 (nullptr = off); [4 roles][kTraceEvents]
   uint32_t idesc, sbo, layout_type;
   uint32_t a_stage_bytes, b_stage_bytes, tmem_cols;
   Epilogue epi;

@@ -29,14 +29,6 @@ constexpr int kUmmaThreads = 320;
 constexpr int kMaxStages = 8;
 constexpr int kAuxBoxBytes = 128 * 128;   // 128 rows x 64 channels x 2 B
 
-// 8 consecutive channels of one pixel from the aux tile in shared memory (SWIZZLE_128B: 16-byte unit u of row m
-// lives at unit u ^ (m & 7)).
-__device__ __forceinline__ uint4 aux_load8(const uint8_t* aux, int m, int c_local) {
-  const int box = c_local >> 6;
-  const int u = (c_local & 63) >> 3;
-  return *reinterpret_cast<const uint4*>(aux + box * kAuxBoxBytes + m * 128 + ((u ^ (m & 7)) << 4));
-}
-
 template <typename T>
 __device__ __forceinline__ void add8(float (&v)[8], const uint4& r) {
   const float2 a = TypeOps<T>::unpack2(r.x), b = TypeOps<T>::unpack2(r.y), c = TypeOps<T>::unpack2(r.z), d = TypeOps<T>::unpack2(r.w);
@@ -52,44 +44,67 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
 }
 
 // c: first of 8 consecutive output channels (multiple of 8, < n_valid); c_local = c - n0.
-// Swizzled (SWIZZLE_128B) address of the 16-byte unit that holds channels [c_local, c_local+8) of tile row m inside a
-// buffer of 64-channel boxes — the layout TMA loads produce and TMA stores consume.
-__device__ __forceinline__ uint8_t* box_unit(uint8_t* buf, int m, int c_local) {
-  const int box = c_local >> 6;
-  const int u = (c_local & 63) >> 3;
-  return buf + box * kAuxBoxBytes + m * 128 + ((u ^ (m & 7)) << 4);
+// Shared-memory accesses of the epilogue use explicit shared-space addresses: generic-pointer loads cost the
+// epilogue ~3x (profiles/r01_trace_*).
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_u4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
+// Shared-space address of the 16-byte unit that holds channels [c_local, c_local+8) of tile row m inside a buffer of
+// 64-channel SWIZZLE_128B boxes (unit u of row m lives at u ^ (m & 7)) — the layout TMA loads produce and TMA
+// stores consume.  row_off = m * 128, row_xor = (m & 7) << 4 are per-thread constants.
+__device__ __forceinline__ uint32_t box_unit(uint32_t buf, uint32_t row_off, uint32_t row_xor, int c_local) {
+  return buf + static_cast<uint32_t>(c_local >> 6) * kAuxBoxBytes + row_off + ((static_cast<uint32_t>(c_local & 56) << 1) ^ row_xor);
+}
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void named_bar(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
+// Per-thread, per-tile constants of the epilogue, all in registers.
+struct EpiCtx {
+  uint32_t scale_addr, shift_addr;   // shared-space addresses of the staged per-channel vectors
+  uint32_t aux, stage;               // shared-space addresses of this warpgroup's aux / staging buffers
+  uint32_t row_off, row_xor;         // m * 128, (m & 7) << 4
+  int aux_mode, n_split;
+  bool staged, pre_relu, post_relu, f32;
+};
+
 // One group of 8 consecutive output channels of one pixel: BN scale/shift, ReLUs, residual, routing.
-//   c: first channel (multiple of 8, < n_valid); c_local = c - n0; m = tile row.
-// Staged mode (stage != nullptr or aux in place): 16-bit results go to swizzled shared-memory boxes that one thread
-// later hands to TMA stores; secondary-destination channels and the fp32 form are stored directly.
+//   c: first channel (multiple of 8, < n_valid); c_local = c - n0.
+// Staged mode: 16-bit results go to swizzled shared-memory boxes that one thread later hands to TMA stores (the
+// residual tile is overwritten in place); secondary-destination channels and the fp32 form are stored directly.
 template <typename T>
-__device__ __forceinline__ void epilogue8(const Epilogue& e, float (&v)[8], int c, int c_local, size_t pix, int row, int m,
-                                          bool in_range, bool valid, uint8_t* aux, int aux_mode, uint8_t* stage, bool staged,
-                                          const float* s_scale, const float* s_shift) {
-  if (e.pre_relu) {
+__device__ __forceinline__ void epilogue8(const Epilogue& e, const EpiCtx& x, float (&v)[8], int c, int c_local, size_t pix, int row,
+                                          bool in_range, bool valid) {
+  const float4 s0 = lds_f4(x.scale_addr + c * 4), s1 = lds_f4(x.scale_addr + c * 4 + 16);
+  const float4 b0 = lds_f4(x.shift_addr + c * 4), b1 = lds_f4(x.shift_addr + c * 4 + 16);
+  const bool prim = c < x.n_split;
+  const uint32_t au = box_unit(x.aux, x.row_off, x.row_xor, c_local);
+  uint4 ax = make_uint4(0, 0, 0, 0);
+  if (x.aux_mode != 0 && prim) ax = lds_u4(au);
+  if (x.pre_relu) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
   }
-  {   // per-channel scale / shift staged in shared memory at kernel start (1 / 0 when the conv has no BN)
-    const float4 s0 = *reinterpret_cast<const float4*>(s_scale + c);
-    const float4 s1 = *reinterpret_cast<const float4*>(s_scale + c + 4);
-    const float4 b0 = *reinterpret_cast<const float4*>(s_shift + c);
-    const float4 b1 = *reinterpret_cast<const float4*>(s_shift + c + 4);
-    v[0] = fmaf(v[0], s0.x, b0.x); v[1] = fmaf(v[1], s0.y, b0.y); v[2] = fmaf(v[2], s0.z, b0.z); v[3] = fmaf(v[3], s0.w, b0.w);
-    v[4] = fmaf(v[4], s1.x, b1.x); v[5] = fmaf(v[5], s1.y, b1.y); v[6] = fmaf(v[6], s1.z, b1.z); v[7] = fmaf(v[7], s1.w, b1.w);
-  }
-  if (e.out_f32) {
+  v[0] = fmaf(v[0], s0.x, b0.x); v[1] = fmaf(v[1], s0.y, b0.y); v[2] = fmaf(v[2], s0.z, b0.z); v[3] = fmaf(v[3], s0.w, b0.w);
+  v[4] = fmaf(v[4], s1.x, b1.x); v[5] = fmaf(v[5], s1.y, b1.y); v[6] = fmaf(v[6], s1.z, b1.z); v[7] = fmaf(v[7], s1.w, b1.w);
+  if (x.f32) {
     if (!in_range) return;
     float* o = e.out_f32 + static_cast<size_t>(row) * e.ldf + c;
     if (!valid) {
@@ -100,40 +115,48 @@ __device__ __forceinline__ void epilogue8(const Epilogue& e, float (&v)[8], int 
     *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
     return;
   }
-  if (c < e.n_split) {
-    uint4* ap = reinterpret_cast<uint4*>(box_unit(aux, m, c_local));
-    if (aux_mode == 1) add8<T>(v, *ap);
+  if (x.aux_mode == 1 && prim) add8<T>(v, ax);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (e.post_relu) v[j] = fmaxf(v[j], 0.f);
-      if (!valid) v[j] = 0.f;
-    }
-    if (!staged) {                                              // direct 16-byte stores (debug / fallback form)
+  for (int j = 0; j < 8; ++j) {
+    if (x.post_relu) v[j] = fmaxf(v[j], 0.f);
+    if (!valid) v[j] = 0.f;
+  }
+  const uint4 o = pack8<T>(v);
+  if (prim) {
+    if (!x.staged) {                                            // direct 16-byte stores (debug / fallback form)
       if (!in_range) return;
-      *reinterpret_cast<uint4*>(static_cast<T*>(e.out) + pix * e.out_C + e.out_coff + c) = pack8<T>(v);
-      if (aux_mode == 2) {
-        if (valid) add8<T>(v, *ap);
+      *reinterpret_cast<uint4*>(static_cast<T*>(e.out) + pix * e.out_C + e.out_coff + c) = o;
+      if (x.aux_mode == 2) {
+        if (valid) add8<T>(v, ax);
         *reinterpret_cast<uint4*>(static_cast<T*>(e.out2) + pix * e.out2_C + e.out2_coff + c) = pack8<T>(v);
       }
-    } else if (aux_mode == 1) {
-      *ap = pack8<T>(v);                                        // residual tile is overwritten in place and stored from there
+    } else if (x.aux_mode == 1) {
+      sts_u4(au, o);                                            // residual tile overwritten in place, stored from there
     } else {
-      *reinterpret_cast<uint4*>(box_unit(stage, m, c_local)) = pack8<T>(v);
-      if (aux_mode == 2) {                                      // out2 = v + add2, in place on the add2 tile
-        if (valid) add8<T>(v, *ap);
-        *ap = pack8<T>(v);
+      sts_u4(box_unit(x.stage, x.row_off, x.row_xor, c_local), o);
+      if (x.aux_mode == 2) {                                    // out2 = v + add2, in place on the add2 tile
+        if (valid) add8<T>(v, ax);
+        sts_u4(au, pack8<T>(v));
       }
     }
   } else {
     if (!in_range) return;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (e.post_relu) v[j] = fmaxf(v[j], 0.f);
-      if (!valid) v[j] = 0.f;
-    }
-    *reinterpret_cast<uint4*>(static_cast<T*>(e.outb) + pix * e.outb_C + e.outb_coff + (c - e.n_split)) = pack8<T>(v);
+    *reinterpret_cast<uint4*>(static_cast<T*>(e.outb) + pix * e.outb_C + e.outb_coff + (c - e.n_split)) = o;
   }
 }
+
+// debug timeline: event (role, code) stamped with the global ns timer, CTA 0 only
+struct Tracer {
+  unsigned long long* buf; int n;
+  __device__ __forceinline__ void init(unsigned long long* base, int role) { buf = (base && blockIdx.x == 0) ? base + role * kTraceEvents : nullptr; n = 0; }
+  __device__ __forceinline__ void ev(int code) {
+    if (buf && n < kTraceEvents) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      buf[n++] = (t << 8) | static_cast<unsigned long long>(code & 0xff);
+    }
+  }
+};
 
 template <typename T>
 __global__ void __launch_bounds__(kUmmaThreads, 1)
@@ -222,13 +245,16 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p, const __grid_constant
       const int a_c0 = n_blk * p.a_c_step;
       uint32_t it = 0;
       int local = 0;
+      Tracer tr; tr.init(p.trace, 0);
       for (int mt = my_group; mt < m_tiles; mt += groups, ++local) {
         const int row0 = (mt / p.w_tiles) * p.h_box;
         const int w0 = (mt % p.w_tiles) * p.w_box;
+        tr.ev(1);                                             // tile start
         if (aux_mode) {
           const int b = local & 1;
           const int boxes = min(p.aux_boxes, (p.aux_width - n0 + 63) >> 6);
           mbar_wait(&aux_empty_bar[b], ((local >> 1) & 1) ^ 1);
+          tr.ev(2);                                           // aux buffer free
           if (boxes > 0) {
             mbar_expect_tx(&aux_full_bar[b], static_cast<uint32_t>(boxes) * kAuxBoxBytes);
             for (int j = 0; j < boxes; ++j)
@@ -258,6 +284,7 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p, const __grid_constant
             if (!b_res) tma_load_2d(a_dst + p.a_stage_bytes, &bmap, &full_bar[s], (tap * p.nkc + kc) * p.kbox, n0);
           }
         }
+        tr.ev(3);                                             // all loads of the tile issued
       }
     }
   } else if (warp == 1) {
@@ -266,9 +293,12 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p, const __grid_constant
       if (b_res) mbar_wait(bres_bar, 0);
       uint32_t it = 0;
       int local = 0;
+      Tracer tr; tr.init(lane == 0 ? p.trace : nullptr, 1);
       for (int mt = my_group; mt < m_tiles; mt += groups, ++local) {
         const int b = local & 1;
+        tr.ev(1);
         mbar_wait(&tmem_empty_bar[b], ((local >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
+        tr.ev(2);                                                   // accumulator free
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(b * p.n_tile);
         for (int i = 0; i < total_it; ++i, ++it) {
@@ -295,7 +325,9 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p, const __grid_constant
             if (i == total_it - 1) umma_commit(&tmem_full_bar[b]);
           }
           __syncwarp();
+          if (i == 0) tr.ev(3);                                     // first operands landed
         }
+        tr.ev(4);                                                   // all MMAs issued
       }
     }
   } else if (active) {
@@ -305,27 +337,47 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p, const __grid_constant
     const int h = m / p.w_box;
     const int w = m - h * p.w_box;
     const bool leader = (warp - 2) == wg * 4 && lane == 0;
-    uint8_t* aux = aux_smem + wg * p.aux_bytes;
-    uint8_t* stage = stage_smem + wg * p.stage_bytes;
+    EpiCtx x;
+    x.scale_addr = smem_u32(s_scale); x.shift_addr = smem_u32(s_shift);
+    x.aux = smem_u32(aux_smem + wg * p.aux_bytes); x.stage = smem_u32(stage_smem + wg * p.stage_bytes);
+    x.row_off = static_cast<uint32_t>(m) * 128u; x.row_xor = static_cast<uint32_t>(m & 7) << 4;
+    x.aux_mode = aux_mode; x.n_split = p.epi.n_split; x.staged = staged;
+    x.pre_relu = p.epi.pre_relu != 0; x.post_relu = p.epi.post_relu != 0; x.f32 = p.epi.out_f32 != nullptr;
+    const int n_valid = p.epi.n_valid;
     int local = wg;
+    // the segment id of this thread's row is fetched one tile ahead: the load competes with saturated TMA traffic
+    // and would otherwise sit on the critical path of every tile
+    auto seg_fetch = [&](int mt_) -> int {
+      if (mt_ >= m_tiles) return -1;
+      const int row_ = (mt_ / p.w_tiles) * p.h_box + h;
+      const int col_ = (mt_ % p.w_tiles) * p.w_box + w;
+      if (row_ >= p.out_rows || col_ >= p.out_W) return -1;
+      return p.epi.seg_of_row ? p.epi.seg_of_row[row_] : 0;
+    };
+    int seg_next = seg_fetch(my_group + wg * groups);
+    Tracer tr; tr.init(leader ? p.trace : nullptr, 2 + wg);
     for (int mt = my_group + wg * groups; mt < m_tiles; mt += 2 * groups, local += 2) {
       const int row0 = (mt / p.w_tiles) * p.h_box;
       const int w0 = (mt % p.w_tiles) * p.w_box;
       const int row = row0 + h;
       const int col = w0 + w;
       const bool in_range = (row < p.out_rows) && (col < p.out_W);
-      bool valid = in_range;
-      if (in_range && p.epi.seg_of_row) valid = p.epi.seg_of_row[row] >= 0;
+      const int seg_cur = seg_next;
+      seg_next = seg_fetch(mt + 2 * groups);
       const size_t pix = static_cast<size_t>(row) * p.out_W + col;
       const uint32_t ph = (local >> 1) & 1;
       if (staged && p.stage_bytes) {          // the previous tile's TMA store must have finished reading the staging boxes
         if (leader) bulk_wait_read0();
         named_bar(1 + wg, 128);
       }
+      tr.ev(1);
       if (aux_mode) mbar_wait(&aux_full_bar[wg], ph);
+      tr.ev(2);                                                     // aux tile landed
       mbar_wait(&tmem_full_bar[wg], ph);
+      tr.ev(3);                                                     // accumulator ready
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(wg * p.n_tile);
+      const bool valid = in_range && seg_cur >= 0;
       // two register buffers: the TMEM load of chunk i+1 is in flight while chunk i is converted and stored
       uint32_t ra[16], rb[16];
       tmem_ld16(taddr, ra);
@@ -336,11 +388,11 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p, const __grid_constant
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             const int c = n0 + c0 + g * 8;
-            if (c < p.epi.n_valid) {
+            if (c < n_valid) {
               float v[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(ra[g * 8 + j]);
-              epilogue8<T>(p.epi, v, c, c0 + g * 8, pix, row, m, in_range, valid, aux, aux_mode, stage, staged, s_scale, s_shift);
+              epilogue8<T>(p.epi, x, v, c, c0 + g * 8, pix, row, in_range, valid);
             }
           }
         }
@@ -351,11 +403,11 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p, const __grid_constant
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
               const int c = n0 + c0 + 16 + g * 8;
-              if (c < p.epi.n_valid) {
+              if (c < n_valid) {
                 float v[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(rb[g * 8 + j]);
-                epilogue8<T>(p.epi, v, c, c0 + 16 + g * 8, pix, row, m, in_range, valid, aux, aux_mode, stage, staged, s_scale, s_shift);
+                epilogue8<T>(p.epi, x, v, c, c0 + 16 + g * 8, pix, row, in_range, valid);
               }
             }
           }
@@ -364,22 +416,25 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[wg]);
+      tr.ev(4);                                                     // tile converted
       if (staged) {
         fence_proxy_async();                  // generic-proxy writes to the boxes → visible to the TMA (async proxy)
         named_bar(1 + wg, 128);
         if (leader) {
           // primary destination: 64-channel boxes, clipped by the tensor map at the slice width (n_split)
           const int prim_hi = min(p.epi.n_split, p.epi.n_valid);
-          uint8_t* src = aux_mode == 1 ? aux : stage;
+          const uint32_t src = aux_mode == 1 ? x.aux : x.stage;
           for (int j = 0; n0 + j * 64 < min(prim_hi, n0 + p.n_tile); ++j)
             tma_store_3d(&omaps.m[0], src + j * kAuxBoxBytes, n0 + j * 64, w0, row0);
           if (aux_mode == 2)
             for (int j = 0; n0 + j * 64 < min(prim_hi, n0 + p.n_tile); ++j)
-              tma_store_3d(&omaps.m[1], aux + j * kAuxBoxBytes, n0 + j * 64, w0, row0);
+              tma_store_3d(&omaps.m[1], x.aux + j * kAuxBoxBytes, n0 + j * 64, w0, row0);
           bulk_commit();
+          tr.ev(5);                                                 // stores issued
           if (aux_mode) {                     // the producer may refill this aux buffer once the stores have read it
             bulk_wait_read0();
             mbar_arrive(&aux_empty_bar[wg]);
+            tr.ev(6);                                               // stores have read the boxes
           }
         }
       } else if (aux_mode && lane == 0) {
@@ -422,6 +477,8 @@ bool conv_umma_finish_params(UmmaConvParams& p) {
   long long stages = budget / static_cast<long long>(ring_stage_bytes(p));
   if (stages < 2) return false;
   if (stages > kMaxStages) stages = kMaxStages;
+  static const int env_stages = getenv("SVX_MAX_STAGES") ? atoi(getenv("SVX_MAX_STAGES")) : 0;   // debug switch
+  if (env_stages >= 2 && stages > env_stages) stages = env_stages;
   p.stages = static_cast<int>(stages);
   uint32_t tc = 32;
   while (tc < 2u * p.n_tile) tc *= 2;

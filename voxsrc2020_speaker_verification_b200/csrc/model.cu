@@ -716,11 +716,29 @@ int Model::launch_conv(ConvDesc& c, cudaStream_t st) {
   const int out_rows = rows_used_[out_stage];
   if (c.use_umma && !force_simple_) {
     c.up.out_rows = out_rows;
+    static const char* trace_dir = getenv("SVX_TRACE_DIR");   // debug: per-launch event timeline of CTA 0
+    static unsigned long long* d_trace = nullptr;
+    static int trace_idx = 0;
+    if (trace_dir) {
+      if (!d_trace) cudaMalloc(&d_trace, 4 * kTraceEvents * 8);
+      cudaMemsetAsync(d_trace, 0, 4 * kTraceEvents * 8, st);
+      c.up.trace = d_trace;
+    }
     if (time_convs_) {
       while (events_.size() < ev_used_ + 2) { cudaEvent_t e; SVX_CUDA(cudaEventCreate(&e)); events_.push_back(e); }
       SVX_CUDA(cudaEventRecord(events_[ev_used_], st));
     }
     SVX_CUDA(launch_conv_umma(c.up, c.amaps, c.bmap, c.auxmap, c.omaps, is_bf16_, st));
+    if (trace_dir) {
+      std::vector<unsigned long long> h(4 * kTraceEvents);
+      cudaStreamSynchronize(st);
+      cudaMemcpy(h.data(), d_trace, h.size() * 8, cudaMemcpyDeviceToHost);
+      char path[512];
+      snprintf(path, sizeof path, "%s/trace%04d_k%dx%d_cin%d_cout%d_s%d_aux%d_st%d.bin", trace_dir, trace_idx++, c.kh, c.kw, c.cin, c.cout,
+               c.stride, c.up.aux_mode, c.up.store_mode);
+      FILE* f = fopen(path, "wb");
+      if (f) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
+    }
     if (time_convs_) {
       SVX_CUDA(cudaEventRecord(events_[ev_used_ + 1], st));
       ev_used_ += 2;

@@ -103,6 +103,10 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 
 // 32 lanes x 16 consecutive fp32 columns → 16 registers per thread (thread = lane = accumulator row).
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+#ifdef SVX_EXP_NOLD
+  for (int i = 0; i < 16; ++i) v[i] = taddr + i;
+  return;
+#endif
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
