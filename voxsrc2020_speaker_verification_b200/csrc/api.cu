@@ -215,7 +215,7 @@ static int cohort_pass(svx_scorer* h, const float* test_dev, int64_t n, const fl
 
   UmmaConvParams up;
   memset(&up, 0, sizeof up);
-  up.out_W = 1; up.w_box = 1; up.h_box = 128; up.w_tiles = 1;
+  up.out_W = 1; up.out_Wp = 1; up.w_box = 1; up.h_box = 128; up.w_tiles = 1;
   up.taps = 1; up.nkc = nkc; up.kbox = kbox; up.n_tile = n_tile; up.n_tiles = c_pad / n_tile;
   const int sw_bytes = kbox * 2;
   up.layout_type = sw_bytes == 128 ? 2u : sw_bytes == 64 ? 4u : 6u;

@@ -40,7 +40,7 @@ struct Epilogue {
 
 // Geometry for the plain CUDA-core kernel (any stride / dilation / groups).
 struct SimpleConvParams {
-  const void* in; int in_C; int in_coff; int in_rows; int in_W;
+  const void* in; int in_C; int in_coff; int in_rows; int in_W; int in_Wp;   // in_Wp: pixels per row in memory (W + zero column)
   const void* wgt;      // [n_pad][taps*kpad] K-major, same buffer the UMMA path uses
   int kpad;             // padded input channels per tap
   int cin_g;            // input channels per group
@@ -48,13 +48,14 @@ struct SimpleConvParams {
   int grp_ntile;        // grouped weights: K positions of row n are relative to input channel
   int grp_cstep;        //   (n / grp_ntile) * grp_cstep   (0/0 for dense: relative to channel 0)
   int kh, kw, sh, sw, dh, dw, ph, pw;
-  int out_rows, out_W;
+  int out_rows, out_W, out_Wp;
   Epilogue epi;
 };
 
 // Geometry for the tcgen05 kernel.  One CTA = one 128-pixel (h_box x w_box) x n_tile output tile.
 struct UmmaConvParams {
   int out_rows, out_W;
+  int out_Wp;                  // row pitch of the output image in pixels (W + zero column)
   int w_box, h_box, w_tiles;
   int taps;
   int8_t tap_map[kMaxTaps];    // which of the (up to 4) A tensor maps the tap reads (stride-2 parity views)
@@ -111,13 +112,13 @@ template <> struct TypeOps<__nv_bfloat16> {
 
 // Scalar epilogue used by the CUDA-core kernel (and as the semantic definition of the fused one).
 template <typename T>
-__device__ __forceinline__ void epilogue_scalar(const Epilogue& e, float acc, int row, int col, int W, int c, bool valid) {
+__device__ __forceinline__ void epilogue_scalar(const Epilogue& e, float acc, int row, int col, int Wp, int c, bool valid) {
   if (c >= e.n_valid) return;
   float v = acc;
   if (e.pre_relu) v = fmaxf(v, 0.f);
   if (e.scale) v *= e.scale[c];
   if (e.shift) v += e.shift[c];
-  const size_t pix = static_cast<size_t>(row) * W + col;
+  const size_t pix = static_cast<size_t>(row) * Wp + col;
   if (e.out_f32) {
     e.out_f32[static_cast<size_t>(row) * e.ldf + c] = valid ? v : 0.f;
     return;
@@ -137,6 +138,45 @@ __device__ __forceinline__ void epilogue_scalar(const Epilogue& e, float acc, in
     static_cast<T*>(e.outb)[pix * e.outb_C + e.outb_coff + (c - e.n_split)] = TypeOps<T>::from_f(v);
   }
 }
+
+
+// ------------------------------------------------------------------------------------------------------------
+// Flat implicit GEMM (conv_flat.cu): stride-1 convs over the image seen as a 1-D pixel sequence p = row*Wp + col
+// (Wp = W + one zero column), so that filter tap (dh, dw) is the constant shift dh*Wp + dw.  One haloed span of
+// pixels is loaded once per K-box; the taps are shifted shared-memory descriptors into it.
+struct FlatConvParams {
+  long long P;                 // pixels to cover in this launch (rows_used * Wp)
+  int mt;                      // 128-pixel sub-tiles per span (share one haloed A load)
+  int halo;                    // max |tap shift|
+  int a_box_rows, a_boxes;     // A stage = a_boxes TMA boxes of a_box_rows pixel rows (<= 256, multiple of 8)
+  int taps;
+  int tap_shift[kMaxTaps];
+  int nkc, kbox, kpad;         // K boxes per tap, elements per box (64/32/16), nkc*kbox
+  int n_tile, n_tiles;
+  int a_stages, b_stages;
+  uint32_t a_stage_bytes, b_item_bytes;
+  int b_resident;
+  uint32_t idesc, sbo, layout_type, tmem_cols;
+  // epilogue
+  const float* scale; const float* shift;
+  int n_valid;                 // real output channels
+  int n_res;                   // residual (aux mode 1) applies to channels < n_res
+  const uint8_t* pix_valid;    // [P_cap] 1 = pixel belongs to a segment and is not the zero column
+  int aux_mode;                // 0 none, 1 residual added before post-ReLU (in place), 2 second output = v + add2
+  int box_ch;                  // channels per staging box: 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B)
+  int boxes;                   // staging boxes per buffer = ceil(n_tile / box_ch)
+  int slots;                   // epilogue slot ring depth PER WARPGROUP (each of the two epilogue warpgroups owns its ring)
+  uint32_t slot_bytes;
+  int prim_width;              // boxes starting at channel >= prim_width are not stored through omap[0]
+  int dup_c0;                  // >= 0: boxes starting at channel >= dup_c0 are (also) stored through omap[1] at channel - dup_c0
+  int pre_relu, post_relu;
+  unsigned long long* trace;
+  unsigned long long* dbg;     // host-mapped words: which barrier wait timed out (written before the trap)
+};
+struct FlatMaps { CUtensorMap a, b, aux, o[3]; };
+cudaError_t conv_flat_init();
+size_t conv_flat_smem_bytes(const FlatConvParams& p);
+cudaError_t launch_conv_flat(const FlatConvParams& p, const FlatMaps& maps, int is_bf16, cudaStream_t stream);
 
 cudaError_t launch_conv_simple(const SimpleConvParams& p, int is_bf16, cudaStream_t stream);
 cudaError_t launch_conv_umma(const UmmaConvParams& p, const AMaps& amaps, const CUtensorMap& bmap, const CUtensorMap& auxmap,

@@ -1,0 +1,497 @@
+// Flat implicit-GEMM convolution for every stride-1 layer (1x1, 3x3, dilated kx1) on tcgen05 tensor cores.
+//
+// The NHWC image is a 1-D sequence of pixels p = row*Wp + col with one all-zero column per row (Wp = W+1) and
+// all-zero gap rows between segments, so filter tap (dh, dw) is the constant shift s = dh*Wp + dw and
+//
+//   D[p, n] = sum_tap sum_k  X[p + s_tap, k] * Wt[n, tap, k]
+//
+// A span of mt*128 pixels plus a halo of max|s| pixels on each side is loaded ONCE per K-box by TMA (2-D boxes
+// {kbox channels, <=256 pixels}, swizzled rows = the canonical K-major UMMA layout); each tap is then just a
+// shared-memory descriptor whose start address is displaced by s rows.  (The swizzle is a function of the
+// absolute shared-memory address, so a row-displaced descriptor with base_offset 0 addresses the tile exactly as
+// TMA wrote it — profiles/r01_experiment_shifted_descriptor.txt.)  Compared with one 128-pixel box per tap this
+// divides the TMA row requests of a 3x3 conv by ~7 (the rate that bounded the previous kernel).
+//
+// Persistent warp-specialised CTA, 384 threads, one per SM; spans dealt round-robin:
+//   warp 0   producer: A spans (ring of a_stages) and weight boxes (resident in smem when small, else a ring)
+//   warp 1   TMEM allocator + single-thread tcgen05.mma issuer; 2 accumulator sets x mt sub-tiles in TMEM
+//   warp 2   aux producer: residual / add2 tiles into the epilogue slots, several sub-tiles ahead
+//   warp 3   store issuer: TMA stores of finished slots, releases slots when the stores have read them
+//   warps 4-7 / 8-11   two epilogue warpgroups (even / odd spans): tcgen05.ld -> scale/shift, ReLU, residual,
+//            second output (x_{i+1} + o_i) -> swizzled smem boxes (in place over the aux tile)
+// The epilogue body is specialised at compile time on <aux mode, pre-ReLU, post-ReLU>; the previous generic
+// body cost ~35 SASS instructions per output value and bounded every 1x1 conv.
+#include "conv.cuh"
+#include "umma.cuh"
+
+namespace svx {
+
+using namespace ptx;
+
+namespace {
+
+constexpr int kFlatThreads = 384;
+constexpr int kRing = 8;
+constexpr uint32_t kHeaderBytes = 3072;   // barriers + progress words (1024) + scale/shift of one n-tile (2 x 256 floats)
+
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_u4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// Bounded wait that says which barrier starved before trapping: code = role*16 + barrier kind, a = ring index, b = counter.
+// On a timeout the thread also copies the CTA's 16 role progress words (prog) so the host can see where every role stood.
+__device__ __forceinline__ void wait_dbg(uint64_t* bar, uint32_t parity, unsigned long long* dbg, int code, int a, unsigned b,
+                                         const volatile uint32_t* prog) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    ++spins;
+    if (spins == (1u << 21) && dbg) {      // first report, then keep waiting so that every starved role can report
+      if ((threadIdx.x & 31) == 0 || (threadIdx.x >> 5) >= 4) {
+        dbg[(blockIdx.x & 3) * 16 + (threadIdx.x >> 5)] = (static_cast<unsigned long long>(b) << 32) | (static_cast<unsigned long long>(blockIdx.x) << 16) |
+                                                        (static_cast<unsigned long long>(a & 0xff) << 8) | static_cast<unsigned long long>(code & 0xff);
+        if ((threadIdx.x & 31) == 0)
+          for (int i = 0; i < 16; ++i) dbg[64 + (blockIdx.x & 3) * 16 + i] = (static_cast<unsigned long long>(blockIdx.x) << 32) | prog[i];
+        __threadfence_system();
+      }
+    }
+    if (spins > (1u << 23)) __trap();
+  }
+}
+
+struct Tracer {
+  unsigned long long* buf; int n;
+  __device__ __forceinline__ void init(unsigned long long* base, int role) { buf = (base && blockIdx.x == 0) ? base + role * kTraceEvents : nullptr; n = 0; }
+  __device__ __forceinline__ void ev(int code) {
+    if (buf && n < kTraceEvents) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      buf[n++] = (t << 8) | static_cast<unsigned long long>(code & 0xff);
+    }
+  }
+};
+
+// 8 consecutive channels of one pixel.  v: accumulators; sc/sh: shared addresses of scale/shift for these channels.
+template <typename T, int AUX, bool PRE, bool POST>
+__device__ __forceinline__ void epi8(const uint32_t* r, uint32_t sc, uint32_t sh, uint32_t ua, uint32_t ub, bool res_here, uint32_t vmask) {
+  const float4 s0 = lds_f4(sc), s1 = lds_f4(sc + 16), b0 = lds_f4(sh), b1 = lds_f4(sh + 16);
+  uint4 ax = make_uint4(0, 0, 0, 0);
+  if (AUX == 1) { if (res_here) ax = lds_u4(ua); }
+  if (AUX == 2) ax = lds_u4(ub);
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    v[j] = __uint_as_float(r[j]);
+    if (PRE) v[j] = fmaxf(v[j], 0.f);
+  }
+  v[0] = fmaf(v[0], s0.x, b0.x); v[1] = fmaf(v[1], s0.y, b0.y); v[2] = fmaf(v[2], s0.z, b0.z); v[3] = fmaf(v[3], s0.w, b0.w);
+  v[4] = fmaf(v[4], s1.x, b1.x); v[5] = fmaf(v[5], s1.y, b1.y); v[6] = fmaf(v[6], s1.z, b1.z); v[7] = fmaf(v[7], s1.w, b1.w);
+  float2 a0, a1, a2, a3;
+  if (AUX != 0) { a0 = TypeOps<T>::unpack2(ax.x); a1 = TypeOps<T>::unpack2(ax.y); a2 = TypeOps<T>::unpack2(ax.z); a3 = TypeOps<T>::unpack2(ax.w); }
+  if (AUX == 1) { v[0] += a0.x; v[1] += a0.y; v[2] += a1.x; v[3] += a1.y; v[4] += a2.x; v[5] += a2.y; v[6] += a3.x; v[7] += a3.y; }
+  if (POST) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+  uint4 o;
+  o.x = TypeOps<T>::pack2(v[0], v[1]) & vmask; o.y = TypeOps<T>::pack2(v[2], v[3]) & vmask;
+  o.z = TypeOps<T>::pack2(v[4], v[5]) & vmask; o.w = TypeOps<T>::pack2(v[6], v[7]) & vmask;
+  sts_u4(ua, o);
+  if (AUX == 2) {   // second output = v + add2, in place over the add2 tile
+    uint4 o2;
+    o2.x = TypeOps<T>::pack2(v[0] + a0.x, v[1] + a0.y) & vmask; o2.y = TypeOps<T>::pack2(v[2] + a1.x, v[3] + a1.y) & vmask;
+    o2.z = TypeOps<T>::pack2(v[4] + a2.x, v[5] + a2.y) & vmask; o2.w = TypeOps<T>::pack2(v[6] + a3.x, v[7] + a3.y) & vmask;
+    sts_u4(ub, o2);
+  }
+}
+
+struct Smem {
+  uint64_t a_full[kRing], a_empty[kRing], b_full[kRing], b_empty[kRing];
+  uint64_t slot_full[kRing], slot_empty[kRing], slot_ready[kRing];
+  uint64_t tmem_full[2], tmem_empty[2];
+  uint64_t bres_bar;
+  uint32_t tmem_slot;
+  volatile uint32_t prog[16];   // debug: progress of each role (warp), dumped by wait_dbg on a timeout
+};
+static_assert(sizeof(Smem) <= 1024, "barrier block");
+
+}  // namespace
+
+template <typename T, int AUX, bool PRE, bool POST>
+__global__ void __launch_bounds__(kFlatThreads, 1)
+conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant__ FlatMaps maps) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  Smem& S = *reinterpret_cast<Smem*>(smem);
+  float* s_scale = reinterpret_cast<float*>(smem + 1024);
+  float* s_shift = s_scale + 256;
+  const int total_items = p.taps * p.nkc;
+  const uint32_t b_bytes = p.b_resident ? static_cast<uint32_t>(total_items) * p.b_item_bytes : static_cast<uint32_t>(p.b_stages) * p.b_item_bytes;
+  uint8_t* b_smem = smem + kHeaderBytes;
+  uint8_t* slot_smem = b_smem + b_bytes;
+  uint8_t* a_smem = slot_smem + 2 * static_cast<size_t>(p.slots) * p.slot_bytes;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int span_px = p.mt * 128;
+  const int n_spans = static_cast<int>((p.P + span_px - 1) / span_px);
+  const int groups = gridDim.x / p.n_tiles;
+  const int my_group = blockIdx.x / p.n_tiles;
+  const int n_blk = blockIdx.x % p.n_tiles;
+  const int n0 = n_blk * p.n_tile;
+  const uint32_t row_bytes = static_cast<uint32_t>(p.kbox) * 2u;
+  const uint32_t box_bytes = 128u * static_cast<uint32_t>(p.box_ch) * 2u;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&maps.a); prefetch_tmap(&maps.b);
+    if (AUX) prefetch_tmap(&maps.aux);
+    prefetch_tmap(&maps.o[0]);
+    if (p.dup_c0 >= 0) prefetch_tmap(&maps.o[1]);
+    if (AUX == 2) prefetch_tmap(&maps.o[2]);
+    for (int i = 0; i < kRing; ++i) {
+      mbar_init(&S.a_full[i], 1); mbar_init(&S.a_empty[i], 1);
+      mbar_init(&S.b_full[i], 1); mbar_init(&S.b_empty[i], 1);
+      mbar_init(&S.slot_full[i], 1); mbar_init(&S.slot_empty[i], 1); mbar_init(&S.slot_ready[i], 128);
+    }
+    for (int b = 0; b < 2; ++b) { mbar_init(&S.tmem_full[b], 1); mbar_init(&S.tmem_empty[b], 4); }
+    mbar_init(&S.bres_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(&S.tmem_slot, p.tmem_cols); tmem_relinquish(); }
+  for (int i = threadIdx.x; i < p.n_tile; i += kFlatThreads) {
+    const int c = n0 + i;
+    s_scale[i] = (p.scale && c < p.n_valid) ? p.scale[c] : 1.f;
+    s_shift[i] = (p.shift && c < p.n_valid) ? p.shift[c] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = S.tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ producer: A spans + weights
+    if (lane == 0) {
+      const uint32_t b_box_bytes = static_cast<uint32_t>(p.n_tile) * row_bytes;
+      const uint32_t a_tx = static_cast<uint32_t>(p.a_boxes) * p.a_box_rows * row_bytes;
+      if (p.b_resident) {
+        mbar_expect_tx(&S.bres_bar, b_box_bytes * total_items);
+        for (int kc = 0; kc < p.nkc; ++kc)
+          for (int tap = 0; tap < p.taps; ++tap)
+            tma_load_2d(b_smem + static_cast<size_t>(kc * p.taps + tap) * p.b_item_bytes, &maps.b, &S.bres_bar,
+                        tap * p.kpad + kc * p.kbox, n0);
+      }
+      Tracer tr; tr.init(p.trace, 0);
+      uint32_t ia = 0, ib = 0;
+      for (int span = my_group; span < n_spans; span += groups) {
+        const int p0 = span * span_px;
+        tr.ev(1);
+        S.prog[0] = ia;
+        for (int kc = 0; kc < p.nkc; ++kc, ++ia) {
+          const int sa = ia % p.a_stages;
+          wait_dbg(&S.a_empty[sa], ((ia / p.a_stages) & 1) ^ 1, p.dbg, 0x01, sa, ia, S.prog);
+          mbar_expect_tx(&S.a_full[sa], a_tx);
+          uint8_t* dst = a_smem + static_cast<size_t>(sa) * p.a_stage_bytes;
+          for (int b = 0; b < p.a_boxes; ++b)
+            tma_load_2d(dst + static_cast<size_t>(b) * p.a_box_rows * row_bytes, &maps.a, &S.a_full[sa], kc * p.kbox,
+                        p0 - p.halo + b * p.a_box_rows);
+          if (!p.b_resident) {
+            for (int tap = 0; tap < p.taps; ++tap, ++ib) {
+              const int sb = ib % p.b_stages;
+              wait_dbg(&S.b_empty[sb], ((ib / p.b_stages) & 1) ^ 1, p.dbg, 0x02, sb, ib, S.prog);
+              mbar_expect_tx(&S.b_full[sb], b_box_bytes);
+              tma_load_2d(b_smem + static_cast<size_t>(sb) * p.b_item_bytes, &maps.b, &S.b_full[sb], tap * p.kpad + kc * p.kbox, n0);
+            }
+          }
+        }
+        tr.ev(2);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    const int ksteps = p.kbox >> 4;
+    if (p.b_resident) wait_dbg(&S.bres_bar, 0, p.dbg, 0x10, 0, 0, S.prog);
+    const uint64_t desc_base = make_kmajor_desc(0, p.sbo, p.layout_type);
+    const uint32_t a_base = smem_u32(a_smem), b_base = smem_u32(b_smem);
+    Tracer tr; tr.init(lane == 0 ? p.trace : nullptr, 1);
+    uint32_t ia = 0, ib = 0;
+    int ls = 0;
+    for (int span = my_group; span < n_spans; span += groups, ++ls) {
+      const int buf = ls & 1;
+      tr.ev(1);
+      if (lane == 0) S.prog[1] = ls;
+      wait_dbg(&S.tmem_empty[buf], ((ls >> 1) & 1) ^ 1, p.dbg, 0x11, buf, ls, S.prog);
+      tr.ev(2);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * p.mt * p.n_tile);
+      for (int kc = 0; kc < p.nkc; ++kc, ++ia) {
+        const int sa = ia % p.a_stages;
+        wait_dbg(&S.a_full[sa], (ia / p.a_stages) & 1, p.dbg, 0x12, sa, ia, S.prog);
+        if (kc == 0) tr.ev(3);
+        const uint32_t a_addr = a_base + static_cast<uint32_t>(sa) * p.a_stage_bytes;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          uint32_t b_addr;
+          int sb = 0;
+          if (p.b_resident) {
+            b_addr = b_base + static_cast<uint32_t>(kc * p.taps + tap) * p.b_item_bytes;
+          } else {
+            sb = ib % p.b_stages;
+            wait_dbg(&S.b_full[sb], (ib / p.b_stages) & 1, p.dbg, 0x13, sb, ib, S.prog);
+            b_addr = b_base + static_cast<uint32_t>(sb) * p.b_item_bytes;
+            ++ib;
+          }
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_tap = a_addr + static_cast<uint32_t>(p.halo + p.tap_shift[tap]) * row_bytes;
+            const bool first = (kc == 0 && tap == 0);
+            for (int j = 0; j < p.mt; ++j) {
+              const uint32_t a_j = a_tap + static_cast<uint32_t>(j) * 128u * row_bytes;
+              const uint32_t d_j = d_tmem + static_cast<uint32_t>(j * p.n_tile);
+              for (int k = 0; k < ksteps; ++k) {
+                const uint64_t adesc = desc_base | static_cast<uint64_t>(((a_j + k * 32) >> 4) & 0x3FFF);
+                const uint64_t bdesc = desc_base | static_cast<uint64_t>(((b_addr + k * 32) >> 4) & 0x3FFF);
+                umma_f16(d_j, adesc, bdesc, p.idesc, (first && k == 0) ? 0u : 1u);
+              }
+            }
+            if (!p.b_resident) umma_commit(&S.b_empty[sb]);
+          }
+          __syncwarp();
+        }
+        if (lane == 0) {
+          umma_commit(&S.a_empty[sa]);
+          if (kc == p.nkc - 1) umma_commit(&S.tmem_full[buf]);
+        }
+        __syncwarp();
+      }
+      tr.ev(4);
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ aux producer (residual / add2 tiles)
+    if (AUX != 0 && lane == 0) {
+      const int aux_hi = AUX == 1 ? p.n_res : p.n_valid;
+      int nb = 0;
+      for (int b = 0; b < p.boxes; ++b)
+        if (n0 + b * p.box_ch < aux_hi) ++nb;
+      const uint32_t buf_off = AUX == 2 ? static_cast<uint32_t>(p.boxes) * box_bytes : 0u;
+      int ls = 0;
+      for (int span = my_group; span < n_spans; span += groups, ++ls) {
+        const int p0 = span * span_px;
+        for (int j = 0; j < p.mt; ++j) {
+          const uint32_t q = static_cast<uint32_t>(ls >> 1) * p.mt + j;      // sub-tile counter of the warpgroup that owns this span
+          const int slot = (ls & 1) * p.slots + q % p.slots;
+          S.prog[2] = (ls << 8) | j;
+          wait_dbg(&S.slot_empty[slot], ((q / p.slots) & 1) ^ 1, p.dbg, 0x21, slot, q, S.prog);
+          if (nb > 0) {
+            mbar_expect_tx(&S.slot_full[slot], static_cast<uint32_t>(nb) * box_bytes);
+            uint8_t* dst = slot_smem + static_cast<size_t>(slot) * p.slot_bytes + buf_off;
+            for (int b = 0; b < nb; ++b)
+              tma_load_2d(dst + static_cast<size_t>(b) * box_bytes, &maps.aux, &S.slot_full[slot], n0 + b * p.box_ch, p0 + j * 128);
+          } else {
+            mbar_arrive(&S.slot_full[slot]);
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ store issuer
+    if (lane == 0) {
+      Tracer tr; tr.init(p.trace, 3);
+      const uint32_t slot_base = smem_u32(slot_smem);
+      int prev_slot = -1;
+      int ls = 0;
+      for (int span = my_group; span < n_spans; span += groups, ++ls) {
+        const int p0 = span * span_px;
+        for (int j = 0; j < p.mt; ++j) {
+          const uint32_t q = static_cast<uint32_t>(ls >> 1) * p.mt + j;
+          const int slot = (ls & 1) * p.slots + q % p.slots;
+          S.prog[3] = (ls << 8) | j;
+          wait_dbg(&S.slot_ready[slot], (q / p.slots) & 1, p.dbg, 0x31, slot, q, S.prog);
+          tr.ev(1);
+          const uint32_t bufA = slot_base + static_cast<uint32_t>(slot) * p.slot_bytes;
+          const uint32_t bufB = bufA + static_cast<uint32_t>(p.boxes) * box_bytes;
+          const int px = p0 + j * 128;
+          for (int b = 0; b < p.boxes; ++b) {
+            const int cg = n0 + b * p.box_ch;
+            if (cg >= p.n_valid) break;
+            if (cg < p.prim_width) tma_store_2d(&maps.o[0], bufA + b * box_bytes, cg, px);
+            if (p.dup_c0 >= 0 && cg >= p.dup_c0) tma_store_2d(&maps.o[1], bufA + b * box_bytes, cg - p.dup_c0, px);
+            if (AUX == 2) tma_store_2d(&maps.o[2], bufB + b * box_bytes, cg, px);
+          }
+          bulk_commit();
+          if (p.slots == 1) {             // a single slot per warpgroup cannot stay held until the next commit
+            bulk_wait_read<0>(); mbar_arrive(&S.slot_empty[slot]);
+          } else {
+            if (prev_slot >= 0) { bulk_wait_read<1>(); mbar_arrive(&S.slot_empty[prev_slot]); }
+            prev_slot = slot;
+          }
+          tr.ev(2);
+        }
+      }
+      if (prev_slot >= 0) { bulk_wait_read<0>(); mbar_arrive(&S.slot_empty[prev_slot]); }
+      bulk_wait_all();
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warpgroups
+    const int wg = (warp - 4) >> 2;
+    const int q4 = warp & 3;
+    const int m = q4 * 32 + lane;
+    uint32_t row_off, row_xor; int bsh; uint32_t bmask;
+    if (p.box_ch == 64) { row_off = static_cast<uint32_t>(m) * 128u; row_xor = static_cast<uint32_t>(m & 7) << 4; bsh = 6; bmask = 63u; }
+    else { row_off = static_cast<uint32_t>(m) * 64u; row_xor = static_cast<uint32_t>((m >> 1) & 3) << 4; bsh = 5; bmask = 31u; }
+    const uint32_t slot_base = smem_u32(slot_smem);
+    const uint32_t sc_base = smem_u32(s_scale), sh_base = smem_u32(s_shift);
+    const uint32_t bufB_off = static_cast<uint32_t>(p.boxes) * box_bytes;
+    Tracer tr; tr.init((q4 == 0 && lane == 0) ? p.trace : nullptr, 4 + wg);
+    int ls = 0;
+    for (int span = my_group; span < n_spans; span += groups, ++ls) {
+      if ((ls & 1) != wg) continue;
+      const long long p0 = static_cast<long long>(span) * span_px;
+      uint32_t vm[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const long long pp = p0 + j * 128 + m;
+        vm[j] = (j < p.mt && pp < p.P && p.pix_valid[pp]) ? 0xffffffffu : 0u;
+      }
+      tr.ev(1);
+      if (lane == 0) S.prog[warp] = 0x10000u | (static_cast<uint32_t>(ls) << 4);
+      wait_dbg(&S.tmem_full[wg], (ls >> 1) & 1, p.dbg, 0x41, wg, ls, S.prog);
+      tr.ev(2);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < p.mt; ++j) {
+        const uint32_t q = static_cast<uint32_t>(ls >> 1) * p.mt + j;   // this warpgroup's own sub-tile counter: its slot ring is private,
+        const int slot = wg * p.slots + q % p.slots;                      // so a parity wait is never more than one phase ahead
+        const uint32_t u = q / p.slots;
+        if (lane == 0) S.prog[warp] = 0x20000u | q;
+        if (AUX != 0) wait_dbg(&S.slot_full[slot], u & 1, p.dbg, 0x42, slot, q, S.prog);
+        else wait_dbg(&S.slot_empty[slot], (u & 1) ^ 1, p.dbg, 0x43, slot, q, S.prog);
+        tr.ev(3);
+        const uint32_t bufA = slot_base + static_cast<uint32_t>(slot) * p.slot_bytes + row_off;
+        const uint32_t vmask = j == 0 ? vm[0] : j == 1 ? vm[1] : j == 2 ? vm[2] : vm[3];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>((wg * p.mt + j) * p.n_tile);
+        uint32_t ra[16], rb[16];
+        tmem_ld16(taddr, ra);
+#pragma unroll 1
+        for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
+          tmem_ld_wait();
+          if (c0 + 16 < p.n_tile) tmem_ld16(taddr + c0 + 16, rb);
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            const int cl = c0 + g * 8, cg = n0 + cl;
+            if (cg < p.n_valid) {
+              const uint32_t ua = bufA + (static_cast<uint32_t>(cl) >> bsh) * box_bytes + ((((static_cast<uint32_t>(cl) & bmask) >> 3) << 4) ^ row_xor);
+              epi8<T, AUX, PRE, POST>(ra + g * 8, sc_base + cl * 4, sh_base + cl * 4, ua, ua + bufB_off, cg < p.n_res, vmask);
+            }
+          }
+          if (c0 + 16 < p.n_tile) {
+            tmem_ld_wait();
+            if (c0 + 32 < p.n_tile) tmem_ld16(taddr + c0 + 32, ra);
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              const int cl = c0 + 16 + g * 8, cg = n0 + cl;
+              if (cg < p.n_valid) {
+                const uint32_t ua = bufA + (static_cast<uint32_t>(cl) >> bsh) * box_bytes + ((((static_cast<uint32_t>(cl) & bmask) >> 3) << 4) ^ row_xor);
+                epi8<T, AUX, PRE, POST>(rb + g * 8, sc_base + cl * 4, sh_base + cl * 4, ua, ua + bufB_off, cg < p.n_res, vmask);
+              }
+            }
+          }
+        }
+        if (j == p.mt - 1) {              // all accumulators of this span are in registers / smem: hand TMEM back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&S.tmem_empty[wg]);
+        }
+        if (lane == 0) S.prog[warp] = 0x30000u | q;
+        fence_proxy_async();              // generic-proxy writes of this thread → visible to the TMA store
+        mbar_arrive(&S.slot_ready[slot]);
+        tr.ev(4);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+size_t conv_flat_smem_bytes(const FlatConvParams& p) {
+  const size_t b = p.b_resident ? static_cast<size_t>(p.taps) * p.nkc * p.b_item_bytes : static_cast<size_t>(p.b_stages) * p.b_item_bytes;
+  return 1024 + kHeaderBytes + b + 2 * static_cast<size_t>(p.slots) * p.slot_bytes + static_cast<size_t>(p.a_stages) * p.a_stage_bytes;
+}
+
+static int g_flat_sms = 0;
+
+template <typename T, int AUX, bool PRE, bool POST>
+static cudaError_t set_attr() {
+  return cudaFuncSetAttribute(conv_flat_kernel<T, AUX, PRE, POST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+
+template <typename T>
+static cudaError_t init_type() {
+  cudaError_t e;
+  if ((e = set_attr<T, 0, false, false>()) != cudaSuccess) return e;
+  if ((e = set_attr<T, 0, false, true>()) != cudaSuccess) return e;
+  if ((e = set_attr<T, 0, true, false>()) != cudaSuccess) return e;
+  if ((e = set_attr<T, 1, false, false>()) != cudaSuccess) return e;
+  if ((e = set_attr<T, 1, false, true>()) != cudaSuccess) return e;
+  if ((e = set_attr<T, 2, false, true>()) != cudaSuccess) return e;
+  return cudaSuccess;
+}
+
+cudaError_t conv_flat_init() {
+  cudaError_t e = init_type<__half>();
+  if (e != cudaSuccess) return e;
+  e = init_type<__nv_bfloat16>();
+  if (e != cudaSuccess) return e;
+  int dev = 0;
+  e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  return cudaDeviceGetAttribute(&g_flat_sms, cudaDevAttrMultiProcessorCount, dev);
+}
+
+template <typename T>
+static cudaError_t launch_typed(const FlatConvParams& p, const FlatMaps& maps, dim3 grid, size_t smem, cudaStream_t st) {
+#define SVX_FLAT(AUX, PRE, POST) conv_flat_kernel<T, AUX, PRE, POST><<<grid, kFlatThreads, smem, st>>>(p, maps)
+  if (p.aux_mode == 0) {
+    if (p.pre_relu && !p.post_relu) SVX_FLAT(0, true, false);
+    else if (!p.pre_relu && p.post_relu) SVX_FLAT(0, false, true);
+    else if (!p.pre_relu && !p.post_relu) SVX_FLAT(0, false, false);
+    else return cudaErrorInvalidValue;
+  } else if (p.aux_mode == 1) {
+    if (p.pre_relu) return cudaErrorInvalidValue;
+    if (p.post_relu) SVX_FLAT(1, false, true); else SVX_FLAT(1, false, false);
+  } else {
+    if (p.pre_relu || !p.post_relu) return cudaErrorInvalidValue;
+    SVX_FLAT(2, false, true);
+  }
+#undef SVX_FLAT
+  return cudaGetLastError();
+}
+
+cudaError_t launch_conv_flat(const FlatConvParams& p, const FlatMaps& maps, int is_bf16, cudaStream_t stream) {
+  if (p.P <= 0) return cudaSuccess;
+  const long long n_spans = (p.P + p.mt * 128 - 1) / (p.mt * 128);
+  const int sms = g_flat_sms > 0 ? g_flat_sms : 148;
+  long long groups = sms / p.n_tiles;
+  if (groups < 1) groups = 1;
+  if (groups > n_spans) groups = n_spans;
+  dim3 grid(static_cast<unsigned>(groups * p.n_tiles), 1, 1);
+  const size_t smem = conv_flat_smem_bytes(p);
+  return is_bf16 ? launch_typed<__nv_bfloat16>(p, maps, grid, smem, stream) : launch_typed<__half>(p, maps, grid, smem, stream);
+}
+
+}  // namespace svx

@@ -29,13 +29,13 @@ __global__ void __launch_bounds__(256) conv_simple_kernel(const SimpleConvParams
       for (int s = 0; s < p.kw; ++s) {
         const int ic = col * p.sw + s * p.dw - p.pw;
         if (ic < 0 || ic >= p.in_W) continue;
-        const T* x = in + (static_cast<size_t>(ir) * p.in_W + ic) * p.in_C + p.in_coff + cin0;
+        const T* x = in + (static_cast<size_t>(ir) * p.in_Wp + ic) * p.in_C + p.in_coff + cin0;
         const T* wk = w + (r * p.kw + s) * p.kpad + (cin0 - abase);
         for (int ci = 0; ci < p.cin_g; ++ci) acc += TypeOps<T>::to_f(x[ci]) * TypeOps<T>::to_f(wk[ci]);
       }
     }
   }
-  epilogue_scalar<T>(p.epi, acc, row, col, p.out_W, c, valid);
+  epilogue_scalar<T>(p.epi, acc, row, col, p.out_Wp, c, valid);
 }
 
 cudaError_t launch_conv_simple(const SimpleConvParams& p, int is_bf16, cudaStream_t stream) {

@@ -364,7 +364,7 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p, const __grid_constant
       const bool in_range = (row < p.out_rows) && (col < p.out_W);
       const int seg_cur = seg_next;
       seg_next = seg_fetch(mt + 2 * groups);
-      const size_t pix = static_cast<size_t>(row) * p.out_W + col;
+      const size_t pix = static_cast<size_t>(row) * p.out_Wp + col;
       const uint32_t ph = (local >> 1) & 1;
       if (staged && p.stage_bytes) {          // the previous tile's TMA store must have finished reading the staging boxes
         if (leader) bulk_wait_read0();

@@ -29,6 +29,23 @@ cudaError_t launch_fill_seg_of_row(int32_t* seg_of_row, int rows, const int32_t*
   return cudaGetLastError();
 }
 
+// pix_valid[p] for the flat pixel sequence p = row*Wp + col: 1 when the row belongs to a segment and col < W
+// (0 on gap rows and on the zero column).
+__global__ void fill_pix_valid_kernel(uint8_t* pix_valid, long long n, const int32_t* seg_of_row, int W, int Wp) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int row = static_cast<int>(i / Wp);
+  const int col = static_cast<int>(i - static_cast<long long>(row) * Wp);
+  pix_valid[i] = (col < W && seg_of_row[row] >= 0) ? 1 : 0;
+}
+
+cudaError_t launch_fill_pix_valid(uint8_t* pix_valid, int rows, const int32_t* seg_of_row, int W, int Wp, cudaStream_t st) {
+  const long long n = static_cast<long long>(rows) * Wp;
+  if (n <= 0) return cudaSuccess;
+  fill_pix_valid_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(pix_valid, n, seg_of_row, W, Wp);
+  return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // TDNN input: fp32 [frames, F] per segment → tall image [rows, 1, Cpad] 16-bit (reference tf_extract.py:32 with
 // expand_dim=2: the feature axis is the channel axis).  Padding rows and channels F..Cpad-1 are zero.
@@ -68,7 +85,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) stem_conv_kernel(const float* feats, const int32_t* seg_frame_off, const int32_t* seg_row_off,
                                                         const int32_t* seg_h, const int32_t* seg_of_row, const float* w9,
                                                         const float* scale, const float* shift, T* out, int rows, int F,
-                                                        int C, int Cpad) {
+                                                        int Wp, int C, int Cpad) {
   extern __shared__ float sw[];   // [9][Cpad] weights, then scale[Cpad], shift[Cpad]
   for (int i = threadIdx.x; i < 9 * Cpad; i += blockDim.x) {
     const int c = i % Cpad;
@@ -115,22 +132,22 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* feats, cons
   uint4 o;
   o.x = TypeOps<T>::pack2(v[0], v[1]); o.y = TypeOps<T>::pack2(v[2], v[3]);
   o.z = TypeOps<T>::pack2(v[4], v[5]); o.w = TypeOps<T>::pack2(v[6], v[7]);
-  *reinterpret_cast<uint4*>(out + pix * Cpad + g * 8) = o;
+  *reinterpret_cast<uint4*>(out + (static_cast<size_t>(row) * Wp + f) * Cpad + g * 8) = o;
 }
 
 cudaError_t launch_stem_conv(const float* feats, const int32_t* seg_frame_off, const int32_t* seg_row_off, const int32_t* seg_h,
                              const int32_t* seg_of_row, const float* w9, const float* scale, const float* shift, void* out,
-                             int rows, int F, int C, int Cpad, int is_bf16, cudaStream_t st) {
+                             int rows, int F, int Wp, int C, int Cpad, int is_bf16, cudaStream_t st) {
   const long long total = static_cast<long long>(rows) * F * (Cpad / 8);
   if (total <= 0) return cudaSuccess;
   const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
   const size_t smem = 11 * Cpad * sizeof(float);
   if (is_bf16)
     stem_conv_kernel<__nv_bfloat16><<<blocks, 256, smem, st>>>(feats, seg_frame_off, seg_row_off, seg_h, seg_of_row, w9, scale,
-                                                                shift, static_cast<__nv_bfloat16*>(out), rows, F, C, Cpad);
+                                                                shift, static_cast<__nv_bfloat16*>(out), rows, F, Wp, C, Cpad);
   else
     stem_conv_kernel<__half><<<blocks, 256, smem, st>>>(feats, seg_frame_off, seg_row_off, seg_h, seg_of_row, w9, scale, shift,
-                                                         static_cast<__half*>(out), rows, F, C, Cpad);
+                                                         static_cast<__half*>(out), rows, F, Wp, C, Cpad);
   return cudaGetLastError();
 }
 
@@ -139,8 +156,8 @@ cudaError_t launch_stem_conv(const float* feats, const int32_t* seg_frame_off, c
 // (DPN pre-activation BN→ReLU, dpn_model.py:41-42, for the block input that several convs normalise differently;
 // the stride-2 1x1 projection, dpn_model.py:75, samples even positions of each segment [ext: TF SAME, k=1]).
 template <typename T>
-__global__ void __launch_bounds__(256) bn_relu_kernel(const T* in, int in_C, int in_coff, int in_W, const float* scale,
-                                                      const float* shift, T* out, int out_C, int out_rows, int out_W, int C,
+__global__ void __launch_bounds__(256) bn_relu_kernel(const T* in, int in_C, int in_coff, int in_Wp, const float* scale,
+                                                      const float* shift, T* out, int out_C, int out_rows, int out_W, int out_Wp, int C,
                                                       int stride, const int32_t* out_seg_of_row, const int32_t* out_seg_row_off,
                                                       const int32_t* in_seg_row_off) {
   const int groups = C >> 3;
@@ -156,7 +173,7 @@ __global__ void __launch_bounds__(256) bn_relu_kernel(const T* in, int in_C, int
   if (seg >= 0) {
     const int in_row = stride == 1 ? row : in_seg_row_off[seg] + (row - out_seg_row_off[seg]) * stride;
     const int in_col = col * stride;
-    const uint4 x = *reinterpret_cast<const uint4*>(in + (static_cast<size_t>(in_row) * in_W + in_col) * in_C + in_coff + g * 8);
+    const uint4 x = *reinterpret_cast<const uint4*>(in + (static_cast<size_t>(in_row) * in_Wp + in_col) * in_C + in_coff + g * 8);
     const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
     uint32_t os[4];
 #pragma unroll
@@ -169,22 +186,22 @@ __global__ void __launch_bounds__(256) bn_relu_kernel(const T* in, int in_C, int
     }
     o = make_uint4(os[0], os[1], os[2], os[3]);
   }
-  *reinterpret_cast<uint4*>(out + pix * out_C + g * 8) = o;
+  *reinterpret_cast<uint4*>(out + (static_cast<size_t>(row) * out_Wp + col) * out_C + g * 8) = o;
 }
 
-cudaError_t launch_bn_relu(const void* in, int in_C, int in_coff, int in_W, const float* scale, const float* shift, void* out,
-                           int out_C, int out_rows, int out_W, int C, int stride, const int32_t* out_seg_of_row,
+cudaError_t launch_bn_relu(const void* in, int in_C, int in_coff, int in_Wp, const float* scale, const float* shift, void* out,
+                           int out_C, int out_rows, int out_W, int out_Wp, int C, int stride, const int32_t* out_seg_of_row,
                            const int32_t* out_seg_row_off, const int32_t* in_seg_row_off, int is_bf16, cudaStream_t st) {
   const long long total = static_cast<long long>(out_rows) * out_W * (C / 8);
   if (total <= 0) return cudaSuccess;
   const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
   if (is_bf16)
-    bn_relu_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), in_C, in_coff, in_W, scale, shift,
-                                                           static_cast<__nv_bfloat16*>(out), out_C, out_rows, out_W, C, stride,
+    bn_relu_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), in_C, in_coff, in_Wp, scale, shift,
+                                                           static_cast<__nv_bfloat16*>(out), out_C, out_rows, out_W, out_Wp, C, stride,
                                                            out_seg_of_row, out_seg_row_off, in_seg_row_off);
   else
-    bn_relu_kernel<__half><<<blocks, 256, 0, st>>>(static_cast<const __half*>(in), in_C, in_coff, in_W, scale, shift,
-                                                    static_cast<__half*>(out), out_C, out_rows, out_W, C, stride, out_seg_of_row,
+    bn_relu_kernel<__half><<<blocks, 256, 0, st>>>(static_cast<const __half*>(in), in_C, in_coff, in_Wp, scale, shift,
+                                                    static_cast<__half*>(out), out_C, out_rows, out_W, out_Wp, C, stride, out_seg_of_row,
                                                     out_seg_row_off, in_seg_row_off);
   return cudaGetLastError();
 }
@@ -193,8 +210,8 @@ cudaError_t launch_bn_relu(const void* in, int in_C, int in_coff, int in_W, cons
 // Res2Net stride-2 last split: avg_pool 3x3 / 2, VALID over the (1,1) zero-padded tensor → divisor always 9
 // (res2net_model.py:76-77).  Uniform row map in_row = 2*out_row + r - 1 (layout guarantees it per segment).
 template <typename T>
-__global__ void __launch_bounds__(256) avgpool3x3s2_kernel(const T* in, int in_C, int in_coff, int in_rows, int in_W, T* out,
-                                                           int out_C, int out_coff, int out_rows, int out_W, int C,
+__global__ void __launch_bounds__(256) avgpool3x3s2_kernel(const T* in, int in_C, int in_coff, int in_rows, int in_W, int in_Wp, T* out,
+                                                           int out_C, int out_coff, int out_rows, int out_W, int out_Wp, int C,
                                                            const int32_t* out_seg_of_row) {
   const int groups = C >> 3;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -214,7 +231,7 @@ __global__ void __launch_bounds__(256) avgpool3x3s2_kernel(const T* in, int in_C
       for (int s = 0; s < 3; ++s) {
         const int ic = 2 * col + s - 1;
         if (ic < 0 || ic >= in_W) continue;
-        const uint4 x = *reinterpret_cast<const uint4*>(in + (static_cast<size_t>(ir) * in_W + ic) * in_C + in_coff + g * 8);
+        const uint4 x = *reinterpret_cast<const uint4*>(in + (static_cast<size_t>(ir) * in_Wp + ic) * in_C + in_coff + g * 8);
         const float2 a = TypeOps<T>::unpack2(x.x), b = TypeOps<T>::unpack2(x.y), c = TypeOps<T>::unpack2(x.z),
                      d = TypeOps<T>::unpack2(x.w);
         acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
@@ -225,21 +242,21 @@ __global__ void __launch_bounds__(256) avgpool3x3s2_kernel(const T* in, int in_C
   uint4 o;
   o.x = TypeOps<T>::pack2(acc[0] * k, acc[1] * k); o.y = TypeOps<T>::pack2(acc[2] * k, acc[3] * k);
   o.z = TypeOps<T>::pack2(acc[4] * k, acc[5] * k); o.w = TypeOps<T>::pack2(acc[6] * k, acc[7] * k);
-  *reinterpret_cast<uint4*>(out + pix * out_C + out_coff + g * 8) = o;
+  *reinterpret_cast<uint4*>(out + (static_cast<size_t>(row) * out_Wp + col) * out_C + out_coff + g * 8) = o;
 }
 
-cudaError_t launch_avgpool3x3s2(const void* in, int in_C, int in_coff, int in_rows, int in_W, void* out, int out_C, int out_coff,
-                                int out_rows, int out_W, int C, const int32_t* out_seg_of_row, int is_bf16, cudaStream_t st) {
+cudaError_t launch_avgpool3x3s2(const void* in, int in_C, int in_coff, int in_rows, int in_W, int in_Wp, void* out, int out_C, int out_coff,
+                                int out_rows, int out_W, int out_Wp, int C, const int32_t* out_seg_of_row, int is_bf16, cudaStream_t st) {
   const long long total = static_cast<long long>(out_rows) * out_W * (C / 8);
   if (total <= 0) return cudaSuccess;
   const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
   if (is_bf16)
-    avgpool3x3s2_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), in_C, in_coff, in_rows, in_W,
+    avgpool3x3s2_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), in_C, in_coff, in_rows, in_W, in_Wp,
                                                                 static_cast<__nv_bfloat16*>(out), out_C, out_coff, out_rows,
-                                                                out_W, C, out_seg_of_row);
+                                                                out_W, out_Wp, C, out_seg_of_row);
   else
-    avgpool3x3s2_kernel<__half><<<blocks, 256, 0, st>>>(static_cast<const __half*>(in), in_C, in_coff, in_rows, in_W,
-                                                         static_cast<__half*>(out), out_C, out_coff, out_rows, out_W, C,
+    avgpool3x3s2_kernel<__half><<<blocks, 256, 0, st>>>(static_cast<const __half*>(in), in_C, in_coff, in_rows, in_W, in_Wp,
+                                                         static_cast<__half*>(out), out_C, out_coff, out_rows, out_W, out_Wp, C,
                                                          out_seg_of_row);
   return cudaGetLastError();
 }
@@ -250,7 +267,7 @@ cudaError_t launch_avgpool3x3s2(const void* in, int in_C, int in_coff, int in_ro
 // (DPN concat_bn_relu, dpn_model.py:24-29).  Output fp32 [n_seg, W*2C], index w*2C + {c | C + c}.
 // One thread = 2 adjacent channels of one (segment, w); lanes run along channels → coalesced 4-byte loads.
 template <typename T>
-__global__ void __launch_bounds__(256) stats_pool_kernel(const T* in, int C_tot, int C, int W, const int32_t* seg_row_off,
+__global__ void __launch_bounds__(256) stats_pool_kernel(const T* in, int C_tot, int C, int W, int Wp, const int32_t* seg_row_off,
                                                          const int32_t* seg_h, const float* scale, const float* shift, float* out,
                                                          float eps) {
   const int seg = blockIdx.y;
@@ -264,8 +281,8 @@ __global__ void __launch_bounds__(256) stats_pool_kernel(const T* in, int C_tot,
   float s0 = 1.f, s1 = 1.f, b0 = 0.f, b1 = 0.f;
   const bool act = scale != nullptr;
   if (act) { s0 = scale[c]; s1 = scale[c + 1]; b0 = shift[c]; b1 = shift[c + 1]; }
-  const T* base = in + (static_cast<size_t>(r0) * W + w) * C_tot + c;
-  const size_t rstride = static_cast<size_t>(W) * C_tot;
+  const T* base = in + (static_cast<size_t>(r0) * Wp + w) * C_tot + c;
+  const size_t rstride = static_cast<size_t>(Wp) * C_tot;
   float m0 = 0.f, m1 = 0.f;
   for (int h = 0; h < H; ++h) {
     float2 f = TypeOps<T>::unpack2(*reinterpret_cast<const uint32_t*>(base + h * rstride));
@@ -286,15 +303,15 @@ __global__ void __launch_bounds__(256) stats_pool_kernel(const T* in, int C_tot,
   *reinterpret_cast<float2*>(o + C + c) = make_float2(sqrtf(v0 * inv + eps), sqrtf(v1 * inv + eps));
 }
 
-cudaError_t launch_stats_pool(const void* in, int C_tot, int C, int W, const int32_t* seg_row_off, const int32_t* seg_h, int n_seg,
+cudaError_t launch_stats_pool(const void* in, int C_tot, int C, int W, int Wp, const int32_t* seg_row_off, const int32_t* seg_h, int n_seg,
                               const float* scale, const float* shift, float* out, float eps, int is_bf16, cudaStream_t st) {
   if (n_seg <= 0) return cudaSuccess;
   dim3 grid((W * (C / 2) + 255) / 256, n_seg);
   if (is_bf16)
-    stats_pool_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), C_tot, C, W, seg_row_off, seg_h,
+    stats_pool_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), C_tot, C, W, Wp, seg_row_off, seg_h,
                                                             scale, shift, out, eps);
   else
-    stats_pool_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(in), C_tot, C, W, seg_row_off, seg_h, scale, shift,
+    stats_pool_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(in), C_tot, C, W, Wp, seg_row_off, seg_h, scale, shift,
                                                      out, eps);
   return cudaGetLastError();
 }

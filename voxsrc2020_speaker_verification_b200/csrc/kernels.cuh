@@ -6,17 +6,18 @@ namespace svx {
 
 cudaError_t launch_fill_seg_of_row(int32_t* seg_of_row, int rows, const int32_t* seg_row_off, const int32_t* seg_h, int n_seg,
                                    cudaStream_t st);
+cudaError_t launch_fill_pix_valid(uint8_t* pix_valid, int rows, const int32_t* seg_of_row, int W, int Wp, cudaStream_t st);
 cudaError_t launch_pack_input(const float* feats, const int32_t* seg_frame_off, const int32_t* seg_row_off,
                               const int32_t* seg_of_row, void* out, int rows, int F, int Cpad, int is_bf16, cudaStream_t st);
 cudaError_t launch_stem_conv(const float* feats, const int32_t* seg_frame_off, const int32_t* seg_row_off, const int32_t* seg_h,
                              const int32_t* seg_of_row, const float* w9, const float* scale, const float* shift, void* out,
-                             int rows, int F, int C, int Cpad, int is_bf16, cudaStream_t st);
-cudaError_t launch_bn_relu(const void* in, int in_C, int in_coff, int in_W, const float* scale, const float* shift, void* out,
-                           int out_C, int out_rows, int out_W, int C, int stride, const int32_t* out_seg_of_row,
+                             int rows, int F, int Wp, int C, int Cpad, int is_bf16, cudaStream_t st);
+cudaError_t launch_bn_relu(const void* in, int in_C, int in_coff, int in_Wp, const float* scale, const float* shift, void* out,
+                           int out_C, int out_rows, int out_W, int out_Wp, int C, int stride, const int32_t* out_seg_of_row,
                            const int32_t* out_seg_row_off, const int32_t* in_seg_row_off, int is_bf16, cudaStream_t st);
-cudaError_t launch_avgpool3x3s2(const void* in, int in_C, int in_coff, int in_rows, int in_W, void* out, int out_C, int out_coff,
-                                int out_rows, int out_W, int C, const int32_t* out_seg_of_row, int is_bf16, cudaStream_t st);
-cudaError_t launch_stats_pool(const void* in, int C_tot, int C, int W, const int32_t* seg_row_off, const int32_t* seg_h, int n_seg,
+cudaError_t launch_avgpool3x3s2(const void* in, int in_C, int in_coff, int in_rows, int in_W, int in_Wp, void* out, int out_C, int out_coff,
+                                int out_rows, int out_W, int out_Wp, int C, const int32_t* out_seg_of_row, int is_bf16, cudaStream_t st);
+cudaError_t launch_stats_pool(const void* in, int C_tot, int C, int W, int Wp, const int32_t* seg_row_off, const int32_t* seg_h, int n_seg,
                               const float* scale, const float* shift, float* out, float eps, int is_bf16, cudaStream_t st);
 int fc_splits(int D);
 cudaError_t launch_fc(const float* pooled, const float* Wf, const float* bias, float* partial, float* out, int n, int D, int E,

@@ -85,6 +85,7 @@ Model::~Model() {
   for (auto p : d_seg_row_off_) cudaFree(p);
   for (auto p : d_seg_h_) cudaFree(p);
   for (auto p : d_seg_of_row_) cudaFree(p);
+  for (auto p : d_pix_valid_) cudaFree(p);
   cudaFree(d_seg_frame_off_); cudaFree(d_seg_len_); cudaFree(d_utt_seg_off_);
   cudaFree(d_pooled_); cudaFree(d_fc_partial_); cudaFree(d_seg_emb_); cudaFree(d_feats_); cudaFree(d_out_);
   if (h_stage_) cudaFreeHost(h_stage_);
@@ -117,7 +118,7 @@ int Model::build() {
 
 void Model::build_tdnn() {
   std::map<std::string, int> root;
-  n_stages_ = 1; gap_ = 3; stage_W_ = {1};
+  n_stages_ = 1; gap_ = 3; stage_W_ = {1}; stage_Wp_ = {1};
   const int F = cfg_.feat_dim;
   int cur = new_tensor(0, round_up(F, 8));
   { Op op; op.kind = OP_PACK_INPUT; op.out = {cur, 0}; ops_.push_back(op); }
@@ -152,6 +153,7 @@ void Model::build_res2net() {
   n_stages_ = 1; gap_ = 1; stage_W_ = {F};
   for (int li = 0; li < 4; ++li)
     if (cfg_.block_strides[li] == 2) { stage_W_.push_back(ceil_half(stage_W_.back())); ++n_stages_; }
+  for (int w : stage_W_) stage_Wp_.push_back(w + 1);
   int stage = 0;
   // stem (res2net_model.py:192-203)
   const int c0 = cfg_.num_filters[0];
@@ -193,7 +195,7 @@ void Model::build_res2net() {
         c.bn_name = next_name(root, "", "batch_normalization");
         add_var(c.bn_name + "/moving_mean", {mid}); add_var(c.bn_name + "/moving_variance", {mid});
         c.in = {cur, 0}; c.cin = cin; c.cout = mid; c.post_relu = 1;
-        if (bstride == 1) { c.out = {m, 0}; c.n_split = (S - 1) * w; c.outb = {y, (S - 1) * w}; }   // last split passes through (:74-75)
+        if (bstride == 1) { c.out = {m, 0}; c.n_split = (S - 1) * w; c.outb = {y, (S - 1) * w}; c.dup_ok = true; }   // last split passes through (:74-75)
         else { c.out = {mp, 0}; }
         ops_.push_back(op);
       }
@@ -244,6 +246,7 @@ void Model::build_dpn() {
   std::map<std::string, int> root;
   const int F = cfg_.feat_dim;
   n_stages_ = 4; gap_ = 1; stage_W_ = {F, ceil_half(F), ceil_half(ceil_half(F)), ceil_half(ceil_half(ceil_half(F)))};
+  for (int w : stage_W_) stage_Wp_.push_back(w + 1);
   const int c0 = cfg_.init_features;
   int cur = new_tensor(0, round_up(c0, 8));   // raw block input of the next stage (S0 first, then X[s])
   {
@@ -467,6 +470,7 @@ int Model::finalize() {
   for (const auto& v : vars_)
     if (!host_.count(v.name) || !host_[v.name].set) { set_last_error("tensor not set: " + v.name); return 1; }
   SVX_CUDA(conv_umma_init());
+  SVX_CUDA(conv_flat_init());
   for (Op& op : ops_) {
     if (op.kind == OP_CONV) {
       if (upload_conv_weights(op.conv)) return 1;
@@ -515,6 +519,7 @@ int Model::finalize() {
 int Model::set_option(const char* key, int value) {
   if (!strcmp(key, "force_simple")) { force_simple_ = value; return 0; }
   if (!strcmp(key, "time_convs")) { time_convs_ = value; return 0; }
+  if (!strcmp(key, "no_flat")) { force_no_flat_ = value; return 0; }
   set_last_error(std::string("unknown option: ") + key);
   return 1;
 }
@@ -524,6 +529,7 @@ int Model::plan_conv(ConvDesc& c) {
   const ActTensor& tin = tensors_[c.in.id];
   const ActTensor& tout = tensors_[c.out.id];
   const int in_W = stage_W_[tin.stage], out_W = stage_W_[tout.stage];
+  const int in_Wp = stage_Wp_[tin.stage], out_Wp = stage_Wp_[tout.stage];
   const int in_rows = rows_cap_[tin.stage];
   auto tptr = [&](const TensorRef& r) -> void* { return r.id >= 0 ? tensors_[r.id].ptr : nullptr; };
   auto tC = [&](const TensorRef& r) -> int { return r.id >= 0 ? tensors_[r.id].C : 0; };
@@ -539,10 +545,12 @@ int Model::plan_conv(ConvDesc& c) {
   e.seg_of_row = d_seg_of_row_[tout.stage];
   // ---- CUDA-core form
   SimpleConvParams& sp = c.sp;
-  sp.in = tin.ptr; sp.in_C = tin.C; sp.in_coff = c.in.coff; sp.in_rows = in_rows; sp.in_W = in_W;
+  sp.in = tin.ptr; sp.in_C = tin.C; sp.in_coff = c.in.coff; sp.in_rows = in_rows; sp.in_W = in_W; sp.in_Wp = in_Wp;
   sp.wgt = c.d_wgt; sp.kpad = c.kpad; sp.cin_g = c.cin / c.groups; sp.cout_g = c.cout / c.groups;
   sp.kh = c.kh; sp.kw = c.kw; sp.sh = c.stride; sp.sw = c.stride; sp.dh = c.dil; sp.dw = 1; sp.ph = c.ph; sp.pw = c.pw;
-  sp.out_rows = 0; sp.out_W = out_W; sp.epi = e;
+  sp.out_rows = 0; sp.out_W = out_W; sp.out_Wp = out_Wp; sp.epi = e;
+  c.use_flat = false;
+  if (plan_flat(c)) return 1;
   // ---- tcgen05 form
   c.use_umma = false;
   const int taps = c.kh * c.kw;
@@ -557,7 +565,7 @@ int Model::plan_conv(ConvDesc& c) {
   const size_t esz = 2;
   int w_box = 1;
   while (w_box < 128 && out_W % (w_box * 2) == 0) w_box *= 2;
-  up.out_rows = 0; up.out_W = out_W; up.w_box = w_box; up.h_box = 128 / w_box; up.w_tiles = out_W / w_box;
+  up.out_rows = 0; up.out_W = out_W; up.out_Wp = out_Wp; up.w_box = w_box; up.h_box = 128 / w_box; up.w_tiles = out_W / w_box;
   up.taps = taps; up.nkc = c.nkc; up.kbox = c.kbox; up.a_c_step = 0; up.n_tile = c.n_tile; up.n_tiles = c.n_tiles;
   up.aux_mode = e.res ? 1 : (e.out2 ? 2 : 0);
   up.aux_boxes = up.aux_mode ? (c.n_tile + 63) / 64 : 0;
@@ -595,14 +603,14 @@ int Model::plan_conv(ConvDesc& c) {
   {   // TMA-store maps over the destination slices (64-channel boxes, clipped at the slice width)
     const uint32_t obox[3] = {64u, static_cast<uint32_t>(w_box), static_cast<uint32_t>(128 / w_box)};
     const uint64_t dims[3] = {static_cast<uint64_t>(e.n_split), static_cast<uint64_t>(out_W), static_cast<uint64_t>(rows_cap_[tout.stage])};
-    const uint64_t str[2] = {static_cast<uint64_t>(tout.C) * esz, static_cast<uint64_t>(out_W) * tout.C * esz};
+    const uint64_t str[2] = {static_cast<uint64_t>(tout.C) * esz, static_cast<uint64_t>(out_Wp) * tout.C * esz};
     if (encode_tmap(&c.omaps.m[0], is_bf16_, static_cast<uint8_t*>(tout.ptr) + static_cast<size_t>(c.out.coff) * esz, 3, dims, str, obox, 128))
       return 1;
     c.omaps.m[1] = c.omaps.m[0];
     if (c.out2.id >= 0) {
       const ActTensor& t2 = tensors_[c.out2.id];
       const uint64_t d2[3] = {static_cast<uint64_t>(c.cout), static_cast<uint64_t>(out_W), static_cast<uint64_t>(rows_cap_[t2.stage])};
-      const uint64_t s2[2] = {static_cast<uint64_t>(t2.C) * esz, static_cast<uint64_t>(out_W) * t2.C * esz};
+      const uint64_t s2[2] = {static_cast<uint64_t>(t2.C) * esz, static_cast<uint64_t>(out_Wp) * t2.C * esz};
       if (encode_tmap(&c.omaps.m[1], is_bf16_, static_cast<uint8_t*>(t2.ptr) + static_cast<size_t>(c.out2.coff) * esz, 3, d2, s2, obox, 128))
         return 1;
     }
@@ -611,13 +619,13 @@ int Model::plan_conv(ConvDesc& c) {
     const TensorRef& ar = up.aux_mode == 1 ? c.res : c.add2;
     const ActTensor& ta = tensors_[ar.id];
     const uint64_t dims[3] = {static_cast<uint64_t>(up.aux_width), static_cast<uint64_t>(out_W), static_cast<uint64_t>(rows_cap_[ta.stage])};
-    const uint64_t str[2] = {static_cast<uint64_t>(ta.C) * esz, static_cast<uint64_t>(out_W) * ta.C * esz};
+    const uint64_t str[2] = {static_cast<uint64_t>(ta.C) * esz, static_cast<uint64_t>(out_Wp) * ta.C * esz};
     const uint32_t abox[3] = {64u, static_cast<uint32_t>(w_box), static_cast<uint32_t>(128 / w_box)};
     if (encode_tmap(&c.auxmap, is_bf16_, static_cast<uint8_t*>(ta.ptr) + static_cast<size_t>(ar.coff) * esz, 3, dims, str, abox, 128)) return 1;
   }
   if (c.stride == 1) {
     const uint64_t dims[3] = {static_cast<uint64_t>(c.cin), static_cast<uint64_t>(in_W), static_cast<uint64_t>(in_rows)};
-    const uint64_t str[2] = {static_cast<uint64_t>(tin.C) * esz, static_cast<uint64_t>(in_W) * tin.C * esz};
+    const uint64_t str[2] = {static_cast<uint64_t>(tin.C) * esz, static_cast<uint64_t>(in_Wp) * tin.C * esz};
     if (encode_tmap(&c.amaps.m[0], is_bf16_, base + static_cast<size_t>(c.in.coff) * esz, 3, dims, str, box, sw_bytes)) return 1;
     for (int i = 1; i < 4; ++i) c.amaps.m[i] = c.amaps.m[0];
   } else {
@@ -626,8 +634,8 @@ int Model::plan_conv(ConvDesc& c) {
         const int wv = (in_W - q + 1) / 2, rv = (in_rows - p + 1) / 2;
         if (wv <= 0 || rv <= 0) { c.amaps.m[p * 2 + q] = c.amaps.m[0]; continue; }
         const uint64_t dims[3] = {static_cast<uint64_t>(c.cin), static_cast<uint64_t>(wv), static_cast<uint64_t>(rv)};
-        const uint64_t str[2] = {2ull * tin.C * esz, 2ull * in_W * tin.C * esz};
-        uint8_t* b = base + (static_cast<size_t>(p) * in_W + q) * tin.C * esz + static_cast<size_t>(c.in.coff) * esz;
+        const uint64_t str[2] = {2ull * tin.C * esz, 2ull * in_Wp * tin.C * esz};
+        uint8_t* b = base + (static_cast<size_t>(p) * in_Wp + q) * tin.C * esz + static_cast<size_t>(c.in.coff) * esz;
         if (encode_tmap(&c.amaps.m[p * 2 + q], is_bf16_, b, 3, dims, str, box, sw_bytes)) return 1;
       }
   }
@@ -641,22 +649,186 @@ int Model::plan_conv(ConvDesc& c) {
   return 0;
 }
 
+// Flat plan (conv_flat.cu) for stride-1, ungrouped convs: tap shifts in the pixel sequence, tile shape and the
+// shared-memory budget (A span ring, weights resident or ringed, epilogue slots).  Leaves use_flat = false when the
+// layer does not qualify; the caller then plans the 2-D tiled kernel.
+int Model::plan_flat(ConvDesc& c) {
+  static const bool disabled = getenv("SVX_NO_FLAT") != nullptr;   // debug switch
+  if (disabled) return 0;
+  const ActTensor& tin = tensors_[c.in.id];
+  const ActTensor& tout = tensors_[c.out.id];
+  if (c.groups != 1 || c.stride != 1 || tin.stage != tout.stage) return 0;
+  const int taps = c.kh * c.kw;
+  if (taps > kMaxTaps) return 0;
+  const int Wp = stage_Wp_[tout.stage], W = stage_W_[tout.stage];
+  if (c.kw > 1 && (Wp <= W || c.pw > 1 || c.kw - 1 - c.pw > 1)) return 0;   // one zero column covers |dw| <= 1 only
+  auto mult8 = [](int v) { return v % 8 == 0; };
+  auto tC = [&](const TensorRef& r) -> int { return r.id >= 0 ? tensors_[r.id].C : 0; };
+  const int n_split = c.n_split < 0 ? c.cout : c.n_split;
+  if (!(mult8(tin.C) && mult8(c.in.coff) && mult8(c.cout) && mult8(tout.C) && mult8(c.out.coff) && mult8(n_split))) return 0;
+  if (c.res.id >= 0 && !(mult8(tC(c.res)) && mult8(c.res.coff))) return 0;
+  if (c.outb.id >= 0 && !(mult8(tC(c.outb)) && mult8(c.outb.coff))) return 0;
+  if (c.out2.id >= 0 && !(mult8(tC(c.out2)) && mult8(c.out2.coff) && mult8(tC(c.add2)) && mult8(c.add2.coff))) return 0;
+  if (c.res.id >= 0 && c.out2.id >= 0) return 0;
+  if (c.pre_relu && (c.post_relu || c.res.id >= 0 || c.out2.id >= 0)) return 0;
+  if (c.out2.id >= 0 && (!c.post_relu || n_split != c.cout)) return 0;
+  const int aux_mode = c.res.id >= 0 ? 1 : (c.out2.id >= 0 ? 2 : 0);
+
+  FlatConvParams fp;
+  memset(&fp, 0, sizeof fp);
+  fp.taps = taps; fp.nkc = c.nkc; fp.kbox = c.kbox; fp.kpad = c.kpad;
+  int halo = 0;
+  for (int t = 0; t < taps; ++t) {
+    const int r = t / c.kw, s = t % c.kw;
+    fp.tap_shift[t] = (r * c.dil - c.ph) * Wp + (s - c.pw);
+    halo = std::max(halo, std::abs(fp.tap_shift[t]));
+  }
+  fp.halo = halo;
+  const uint32_t row_bytes = static_cast<uint32_t>(c.kbox) * 2u;
+  fp.layout_type = row_bytes == 128 ? 2u : row_bytes == 64 ? 4u : 6u;
+  fp.sbo = 8u * row_bytes;
+  fp.scale = c.d_scale; fp.shift = c.d_shift; fp.n_valid = c.cout;
+  fp.pix_valid = d_pix_valid_[tout.stage];
+  fp.aux_mode = aux_mode; fp.pre_relu = c.pre_relu; fp.post_relu = c.post_relu;
+  fp.n_res = aux_mode == 1 ? n_split : 0;
+
+  // search: widest n-tile first, then the most sub-tiles per span, then the deepest rings that fit
+  const long long budget = 227 * 1024 - 1024 - 3072;
+  const int n16 = round_up(c.cout, 16);
+  std::vector<int> cands;
+  if (n16 <= 256) cands.push_back(n16);
+  for (int t : {256, 192, 128, 64, 32})
+    if (t < n16 && c.cout % t == 0) cands.push_back(t);
+  bool found = false;
+  for (int n_tile : cands) {
+    const int n_tiles = (c.cout + n_tile - 1) / n_tile;
+    for (int box_ch : {64, 32}) {
+      if (found) break;
+      if (box_ch == 64 && n_tile <= 32) continue;                              // narrow tiles: 32-channel boxes halve the slot size
+      static const int env_box = getenv("SVX_FLAT_BOX") ? atoi(getenv("SVX_FLAT_BOX")) : 0;   // debug switch
+      if (env_box && box_ch != env_box && n_tile <= 32) continue;
+      if (n_tiles > 1 && n_tile % box_ch != 0) continue;
+      if (box_ch == 32 && n_tile > 32 && n_tile % 64 == 0) continue;       // 64-channel boxes are never worse there
+      // routing of channels >= n_split
+      int prim_width = c.cout, dup_c0 = -1;
+      if (n_split < c.cout) {
+        if (n_split % box_ch == 0) { prim_width = n_split; dup_c0 = n_split; }
+        else if (c.dup_ok && aux_mode == 0) { dup_c0 = n_split / box_ch * box_ch; }
+        else continue;
+        if (c.outb.coff - (n_split - dup_c0) < 0) continue;
+      }
+      const int boxes = (n_tile + box_ch - 1) / box_ch;
+      const uint32_t box_bytes = 128u * box_ch * 2u;
+      const uint32_t slot_bytes = boxes * box_bytes * (aux_mode == 2 ? 2u : 1u);
+      const uint32_t b_item = static_cast<uint32_t>(round_up(n_tile * static_cast<int>(row_bytes), 1024));
+      const long long b_total = static_cast<long long>(taps) * c.nkc * b_item;
+      static const int env_maxmt = getenv("SVX_FLAT_MAXMT") ? atoi(getenv("SVX_FLAT_MAXMT")) : 4;          // debug switches
+      static const int env_maxslots = getenv("SVX_FLAT_MAXSLOTS") ? atoi(getenv("SVX_FLAT_MAXSLOTS")) : 4;
+      for (int mt : {4, 2, 1}) {
+        if (found) break;
+        if (mt > env_maxmt) continue;
+        if (taps == 1 && mt != 1) continue;
+        if (mt * n_tile > 256) continue;
+        const int a_rows_min = mt * 128 + 2 * halo;
+        const int a_boxes = (a_rows_min + 255) / 256;
+        const int a_box_rows = round_up((a_rows_min + a_boxes - 1) / a_boxes, 8);
+        const uint32_t a_stage = static_cast<uint32_t>(round_up(a_boxes * a_box_rows * static_cast<int>(row_bytes), 1024));
+        const int min_slots = (aux_mode || mt > 1) ? 2 : 1;                     // per warpgroup
+        for (int b_res : {1, 0}) {
+          if (b_res && b_total > 72 * 1024) continue;
+          const int b_stages = b_res ? 0 : std::min(4, taps * c.nkc < 2 ? 2 : taps * c.nkc);
+          const long long b_bytes = b_res ? b_total : static_cast<long long>(std::max(b_stages, 2)) * b_item;
+          long long left = budget - b_bytes - 2LL * a_stage - 2LL * min_slots * slot_bytes;
+          if (left < 0) continue;
+          int a_stages = 2, slots = min_slots;
+          // spend what is left: a third A stage first, then slots up to 6, then a fourth A stage
+          if (left >= a_stage) { ++a_stages; left -= a_stage; }
+          while (slots < std::min(4, std::max(env_maxslots, min_slots)) && left >= 2LL * slot_bytes) { ++slots; left -= 2LL * slot_bytes; }
+          if (a_stages < 4 && left >= a_stage) { ++a_stages; left -= a_stage; }
+          fp.mt = mt; fp.a_box_rows = a_box_rows; fp.a_boxes = a_boxes; fp.n_tile = n_tile; fp.n_tiles = n_tiles;
+          fp.a_stages = a_stages; fp.b_stages = b_res ? 0 : std::max(b_stages, 2); fp.a_stage_bytes = a_stage; fp.b_item_bytes = b_item;
+          fp.b_resident = b_res; fp.box_ch = box_ch; fp.boxes = boxes; fp.slots = slots; fp.slot_bytes = slot_bytes;
+          fp.prim_width = prim_width; fp.dup_c0 = dup_c0;
+          found = true;
+          break;
+        }
+      }
+    }
+    if (found) break;
+  }
+  if (!found) return 0;
+  uint32_t tc = 32;
+  while (tc < 2u * fp.mt * fp.n_tile) tc *= 2;
+  if (tc > 512) return 0;
+  fp.tmem_cols = tc;
+  fp.idesc = ptx::make_idesc_f16(is_bf16_ ? 1u : 0u, 128u, static_cast<uint32_t>(fp.n_tile));
+
+  // tensor maps over the flat pixel sequence
+  const size_t esz = 2;
+  const uint64_t P_cap = static_cast<uint64_t>(rows_cap_[tout.stage]) * Wp;
+  const int sw_box = fp.box_ch * 2;   // 128 or 64
+  FlatMaps& fm = c.fmaps;
+  memset(&fm, 0, sizeof fm);
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(c.cin), P_cap};
+    const uint64_t str[1] = {static_cast<uint64_t>(tin.C) * esz};
+    const uint32_t box[2] = {static_cast<uint32_t>(c.kbox), static_cast<uint32_t>(fp.a_box_rows)};
+    if (encode_tmap(&fm.a, is_bf16_, static_cast<uint8_t*>(tin.ptr) + static_cast<size_t>(c.in.coff) * esz, 2, dims, str, box, row_bytes)) return 1;
+  }
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(taps) * c.kpad, static_cast<uint64_t>(c.n_pad)};
+    const uint64_t str[1] = {static_cast<uint64_t>(taps) * c.kpad * esz};
+    const uint32_t box[2] = {static_cast<uint32_t>(c.kbox), static_cast<uint32_t>(fp.n_tile)};
+    if (encode_tmap(&fm.b, is_bf16_, c.d_wgt, 2, dims, str, box, row_bytes)) return 1;
+  }
+  auto slice_map = [&](CUtensorMap* m, const ActTensor& t, int coff, int width) -> int {
+    const uint64_t dims[2] = {static_cast<uint64_t>(width), P_cap};
+    const uint64_t str[1] = {static_cast<uint64_t>(t.C) * esz};
+    const uint32_t box[2] = {static_cast<uint32_t>(fp.box_ch), 128u};
+    return encode_tmap(m, is_bf16_, static_cast<uint8_t*>(t.ptr) + static_cast<size_t>(coff) * esz, 2, dims, str, box, sw_box);
+  };
+  if (slice_map(&fm.o[0], tout, c.out.coff, fp.prim_width)) return 1;
+  if (fp.dup_c0 >= 0) {
+    const ActTensor& tb = tensors_[c.outb.id];
+    if (tb.stage != tout.stage) return 0;
+    if (slice_map(&fm.o[1], tb, c.outb.coff - (n_split - fp.dup_c0), c.cout - fp.dup_c0)) return 1;
+  }
+  if (aux_mode == 1) {
+    const ActTensor& tr = tensors_[c.res.id];
+    if (tr.stage != tout.stage) return 0;
+    if (slice_map(&fm.aux, tr, c.res.coff, n_split)) return 1;
+  } else if (aux_mode == 2) {
+    const ActTensor& ta = tensors_[c.add2.id];
+    const ActTensor& t2 = tensors_[c.out2.id];
+    if (ta.stage != tout.stage || t2.stage != tout.stage) return 0;
+    if (slice_map(&fm.aux, ta, c.add2.coff, c.cout)) return 1;
+    if (slice_map(&fm.o[2], t2, c.out2.coff, c.cout)) return 1;
+  }
+  if (conv_flat_smem_bytes(fp) > 227 * 1024) return 0;
+  c.fp = fp;
+  c.use_flat = true;
+  return 0;
+}
+
 int Model::ensure_capacity(int rows0) {
   if (!rows_cap_.empty() && rows0 <= rows_cap_[0]) return 0;
   SVX_CUDA(cudaDeviceSynchronize());
   for (void* p : act_bufs_) cudaFree(p);
   act_bufs_.clear();
   for (auto p : d_seg_of_row_) cudaFree(p);
+  for (auto p : d_pix_valid_) cudaFree(p);
   d_seg_of_row_.assign(n_stages_, nullptr);
+  d_pix_valid_.assign(n_stages_, nullptr);
   rows_cap_.assign(n_stages_, 0);
   int rows = round_up(std::max(rows0, 256), 256);
   for (int s = 0; s < n_stages_; ++s) {
     rows_cap_[s] = rows;
     SVX_CUDA(cudaMalloc(&d_seg_of_row_[s], static_cast<size_t>(rows) * 4));
+    SVX_CUDA(cudaMalloc(&d_pix_valid_[s], static_cast<size_t>(rows) * stage_Wp_[s]));
     rows = rows / 2 + 8;
   }
   for (ActTensor& t : tensors_) {
-    const size_t bytes = static_cast<size_t>(rows_cap_[t.stage]) * stage_W_[t.stage] * t.C * 2;
+    const size_t bytes = static_cast<size_t>(rows_cap_[t.stage]) * stage_Wp_[t.stage] * t.C * 2;
     SVX_CUDA(cudaMalloc(&t.ptr, bytes));
     SVX_CUDA(cudaMemset(t.ptr, 0, bytes));
     act_bufs_.push_back(t.ptr);
@@ -711,31 +883,52 @@ int Model::conv_time(double* ms, double* flops) {
   return 0;
 }
 
+// Host-mapped diagnostic words of the flat kernel's bounded barrier waits (conv_flat.cu wait_dbg); they survive the trap.
+static unsigned long long* g_flat_dbg_host = nullptr;
+static unsigned long long* flat_dbg_words() {
+  static unsigned long long* dev = nullptr;
+  if (!g_flat_dbg_host) {
+    if (cudaHostAlloc(&g_flat_dbg_host, 128 * 8, cudaHostAllocMapped) != cudaSuccess) return nullptr;
+    memset(g_flat_dbg_host, 0, 128 * 8);
+    if (cudaHostGetDevicePointer(&dev, g_flat_dbg_host, 0) != cudaSuccess) dev = nullptr;
+  }
+  return dev;
+}
+
 int Model::launch_conv(ConvDesc& c, cudaStream_t st) {
   const int out_stage = tensors_[c.out.id].stage;
   const int out_rows = rows_used_[out_stage];
-  if (c.use_umma && !force_simple_) {
-    c.up.out_rows = out_rows;
+  const bool flat = c.use_flat && !force_simple_ && !force_no_flat_;
+  const bool umma = !flat && c.use_umma && !force_simple_;
+  if (flat || umma) {
     static const char* trace_dir = getenv("SVX_TRACE_DIR");   // debug: per-launch event timeline of CTA 0
     static unsigned long long* d_trace = nullptr;
     static int trace_idx = 0;
     if (trace_dir) {
-      if (!d_trace) cudaMalloc(&d_trace, 4 * kTraceEvents * 8);
-      cudaMemsetAsync(d_trace, 0, 4 * kTraceEvents * 8, st);
-      c.up.trace = d_trace;
+      if (!d_trace) cudaMalloc(&d_trace, 6 * kTraceEvents * 8);
+      cudaMemsetAsync(d_trace, 0, 6 * kTraceEvents * 8, st);
     }
     if (time_convs_) {
       while (events_.size() < ev_used_ + 2) { cudaEvent_t e; SVX_CUDA(cudaEventCreate(&e)); events_.push_back(e); }
       SVX_CUDA(cudaEventRecord(events_[ev_used_], st));
     }
-    SVX_CUDA(launch_conv_umma(c.up, c.amaps, c.bmap, c.auxmap, c.omaps, is_bf16_, st));
+    if (flat) {
+      c.fp.P = static_cast<long long>(out_rows) * stage_Wp_[out_stage];
+      c.fp.trace = trace_dir ? d_trace : nullptr;
+      c.fp.dbg = flat_dbg_words();
+      SVX_CUDA(launch_conv_flat(c.fp, c.fmaps, is_bf16_, st));
+    } else {
+      c.up.out_rows = out_rows;
+      c.up.trace = trace_dir ? d_trace : nullptr;
+      SVX_CUDA(launch_conv_umma(c.up, c.amaps, c.bmap, c.auxmap, c.omaps, is_bf16_, st));
+    }
     if (trace_dir) {
-      std::vector<unsigned long long> h(4 * kTraceEvents);
+      std::vector<unsigned long long> h(6 * kTraceEvents);
       cudaStreamSynchronize(st);
       cudaMemcpy(h.data(), d_trace, h.size() * 8, cudaMemcpyDeviceToHost);
       char path[512];
-      snprintf(path, sizeof path, "%s/trace%04d_k%dx%d_cin%d_cout%d_s%d_aux%d_st%d.bin", trace_dir, trace_idx++, c.kh, c.kw, c.cin, c.cout,
-               c.stride, c.up.aux_mode, c.up.store_mode);
+      snprintf(path, sizeof path, "%s/trace%04d_%s_k%dx%d_cin%d_cout%d_s%d_aux%d.bin", trace_dir, trace_idx++, flat ? "flat" : "umma", c.kh, c.kw,
+               c.cin, c.cout, c.stride, flat ? c.fp.aux_mode : c.up.aux_mode);
       FILE* f = fopen(path, "wb");
       if (f) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
     }
@@ -829,7 +1022,8 @@ int Model::run_segments(const float* d_feats, const int32_t* h_frame_off, int n_
     SVX_CUDA(cudaMemcpyAsync(d_seg_frame_off_, hp, nb * 4, cudaMemcpyHostToDevice, st));
     for (int s = 0; s < n_stages_; ++s) {
       SVX_CUDA(launch_fill_seg_of_row(d_seg_of_row_[s], rows_used_[s], d_seg_row_off_[s], d_seg_h_[s], nb, st));
-      ++launches_;
+      SVX_CUDA(launch_fill_pix_valid(d_pix_valid_[s], rows_used_[s], d_seg_of_row_[s], stage_W_[s], stage_Wp_[s], st));
+      launches_ += 2;
     }
     if (grow(&d_pooled_, &pooled_bytes_, static_cast<size_t>(nb) * flat_dim_ * 4) ||
         grow(&d_fc_partial_, &fc_partial_bytes_, static_cast<size_t>(fc_splits(flat_dim_)) * nb * cfg_.embed_dim * 4)) {
@@ -846,12 +1040,12 @@ int Model::run_segments(const float* d_feats, const int32_t* h_frame_off, int n_
           if (r.id < 0) return;
           cudaStreamSynchronize(st);
           const ActTensor& t = m->tensors_[r.id];
-          const size_t bytes = static_cast<size_t>(m->rows_used_[t.stage]) * m->stage_W_[t.stage] * t.C * 2;
+          const size_t bytes = static_cast<size_t>(m->rows_used_[t.stage]) * m->stage_Wp_[t.stage] * t.C * 2;
           std::vector<char> h(bytes);
           cudaMemcpy(h.data(), t.ptr, bytes, cudaMemcpyDeviceToHost);
           char path[512];
           snprintf(path, sizeof path, "%s/op%03d_k%d_t%d_r%d_w%d_c%d_off%d_n%d.bin", dir, idx, (int)op.kind, r.id, m->rows_used_[t.stage],
-                   m->stage_W_[t.stage], t.C, r.coff, op.kind == OP_CONV ? op.conv.cout : op.C);
+                   m->stage_Wp_[t.stage], t.C, r.coff, op.kind == OP_CONV ? op.conv.cout : op.C);
           FILE* f = fopen(path, "wb");
           if (f) { fwrite(h.data(), 1, bytes, f); fclose(f); }
         }
@@ -867,7 +1061,7 @@ int Model::run_segments(const float* d_feats, const int32_t* h_frame_off, int n_
         case OP_STEM: {
           const ActTensor& t = tensors_[op.out.id];
           SVX_CUDA(launch_stem_conv(d_feats, d_seg_frame_off_, d_seg_row_off_[0], d_seg_h_[0], d_seg_of_row_[0], op.d_w9, op.d_scale,
-                                    op.d_shift, t.ptr, rows_used_[0], cfg_.feat_dim, op.C, t.C, is_bf16_, st));
+                                    op.d_shift, t.ptr, rows_used_[0], cfg_.feat_dim, stage_Wp_[0], op.C, t.C, is_bf16_, st));
           ++launches_;
           break;
         }
@@ -877,8 +1071,8 @@ int Model::run_segments(const float* d_feats, const int32_t* h_frame_off, int n_
         case OP_BN_RELU: {
           const ActTensor& ti = tensors_[op.in.id];
           const ActTensor& to = tensors_[op.out.id];
-          SVX_CUDA(launch_bn_relu(ti.ptr, ti.C, op.in.coff, stage_W_[ti.stage], op.d_scale, op.d_shift, to.ptr, to.C,
-                                  rows_used_[to.stage], stage_W_[to.stage], round_up(op.C, 8), op.stride, d_seg_of_row_[to.stage],
+          SVX_CUDA(launch_bn_relu(ti.ptr, ti.C, op.in.coff, stage_Wp_[ti.stage], op.d_scale, op.d_shift, to.ptr, to.C,
+                                  rows_used_[to.stage], stage_W_[to.stage], stage_Wp_[to.stage], round_up(op.C, 8), op.stride, d_seg_of_row_[to.stage],
                                   d_seg_row_off_[to.stage], d_seg_row_off_[ti.stage], is_bf16_, st));
           ++launches_;
           break;
@@ -886,16 +1080,45 @@ int Model::run_segments(const float* d_feats, const int32_t* h_frame_off, int n_
         case OP_AVGPOOL: {
           const ActTensor& ti = tensors_[op.in.id];
           const ActTensor& to = tensors_[op.out.id];
-          SVX_CUDA(launch_avgpool3x3s2(ti.ptr, ti.C, op.in.coff, rows_cap_[ti.stage], stage_W_[ti.stage], to.ptr, to.C, op.out.coff,
-                                       rows_used_[to.stage], stage_W_[to.stage], op.C, d_seg_of_row_[to.stage], is_bf16_, st));
+          SVX_CUDA(launch_avgpool3x3s2(ti.ptr, ti.C, op.in.coff, rows_cap_[ti.stage], stage_W_[ti.stage], stage_Wp_[ti.stage], to.ptr, to.C,
+                                       op.out.coff, rows_used_[to.stage], stage_W_[to.stage], stage_Wp_[to.stage], op.C, d_seg_of_row_[to.stage], is_bf16_, st));
           ++launches_;
           break;
         }
         default: break;
       }
+      static const bool sync_each = getenv("SVX_SYNC_EACH") != nullptr;   // debug: localise a failing launch
+      if (sync_each) {
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+          char buf[512];
+          const ConvDesc& c = op.conv;
+          snprintf(buf, sizeof buf, "op %d kind %d failed: %s (conv %dx%d cin %d cout %d stride %d flat %d mt %d n_tile %d n_tiles %d slots %d a_stages %d "
+                   "b_res %d box_ch %d aux %d halo %d)", op_index - 1, (int)op.kind, cudaGetErrorString(e), c.kh, c.kw, c.cin, c.cout, c.stride,
+                   (int)c.use_flat, c.fp.mt, c.fp.n_tile, c.fp.n_tiles, c.fp.slots, c.fp.a_stages, c.fp.b_resident, c.fp.box_ch, c.fp.aux_mode, c.fp.halo);
+          std::string msg = buf;
+          if (g_flat_dbg_host)
+            for (int i = 0; i < 64; ++i)
+              if (g_flat_dbg_host[i]) {
+                snprintf(buf, sizeof buf, " [wait code 0x%02llx idx %llu cta %llu warp %d count %llu]", g_flat_dbg_host[i] & 0xff,
+                         (g_flat_dbg_host[i] >> 8) & 0xff, (g_flat_dbg_host[i] >> 16) & 0xffff, i & 15, g_flat_dbg_host[i] >> 32);
+                msg += buf;
+              }
+          if (g_flat_dbg_host)
+            for (int g = 0; g < 4; ++g) {
+              if (!g_flat_dbg_host[64 + g * 16]) continue;
+              snprintf(buf, sizeof buf, " {cta %llu prog:", g_flat_dbg_host[64 + g * 16] >> 32);
+              msg += buf;
+              for (int i = 0; i < 12; ++i) { snprintf(buf, sizeof buf, " %x", (unsigned)(g_flat_dbg_host[64 + g * 16 + i] & 0xffffffffu)); msg += buf; }
+              msg += "}";
+            }
+          set_last_error(msg);
+          return 1;
+        }
+      }
     }
     const ActTensor& tp = tensors_[pool_tensor_];
-    SVX_CUDA(launch_stats_pool(tp.ptr, tp.C, pool_C_, stage_W_[tp.stage], d_seg_row_off_[tp.stage], d_seg_h_[tp.stage], nb,
+    SVX_CUDA(launch_stats_pool(tp.ptr, tp.C, pool_C_, stage_W_[tp.stage], stage_Wp_[tp.stage], d_seg_row_off_[tp.stage], d_seg_h_[tp.stage], nb,
                                d_pool_scale_, d_pool_shift_, d_pooled_, kPoolEps, is_bf16_, st));
     SVX_CUDA(launch_fc(d_pooled_, d_Wf_, d_bias_, d_fc_partial_, d_out + static_cast<size_t>(i0) * cfg_.embed_dim, nb, flat_dim_,
                        cfg_.embed_dim, st));

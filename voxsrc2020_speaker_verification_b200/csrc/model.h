@@ -51,6 +51,8 @@ struct ConvDesc {
   float* d_scale = nullptr; float* d_shift = nullptr;
   bool use_umma = false; bool no_staged = false;
   UmmaConvParams up; AMaps amaps; CUtensorMap bmap; CUtensorMap auxmap; OMaps omaps;
+  bool use_flat = false; bool dup_ok = false;   // dup_ok: channels [n_split, cout) may also land in `out` (see plan_flat)
+  FlatConvParams fp; FlatMaps fmaps;
   SimpleConvParams sp;
 };
 
@@ -96,6 +98,7 @@ class Model {
   void build_dpn();
   int ensure_capacity(int rows0);
   int plan_conv(ConvDesc& c);
+  int plan_flat(ConvDesc& c);
   int fold_bn(const std::string& bn, int C, bool four_d, std::vector<float>& scale, std::vector<float>& shift);
   int upload_conv_weights(ConvDesc& c);
   int launch_conv(ConvDesc& c, cudaStream_t st);
@@ -114,6 +117,9 @@ class Model {
   int n_stages_ = 1;
   int gap_ = 1;
   std::vector<int> stage_W_;
+  std::vector<int> stage_Wp_;        // pixels per row in memory: W + 1 zero column for the 2-D networks, W for the TDNN
+  std::vector<uint8_t*> d_pix_valid_;
+  int force_no_flat_ = 0;
   std::vector<int> rows_cap_, rows_used_;
   int seg_cap_ = 0;
   // per stage device tables
