@@ -1,18 +1,22 @@
-"""Print the steady-state per-tile timeline of CTA 0 from SVX_TRACE_DIR dumps."""
+"""Print the steady-state per-span timeline of CTA 0 from SVX_TRACE_DIR dumps (flat kernel: 6 roles)."""
 import glob, os, sys
 import numpy as np
 K = 4096
-names = {0: {1: "tile", 2: "auxfree", 3: "issued"}, 1: {1: "tile", 2: "accfree", 3: "opnd", 4: "mma_done"},
-         2: {1: "tile", 2: "aux", 3: "acc", 4: "conv", 5: "st_iss", 6: "st_read"}, 3: {1: "tile", 2: "aux", 3: "acc", 4: "conv", 5: "st_iss", 6: "st_read"}}
-for path in sorted(glob.glob(sys.argv[1] + "/trace*.bin"))[: int(sys.argv[2]) if len(sys.argv) > 2 else 8]:
-    a = np.fromfile(path, np.uint64).reshape(4, K)
+names = {0: {1: "span", 2: "issued"}, 1: {1: "span", 2: "accfree", 3: "opnd", 4: "mma_issued"},
+         3: {1: "ready", 2: "st_issued"}, 4: {1: "span", 2: "acc", 3: "slot", 4: "conv"}, 5: {1: "span", 2: "acc", 3: "slot", 4: "conv"}}
+pat = sys.argv[3] if len(sys.argv) > 3 else ""
+files = [f for f in sorted(glob.glob(sys.argv[1] + "/trace*.bin")) if pat in f]
+for path in files[: int(sys.argv[2]) if len(sys.argv) > 2 else 8]:
+    a = np.fromfile(path, np.uint64).reshape(6, K)
     print("==", os.path.basename(path))
-    t0 = min(int(a[r][0] >> 8) for r in range(4) if a[r][0])
-    for role in range(4):
+    firsts = [int(a[r][0] >> 8) for r in range(6) if a[r][0]]
+    if not firsts:
+        continue
+    t0 = min(firsts)
+    for role in (0, 1, 3, 4, 5):
         ev = [(int(x >> 8) - t0, int(x & 0xff)) for x in a[role] if x]
         if not ev:
             continue
-        # split into tiles at code 1
         tiles, cur = [], []
         for t, c in ev:
             if c == 1 and cur:
@@ -20,9 +24,8 @@ for path in sorted(glob.glob(sys.argv[1] + "/trace*.bin"))[: int(sys.argv[2]) if
             cur.append((t, c))
         tiles.append(cur)
         n = len(tiles)
-        mid = tiles[n // 2: n // 2 + 4]
         starts = [tl[0][0] for tl in tiles]
         per = (starts[-1] - starts[len(starts) // 4]) / max(1, (len(starts) - 1 - len(starts) // 4))
-        print(" role %d: %d tiles, steady %.0f ns/tile" % (role, n, per))
-        for tl in mid:
-            print("    " + "  ".join("%s+%d" % (names[role].get(c, str(c)), t - tl[0][0]) for t, c in tl) + "   @%d" % tl[0][0])
+        print(" role %d: %d units, steady %.0f ns/unit, total %d ns" % (role, n, per, ev[-1][0]))
+        for tl in tiles[n // 2: n // 2 + 3]:
+            print("    " + "  ".join("%s+%d" % (names[role].get(c, str(c)), t - tl[0][0]) for t, c in tl[:14]) + "   @%d" % tl[0][0])

@@ -33,6 +33,10 @@ struct Epilogue {
   // optional second output for channels [0, n_split): out2 = v + add2   (Res2Net x_{i+1} + o_i, res2net_model.py:65-66)
   void* out2; int out2_C; int out2_coff;
   const void* add2; int add2_C; int add2_coff;
+  // planar splits (Res2Net conv1 → hierarchical 3x3 inputs): channel c = s*split_wp + j (j < split_w) goes to
+  // split_ptr[s][pix*split_C[s] + split_coff[s] + j]; j >= split_w are padding channels.  n_splits = 0: unused.
+  int n_splits, split_wp, split_w;
+  void* split_ptr[8]; int split_C[8]; int split_coff[8];
   // fp32 row-major output instead of 16-bit NHWC (scoring GEMM): out_f32[row*ldf + c]
   float* out_f32; int ldf;
   const int32_t* seg_of_row;   // nullptr → every row valid
@@ -119,6 +123,14 @@ __device__ __forceinline__ void epilogue_scalar(const Epilogue& e, float acc, in
   if (e.scale) v *= e.scale[c];
   if (e.shift) v += e.shift[c];
   const size_t pix = static_cast<size_t>(row) * Wp + col;
+  if (e.n_splits > 0) {
+    const int s_ = c / e.split_wp, j_ = c - s_ * e.split_wp;
+    if (j_ >= e.split_w) return;
+    if (e.post_relu) v = fmaxf(v, 0.f);
+    if (!valid) v = 0.f;
+    static_cast<T*>(e.split_ptr[s_])[pix * e.split_C[s_] + e.split_coff[s_] + j_] = TypeOps<T>::from_f(v);
+    return;
+  }
   if (e.out_f32) {
     e.out_f32[static_cast<size_t>(row) * e.ldf + c] = valid ? v : 0.f;
     return;
@@ -167,13 +179,13 @@ struct FlatConvParams {
   int boxes;                   // staging boxes per buffer = ceil(n_tile / box_ch)
   int slots;                   // epilogue slot ring depth PER WARPGROUP (each of the two epilogue warpgroups owns its ring)
   uint32_t slot_bytes;
-  int prim_width;              // boxes starting at channel >= prim_width are not stored through omap[0]
-  int dup_c0;                  // >= 0: boxes starting at channel >= dup_c0 are (also) stored through omap[1] at channel - dup_c0
+  uint8_t route_map[16];       // per global staging box (n0/box_ch + b): which output map it is stored through (0xff: none)
+  int32_t route_c[16];         //   and at which channel coordinate of that map
   int pre_relu, post_relu;
   unsigned long long* trace;
   unsigned long long* dbg;     // host-mapped words: which barrier wait timed out (written before the trap)
 };
-struct FlatMaps { CUtensorMap a, b, aux, o[3]; };
+struct FlatMaps { CUtensorMap a, b, aux, o2, o[8]; };   // o2: second output of aux mode 2
 cudaError_t conv_flat_init();
 size_t conv_flat_smem_bytes(const FlatConvParams& p);
 cudaError_t launch_conv_flat(const FlatConvParams& p, const FlatMaps& maps, int is_bf16, cudaStream_t stream);

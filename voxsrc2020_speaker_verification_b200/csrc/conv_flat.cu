@@ -162,8 +162,7 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
     prefetch_tmap(&maps.a); prefetch_tmap(&maps.b);
     if (AUX) prefetch_tmap(&maps.aux);
     prefetch_tmap(&maps.o[0]);
-    if (p.dup_c0 >= 0) prefetch_tmap(&maps.o[1]);
-    if (AUX == 2) prefetch_tmap(&maps.o[2]);
+    if (AUX == 2) prefetch_tmap(&maps.o2);
     for (int i = 0; i < kRing; ++i) {
       mbar_init(&S.a_full[i], 1); mbar_init(&S.a_empty[i], 1);
       mbar_init(&S.b_full[i], 1); mbar_init(&S.b_empty[i], 1);
@@ -224,10 +223,16 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
+    // The whole warp runs the loop CONVERGED and computes the descriptors (uniform values → uniform registers); only the
+    // tcgen05 instructions themselves sit under the elected-lane branch.  Computing them inside an `if (lane == 0)` region
+    // made ptxas wrap every UTCHMMA in an ELECT / 5x R2UR.BROADCAST waterfall: ~200 ns per MMA whatever its shape.
     const int ksteps = p.kbox >> 4;
+    const bool leader = elect_one();
     if (p.b_resident) wait_dbg(&S.bres_bar, 0, p.dbg, 0x10, 0, 0, S.prog);
     const uint64_t desc_base = make_kmajor_desc(0, p.sbo, p.layout_type);
     const uint32_t a_base = smem_u32(a_smem), b_base = smem_u32(b_smem);
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t sub_bytes = 128u * row_bytes;
     Tracer tr; tr.init(lane == 0 ? p.trace : nullptr, 1);
     uint32_t ia = 0, ib = 0;
     int ls = 0;
@@ -238,7 +243,7 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
       wait_dbg(&S.tmem_empty[buf], ((ls >> 1) & 1) ^ 1, p.dbg, 0x11, buf, ls, S.prog);
       tr.ev(2);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * p.mt * p.n_tile);
+      const uint32_t d_tmem = tb + static_cast<uint32_t>(buf * p.mt * p.n_tile);
       for (int kc = 0; kc < p.nkc; ++kc, ++ia) {
         const int sa = ia % p.a_stages;
         wait_dbg(&S.a_full[sa], (ia / p.a_stages) & 1, p.dbg, 0x12, sa, ia, S.prog);
@@ -256,27 +261,24 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
             ++ib;
           }
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t a_tap = a_addr + static_cast<uint32_t>(p.halo + p.tap_shift[tap]) * row_bytes;
-            const bool first = (kc == 0 && tap == 0);
-            for (int j = 0; j < p.mt; ++j) {
-              const uint32_t a_j = a_tap + static_cast<uint32_t>(j) * 128u * row_bytes;
-              const uint32_t d_j = d_tmem + static_cast<uint32_t>(j * p.n_tile);
-              for (int k = 0; k < ksteps; ++k) {
-                const uint64_t adesc = desc_base | static_cast<uint64_t>(((a_j + k * 32) >> 4) & 0x3FFF);
-                const uint64_t bdesc = desc_base | static_cast<uint64_t>(((b_addr + k * 32) >> 4) & 0x3FFF);
-                umma_f16(d_j, adesc, bdesc, p.idesc, (first && k == 0) ? 0u : 1u);
-              }
+          const uint32_t a_tap = a_addr + static_cast<uint32_t>(p.halo + p.tap_shift[tap]) * row_bytes;
+          const uint32_t first = (kc == 0 && tap == 0) ? 0u : 1u;
+          for (int j = 0; j < p.mt; ++j) {
+            const uint32_t a_j = a_tap + static_cast<uint32_t>(j) * sub_bytes;
+            const uint32_t d_j = d_tmem + static_cast<uint32_t>(j * p.n_tile);
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t adesc = desc_base | static_cast<uint64_t>(((a_j + k * 32) >> 4) & 0x3FFF);
+              const uint64_t bdesc = desc_base | static_cast<uint64_t>(((b_addr + k * 32) >> 4) & 0x3FFF);
+              const uint32_t acc = k == 0 ? first : 1u;
+              if (leader) umma_f16(d_j, adesc, bdesc, p.idesc, acc);
             }
-            if (!p.b_resident) umma_commit(&S.b_empty[sb]);
           }
-          __syncwarp();
+          if (!p.b_resident && leader) umma_commit(&S.b_empty[sb]);
         }
-        if (lane == 0) {
+        if (leader) {
           umma_commit(&S.a_empty[sa]);
           if (kc == p.nkc - 1) umma_commit(&S.tmem_full[buf]);
         }
-        __syncwarp();
       }
       tr.ev(4);
     }
@@ -328,9 +330,9 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
           for (int b = 0; b < p.boxes; ++b) {
             const int cg = n0 + b * p.box_ch;
             if (cg >= p.n_valid) break;
-            if (cg < p.prim_width) tma_store_2d(&maps.o[0], bufA + b * box_bytes, cg, px);
-            if (p.dup_c0 >= 0 && cg >= p.dup_c0) tma_store_2d(&maps.o[1], bufA + b * box_bytes, cg - p.dup_c0, px);
-            if (AUX == 2) tma_store_2d(&maps.o[2], bufB + b * box_bytes, cg, px);
+            const int gb = n_blk * p.boxes + b;
+            if (p.route_map[gb] != 0xff) tma_store_2d(&maps.o[p.route_map[gb]], bufA + b * box_bytes, p.route_c[gb], px);
+            if (AUX == 2) tma_store_2d(&maps.o2, bufB + b * box_bytes, cg, px);
           }
           bulk_commit();
           if (p.slots == 1) {             // a single slot per warpgroup cannot stay held until the next commit

@@ -50,7 +50,7 @@ static PFN_encodeTiled get_encode() {
 }
 
 int encode_tmap(CUtensorMap* m, int is_bf16, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                const uint32_t* box, int swizzle_bytes) {
+                const uint32_t* box, int swizzle_bytes, int l2_promo_bytes) {
   PFN_encodeTiled fn = get_encode();
   if (!fn) { set_last_error("cuTensorMapEncodeTiled entry point not available"); return 1; }
   cuuint64_t gdim[5]; cuuint64_t gstr[5]; cuuint32_t bdim[5]; cuuint32_t estr[5];
@@ -60,7 +60,10 @@ int encode_tmap(CUtensorMap* m, int is_bf16, void* base, int rank, const uint64_
                         : swizzle_bytes == 64  ? CU_TENSOR_MAP_SWIZZLE_64B
                         : swizzle_bytes == 32  ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
   CUresult r = fn(m, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, base, gdim, gstr, bdim,
-                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  l2_promo_bytes >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : l2_promo_bytes == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                                                                                    : CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[256];
     snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu box %u %u %u stride0 %llu", (int)r, rank,
@@ -173,7 +176,13 @@ void Model::build_res2net() {
     const int in_stage = stage;
     if (st == 2) ++stage;
     const int xa = new_tensor(stage, cout), xb = new_tensor(stage, cout), sc = new_tensor(stage, cout);
-    const int m = new_tensor(stage, mid), z = new_tensor(stage, mid), y = new_tensor(stage, mid);
+    // stride-1 blocks keep the splits of the 1x1 output (x_i) and the running sums (x_{i+1} + o_i) PLANAR, one dense
+    // [pixels, w] tensor each: a 3x3 then reads whole DRAM lines instead of a w-channel slice of every S*w-channel row
+    // (measured 3.7-4.8x read amplification on the interleaved layout).  y (the concat, conv3's input) stays interleaved.
+    std::vector<int> ms(S, -1), zs(S, -1);
+    for (int i = 0; i + 1 < S; ++i) ms[i] = new_tensor(stage, w);
+    for (int i = 1; i + 1 < S; ++i) zs[i] = new_tensor(stage, w);
+    const int y = new_tensor(stage, mid);
     const int mp = st == 2 ? new_tensor(in_stage, mid) : -1;
     int out_t = xa;
     for (int b = 0; b < cfg_.block_sizes[li]; ++b) {
@@ -195,8 +204,11 @@ void Model::build_res2net() {
         c.bn_name = next_name(root, "", "batch_normalization");
         add_var(c.bn_name + "/moving_mean", {mid}); add_var(c.bn_name + "/moving_variance", {mid});
         c.in = {cur, 0}; c.cin = cin; c.cout = mid; c.post_relu = 1;
-        if (bstride == 1) { c.out = {m, 0}; c.n_split = (S - 1) * w; c.outb = {y, (S - 1) * w}; c.dup_ok = true; }   // last split passes through (:74-75)
-        else { c.out = {mp, 0}; }
+        if (bstride == 1) {   // x_0..x_{S-2} to their planar tensors, the last split passes straight into the concat (:74-75)
+          c.out = {y, 0}; c.split_w = w;
+          for (int i = 0; i + 1 < S; ++i) c.split_out.push_back({ms[i], 0});
+          c.split_out.push_back({y, (S - 1) * w});
+        } else { c.out = {mp, 0}; }
         ops_.push_back(op);
       }
       {   // hierarchical 3x3 (res2net_model.py:26-78)
@@ -211,8 +223,8 @@ void Model::build_res2net() {
           c.kh = c.kw = 3; c.stride = bstride; c.ph = c.pw = 1; c.cin = w; c.cout = w; c.post_relu = 1;
           c.out = {y, i * w};
           if (bstride == 1) {
-            c.in = {i == 0 ? m : z, i * w};
-            if (i < S - 2) { c.out2 = {z, (i + 1) * w}; c.add2 = {m, (i + 1) * w}; }   // x_{i+1} + o_i (:65-66)
+            c.in = {i == 0 ? ms[0] : zs[i], 0};
+            if (i < S - 2) { c.out2 = {zs[i + 1], 0}; c.add2 = {ms[i + 1], 0}; }       // x_{i+1} + o_i (:65-66)
           } else {
             c.in = {mp, i * w};                                                        // no cross-split add when strided
           }
@@ -414,8 +426,17 @@ int Model::upload_conv_weights(ConvDesc& c) {
     c.n_tile = pick_ntile(c.cout, c.add2.id >= 0 ? 64 : 128);
     if (c.n_tile == 0) { c.n_tile = 128; c.no_staged = true; }
   }
-  c.n_pad = round_up(c.cout, c.n_tile);
+  c.n_gemm = c.cout;
+  if (c.split_w > 0) {   // box size and padded group width of the planar splits (see plan_flat)
+    const int sw = c.split_w;
+    c.split_box = (sw % 64 == 0) ? 64 : (sw % 32 == 0 || sw < 32) ? 32 : 64;
+    c.split_wp = round_up(sw, c.split_box);
+    c.n_gemm = static_cast<int>(c.split_out.size()) * c.split_wp;
+    c.n_tile = std::min(256, c.n_gemm);
+  }
+  c.n_pad = round_up(c.n_gemm, c.n_tile);
   c.n_tiles = c.n_pad / c.n_tile;
+  auto gemm_row = [&](int n) { return c.split_w > 0 ? (n / c.split_w) * c.split_wp + n % c.split_w : n; };
   const size_t K = static_cast<size_t>(taps) * c.kpad;
   std::vector<float> w(static_cast<size_t>(c.n_pad) * K, 0.f);
   for (int n = 0; n < c.cout; ++n) {
@@ -424,7 +445,7 @@ int Model::upload_conv_weights(ConvDesc& c) {
     for (int t = 0; t < taps; ++t)
       for (int ci = 0; ci < cin_g; ++ci) {
         const int j = g * cin_g + ci - abase;     // position inside the k-box row
-        w[static_cast<size_t>(n) * K + static_cast<size_t>(t) * c.kpad + j] =
+        w[static_cast<size_t>(gemm_row(n)) * K + static_cast<size_t>(t) * c.kpad + j] =
             k.data[(static_cast<size_t>(t) * cin_g + ci) * cout_total + c.kernel_out_off + n];
       }
   }
@@ -445,6 +466,11 @@ int Model::upload_conv_weights(ConvDesc& c) {
   if (!c.bn_name.empty()) {
     std::vector<float> sc, sh;
     fold_bn(c.bn_name, c.cout, true, sc, sh);
+    if (c.split_w > 0) {
+      std::vector<float> sc2(c.n_pad, 0.f), sh2(c.n_pad, 0.f);
+      for (int n = 0; n < c.cout; ++n) { sc2[gemm_row(n)] = sc[n]; sh2[gemm_row(n)] = sh[n]; }
+      sc.swap(sc2); sh.swap(sh2);
+    }
     sc.resize(c.n_pad, 0.f); sh.resize(c.n_pad, 0.f);
     float* ds = nullptr; float* dh = nullptr;
     SVX_CUDA(cudaMalloc(&ds, c.n_pad * 4)); owned_.push_back(ds);
@@ -535,7 +561,13 @@ int Model::plan_conv(ConvDesc& c) {
   auto tC = [&](const TensorRef& r) -> int { return r.id >= 0 ? tensors_[r.id].C : 0; };
   Epilogue e;
   memset(&e, 0, sizeof e);
-  e.scale = c.d_scale; e.shift = c.d_shift; e.pre_relu = c.pre_relu; e.post_relu = c.post_relu; e.n_valid = c.cout;
+  e.scale = c.d_scale; e.shift = c.d_shift; e.pre_relu = c.pre_relu; e.post_relu = c.post_relu; e.n_valid = c.n_gemm;
+  if (c.split_w > 0) {
+    e.n_splits = static_cast<int>(c.split_out.size()); e.split_wp = c.split_wp; e.split_w = c.split_w;
+    for (int i = 0; i < e.n_splits; ++i) {
+      e.split_ptr[i] = tensors_[c.split_out[i].id].ptr; e.split_C[i] = tensors_[c.split_out[i].id].C; e.split_coff[i] = c.split_out[i].coff;
+    }
+  }
   e.out = tptr(c.out); e.out_C = tC(c.out); e.out_coff = c.out.coff;
   e.res = tptr(c.res); e.res_C = tC(c.res); e.res_coff = c.res.coff;
   e.n_split = c.n_split < 0 ? c.cout : c.n_split;
@@ -546,7 +578,7 @@ int Model::plan_conv(ConvDesc& c) {
   // ---- CUDA-core form
   SimpleConvParams& sp = c.sp;
   sp.in = tin.ptr; sp.in_C = tin.C; sp.in_coff = c.in.coff; sp.in_rows = in_rows; sp.in_W = in_W; sp.in_Wp = in_Wp;
-  sp.wgt = c.d_wgt; sp.kpad = c.kpad; sp.cin_g = c.cin / c.groups; sp.cout_g = c.cout / c.groups;
+  sp.wgt = c.d_wgt; sp.kpad = c.kpad; sp.cin_g = c.cin / c.groups; sp.cout_g = c.n_gemm / c.groups;
   sp.kh = c.kh; sp.kw = c.kw; sp.sh = c.stride; sp.sw = c.stride; sp.dh = c.dil; sp.dw = 1; sp.ph = c.ph; sp.pw = c.pw;
   sp.out_rows = 0; sp.out_W = out_W; sp.out_Wp = out_Wp; sp.epi = e;
   c.use_flat = false;
@@ -555,7 +587,7 @@ int Model::plan_conv(ConvDesc& c) {
   c.use_umma = false;
   const int taps = c.kh * c.kw;
   auto mult8 = [](int v) { return v % 8 == 0; };
-  bool ok = c.groups == 1 && taps <= kMaxTaps && (c.stride == 1 || (c.stride == 2 && c.dil == 1)) && mult8(tin.C) && mult8(c.in.coff) &&
+  bool ok = c.split_w == 0 && c.groups == 1 && taps <= kMaxTaps && (c.stride == 1 || (c.stride == 2 && c.dil == 1)) && mult8(tin.C) && mult8(c.in.coff) &&
             mult8(c.cout) && mult8(e.out_C) && mult8(e.out_coff) && mult8(e.n_split) &&
             (!e.res || (mult8(e.res_C) && mult8(e.res_coff))) && (!e.outb || (mult8(e.outb_C) && mult8(e.outb_coff))) &&
             (!e.out2 || (mult8(e.out2_C) && mult8(e.out2_coff) && mult8(e.add2_C) && mult8(e.add2_coff)));
@@ -672,6 +704,9 @@ int Model::plan_flat(ConvDesc& c) {
   if (c.res.id >= 0 && c.out2.id >= 0) return 0;
   if (c.pre_relu && (c.post_relu || c.res.id >= 0 || c.out2.id >= 0)) return 0;
   if (c.out2.id >= 0 && (!c.post_relu || n_split != c.cout)) return 0;
+  const bool split = c.split_w > 0;
+  if (split && (c.res.id >= 0 || c.out2.id >= 0 || c.outb.id >= 0 || c.split_out.size() > 8)) return 0;
+  const int N = c.n_gemm;
   const int aux_mode = c.res.id >= 0 ? 1 : (c.out2.id >= 0 ? 2 : 0);
 
   FlatConvParams fp;
@@ -687,75 +722,107 @@ int Model::plan_flat(ConvDesc& c) {
   const uint32_t row_bytes = static_cast<uint32_t>(c.kbox) * 2u;
   fp.layout_type = row_bytes == 128 ? 2u : row_bytes == 64 ? 4u : 6u;
   fp.sbo = 8u * row_bytes;
-  fp.scale = c.d_scale; fp.shift = c.d_shift; fp.n_valid = c.cout;
+  fp.scale = c.d_scale; fp.shift = c.d_shift; fp.n_valid = N;
   fp.pix_valid = d_pix_valid_[tout.stage];
   fp.aux_mode = aux_mode; fp.pre_relu = c.pre_relu; fp.post_relu = c.post_relu;
   fp.n_res = aux_mode == 1 ? n_split : 0;
 
-  // search: widest n-tile first, then the most sub-tiles per span, then the deepest rings that fit
+  // Search over tile shapes with a small cost model (cycles per 128 output pixels, all n-tiles): tensor pipe (bounded by
+  // operand reads from shared memory when N is small), TMA row requests (~5.6 cycles per box row per SM with every SM
+  // pulling from L2, profiles/r01_microbench_tma_rate.txt), load latency over the bytes the rings keep in flight, and
+  // the epilogue's issue slots.  The cheapest shape that fits the 227 KB of shared memory wins.
   const long long budget = 227 * 1024 - 1024 - 3072;
-  const int n16 = round_up(c.cout, 16);
+  const int n16 = round_up(N, 16);
   std::vector<int> cands;
   if (n16 <= 256) cands.push_back(n16);
-  for (int t : {256, 192, 128, 64, 32})
-    if (t < n16 && c.cout % t == 0) cands.push_back(t);
+  if (split) {
+    for (int k = 4; k >= 1; --k)
+      if (k * c.split_wp < n16 && k * c.split_wp <= 256 && N % (k * c.split_wp) == 0) cands.push_back(k * c.split_wp);
+  } else {
+    for (int t : {256, 192, 128, 64, 32})
+      if (t < n16 && N % t == 0) cands.push_back(t);
+  }
+  static const int env_maxmt = getenv("SVX_FLAT_MAXMT") ? atoi(getenv("SVX_FLAT_MAXMT")) : 4;          // debug switches
+  static const bool plan_log = getenv("SVX_PLAN_LOG") != nullptr;
+  const int ksteps = c.kbox / 16;
   bool found = false;
+  double best = 1e30;
   for (int n_tile : cands) {
-    const int n_tiles = (c.cout + n_tile - 1) / n_tile;
+    const int n_tiles = (N + n_tile - 1) / n_tile;
     for (int box_ch : {64, 32}) {
-      if (found) break;
-      if (box_ch == 64 && n_tile <= 32) continue;                              // narrow tiles: 32-channel boxes halve the slot size
-      static const int env_box = getenv("SVX_FLAT_BOX") ? atoi(getenv("SVX_FLAT_BOX")) : 0;   // debug switch
-      if (env_box && box_ch != env_box && n_tile <= 32) continue;
+      if (split && box_ch != c.split_box) continue;
+      if (!split && box_ch == 64 && n_tile <= 32) continue;                              // narrow tiles: 32-channel boxes halve the slot size
       if (n_tiles > 1 && n_tile % box_ch != 0) continue;
-      if (box_ch == 32 && n_tile > 32 && n_tile % 64 == 0) continue;       // 64-channel boxes are never worse there
+      if (!split && box_ch == 32 && n_tile > 32 && n_tile % 64 == 0) continue;   // 64-channel boxes are never worse there
       // routing of channels >= n_split
-      int prim_width = c.cout, dup_c0 = -1;
-      if (n_split < c.cout) {
-        if (n_split % box_ch == 0) { prim_width = n_split; dup_c0 = n_split; }
-        else if (c.dup_ok && aux_mode == 0) { dup_c0 = n_split / box_ch * box_ch; }
-        else continue;
-        if (c.outb.coff - (n_split - dup_c0) < 0) continue;
-      }
+      if (!split && n_split < c.cout && n_split % box_ch != 0) continue;       // a staging box has exactly one destination
+      if ((N + box_ch - 1) / box_ch > 16) continue;                              // routing table size
       const int boxes = (n_tile + box_ch - 1) / box_ch;
       const uint32_t box_bytes = 128u * box_ch * 2u;
       const uint32_t slot_bytes = boxes * box_bytes * (aux_mode == 2 ? 2u : 1u);
       const uint32_t b_item = static_cast<uint32_t>(round_up(n_tile * static_cast<int>(row_bytes), 1024));
-      const long long b_total = static_cast<long long>(taps) * c.nkc * b_item;
-      static const int env_maxmt = getenv("SVX_FLAT_MAXMT") ? atoi(getenv("SVX_FLAT_MAXMT")) : 4;          // debug switches
-      static const int env_maxslots = getenv("SVX_FLAT_MAXSLOTS") ? atoi(getenv("SVX_FLAT_MAXSLOTS")) : 4;
+      const int items = taps * c.nkc;
+      const long long b_total = static_cast<long long>(items) * b_item;
       for (int mt : {4, 2, 1}) {
-        if (found) break;
         if (mt > env_maxmt) continue;
-        if (taps == 1 && mt != 1) continue;
         if (mt * n_tile > 256) continue;
         const int a_rows_min = mt * 128 + 2 * halo;
         const int a_boxes = (a_rows_min + 255) / 256;
         const int a_box_rows = round_up((a_rows_min + a_boxes - 1) / a_boxes, 8);
         const uint32_t a_stage = static_cast<uint32_t>(round_up(a_boxes * a_box_rows * static_cast<int>(row_bytes), 1024));
-        const int min_slots = (aux_mode || mt > 1) ? 2 : 1;                     // per warpgroup
+        const int min_slots = aux_mode ? 2 : 1;                                  // per warpgroup
         for (int b_res : {1, 0}) {
-          if (b_res && b_total > 72 * 1024) continue;
-          const int b_stages = b_res ? 0 : std::min(4, taps * c.nkc < 2 ? 2 : taps * c.nkc);
-          const long long b_bytes = b_res ? b_total : static_cast<long long>(std::max(b_stages, 2)) * b_item;
-          long long left = budget - b_bytes - 2LL * a_stage - 2LL * min_slots * slot_bytes;
+          if (b_res && b_total > 96 * 1024) continue;
+          if (!b_res && items < 2) continue;
+          int a_stages = 2, b_stages = b_res ? 0 : 2, slots = min_slots;
+          long long left = budget - (b_res ? b_total : 2LL * b_item) - 2LL * a_stage - 2LL * slots * slot_bytes;
           if (left < 0) continue;
-          int a_stages = 2, slots = min_slots;
-          // spend what is left: a third A stage first, then slots up to 6, then a fourth A stage
-          if (left >= a_stage) { ++a_stages; left -= a_stage; }
-          while (slots < std::min(4, std::max(env_maxslots, min_slots)) && left >= 2LL * slot_bytes) { ++slots; left -= 2LL * slot_bytes; }
-          if (a_stages < 4 && left >= a_stage) { ++a_stages; left -= a_stage; }
-          fp.mt = mt; fp.a_box_rows = a_box_rows; fp.a_boxes = a_boxes; fp.n_tile = n_tile; fp.n_tiles = n_tiles;
-          fp.a_stages = a_stages; fp.b_stages = b_res ? 0 : std::max(b_stages, 2); fp.a_stage_bytes = a_stage; fp.b_item_bytes = b_item;
-          fp.b_resident = b_res; fp.box_ch = box_ch; fp.boxes = boxes; fp.slots = slots; fp.slot_bytes = slot_bytes;
-          fp.prim_width = prim_width; fp.dup_c0 = dup_c0;
-          found = true;
-          break;
+          auto inflight = [&]() { return static_cast<long long>(a_stages) * a_stage + static_cast<long long>(b_stages) * b_item; };
+          // rings first (up to ~128 KB in flight), then a second / third slot per warpgroup, then deeper rings
+          for (int pass = 0; pass < 2; ++pass) {
+            bool grew = true;
+            while (grew && (pass == 1 || inflight() < 128 * 1024)) {
+              grew = false;
+              if (a_stages < 8 && a_stages < std::max(2, 2 * c.nkc) && left >= a_stage) { ++a_stages; left -= a_stage; grew = true; }
+              if (!b_res && b_stages < 8 && b_stages < items && left >= b_item && (pass == 1 || inflight() < 128 * 1024)) {
+                ++b_stages; left -= b_item; grew = true;
+              }
+            }
+            if (pass == 0)
+              while (slots < (aux_mode ? 3 : 2) && left >= 2LL * slot_bytes) { ++slots; left -= 2LL * slot_bytes; }
+          }
+          // ---- cost per 128 output pixels
+          const double halo_ovh = 1.0 + 2.0 * halo / (mt * 128.0);
+          const double a_rows = static_cast<double>(n_tiles) * c.nkc * 128.0 * halo_ovh;
+          const double b_rows = b_res ? 0.0 : static_cast<double>(n_tiles) * items * n_tile / mt;
+          const int aux_boxes = aux_mode ? boxes : 0;
+          const double aux_rows = static_cast<double>(n_tiles) * aux_boxes * 128.0;
+          const double st_rows = static_cast<double>(n_tiles) * boxes * 128.0 * (aux_mode == 2 ? 2.0 : 1.0);
+          const double t_req = (a_rows + b_rows + aux_rows) * 5.6;
+          const double t_st = st_rows * 4.6;
+          const double load_bytes = (a_rows + b_rows) * row_bytes;
+          const double t_lat = load_bytes * 3000.0 / static_cast<double>(inflight());
+          const double mma_cyc = std::max(n_tile / 2.0, (4096.0 + n_tile * 32.0) / 128.0) + 6.0;
+          const double t_mma = static_cast<double>(n_tiles) * items * ksteps * mma_cyc;
+          const double t_epi = static_cast<double>(n_tiles) * (n_tile / 16.0) * 150.0;
+          const double score = std::max(std::max(t_req, t_st), std::max(std::max(t_lat, t_mma), t_epi)) + 0.01 * n_tiles - 0.001 * mt;
+          if (plan_log)
+            fprintf(stderr, "  cand n_tile %d box %d mt %d bres %d a_st %d b_st %d slots %d: req %.0f st %.0f lat %.0f mma %.0f epi %.0f -> %.0f\n", n_tile,
+                    box_ch, mt, b_res, a_stages, b_stages, slots, t_req, t_st, t_lat, t_mma, t_epi, score);
+          if (score < best) {
+            best = score;
+            fp.mt = mt; fp.a_box_rows = a_box_rows; fp.a_boxes = a_boxes; fp.n_tile = n_tile; fp.n_tiles = n_tiles;
+            fp.a_stages = a_stages; fp.b_stages = b_stages; fp.a_stage_bytes = a_stage; fp.b_item_bytes = b_item;
+            fp.b_resident = b_res; fp.box_ch = box_ch; fp.boxes = boxes; fp.slots = slots; fp.slot_bytes = slot_bytes;
+            found = true;
+          }
         }
       }
     }
-    if (found) break;
   }
+  if (found && plan_log)
+    fprintf(stderr, "plan %dx%d cin %d cout %d aux %d: n_tile %d x%d box %d mt %d bres %d a_st %d b_st %d slots %d score %.0f\n", c.kh, c.kw, c.cin,
+            c.cout, aux_mode, fp.n_tile, fp.n_tiles, fp.box_ch, fp.mt, fp.b_resident, fp.a_stages, fp.b_stages, fp.slots, best);
   if (!found) return 0;
   uint32_t tc = 32;
   while (tc < 2u * fp.mt * fp.n_tile) tc *= 2;
@@ -773,7 +840,11 @@ int Model::plan_flat(ConvDesc& c) {
     const uint64_t dims[2] = {static_cast<uint64_t>(c.cin), P_cap};
     const uint64_t str[1] = {static_cast<uint64_t>(tin.C) * esz};
     const uint32_t box[2] = {static_cast<uint32_t>(c.kbox), static_cast<uint32_t>(fp.a_box_rows)};
-    if (encode_tmap(&fm.a, is_bf16_, static_cast<uint8_t*>(tin.ptr) + static_cast<size_t>(c.in.coff) * esz, 2, dims, str, box, row_bytes)) return 1;
+    static const int env_promo = getenv("SVX_L2_PROMO") ? atoi(getenv("SVX_L2_PROMO")) : -1;   // debug switch (see promo_for below)
+    const int pitch = tin.C * 2, off = c.in.coff * 2, wb = c.cin * 2;
+    const int promo = env_promo >= 0 ? env_promo : (c.cin == tin.C) ? 128 : (pitch % 128 == 0 && off % 128 == 0 && wb % 128 == 0) ? 128
+                                                 : (pitch % 64 == 0 && off % 64 == 0 && wb % 64 == 0) ? 64 : 0;
+    if (encode_tmap(&fm.a, is_bf16_, static_cast<uint8_t*>(tin.ptr) + static_cast<size_t>(c.in.coff) * esz, 2, dims, str, box, row_bytes, promo)) return 1;
   }
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(taps) * c.kpad, static_cast<uint64_t>(c.n_pad)};
@@ -781,17 +852,50 @@ int Model::plan_flat(ConvDesc& c) {
     const uint32_t box[2] = {static_cast<uint32_t>(c.kbox), static_cast<uint32_t>(fp.n_tile)};
     if (encode_tmap(&fm.b, is_bf16_, c.d_wgt, 2, dims, str, box, row_bytes)) return 1;
   }
+  // L2 promotion widens every TMA request to the promotion size; on a narrow channel slice of a wider row that
+  // multiplies the DRAM traffic (measured 3.7-4.8x on the 24-channel Res2Net splits), so promote only what the
+  // slice geometry fills.
+  auto promo_for = [&](const ActTensor& t, int coff, int width) -> int {
+    static const int env_promo = getenv("SVX_L2_PROMO") ? atoi(getenv("SVX_L2_PROMO")) : -1;   // debug switch
+    if (env_promo >= 0) return env_promo;
+    const int pitch = t.C * 2, off = coff * 2, wb = width * 2;
+    if (width == t.C) return 128;                                  // dense tensor: every fetched byte is used
+    if (pitch % 128 == 0 && off % 128 == 0 && wb % 128 == 0) return 128;
+    if (pitch % 64 == 0 && off % 64 == 0 && wb % 64 == 0) return 64;
+    return 0;
+  };
   auto slice_map = [&](CUtensorMap* m, const ActTensor& t, int coff, int width) -> int {
     const uint64_t dims[2] = {static_cast<uint64_t>(width), P_cap};
     const uint64_t str[1] = {static_cast<uint64_t>(t.C) * esz};
     const uint32_t box[2] = {static_cast<uint32_t>(fp.box_ch), 128u};
-    return encode_tmap(m, is_bf16_, static_cast<uint8_t*>(t.ptr) + static_cast<size_t>(coff) * esz, 2, dims, str, box, sw_box);
+    return encode_tmap(m, is_bf16_, static_cast<uint8_t*>(t.ptr) + static_cast<size_t>(coff) * esz, 2, dims, str, box, sw_box,
+                       promo_for(t, coff, width));
   };
-  if (slice_map(&fm.o[0], tout, c.out.coff, fp.prim_width)) return 1;
-  if (fp.dup_c0 >= 0) {
-    const ActTensor& tb = tensors_[c.outb.id];
-    if (tb.stage != tout.stage) return 0;
-    if (slice_map(&fm.o[1], tb, c.outb.coff - (n_split - fp.dup_c0), c.cout - fp.dup_c0)) return 1;
+  // destinations: one output map per planar split, or map 0 = primary slice and map 1 = the channels past n_split
+  memset(fp.route_map, 0xff, sizeof fp.route_map);
+  const int n_boxes_total = (N + fp.box_ch - 1) / fp.box_ch;
+  if (split) {
+    for (size_t i = 0; i < c.split_out.size(); ++i) {
+      const ActTensor& ts = tensors_[c.split_out[i].id];
+      if (ts.stage != tout.stage) return 0;
+      if (slice_map(&fm.o[i], ts, c.split_out[i].coff, c.split_w)) return 1;
+    }
+    for (int gb = 0; gb < n_boxes_total; ++gb) {
+      const int ch = gb * fp.box_ch, sidx = ch / c.split_wp, j0 = ch - sidx * c.split_wp;
+      if (j0 < c.split_w) { fp.route_map[gb] = static_cast<uint8_t>(sidx); fp.route_c[gb] = j0; }
+    }
+  } else {
+    if (slice_map(&fm.o[0], tout, c.out.coff, n_split)) return 1;
+    if (n_split < c.cout) {
+      const ActTensor& tb = tensors_[c.outb.id];
+      if (tb.stage != tout.stage) return 0;
+      if (slice_map(&fm.o[1], tb, c.outb.coff, c.cout - n_split)) return 1;
+    }
+    for (int gb = 0; gb < n_boxes_total; ++gb) {
+      const int ch = gb * fp.box_ch;
+      if (ch < n_split) { fp.route_map[gb] = 0; fp.route_c[gb] = ch; }
+      else { fp.route_map[gb] = 1; fp.route_c[gb] = ch - n_split; }
+    }
   }
   if (aux_mode == 1) {
     const ActTensor& tr = tensors_[c.res.id];
@@ -802,7 +906,7 @@ int Model::plan_flat(ConvDesc& c) {
     const ActTensor& t2 = tensors_[c.out2.id];
     if (ta.stage != tout.stage || t2.stage != tout.stage) return 0;
     if (slice_map(&fm.aux, ta, c.add2.coff, c.cout)) return 1;
-    if (slice_map(&fm.o[2], t2, c.out2.coff, c.cout)) return 1;
+    if (slice_map(&fm.o2, t2, c.out2.coff, c.cout)) return 1;
   }
   if (conv_flat_smem_bytes(fp) > 227 * 1024) return 0;
   c.fp = fp;

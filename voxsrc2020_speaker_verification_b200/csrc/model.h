@@ -51,7 +51,11 @@ struct ConvDesc {
   float* d_scale = nullptr; float* d_shift = nullptr;
   bool use_umma = false; bool no_staged = false;
   UmmaConvParams up; AMaps amaps; CUtensorMap bmap; CUtensorMap auxmap; OMaps omaps;
-  bool use_flat = false; bool dup_ok = false;   // dup_ok: channels [n_split, cout) may also land in `out` (see plan_flat)
+  bool use_flat = false;
+  // planar splits: output channel group s (split_w wide) goes to split_out[s]; the GEMM's N axis is laid out as
+  // n_splits groups padded to split_wp channels (weights, scale and shift are permuted accordingly at upload)
+  std::vector<TensorRef> split_out; int split_w = 0, split_wp = 0, split_box = 0;
+  int n_gemm = 0;                     // GEMM N: cout, or n_splits * split_wp
   FlatConvParams fp; FlatMaps fmaps;
   SimpleConvParams sp;
 };
@@ -150,6 +154,6 @@ class Model {
 
 // TMA descriptor encode through the driver entry point (no link-time libcuda dependency).
 int encode_tmap(CUtensorMap* m, int elem_bytes_is2, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                const uint32_t* box, int swizzle_bytes);
+                const uint32_t* box, int swizzle_bytes, int l2_promo_bytes = 128);
 
 }  // namespace svx
