@@ -121,6 +121,22 @@ __device__ __forceinline__ void epi8(const uint32_t* r, uint32_t sc, uint32_t sh
   }
 }
 
+// All MMAs of one filter tap: MT sub-tiles x KS K-steps, fully unrolled so that every descriptor is the tap's base
+// (one value) plus a compile-time constant.  A generic loop costs ~150 cycles of issue per MMA (descriptor arithmetic in
+// vector registers + 5 R2UR each, tools/microbench/mma_rate.cu) against 16-64 cycles of tensor-pipe time.
+template <int MT, int KS>
+__device__ __forceinline__ void issue_tap(uint64_t adesc0, uint64_t bdesc0, uint32_t d_tmem, uint32_t n_tile, uint32_t idesc, uint32_t first) {
+  constexpr uint32_t kSub16 = 256u * KS;      // (128 rows x 32*KS bytes) >> 4
+  if (elect_one()) {      // one elected region for the whole tap: the R2UR traffic of consecutive MMAs overlaps
+#pragma unroll
+    for (int j = 0; j < MT; ++j) {
+#pragma unroll
+      for (int k = 0; k < KS; ++k)
+        umma_f16(d_tmem + j * n_tile, adesc0 + (j * kSub16 + k * 2), bdesc0 + k * 2, idesc, k == 0 ? first : 1u);
+    }
+  }
+}
+
 struct Smem {
   uint64_t a_full[kRing], a_empty[kRing], b_full[kRing], b_empty[kRing];
   uint64_t slot_full[kRing], slot_empty[kRing], slot_ready[kRing];
@@ -227,12 +243,11 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
     // tcgen05 instructions themselves sit under the elected-lane branch.  Computing them inside an `if (lane == 0)` region
     // made ptxas wrap every UTCHMMA in an ELECT / 5x R2UR.BROADCAST waterfall: ~200 ns per MMA whatever its shape.
     const int ksteps = p.kbox >> 4;
-    const bool leader = elect_one();
     if (p.b_resident) wait_dbg(&S.bres_bar, 0, p.dbg, 0x10, 0, 0, S.prog);
     const uint64_t desc_base = make_kmajor_desc(0, p.sbo, p.layout_type);
     const uint32_t a_base = smem_u32(a_smem), b_base = smem_u32(b_smem);
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
-    const uint32_t sub_bytes = 128u * row_bytes;
+    const int mtks = (p.mt << 4) | ksteps;
     Tracer tr; tr.init(lane == 0 ? p.trace : nullptr, 1);
     uint32_t ia = 0, ib = 0;
     int ls = 0;
@@ -263,19 +278,22 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
           tc_fence_after();
           const uint32_t a_tap = a_addr + static_cast<uint32_t>(p.halo + p.tap_shift[tap]) * row_bytes;
           const uint32_t first = (kc == 0 && tap == 0) ? 0u : 1u;
-          for (int j = 0; j < p.mt; ++j) {
-            const uint32_t a_j = a_tap + static_cast<uint32_t>(j) * sub_bytes;
-            const uint32_t d_j = d_tmem + static_cast<uint32_t>(j * p.n_tile);
-            for (int k = 0; k < ksteps; ++k) {
-              const uint64_t adesc = desc_base | static_cast<uint64_t>(((a_j + k * 32) >> 4) & 0x3FFF);
-              const uint64_t bdesc = desc_base | static_cast<uint64_t>(((b_addr + k * 32) >> 4) & 0x3FFF);
-              const uint32_t acc = k == 0 ? first : 1u;
-              if (leader) umma_f16(d_j, adesc, bdesc, p.idesc, acc);
-            }
+          const uint64_t adesc0 = desc_base + (a_tap >> 4), bdesc0 = desc_base + (b_addr >> 4);   // smem < 256 KB: no carry out of the field
+          const uint32_t nt = static_cast<uint32_t>(p.n_tile);
+          switch (mtks) {
+            case 0x11: issue_tap<1, 1>(adesc0, bdesc0, d_tmem, nt, p.idesc, first); break;
+            case 0x12: issue_tap<1, 2>(adesc0, bdesc0, d_tmem, nt, p.idesc, first); break;
+            case 0x14: issue_tap<1, 4>(adesc0, bdesc0, d_tmem, nt, p.idesc, first); break;
+            case 0x21: issue_tap<2, 1>(adesc0, bdesc0, d_tmem, nt, p.idesc, first); break;
+            case 0x22: issue_tap<2, 2>(adesc0, bdesc0, d_tmem, nt, p.idesc, first); break;
+            case 0x24: issue_tap<2, 4>(adesc0, bdesc0, d_tmem, nt, p.idesc, first); break;
+            case 0x41: issue_tap<4, 1>(adesc0, bdesc0, d_tmem, nt, p.idesc, first); break;
+            case 0x42: issue_tap<4, 2>(adesc0, bdesc0, d_tmem, nt, p.idesc, first); break;
+            default:   issue_tap<4, 4>(adesc0, bdesc0, d_tmem, nt, p.idesc, first); break;
           }
-          if (!p.b_resident && leader) umma_commit(&S.b_empty[sb]);
+          if (!p.b_resident && elect_one()) umma_commit(&S.b_empty[sb]);
         }
-        if (leader) {
+        if (elect_one()) {
           umma_commit(&S.a_empty[sa]);
           if (kc == p.nkc - 1) umma_commit(&S.tmem_full[buf]);
         }
