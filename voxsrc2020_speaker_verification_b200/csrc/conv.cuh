@@ -173,6 +173,7 @@ struct FlatConvParams {
   const float* scale; const float* shift;
   int n_valid;                 // real output channels
   int n_res;                   // residual (aux mode 1) applies to channels < n_res
+  int grp_mask, grp_w;         // padded planar splits: channel groups with (c & grp_mask) >= grp_w are padding and are skipped
   const uint8_t* pix_valid;    // [P_cap] 1 = pixel belongs to a segment and is not the zero column
   int aux_mode;                // 0 none, 1 residual added before post-ReLU (in place), 2 second output = v + add2
   int box_ch;                  // channels per staging box: 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B)

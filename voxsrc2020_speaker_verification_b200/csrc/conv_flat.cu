@@ -413,7 +413,7 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             const int cl = c0 + g * 8, cg = n0 + cl;
-            if (cg < p.n_valid) {
+            if (cg < p.n_valid && (cg & p.grp_mask) < p.grp_w) {
               const uint32_t ua = bufA + (static_cast<uint32_t>(cl) >> bsh) * box_bytes + ((((static_cast<uint32_t>(cl) & bmask) >> 3) << 4) ^ row_xor);
               epi8<T, AUX, PRE, POST>(ra + g * 8, sc_base + cl * 4, sh_base + cl * 4, ua, ua + bufB_off, cg < p.n_res, vmask);
             }
@@ -424,7 +424,7 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
               const int cl = c0 + 16 + g * 8, cg = n0 + cl;
-              if (cg < p.n_valid) {
+              if (cg < p.n_valid && (cg & p.grp_mask) < p.grp_w) {
                 const uint32_t ua = bufA + (static_cast<uint32_t>(cl) >> bsh) * box_bytes + ((((static_cast<uint32_t>(cl) & bmask) >> 3) << 4) ^ row_xor);
                 epi8<T, AUX, PRE, POST>(rb + g * 8, sc_base + cl * 4, sh_base + cl * 4, ua, ua + bufB_off, cg < p.n_res, vmask);
               }

@@ -726,6 +726,8 @@ int Model::plan_flat(ConvDesc& c) {
   fp.pix_valid = d_pix_valid_[tout.stage];
   fp.aux_mode = aux_mode; fp.pre_relu = c.pre_relu; fp.post_relu = c.post_relu;
   fp.n_res = aux_mode == 1 ? n_split : 0;
+  fp.grp_mask = 0; fp.grp_w = 1;
+  if (split && (c.split_wp & (c.split_wp - 1)) == 0 && c.split_w < c.split_wp) { fp.grp_mask = c.split_wp - 1; fp.grp_w = c.split_w; }
 
   // Search over tile shapes with a small cost model (cycles per 128 output pixels, all n-tiles): tensor pipe (bounded by
   // operand reads from shared memory when N is small), TMA row requests (~5.6 cycles per box row per SM with every SM
@@ -770,28 +772,13 @@ int Model::plan_flat(ConvDesc& c) {
         const int a_boxes = (a_rows_min + 255) / 256;
         const int a_box_rows = round_up((a_rows_min + a_boxes - 1) / a_boxes, 8);
         const uint32_t a_stage = static_cast<uint32_t>(round_up(a_boxes * a_box_rows * static_cast<int>(row_bytes), 1024));
-        const int min_slots = aux_mode ? 2 : 1;                                  // per warpgroup
         for (int b_res : {1, 0}) {
           if (b_res && b_total > 96 * 1024) continue;
           if (!b_res && items < 2) continue;
-          int a_stages = 2, b_stages = b_res ? 0 : 2, slots = min_slots;
+          int a_stages = 2, b_stages = b_res ? 0 : 2, slots = 1;               // slots: per warpgroup
           long long left = budget - (b_res ? b_total : 2LL * b_item) - 2LL * a_stage - 2LL * slots * slot_bytes;
           if (left < 0) continue;
-          auto inflight = [&]() { return static_cast<long long>(a_stages) * a_stage + static_cast<long long>(b_stages) * b_item; };
-          // rings first (up to ~128 KB in flight), then a second / third slot per warpgroup, then deeper rings
-          for (int pass = 0; pass < 2; ++pass) {
-            bool grew = true;
-            while (grew && (pass == 1 || inflight() < 128 * 1024)) {
-              grew = false;
-              if (a_stages < 8 && a_stages < std::max(2, 2 * c.nkc) && left >= a_stage) { ++a_stages; left -= a_stage; grew = true; }
-              if (!b_res && b_stages < 8 && b_stages < items && left >= b_item && (pass == 1 || inflight() < 128 * 1024)) {
-                ++b_stages; left -= b_item; grew = true;
-              }
-            }
-            if (pass == 0)
-              while (slots < (aux_mode ? 3 : 2) && left >= 2LL * slot_bytes) { ++slots; left -= 2LL * slot_bytes; }
-          }
-          // ---- cost per 128 output pixels
+          // ---- cost per 128 output pixels (cycles)
           const double halo_ovh = 1.0 + 2.0 * halo / (mt * 128.0);
           const double a_rows = static_cast<double>(n_tiles) * c.nkc * 128.0 * halo_ovh;
           const double b_rows = b_res ? 0.0 : static_cast<double>(n_tiles) * items * n_tile / mt;
@@ -801,14 +788,43 @@ int Model::plan_flat(ConvDesc& c) {
           const double t_req = (a_rows + b_rows + aux_rows) * 5.6;
           const double t_st = st_rows * 4.6;
           const double load_bytes = (a_rows + b_rows) * row_bytes;
-          const double t_lat = load_bytes * 3000.0 / static_cast<double>(inflight());
           const double mma_cyc = std::max(n_tile / 2.0, (4096.0 + n_tile * 32.0) / 128.0) + 6.0;
           const double t_mma = static_cast<double>(n_tiles) * items * ksteps * mma_cyc;
           const double t_epi = static_cast<double>(n_tiles) * (n_tile / 16.0) * 150.0;
-          const double score = std::max(std::max(t_req, t_st), std::max(std::max(t_lat, t_mma), t_epi)) + 0.01 * n_tiles - 0.001 * mt;
+          const double t_fixed = std::max(std::max(t_req, t_st), std::max(t_mma, t_epi));
+          // latency terms shrink with ring depth: loads in flight against ~1.5 us, and slots held ~4 us with an aux tile
+          // (prefetch → conversion → store read), ~1.5 us without (profiles/r01_trace_flat_*.txt); 2*slots are in flight
+          auto t_lat = [&]() {
+            return load_bytes * 3000.0 / static_cast<double>(static_cast<long long>(a_stages) * a_stage + static_cast<long long>(b_stages) * b_item);
+          };
+          auto t_slot = [&]() { return static_cast<double>(n_tiles) * (aux_mode ? 7600.0 : 2900.0) / (2.0 * slots); };
+          for (;;) {   // grow whichever ring currently bounds the tile, while it fits
+            const double tl = t_lat(), ts = t_slot();
+            if (std::max(tl, ts) <= t_fixed) break;
+            bool grew = false;
+            if (ts >= tl) {
+              if (slots < 4 && left >= 2LL * slot_bytes) { ++slots; left -= 2LL * slot_bytes; grew = true; }
+            }
+            if (!grew) {
+              const bool want_b = !b_res && b_stages < 8 && b_stages < items && static_cast<long long>(b_stages) * b_item <= static_cast<long long>(a_stages) * a_stage;
+              if (want_b && left >= b_item) { ++b_stages; left -= b_item; grew = true; }
+              else if (a_stages < 8 && left >= a_stage) { ++a_stages; left -= a_stage; grew = true; }
+              else if (!b_res && b_stages < 8 && b_stages < items && left >= b_item) { ++b_stages; left -= b_item; grew = true; }
+            }
+            if (!grew && ts < tl && slots < 4 && left >= 2LL * slot_bytes && ts > t_fixed) { ++slots; left -= 2LL * slot_bytes; grew = true; }
+            if (!grew) break;
+          }
+          // the model is optimistic about overlap: when shared memory is left over, take a second slot per warpgroup (convert
+          // j+1 while j is being stored), a third A stage, and a third slot for aux tiles
+          if (slots < 2 && left >= 2LL * slot_bytes) { ++slots; left -= 2LL * slot_bytes; }
+          if (a_stages < 3 && left >= a_stage) { ++a_stages; left -= a_stage; }
+          if (aux_mode && slots < 3 && left >= 2LL * slot_bytes) { ++slots; left -= 2LL * slot_bytes; }
+          if (!b_res && b_stages < 4 && b_stages < items && left >= b_item) { ++b_stages; left -= b_item; }
+          const double score = std::max(t_fixed, std::max(t_lat(), t_slot())) + 0.01 * n_tiles - 0.001 * mt;
+          const double t_latv = t_lat(), t_slotv = t_slot();
           if (plan_log)
-            fprintf(stderr, "  cand n_tile %d box %d mt %d bres %d a_st %d b_st %d slots %d: req %.0f st %.0f lat %.0f mma %.0f epi %.0f -> %.0f\n", n_tile,
-                    box_ch, mt, b_res, a_stages, b_stages, slots, t_req, t_st, t_lat, t_mma, t_epi, score);
+            fprintf(stderr, "  cand n_tile %d box %d mt %d bres %d a_st %d b_st %d slots %d: req %.0f st %.0f lat %.0f mma %.0f epi %.0f slot %.0f -> %.0f\n", n_tile,
+                    box_ch, mt, b_res, a_stages, b_stages, slots, t_req, t_st, t_latv, t_mma, t_epi, t_slotv, score);
           if (score < best) {
             best = score;
             fp.mt = mt; fp.a_box_rows = a_box_rows; fp.a_boxes = a_boxes; fp.n_tile = n_tile; fp.n_tiles = n_tiles;
