@@ -248,6 +248,7 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
     const uint32_t a_base = smem_u32(a_smem), b_base = smem_u32(b_smem);
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
     const int mtks = (p.mt << 4) | ksteps;
+    const bool jmajor = false;   // sub-tile-major issue order measured slower (62 vs 50 ns per MMA): per-call overhead dominates
     Tracer tr; tr.init(lane == 0 ? p.trace : nullptr, 1);
     uint32_t ia = 0, ib = 0;
     int ls = 0;
@@ -264,6 +265,22 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
         wait_dbg(&S.a_full[sa], (ia / p.a_stages) & 1, p.dbg, 0x12, sa, ia, S.prog);
         if (kc == 0) tr.ev(3);
         const uint32_t a_addr = a_base + static_cast<uint32_t>(sa) * p.a_stage_bytes;
+        if (p.b_resident && p.mt > 1 && jmajor) {
+          // resident weights: any order is legal; sub-tile-major keeps each accumulator's MMAs back to back
+          tc_fence_after();
+          const uint32_t nt = static_cast<uint32_t>(p.n_tile);
+          for (int j = 0; j < p.mt; ++j) {
+            for (int tap = 0; tap < p.taps; ++tap) {
+              const uint32_t b_addr = b_base + static_cast<uint32_t>(kc * p.taps + tap) * p.b_item_bytes;
+              const uint32_t a_tap = a_addr + static_cast<uint32_t>(p.halo + p.tap_shift[tap] + j * 128) * row_bytes;
+              const uint32_t first = (kc == 0 && tap == 0) ? 0u : 1u;
+              const uint64_t adesc0 = desc_base + (a_tap >> 4), bdesc0 = desc_base + (b_addr >> 4);
+              if (ksteps == 4) issue_tap<1, 4>(adesc0, bdesc0, d_tmem + j * nt, nt, p.idesc, first);
+              else if (ksteps == 2) issue_tap<1, 2>(adesc0, bdesc0, d_tmem + j * nt, nt, p.idesc, first);
+              else issue_tap<1, 1>(adesc0, bdesc0, d_tmem + j * nt, nt, p.idesc, first);
+            }
+          }
+        } else
         for (int tap = 0; tap < p.taps; ++tap) {
           uint32_t b_addr;
           int sb = 0;

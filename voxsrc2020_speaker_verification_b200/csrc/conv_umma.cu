@@ -306,23 +306,34 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p, const __grid_constant
           const uint32_t ph = (it / p.stages) & 1;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          if (lane == 0) {
+          {
+            // descriptors are computed by the whole (converged) warp and only the tcgen05 instructions sit under the elected
+            // lane, fully unrolled: inside an `if (lane == 0)` region ptxas wrapped every UTCHMMA in an ELECT / R2UR.BROADCAST
+            // waterfall that cost ~200 ns per MMA (tools/microbench/mma_rate.cu)
             const uint32_t a_addr0 = smem_u32(tiles + static_cast<size_t>(s) * ring_bytes);
             const uint32_t b_addr = b_res ? smem_u32(bres + static_cast<size_t>(i) * p.b_stage_bytes) : a_addr0 + p.a_stage_bytes;
 #ifdef SVX_ASHIFT
             const uint32_t a_addr = a_addr0 + SVX_ASHIFT * p.kbox * 2;
-            const uint32_t a_bo = SVX_BASEOFF_MODE == 0 ? 0u : ((a_addr >> 7) & 7u);
 #else
             const uint32_t a_addr = a_addr0;
-            const uint32_t a_bo = 0u;
 #endif
-            for (int k = 0; k < ksteps; ++k) {
-              const uint64_t adesc = make_kmajor_desc(a_addr + k * 32, p.sbo, p.layout_type, a_bo);
-              const uint64_t bdesc = make_kmajor_desc(b_addr + k * 32, p.sbo, p.layout_type);
-              umma_f16(d_tmem, adesc, bdesc, p.idesc, (i | k) != 0 ? 1u : 0u);
+            const uint64_t dbase = make_kmajor_desc(0, p.sbo, p.layout_type);
+            const uint64_t adesc0 = dbase + (a_addr >> 4), bdesc0 = dbase + (b_addr >> 4);
+            const uint32_t first = i != 0 ? 1u : 0u;
+            const bool last = i == total_it - 1;
+            if (elect_one()) {
+              if (ksteps == 4) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16(d_tmem, adesc0 + 2 * k, bdesc0 + 2 * k, p.idesc, k == 0 ? first : 1u);
+              } else if (ksteps == 2) {
+#pragma unroll
+                for (int k = 0; k < 2; ++k) umma_f16(d_tmem, adesc0 + 2 * k, bdesc0 + 2 * k, p.idesc, k == 0 ? first : 1u);
+              } else {
+                umma_f16(d_tmem, adesc0, bdesc0, p.idesc, first);
+              }
+              umma_commit(&empty_bar[s]);                       // frees the smem slot when these MMAs retire
+              if (last) umma_commit(&tmem_full_bar[b]);
             }
-            umma_commit(&empty_bar[s]);                       // frees the smem slot when these MMAs retire
-            if (i == total_it - 1) umma_commit(&tmem_full_bar[b]);
           }
           __syncwarp();
           if (i == 0) tr.ev(3);                                     // first operands landed

@@ -775,9 +775,11 @@ int Model::plan_flat(ConvDesc& c) {
         for (int b_res : {1, 0}) {
           if (b_res && b_total > 96 * 1024) continue;
           if (!b_res && items < 2) continue;
-          int a_stages = 2, b_stages = b_res ? 0 : 2, slots = 1;               // slots: per warpgroup
+          int a_stages = 2, b_stages = b_res ? 0 : 2, slots = 2;               // slots: per warpgroup (2: convert j+1 while j is stored)
           long long left = budget - (b_res ? b_total : 2LL * b_item) - 2LL * a_stage - 2LL * slots * slot_bytes;
+          if (left < 0) { slots = 1; left += 2LL * slot_bytes; }
           if (left < 0) continue;
+          if (slots == 1 && b_res && taps == 1 && mt > 1) continue;            // a 1x1 with resident weights gains less from mt than from a 2nd slot
           // ---- cost per 128 output pixels (cycles)
           const double halo_ovh = 1.0 + 2.0 * halo / (mt * 128.0);
           const double a_rows = static_cast<double>(n_tiles) * c.nkc * 128.0 * halo_ovh;
@@ -820,7 +822,7 @@ int Model::plan_flat(ConvDesc& c) {
           if (a_stages < 3 && left >= a_stage) { ++a_stages; left -= a_stage; }
           if (aux_mode && slots < 3 && left >= 2LL * slot_bytes) { ++slots; left -= 2LL * slot_bytes; }
           if (!b_res && b_stages < 4 && b_stages < items && left >= b_item) { ++b_stages; left -= b_item; }
-          const double score = std::max(t_fixed, std::max(t_lat(), t_slot())) + 0.01 * n_tiles - 0.001 * mt;
+          const double score = std::max(t_fixed, std::max(t_lat(), t_slot())) + 0.01 * n_tiles - 0.001 * mt + (b_res ? 0.0 : 0.005);
           const double t_latv = t_lat(), t_slotv = t_slot();
           if (plan_log)
             fprintf(stderr, "  cand n_tile %d box %d mt %d bres %d a_st %d b_st %d slots %d: req %.0f st %.0f lat %.0f mma %.0f epi %.0f slot %.0f -> %.0f\n", n_tile,
@@ -948,7 +950,8 @@ int Model::ensure_capacity(int rows0) {
     rows = rows / 2 + 8;
   }
   for (ActTensor& t : tensors_) {
-    const size_t bytes = static_cast<size_t>(rows_cap_[t.stage]) * stage_Wp_[t.stage] * t.C * 2;
+    // + 1024 pixels of slack past the last row
+    const size_t bytes = (static_cast<size_t>(rows_cap_[t.stage]) * stage_Wp_[t.stage] + 1024) * t.C * 2;
     SVX_CUDA(cudaMalloc(&t.ptr, bytes));
     SVX_CUDA(cudaMemset(t.ptr, 0, bytes));
     act_bufs_.push_back(t.ptr);
