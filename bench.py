@@ -8,8 +8,10 @@ plus the AS-norm scoring job of BASELINE config 5 (trials/s), on N B200s of one 
 A step = one pass of the extraction hot path over one batch of 256 synthetic utterances per GPU (weak scaling).
 value  = embeddings/s with features already resident in HBM (device in, device out);
 e2e    = the same through the public host API (pinned host features in, host embeddings out, copies timed);
-roofline = the tcgen05 conv kernel: algorithmic conv FLOPs of its launches / their CUDA-event time, against the
-           measured sustained bf16 peak of MEASURED_PEAKS.json;
+roofline = the tcgen05 conv kernels (conv_flat_kernel for stride-1 layers, conv_umma_kernel for stride-2 layers): algorithmic
+           conv FLOPs of their launches / their CUDA-event time, against the measured sustained 16-bit tensor peak of
+           MEASURED_PEAKS.json; the "hbm" view divides the layer-wise algorithmic bytes (212 MB per utterance)
+           by the same time; "traffic" is the DRAM bytes ncu counted for the same launches (profiles/r01_traffic.json);
 cpu_baseline = the oracle port (PyTorch CPU fp32 restatement of the reference graph, batch 1 like tf_extract.py)
            on this box's host cores, on a bounded sample.
 --impl reference times that CPU port alone (TensorFlow 1.x, which the reference needs, cannot be installed).
@@ -32,6 +34,7 @@ if ROOT not in sys.path:
 MODEL_ID, FEAT_DIM, FRAMES, BATCH = "res2net50_w24_s4_c32", 80, 200, 256
 METRIC = "Res2Net50 embeddings/s (200fr 80-d) at 1/2/4/8 B200; asnorm trials/s"
 FLOPS_PER_UTT = 22.367e9            # 2 x conv/dense MACs, 200 frames x 80 bins
+BYTES_PER_UTT = 212e6                # layer-wise fused activation traffic, 16-bit activations
 SCORE_N, SCORE_C, SCORE_D, SCORE_TOPK, SCORE_TRIALS = 145160, 5994, 256, 300, 579818
 
 
@@ -224,6 +227,12 @@ def main():
     ex.set_option("time_convs", 0)
     conv_ms_step = min(conv_ms)
     achieved = conv_flops / (conv_ms_step * 1e-3) / 1e12 if conv_ms_step > 0 else 0.0
+    hbm_achieved = BATCH * BYTES_PER_UTT / (conv_ms_step * 1e-3) / 1e9 if conv_ms_step > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get("conv_dram_bytes_per_step")
 
     # ---- scoring job (BASELINE config 5), test rows sharded across ranks' replicas is the natural layout; the
     # cohort-row-sharded layout with an NCCL all-gather of top-k candidates is svdist.sharded_cohort_mean_std
@@ -273,11 +282,15 @@ def main():
             "e2e": {"value": world * BATCH / (e2e_ms * 1e-3), "unit": "embeddings/s",
                     "h2d_bytes_per_step": BATCH * FRAMES * FEAT_DIM * 4 + (BATCH + 1) * 4, "d2h_bytes_per_step": BATCH * ex.embed_dim * 4},
             "gpu_launches": int(launches_per_step) * args.steps,
-            "roofline": {"bound": "tensor", "kernel": "conv_umma_kernel (all tcgen05 conv launches of one step)", "achieved": achieved,
-                         "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"],
-                         "traffic": None, "peak_source": pk["source"] + " sustained (kernel timed inside a long step)",
+            "roofline": {"bound": "tensor", "kernel": "conv_flat_kernel + conv_umma_kernel (all tcgen05 conv launches of one step)",
+                         "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": achieved / pk["bf16_tflops_sustained"], "traffic": traffic,
+                         "peak_source": pk["source"] + " sustained (kernels timed inside a long step)",
                          "conv_ms_per_step": conv_ms_step, "conv_share_of_step": conv_ms_step / step_ms,
-                         "whole_step_tflops": BATCH * FLOPS_PER_UTT / (step_ms * 1e-3) / 1e12},
+                         "whole_step_tflops": BATCH * FLOPS_PER_UTT / (step_ms * 1e-3) / 1e12,
+                         "hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                 "frac": hbm_achieved / pk["hbm_gbs"], "algorithmic_bytes_per_step": BATCH * BYTES_PER_UTT,
+                                 "note": "layer-wise execution is HBM-bound (arithmetic intensity 106 FLOP/B < ridge ~210)"}},
             "cpu_baseline": cpu,
             "asnorm": score,
         }
