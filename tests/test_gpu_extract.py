@@ -61,14 +61,18 @@ CASES = [
 
 
 @pytest.mark.parametrize("model_id,feat_dim,lens", CASES)
-@pytest.mark.parametrize("path", ["umma", "simple"])
+@pytest.mark.parametrize("path", ["tensor", "tensor_2d_only", "simple"])
 def test_segments_match_oracle(model_id, feat_dim, lens, path):
+    """tensor: flat tcgen05 kernel (stride-1 convs) + 2-D tiled tcgen05 kernel (stride-2 convs); tensor_2d_only: the flat kernel
+    switched off, so every conv the 2-D tiled kernel can take runs there; simple: CUDA-core kernel everywhere."""
     cfg, params, ex = model(model_id, feat_dim)
     ex.set_option("force_simple", 1 if path == "simple" else 0)
+    ex.set_option("no_flat", 1 if path == "tensor_2d_only" else 0)
     rng = np.random.default_rng(1234)
     utts = [net_oracle.synth_feats(rng, 1, t, feat_dim)[0] for t in lens]
     got = run_segments(ex, utts)
     ex.set_option("force_simple", 0)
+    ex.set_option("no_flat", 0)
     want = oracle_segments(cfg, params, utts)
     assert np.isfinite(got).all()
     cos = cosines(got, want)
@@ -123,6 +127,19 @@ def test_extract_bucketed_order():
     a = ex.extract_bucketed(utts, max_frames=300)
     b = ex.extract(utts)
     np.testing.assert_allclose(a, b, atol=1e-5)
+
+
+def test_many_spans_per_cta():
+    """Enough pixels that every persistent CTA walks several spans (ring wrap-around, slot reuse, both TMEM buffers)."""
+    cfg, params, ex = model("res2net50_w24_s4_c32", 80)
+    rng = np.random.default_rng(21)
+    feats = net_oracle.synth_feats(rng, 40, 120, 80)
+    utts = [feats[i] for i in range(40)]
+    a = run_segments(ex, utts)
+    want = oracle_segments(cfg, params, utts[-3:])
+    assert cosines(a[-3:], want).min() >= COS_TOL
+    b = run_segments(ex, utts[-3:])
+    np.testing.assert_allclose(a[-3:], b, atol=1e-5)
 
 
 def test_full_size_properties():

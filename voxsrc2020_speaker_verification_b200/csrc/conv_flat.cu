@@ -325,6 +325,7 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
       for (int b = 0; b < p.boxes; ++b)
         if (n0 + b * p.box_ch < aux_hi) ++nb;
       const uint32_t buf_off = AUX == 2 ? static_cast<uint32_t>(p.boxes) * box_bytes : 0u;
+      Tracer tr; tr.init(p.trace, 2);
       int ls = 0;
       for (int span = my_group; span < n_spans; span += groups, ++ls) {
         const int p0 = span * span_px;
@@ -332,7 +333,9 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
           const uint32_t q = static_cast<uint32_t>(ls >> 1) * p.mt + j;      // sub-tile counter of the warpgroup that owns this span
           const int slot = (ls & 1) * p.slots + q % p.slots;
           S.prog[2] = (ls << 8) | j;
+          tr.ev(1);
           wait_dbg(&S.slot_empty[slot], ((q / p.slots) & 1) ^ 1, p.dbg, 0x21, slot, q, S.prog);
+          tr.ev(2);
           if (nb > 0) {
             mbar_expect_tx(&S.slot_full[slot], static_cast<uint32_t>(nb) * box_bytes);
             uint8_t* dst = slot_smem + static_cast<size_t>(slot) * p.slot_bytes + buf_off;
