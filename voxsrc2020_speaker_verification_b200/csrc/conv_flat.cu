@@ -21,6 +21,9 @@
 //            second output (x_{i+1} + o_i) -> swizzled smem boxes (in place over the aux tile)
 // The epilogue body is specialised at compile time on <aux mode, pre-ReLU, post-ReLU>; the previous generic
 // body cost ~35 SASS instructions per output value and bounded every 1x1 conv.
+#include <cstdlib>
+#include <cstring>
+
 #include "conv.cuh"
 #include "umma.cuh"
 
@@ -187,6 +190,13 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
     for (int b = 0; b < 2; ++b) { mbar_init(&S.tmem_full[b], 1); mbar_init(&S.tmem_empty[b], 4); }
     mbar_init(&S.bres_bar, 1);
     fence_barrier_init();
+    if (p.b_resident) {     // weights are static: fetch them before the dependency wait
+      const uint32_t bb = static_cast<uint32_t>(p.n_tile) * row_bytes;
+      mbar_expect_tx(&S.bres_bar, bb * total_items);
+      for (int kc = 0; kc < p.nkc; ++kc)
+        for (int tap = 0; tap < p.taps; ++tap)
+          tma_load_2d(b_smem + static_cast<size_t>(kc * p.taps + tap) * p.b_item_bytes, &maps.b, &S.bres_bar, tap * p.kpad + kc * p.kbox, n0);
+    }
   }
   if (warp == 1) { tmem_alloc(&S.tmem_slot, p.tmem_cols); tmem_relinquish(); }
   for (int i = threadIdx.x; i < p.n_tile; i += kFlatThreads) {
@@ -198,19 +208,17 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = S.tmem_slot;
+  // Programmatic dependent launch: the next conv's CTAs may be scheduled as soon as SMs free up and run their own prologue
+  // (barriers, TMEM, resident weights, scale/shift — all static data) under this grid's tail; everything that touches
+  // activations waits here for the previous grid to have completed.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0) {
     // ------------------------------------------------------------------ producer: A spans + weights
     if (lane == 0) {
       const uint32_t b_box_bytes = static_cast<uint32_t>(p.n_tile) * row_bytes;
       const uint32_t a_tx = static_cast<uint32_t>(p.a_boxes) * p.a_box_rows * row_bytes;
-      if (p.b_resident) {
-        mbar_expect_tx(&S.bres_bar, b_box_bytes * total_items);
-        for (int kc = 0; kc < p.nkc; ++kc)
-          for (int tap = 0; tap < p.taps; ++tap)
-            tma_load_2d(b_smem + static_cast<size_t>(kc * p.taps + tap) * p.b_item_bytes, &maps.b, &S.bres_bar,
-                        tap * p.kpad + kc * p.kbox, n0);
-      }
       Tracer tr; tr.init(p.trace, 0);
       uint32_t ia = 0, ib = 0;
       for (int span = my_group; span < n_spans; span += groups) {
@@ -505,7 +513,16 @@ cudaError_t conv_flat_init() {
 
 template <typename T>
 static cudaError_t launch_typed(const FlatConvParams& p, const FlatMaps& maps, dim3 grid, size_t smem, cudaStream_t st) {
-#define SVX_FLAT(AUX, PRE, POST) conv_flat_kernel<T, AUX, PRE, POST><<<grid, kFlatThreads, smem, st>>>(p, maps)
+  static const bool no_pdl = getenv("SVX_NO_PDL") != nullptr;   // debug switch
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = grid; cfg.blockDim = dim3(kFlatThreads, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
+  cudaError_t le = cudaSuccess;
+#define SVX_FLAT(AUX, PRE, POST) le = cudaLaunchKernelEx(&cfg, conv_flat_kernel<T, AUX, PRE, POST>, p, maps)
   if (p.aux_mode == 0) {
     if (p.pre_relu && !p.post_relu) SVX_FLAT(0, true, false);
     else if (!p.pre_relu && p.post_relu) SVX_FLAT(0, false, true);
@@ -519,6 +536,7 @@ static cudaError_t launch_typed(const FlatConvParams& p, const FlatMaps& maps, d
     SVX_FLAT(2, false, true);
   }
 #undef SVX_FLAT
+  if (le != cudaSuccess) return le;
   return cudaGetLastError();
 }
 

@@ -779,7 +779,11 @@ int Model::plan_flat(ConvDesc& c) {
           long long left = budget - (b_res ? b_total : 2LL * b_item) - 2LL * a_stage - 2LL * slots * slot_bytes;
           if (left < 0) { slots = 1; left += 2LL * slot_bytes; }
           if (left < 0) continue;
-          if (slots == 1 && b_res && taps == 1 && mt > 1) continue;            // a 1x1 with resident weights gains less from mt than from a 2nd slot
+          {   // a 1x1 with resident weights gains more from a 2nd slot per warpgroup than from mt > 1 — when mt = 1 gets that slot
+            const uint32_t a1 = static_cast<uint32_t>(round_up(128 * static_cast<int>(row_bytes), 1024));
+            const bool mt1_two_slots = budget - b_total - 2LL * a1 - 4LL * slot_bytes >= 0;
+            if (slots == 1 && b_res && taps == 1 && mt > 1 && mt1_two_slots) continue;
+          }
           // ---- cost per 128 output pixels (cycles)
           const double halo_ovh = 1.0 + 2.0 * halo / (mt * 128.0);
           const double a_rows = static_cast<double>(n_tiles) * c.nkc * 128.0 * halo_ovh;
