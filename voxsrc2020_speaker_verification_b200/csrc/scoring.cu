@@ -1,5 +1,7 @@
 // Scoring kernels (reference tensorflow/snorm.py): L2 normalisation, split-bf16 operand preparation for the
 // cohort GEMM, exact per-row top-k mean/std, trial gather + adaptive symmetric normalisation, cohort means.
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace svx {
@@ -238,9 +240,175 @@ __global__ void __launch_bounds__(kTopkThreads) topk_stats_kernel(const float* s
   }
 }
 
+// Register-resident form of the same algorithm for c <= 24*256 (the VoxCeleb2 cohort has 5994 speakers): every thread keeps
+// its 24 scores and their bucket ids in registers, so the row is read once (coalesced) and the select / reduce passes touch
+// no memory.  The generic kernel above spends ~3000 instructions per thread re-reading shared memory and recomputing buckets;
+// this one ~800 (profiles/r01_score_launches.txt).  Same exact-selection logic: 2048 monotone buckets, 8-bit radix select
+// inside the bucket of the k-th largest, ties counted.
+constexpr int kVPT = 24;
+
+__global__ void __launch_bounds__(kTopkThreads, 3) topk_stats_reg_kernel(const float* __restrict__ scores, int ld, int c, int topk,
+                                                                      float* mean_out, float* std_out, float* vals_out, int vals_ld) {
+  __shared__ int hist[kBuckets];
+  __shared__ float red[32];
+  __shared__ int ired[kTopkThreads / 32];
+  __shared__ int sh_bstar, sh_r;
+  __shared__ uint32_t sh_prefix;
+  __shared__ int sh_krem;
+  __shared__ int sh_emit;
+  const long long row = blockIdx.x;
+  const float* src = scores + row * ld;
+  const int tid = threadIdx.x;
+  const int k = min(topk, c);
+
+  float v[kVPT];
+  float vmin = INFINITY, vmax = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < kVPT; ++j) {
+    const int i = tid + j * kTopkThreads;
+    v[j] = i < c ? src[i] : -INFINITY;                 // -inf: never selected, never the minimum of real values' range below
+    if (i < c) { vmin = fminf(vmin, v[j]); vmax = fmaxf(vmax, v[j]); }
+  }
+  for (int i = tid; i < kBuckets; i += kTopkThreads) hist[i] = 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+    vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+  }
+  if ((tid & 31) == 0) { red[tid >> 5] = vmin; red[8 + (tid >> 5)] = vmax; }
+  __syncthreads();
+  vmin = red[0]; vmax = red[8];
+#pragma unroll
+  for (int w = 1; w < kTopkThreads / 32; ++w) { vmin = fminf(vmin, red[w]); vmax = fmaxf(vmax, red[8 + w]); }
+  const float bscale = vmax > vmin ? (static_cast<float>(kBuckets) - 0.5f) / (vmax - vmin) : 0.f;
+
+  uint32_t bk[kVPT / 2];                               // bucket ids, two per register; 0xffff = padding element
+#pragma unroll
+  for (int j = 0; j < kVPT; ++j) {
+    const int i = tid + j * kTopkThreads;
+    uint32_t b = 0xffffu;
+    if (i < c) {
+      b = static_cast<uint32_t>(min(kBuckets - 1, static_cast<int>((v[j] - vmin) * bscale)));
+      atomicAdd(&hist[b], 1);
+    }
+    if (j & 1) bk[j >> 1] |= b << 16; else bk[j >> 1] = b;
+  }
+  __syncthreads();
+  {   // suffix scan over buckets, highest first: thread t owns buckets [hi-7, hi], hi = kBuckets-1-8t
+    const int hi = kBuckets - 1 - 8 * tid;
+    int part = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) part += hist[hi - j];
+    int inc = part;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if ((tid & 31) >= o) inc += t; }
+    if ((tid & 31) == 31) ired[tid >> 5] = inc;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < (tid >> 5); ++w) woff += ired[w];
+    inc += woff;
+    const int exc = inc - part;
+    if (exc < k && inc >= k) {
+      int cum = exc;
+      for (int j = 0; j < 8; ++j) {
+        const int h = hist[hi - j];
+        if (cum + h >= k) { sh_bstar = hi - j; sh_r = k - cum; break; }
+        cum += h;
+      }
+    }
+    __syncthreads();
+  }
+  const uint32_t bstar = static_cast<uint32_t>(sh_bstar);
+  // which of this thread's values sit in the bucket of the k-th largest (usually none)
+  uint32_t in_star = 0;
+#pragma unroll
+  for (int j = 0; j < kVPT; ++j) {
+    const uint32_t b = (j & 1) ? (bk[j >> 1] >> 16) : (bk[j >> 1] & 0xffffu);
+    if (b == bstar) in_star |= 1u << j;
+  }
+  if (tid == 0) { sh_prefix = 0u; sh_krem = sh_r; }
+  uint32_t mask = 0u;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    __syncthreads();
+    hist[tid] = 0;                                     // 256 digits, 256 threads
+    __syncthreads();
+    const uint32_t prefix = sh_prefix;
+    if (in_star) {
+#pragma unroll
+      for (int j = 0; j < kVPT; ++j)
+        if ((in_star >> j) & 1u) {
+          const uint32_t key = f2key(v[j]);
+          if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xFF], 1);
+        }
+    }
+    __syncthreads();
+    if (tid < 32) {
+      const int hi = 255 - 8 * tid;
+      int part = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) part += hist[hi - j];
+      int inc = part;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (tid >= o) inc += t; }
+      const int exc = inc - part;
+      const int krem = sh_krem;
+      if (exc < krem && inc >= krem) {
+        int cum = exc;
+        for (int j = 0; j < 8; ++j) {
+          const int h = hist[hi - j];
+          if (cum + h >= krem) {
+            sh_prefix = prefix | (static_cast<uint32_t>(hi - j) << shift);
+            sh_krem = krem - cum;
+            break;
+          }
+          cum += h;
+        }
+      }
+    }
+    mask |= 0xFFu << shift;
+  }
+  __syncthreads();
+  const uint32_t tkey = sh_prefix;
+  const float tval = key2f(tkey);
+  const float ties = static_cast<float>(sh_krem);
+  // selected = strictly above the threshold key (buckets are monotone in the value, so this equals the bucket test of the
+  // generic kernel); the threshold value itself contributes `ties` copies
+  if (vals_out) {
+    if (tid == 0) sh_emit = 0;
+    __syncthreads();
+    float* vo = vals_out + row * vals_ld;
+#pragma unroll
+    for (int j = 0; j < kVPT; ++j)
+      if (tid + j * kTopkThreads < c && f2key(v[j]) > tkey) vo[atomicAdd(&sh_emit, 1)] = v[j];
+    __syncthreads();
+    const int base = sh_emit;
+    for (int i = base + tid; i < topk; i += kTopkThreads) vo[i] = (i < k) ? tval : kPadValue;
+  }
+  float ssum = 0.f;
+#pragma unroll
+  for (int j = 0; j < kVPT; ++j)
+    if (tid + j * kTopkThreads < c && f2key(v[j]) > tkey) ssum += v[j];
+  const float total = block_sum(ssum, red) + ties * tval;
+  const float mean = total / static_cast<float>(k);
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < kVPT; ++j)
+    if (tid + j * kTopkThreads < c && f2key(v[j]) > tkey) { const float d = v[j] - mean; q += d * d; }
+  const float ss = block_sum(q, red) + ties * (tval - mean) * (tval - mean);
+  if (tid == 0 && mean_out) {
+    mean_out[row] = mean;
+    std_out[row] = sqrtf(ss / static_cast<float>(k));
+  }
+}
+
 cudaError_t launch_topk_stats(const float* scores, int ld, long long n_rows, int c, int topk, float* mean, float* stdv,
                               float* vals_out, int vals_ld, cudaStream_t st) {
   if (n_rows <= 0) return cudaSuccess;
+  static const bool no_reg = getenv("SVX_TOPK_GENERIC") != nullptr;   // debug switch
+  if (c <= kVPT * kTopkThreads && !no_reg) {
+    topk_stats_reg_kernel<<<static_cast<unsigned>(n_rows), kTopkThreads, 0, st>>>(scores, ld, c, topk, mean, stdv, vals_out, vals_ld);
+    return cudaGetLastError();
+  }
   const size_t smem = static_cast<size_t>(c) * sizeof(float);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
