@@ -50,6 +50,9 @@ typedef struct svx_model_config {
   int32_t cardinality;
   int32_t k_sec[4];
   int32_t inc_sec[4];
+  /* attentive statistics pooling (tensorflow/models/models.py:273-303; res2net_model.py:264-280): 0 = plain stats_pool */
+  int32_t att_pool;
+  int32_t att_dim; /* 128 in the reference */
 } svx_model_config;
 
 typedef struct svx_extractor svx_extractor;

@@ -115,6 +115,25 @@ def stats_pool(x):
     return torch.cat([mean, torch.sqrt(var + POOL_EPS)], dim=1)
 
 
+def att_stats_pool(ctx, x, att_dim):
+    """reference models.py:273-303 — attentive statistics pooling (att_with_mean_std=True): per (w, c) a softmax over time
+    of conv1x1(tanh(conv1x1(concat(x, tiled mean, tiled std)))) weights the mean and the second moment."""
+    scope = ctx.root.next("att_stats_pool")
+    inner = arch._Namer(scope + "/")
+    c = x.shape[1]
+    mean = x.mean(dim=2, keepdim=True)
+    var = x.var(dim=2, unbiased=False, keepdim=True)
+    mean_std = torch.cat([mean, torch.sqrt(var + POOL_EPS)], dim=1).expand(-1, -1, x.shape[2], -1)   # tf.tile over time
+    att_in = torch.cat([x, mean_std], dim=1)
+    h = torch.tanh(conv2d(ctx, inner, att_in, att_dim, 1))
+    logits = conv2d(ctx, inner, h, c, 1)
+    w = torch.softmax(logits, dim=2)
+    wmean = (x * w).sum(dim=2, keepdim=True)
+    wss = (x * x * w).sum(dim=2, keepdim=True)
+    wstd = torch.sqrt(wss - wmean * wmean + POOL_EPS)
+    return torch.cat([wmean, wstd], dim=1)
+
+
 def flatten_nhwc(x):
     """tf.layers.flatten of [N,1,W,2C] (NHWC): index = w*2C + k."""
     return x.permute(0, 2, 3, 1).reshape(x.shape[0], -1)
@@ -129,10 +148,11 @@ def _q(ctx, x):
     return ctx.quant(x) if ctx.quant is not None else x
 
 
-def _tail(ctx: _Ctx, x):
-    """stats_pool → flatten → BN → dense → BN (tdnn_model.py:142-153, res2net_model.py:229-243,
+def _tail(ctx: _Ctx, x, cfg=None):
+    """stats_pool (or att_stats_pool) → flatten → BN → dense → BN (tdnn_model.py:142-153, res2net_model.py:229-243,
     dpn_model.py:153-167)."""
-    x = flatten_nhwc(stats_pool(x))
+    pooled = att_stats_pool(ctx, x, cfg.att_dim) if (cfg is not None and cfg.att_pool) else stats_pool(x)
+    x = flatten_nhwc(pooled)
     x = batch_norm(ctx, ctx.root, x)
     x = dense(ctx, x)
     x = batch_norm(ctx, ctx.root, x)
@@ -195,7 +215,7 @@ def res2net_forward(ctx: _Ctx, cfg: ModelConfig, x):
         for b in range(nblocks):
             x = bottleneck_block_v1(ctx, x, cfg.num_filters[li], b == 0,
                                     cfg.block_strides[li] if b == 0 else 1, cfg.split, cfg.width[li])
-    return _tail(ctx, x)
+    return _tail(ctx, x, cfg)
 
 
 # ---------------------------------------------------------------- DPN

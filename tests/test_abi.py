@@ -34,8 +34,8 @@ def test_every_declared_symbol_is_exported_and_bound(built):
 
 
 def test_config_struct_matches_header(built):
-    # 3 + 1 + 24 + 4 + 4 + 1 + 4 + 4 + 4 + 4 + 4 int32 fields
-    assert ctypes.sizeof(built.ModelConfigStruct) == 4 * (3 + 1 + 24 + 4 + 4 + 1 + 4 + 4 + 4 + 4 + 4)
+    # 3 + 1 + 24 + 4 + 4 + 1 + 4 + 4 + 4 + 4 + 4 + 2 int32 fields (the last two: att_pool, att_dim)
+    assert ctypes.sizeof(built.ModelConfigStruct) == 4 * (3 + 1 + 24 + 4 + 4 + 1 + 4 + 4 + 4 + 4 + 4 + 2)
 
 
 def test_no_cpu_fallback(built):

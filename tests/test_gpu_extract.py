@@ -55,6 +55,7 @@ CASES = [
     ("res2net50_w24_s4_c32", 40, [64, 33]),
     ("res2net50_w8_s6_c16", 80, [40, 121]),
     ("res2net50_w24_s4_c64", 40, [48]),
+    ("res2net50_w8_s6_c16_att", 40, [48, 75, 25]),      # attentive statistics pooling (models.py:273-303)
     ("dpn68", 80, [64, 57, 25, 26, 200]),
     ("dpn68", 40, [50, 31]),
 ]

@@ -140,3 +140,43 @@ def test_batch_equals_single_and_extract_utterance():
     np.testing.assert_allclose(e, (a * 1000 + b * 30) / 1030, atol=1e-5)
     with pytest.raises(ZeroDivisionError):
         no.extract_utterance(cfg, params, long[:24])
+
+
+def test_att_stats_pool_matches_naive_loops():
+    """reference models.py:273-303 restated with explicit loops: concat(x, tiled mean, tiled std) -> 1x1 -> tanh -> 1x1 ->
+    softmax over time -> weighted mean / sqrt(weighted second moment - mean^2 + eps)."""
+    import torch
+    from oracle import net_oracle
+    rng = np.random.default_rng(5)
+    n, c, h, w, a = 2, 6, 7, 3, 4
+    x = rng.standard_normal((n, h, w, c)).astype(np.float32)            # NHWC like the reference
+    k1 = rng.standard_normal((1, 1, 3 * c, a)).astype(np.float32)
+    k2 = rng.standard_normal((1, 1, a, c)).astype(np.float32)
+    ctx = net_oracle._Ctx({"att_stats_pool/conv2d/kernel": k1, "att_stats_pool/conv2d_1/kernel": k2})
+    got = net_oracle.att_stats_pool(ctx, torch.from_numpy(x).permute(0, 3, 1, 2), a).permute(0, 2, 3, 1).numpy()   # [n,1,w,2c]
+    want = np.zeros((n, 1, w, 2 * c), np.float64)
+    for i in range(n):
+        for j in range(w):
+            xs = x[i, :, j, :].astype(np.float64)                       # [h, c]
+            mean, std = xs.mean(0), np.sqrt(xs.var(0) + 1e-5)
+            logits = np.zeros((h, c))
+            for t in range(h):
+                att_in = np.concatenate([xs[t], mean, std])
+                logits[t] = np.tanh(att_in @ k1[0, 0].astype(np.float64)) @ k2[0, 0].astype(np.float64)
+            wts = np.exp(logits - logits.max(0))
+            wts /= wts.sum(0)
+            wm = (xs * wts).sum(0)
+            wss = (xs * xs * wts).sum(0)
+            want[i, 0, j, :c] = wm
+            want[i, 0, j, c:] = np.sqrt(wss - wm * wm + 1e-5)
+    np.testing.assert_allclose(got, want, rtol=2e-4, atol=2e-5)
+
+
+def test_att_models_enumerate_attention_kernels():
+    from voxsrc2020_speaker_verification_b200 import arch
+    cfg = arch.get_config("res2net200_w24_s4_c32_att")
+    shapes = arch.enumerate_variables(cfg, 80).shapes()
+    assert shapes["att_stats_pool/conv2d/kernel"] == (1, 1, 3 * 1024, 128)
+    assert shapes["att_stats_pool/conv2d_1/kernel"] == (1, 1, 128, 1024)
+    names = arch.enumerate_variables(cfg, 80).names()
+    assert names.index("att_stats_pool/conv2d_1/kernel") < names.index("dense/kernel")

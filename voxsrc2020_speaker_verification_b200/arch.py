@@ -10,6 +10,7 @@ module-level instances as plain data:
   * ``res2net50_w8_s6_c16``        reference tensorflow/models/res2net_model.py:258-262
   * ``res2net200_w8_s6_c16``       composed: depth-200 block sizes (res2net_model.py:278) with the
                                    w8_s6_c16 widths (res2net_model.py:258-262); named in README.md:47
+  * ``res2net{101,152,200}_w24_s4_c32_att``  reference tensorflow/models/res2net_model.py:264-280 (attentive statistics pooling)
   * ``dpn68``                      reference tensorflow/models/dpn_model.py:171
 
 and enumerates, in TF1 creation order, the variables a frozen ``.pb`` of each model holds
@@ -55,6 +56,9 @@ class ModelConfig:
     cardinality: int = 0
     k_sec: Tuple[int, ...] = ()
     inc_sec: Tuple[int, ...] = ()
+    # attentive statistics pooling instead of plain statistics pooling (models.py:273-303, res2net_model.py:264-280)
+    att_pool: bool = False
+    att_dim: int = 128
 
 
 MODELS: Dict[str, ModelConfig] = {
@@ -74,6 +78,19 @@ MODELS: Dict[str, ModelConfig] = {
     "res2net200_w8_s6_c16": ModelConfig("res2net200_w8_s6_c16", FAMILY_RES2NET, 3, 192,
                                         num_filters=(16, 32, 64, 128), width=(8, 16, 32, 64), split=6,
                                         block_sizes=(3, 24, 36, 3), block_strides=(1, 2, 2, 2)),
+    "res2net101_w24_s4_c32_att": ModelConfig("res2net101_w24_s4_c32_att", FAMILY_RES2NET, 3, 256,
+                                             num_filters=(32, 64, 128, 256), width=(24, 48, 96, 192), split=4,
+                                             block_sizes=(3, 4, 23, 3), block_strides=(1, 2, 2, 2), att_pool=True),
+    "res2net152_w24_s4_c32_att": ModelConfig("res2net152_w24_s4_c32_att", FAMILY_RES2NET, 3, 256,
+                                             num_filters=(32, 64, 128, 256), width=(24, 48, 96, 192), split=4,
+                                             block_sizes=(3, 8, 36, 3), block_strides=(1, 2, 2, 2), att_pool=True),
+    "res2net200_w24_s4_c32_att": ModelConfig("res2net200_w24_s4_c32_att", FAMILY_RES2NET, 3, 256,
+                                             num_filters=(32, 64, 128, 256), width=(24, 48, 96, 192), split=4,
+                                             block_sizes=(3, 24, 36, 3), block_strides=(1, 2, 2, 2), att_pool=True),
+    # small attentive model for tests (not in the reference): res2net50_w8_s6_c16 with att_stats_pool
+    "res2net50_w8_s6_c16_att": ModelConfig("res2net50_w8_s6_c16_att", FAMILY_RES2NET, 3, 192,
+                                           num_filters=(16, 32, 64, 128), width=(8, 16, 32, 64), split=6,
+                                           block_sizes=(3, 4, 6, 3), block_strides=(1, 2, 2, 2), att_pool=True),
     "dpn68": ModelConfig("dpn68", FAMILY_DPN, 3, 256,
                          init_features=10, bw=64, k_r=128, cardinality=32,
                          k_sec=(3, 4, 12, 3), inc_sec=(16, 32, 32, 64)),
@@ -205,6 +222,11 @@ def enumerate_variables(cfg: ModelConfig, feat_dim: int) -> GraphVars:
                 _conv(gv, root, 1, 1, s * w, cout)            # res2net_model.py:98
                 _bn(gv, root, cout)                           # res2net_model.py:99
                 cin = cout
+        if cfg.att_pool:                                      # models.py:273-303: scope att_stats_pool, two bias-free 1x1 convs
+            ascope = root.next("att_stats_pool")
+            ainner = _Namer(ascope + "/")
+            _conv(gv, ainner, 1, 1, 3 * cin, cfg.att_dim)     # on concat(inputs, tiled mean, tiled std)
+            _conv(gv, ainner, 1, 1, cfg.att_dim, cin)
     elif cfg.family == FAMILY_DPN:
         _conv(gv, root, 3, 3, 1, cfg.init_features)           # dpn_model.py:33-34
         _bn(gv, root, cfg.init_features)                      # dpn_model.py:35

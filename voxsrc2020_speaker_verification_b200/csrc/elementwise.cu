@@ -317,6 +317,114 @@ cudaError_t launch_stats_pool(const void* in, int C_tot, int C, int W, int Wp, c
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Attentive statistics pooling (models.py:273-303).  The first 1x1 conv acts on concat(x, tiled mean, tiled std); its
+// mean/std part is constant over time, so it is a per-(segment, w) bias:  bias[seg, w, a] = sum_k pooled[seg, w, k] * Wms[k, a]
+// (pooled = plain statistics [mean | std], Wms = kernel rows C..3C).  One thread per output, fp32.
+__global__ void __launch_bounds__(128) att_bias_kernel(const float* __restrict__ pooled, const float* __restrict__ Wms, float* bias,
+                                                       int n_sw, int C2, int A) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  const int sw = blockIdx.y;
+  if (a >= A || sw >= n_sw) return;
+  const float* p = pooled + static_cast<size_t>(sw) * C2;
+  float acc = 0.f;
+  for (int k = 0; k < C2; ++k) acc += p[k] * Wms[static_cast<size_t>(k) * A + a];
+  bias[static_cast<size_t>(sw) * A + a] = acc;
+}
+
+cudaError_t launch_att_bias(const float* pooled, const float* Wms, float* bias, int n_seg, int W, int C2, int A, cudaStream_t st) {
+  if (n_seg <= 0) return cudaSuccess;
+  dim3 grid((A + 127) / 128, n_seg * W);
+  att_bias_kernel<<<grid, 128, 0, st>>>(pooled, Wms, bias, n_seg * W, C2, A);
+  return cudaGetLastError();
+}
+
+// t = tanh(t + bias[seg(row), col]) in place on the [pixels, A] pre-activations of the first attention conv; 0 outside segments.
+template <typename T>
+__global__ void __launch_bounds__(256) att_tanh_kernel(T* t, int A, long long n_pix, int Wp, int W, const int32_t* seg_of_row,
+                                                       const float* __restrict__ bias) {
+  const int groups = A >> 3;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= n_pix * groups) return;
+  const int g = static_cast<int>(idx % groups);
+  const long long pix = idx / groups;
+  const int row = static_cast<int>(pix / Wp), col = static_cast<int>(pix - static_cast<long long>(row) * Wp);
+  const int seg = seg_of_row[row];
+  uint4* ptr = reinterpret_cast<uint4*>(t + pix * A + g * 8);
+  uint4 o = make_uint4(0, 0, 0, 0);
+  if (seg >= 0 && col < W) {
+    const uint4 x = *ptr;
+    const float* b = bias + (static_cast<size_t>(seg) * W + col) * A + g * 8;
+    const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+    uint32_t os[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 f = TypeOps<T>::unpack2(xs[j]);
+      os[j] = TypeOps<T>::pack2(tanhf(f.x + b[2 * j]), tanhf(f.y + b[2 * j + 1]));
+    }
+    o = make_uint4(os[0], os[1], os[2], os[3]);
+  }
+  *ptr = o;
+}
+
+cudaError_t launch_att_tanh(void* t, int A, long long n_pix, int Wp, int W, const int32_t* seg_of_row, const float* bias, int is_bf16,
+                            cudaStream_t st) {
+  const long long total = n_pix * (A / 8);
+  if (total <= 0) return cudaSuccess;
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  if (is_bf16) att_tanh_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<__nv_bfloat16*>(t), A, n_pix, Wp, W, seg_of_row, bias);
+  else att_tanh_kernel<__half><<<blocks, 256, 0, st>>>(static_cast<__half*>(t), A, n_pix, Wp, W, seg_of_row, bias);
+  return cudaGetLastError();
+}
+
+// Softmax over time of the attention logits per (segment, w, c), then weighted mean and sqrt(weighted second moment - mean^2 + eps)
+// (models.py:298-303).  Same thread mapping and output layout as stats_pool_kernel (index w*2C + {c | C + c}).
+template <typename T>
+__global__ void __launch_bounds__(256) att_pool_kernel(const T* x, const T* logits, int C, int W, int Wp, const int32_t* seg_row_off,
+                                                       const int32_t* seg_h, float* out, float eps) {
+  const int seg = blockIdx.y;
+  const int half_c = C >> 1;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= W * half_c) return;
+  const int w = idx / half_c;
+  const int c = (idx - w * half_c) * 2;
+  const int r0 = seg_row_off[seg];
+  const int H = seg_h[seg];
+  const size_t base = (static_cast<size_t>(r0) * Wp + w) * C + c;
+  const size_t rstride = static_cast<size_t>(Wp) * C;
+  float m0 = -INFINITY, m1 = -INFINITY;
+  for (int h = 0; h < H; ++h) {
+    const float2 l = TypeOps<T>::unpack2(*reinterpret_cast<const uint32_t*>(logits + base + h * rstride));
+    m0 = fmaxf(m0, l.x); m1 = fmaxf(m1, l.y);
+  }
+  float s0 = 0.f, s1 = 0.f, a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
+  for (int h = 0; h < H; ++h) {
+    const float2 l = TypeOps<T>::unpack2(*reinterpret_cast<const uint32_t*>(logits + base + h * rstride));
+    const float2 v = TypeOps<T>::unpack2(*reinterpret_cast<const uint32_t*>(x + base + h * rstride));
+    const float e0 = __expf(l.x - m0), e1 = __expf(l.y - m1);
+    s0 += e0; s1 += e1;
+    a0 += v.x * e0; a1 += v.y * e1;
+    q0 += v.x * v.x * e0; q1 += v.y * v.y * e1;
+  }
+  const float wm0 = a0 / s0, wm1 = a1 / s1;
+  float* o = out + static_cast<size_t>(seg) * W * 2 * C + static_cast<size_t>(w) * 2 * C;
+  *reinterpret_cast<float2*>(o + c) = make_float2(wm0, wm1);
+  *reinterpret_cast<float2*>(o + C + c) = make_float2(sqrtf(q0 / s0 - wm0 * wm0 + eps), sqrtf(q1 / s1 - wm1 * wm1 + eps));
+}
+
+cudaError_t launch_att_pool(const void* x, const void* logits, int C, int W, int Wp, const int32_t* seg_row_off, const int32_t* seg_h,
+                            int n_seg, float* out, float eps, int is_bf16, cudaStream_t st) {
+  if (n_seg <= 0) return cudaSuccess;
+  dim3 grid((W * (C / 2) + 255) / 256, n_seg);
+  if (is_bf16)
+    att_pool_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(logits), C, W, Wp,
+                                                          seg_row_off, seg_h, out, eps);
+  else
+    att_pool_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(x), static_cast<const __half*>(logits), C, W, Wp, seg_row_off,
+                                                   seg_h, out, eps);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Embedding FC with both 2-D batch norms folded in (BN → dense → BN, res2net_model.py:240-242):
 //   out[n, e] = bias[e] + sum_d pooled[n, d] * Wf[d, e]       Wf = diag(s1) W diag(s2), fp32.
 // Split-K: grid = (E/128, n-tiles of 8, K-splits); each thread owns one output column for 8 segments and

@@ -19,6 +19,12 @@ cudaError_t launch_avgpool3x3s2(const void* in, int in_C, int in_coff, int in_ro
                                 int out_rows, int out_W, int out_Wp, int C, const int32_t* out_seg_of_row, int is_bf16, cudaStream_t st);
 cudaError_t launch_stats_pool(const void* in, int C_tot, int C, int W, int Wp, const int32_t* seg_row_off, const int32_t* seg_h, int n_seg,
                               const float* scale, const float* shift, float* out, float eps, int is_bf16, cudaStream_t st);
+// attentive statistics pooling (models.py:273-303)
+cudaError_t launch_att_bias(const float* pooled, const float* Wms, float* bias, int n_seg, int W, int C2, int A, cudaStream_t st);
+cudaError_t launch_att_tanh(void* t, int A, long long n_pix, int Wp, int W, const int32_t* seg_of_row, const float* bias, int is_bf16,
+                            cudaStream_t st);
+cudaError_t launch_att_pool(const void* x, const void* logits, int C, int W, int Wp, const int32_t* seg_row_off, const int32_t* seg_h,
+                            int n_seg, float* out, float eps, int is_bf16, cudaStream_t st);
 int fc_splits(int D);
 cudaError_t launch_fc(const float* pooled, const float* Wf, const float* bias, float* partial, float* out, int n, int D, int E,
                       cudaStream_t st);

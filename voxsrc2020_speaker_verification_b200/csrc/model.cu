@@ -90,6 +90,7 @@ Model::~Model() {
   for (auto p : d_seg_of_row_) cudaFree(p);
   for (auto p : d_pix_valid_) cudaFree(p);
   cudaFree(d_seg_frame_off_); cudaFree(d_seg_len_); cudaFree(d_utt_seg_off_);
+  cudaFree(d_att_bias_);
   cudaFree(d_pooled_); cudaFree(d_fc_partial_); cudaFree(d_seg_emb_); cudaFree(d_feats_); cudaFree(d_out_);
   if (h_stage_) cudaFreeHost(h_stage_);
   for (auto e : events_) cudaEventDestroy(e);
@@ -247,6 +248,16 @@ void Model::build_res2net() {
     }
   }
   pool_tensor_ = cur; pool_C_ = cin; flat_dim_ = stage_W_.back() * 2 * cin;
+  if (cfg_.att_pool) {   // att_stats_pool scope with two bias-free 1x1 convs (models.py:273-303)
+    const int A = cfg_.att_dim > 0 ? cfg_.att_dim : 128;
+    const std::string ascope = next_name(root, "", "att_stats_pool");
+    has_att_ = true;
+    const int t1 = new_tensor(stage, A), t2 = new_tensor(stage, cin);
+    att_a_.kernel_name = ascope + "/conv2d/kernel"; add_var(att_a_.kernel_name, {1, 1, 3 * cin, A});
+    att_a_.in = {cur, 0}; att_a_.cin = cin; att_a_.cout = A; att_a_.out = {t1, 0};      // x part of concat(x, mean, std); the rest is a bias
+    att_b_.kernel_name = ascope + "/conv2d_1/kernel"; add_var(att_b_.kernel_name, {1, 1, A, cin});
+    att_b_.in = {t1, 0}; att_b_.cin = A; att_b_.cout = cin; att_b_.out = {t2, 0};
+  }
   tail_bn1_ = next_name(root, "", "batch_normalization");
   add_var(tail_bn1_ + "/moving_mean", {flat_dim_}); add_var(tail_bn1_ + "/moving_variance", {flat_dim_});
   add_var("dense/kernel", {flat_dim_, cfg_.embed_dim});
@@ -513,6 +524,13 @@ int Model::finalize() {
       sc.resize(cp, 0.f); sh.resize(cp, 0.f);
       if (upload_floats(owned_, sc, &op.d_scale) || upload_floats(owned_, sh, &op.d_shift)) return 1;
     }
+  }
+  if (has_att_) {
+    if (upload_conv_weights(att_a_) || upload_conv_weights(att_b_)) return 1;
+    const HostTensor& k = host_[att_a_.kernel_name];   // [1,1,3C,A]: rows C..3C multiply the tiled [mean | std]
+    const int C = pool_C_, A = att_a_.cout;
+    std::vector<float> wms(k.data.begin() + static_cast<size_t>(C) * A, k.data.begin() + static_cast<size_t>(3 * C) * A);
+    if (upload_floats(owned_, wms, &d_att_wms_)) return 1;
   }
   if (!pool_bn_.empty()) {
     std::vector<float> sc, sh;
@@ -962,6 +980,7 @@ int Model::ensure_capacity(int rows0) {
   }
   for (Op& op : ops_)
     if (op.kind == OP_CONV && plan_conv(op.conv)) return 1;
+  if (has_att_ && (plan_conv(att_a_) || plan_conv(att_b_))) return 1;
   return 0;
 }
 
@@ -1247,6 +1266,20 @@ int Model::run_segments(const float* d_feats, const int32_t* h_frame_off, int n_
     const ActTensor& tp = tensors_[pool_tensor_];
     SVX_CUDA(launch_stats_pool(tp.ptr, tp.C, pool_C_, stage_W_[tp.stage], stage_Wp_[tp.stage], d_seg_row_off_[tp.stage], d_seg_h_[tp.stage], nb,
                                d_pool_scale_, d_pool_shift_, d_pooled_, kPoolEps, is_bf16_, st));
+    if (has_att_) {   // the statistics above feed the attention; the weighted statistics replace them (models.py:280-303)
+      const int A = att_a_.cout, Wl = stage_W_[tp.stage], Wpl = stage_Wp_[tp.stage];
+      if (grow(&d_att_bias_, &att_bias_bytes_, static_cast<size_t>(nb) * Wl * A * 4)) { set_last_error("allocation failed"); return 1; }
+      SVX_CUDA(launch_att_bias(d_pooled_, d_att_wms_, d_att_bias_, nb, Wl, 2 * pool_C_, A, st));
+      if (launch_conv(att_a_, st)) return 1;
+      const ActTensor& t1 = tensors_[att_a_.out.id];
+      SVX_CUDA(launch_att_tanh(t1.ptr, A, static_cast<long long>(rows_used_[tp.stage]) * Wpl, Wpl, Wl, d_seg_of_row_[tp.stage], d_att_bias_,
+                               is_bf16_, st));
+      if (launch_conv(att_b_, st)) return 1;
+      const ActTensor& t2 = tensors_[att_b_.out.id];
+      SVX_CUDA(launch_att_pool(tp.ptr, t2.ptr, pool_C_, Wl, Wpl, d_seg_row_off_[tp.stage], d_seg_h_[tp.stage], nb, d_pooled_, kPoolEps,
+                               is_bf16_, st));
+      launches_ += 3;
+    }
     SVX_CUDA(launch_fc(d_pooled_, d_Wf_, d_bias_, d_fc_partial_, d_out + static_cast<size_t>(i0) * cfg_.embed_dim, nb, flat_dim_,
                        cfg_.embed_dim, st));
     launches_ += 3;

@@ -133,6 +133,10 @@ class Model {
   int32_t* d_utt_seg_off_ = nullptr;
   int32_t* h_stage_ = nullptr;       // pinned staging for the tables
   size_t h_stage_bytes_ = 0;
+  // attentive statistics pooling (models.py:273-303): two 1x1 convs on the tensor-core path + three small kernels
+  bool has_att_ = false;
+  ConvDesc att_a_, att_b_;
+  float* d_att_wms_ = nullptr; float* d_att_bias_ = nullptr; size_t att_bias_bytes_ = 0;
   // tail
   int pool_tensor_ = -1, pool_C_ = 0, flat_dim_ = 0;
   std::string pool_bn_;

@@ -41,6 +41,7 @@ def _cfg_struct(cfg: arch.ModelConfig, feat_dim: int) -> lib.ModelConfigStruct:
         s.k_sec[i] = v
     for i, v in enumerate(cfg.inc_sec):
         s.inc_sec[i] = v
+    s.att_pool, s.att_dim = (1 if cfg.att_pool else 0), cfg.att_dim
     return s
 
 

@@ -25,6 +25,7 @@ class ModelConfigStruct(ctypes.Structure):
         ("block_strides", c_int32 * 4),
         ("init_features", c_int32), ("bw", c_int32), ("k_r", c_int32), ("cardinality", c_int32), ("k_sec", c_int32 * 4),
         ("inc_sec", c_int32 * 4),
+        ("att_pool", c_int32), ("att_dim", c_int32),
     ]
 
 
