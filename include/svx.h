@@ -91,6 +91,12 @@ long long svx_extractor_last_launches(svx_extractor* h);
  * launches of the last call, and their algorithmic FLOPs (2*MACs over valid pixels, no padding waste). */
 int svx_extractor_conv_time(svx_extractor* h, double* ms, double* flops);
 
+/* ---- front-end: replaces the Kaldi pipe `apply-cmvn-sliding --norm-vars=false --center=true --cmn-window=300 scp:... ark:- |`
+ * that tf_extract.py:63 reads its features through.  feats/out: device fp32 [total_frames, feat_dim] (may alias),
+ * frame_offsets_host: int32 [n_utts + 1].  Window mean in double precision, window shifted to stay inside the utterance. */
+int svx_cmvn_sliding(const float* feats_dev, float* out_dev, const int32_t* frame_offsets_host, int n_utts, int feat_dim,
+                     int cmn_window, int center, void* cuda_stream);
+
 /* ---- scoring: replaces the NumPy body of tensorflow/snorm.py.  All pointers are device pointers. */
 typedef struct svx_scorer svx_scorer;
 int svx_scorer_create(int device, svx_scorer** out);

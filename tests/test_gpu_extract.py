@@ -158,3 +158,23 @@ def test_full_size_properties():
     np.testing.assert_allclose(a[:7], c, atol=1e-5)
     want = oracle_segments(cfg, params, utts[:2])
     assert cosines(a[:2], want).min() >= COS_TOL
+
+
+def test_cmvn_sliding_on_device_matches_host_restatement():
+    """svx_cmvn_sliding vs the NumPy restatement of Kaldi's apply-cmvn-sliding (reference tf_extract.py:63 pipe),
+    windows shorter and longer than the utterance, then end to end through extract(cmvn=True)."""
+    from voxsrc2020_speaker_verification_b200 import kaldi_ark
+    cfg, params, ex = model("tdnn", 40)
+    rng = np.random.default_rng(17)
+    lens = [1, 25, 149, 300, 301, 777]
+    utts = [(rng.standard_normal((t, 40)) * 3 + rng.standard_normal(40)).astype(np.float32) for t in lens]
+    offs = np.zeros(len(utts) + 1, np.int32)
+    offs[1:] = np.cumsum(lens)
+    dev = torch.from_numpy(np.concatenate(utts, 0)).cuda()
+    ex.cmvn_sliding(dev, offs)
+    got = dev.cpu().numpy()
+    want = np.concatenate([kaldi_ark.apply_cmvn_sliding(u) for u in utts], 0)
+    np.testing.assert_allclose(got, want, rtol=0, atol=2e-6)
+    a = ex.extract(utts[1:], cmvn=True)
+    b = ex.extract([kaldi_ark.apply_cmvn_sliding(u) for u in utts[1:]])
+    np.testing.assert_allclose(a, b, atol=2e-4)

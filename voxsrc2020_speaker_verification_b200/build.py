@@ -10,7 +10,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libsvx.so")
-SOURCES = ["conv_flat.cu", "conv_umma.cu", "conv_simple.cu", "elementwise.cu", "scoring.cu", "model.cu", "api.cu"]
+SOURCES = ["conv_flat.cu", "conv_umma.cu", "conv_simple.cu", "elementwise.cu", "frontend.cu", "scoring.cu", "model.cu", "api.cu"]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
           "--expt-relaxed-constexpr", "-Xptxas", "-v"]

@@ -153,6 +153,28 @@ int svx_scorer_destroy(svx_scorer* h) {
   return 0;
 }
 
+int svx_cmvn_sliding(const float* feats_dev, float* out_dev, const int32_t* frame_offsets_host, int n_utts, int feat_dim, int cmn_window,
+                     int center, void* cuda_stream) {
+  if (!feats_dev || !out_dev || !frame_offsets_host) { set_last_error("null argument"); return 1; }
+  if (n_utts <= 0) return 0;
+  if (feat_dim <= 0 || feat_dim > 128 || cmn_window <= 0) { set_last_error("feat_dim must be in 1..128 and cmn_window positive"); return 1; }
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const long long total = frame_offsets_host[n_utts];
+  for (int i = 0; i < n_utts; ++i)
+    if (frame_offsets_host[i + 1] <= frame_offsets_host[i]) { set_last_error("empty utterance"); return 1; }
+  // workspaces live for this call only: offsets, frame→utterance map, double running sums (one extra row per utterance)
+  int32_t* d_off = nullptr; int32_t* d_utt = nullptr; double* d_csum = nullptr;
+  API_CUDA(cudaMallocAsync(&d_off, static_cast<size_t>(n_utts + 1) * 4, st));
+  API_CUDA(cudaMallocAsync(&d_utt, static_cast<size_t>(total) * 4, st));
+  API_CUDA(cudaMallocAsync(&d_csum, static_cast<size_t>(total + n_utts) * feat_dim * 8, st));
+  API_CUDA(cudaMemcpyAsync(d_off, frame_offsets_host, static_cast<size_t>(n_utts + 1) * 4, cudaMemcpyHostToDevice, st));
+  cudaError_t e = launch_cmn_sliding(feats_dev, out_dev, d_off, n_utts, total, feat_dim, cmn_window, center, d_csum, d_utt, st);
+  cudaFreeAsync(d_off, st); cudaFreeAsync(d_utt, st); cudaFreeAsync(d_csum, st);
+  API_CUDA(e);
+  API_CUDA(cudaStreamSynchronize(st));   // frame_offsets_host is the caller's buffer
+  return 0;
+}
+
 int svx_l2norm_rows(const float* in_dev, float* out_dev, int64_t n, int d, void* cuda_stream) {
   if (!in_dev || !out_dev) { set_last_error("null argument"); return 1; }
   API_CUDA(launch_l2norm_rows(in_dev, out_dev, n, d, static_cast<cudaStream_t>(cuda_stream)));

@@ -1,0 +1,72 @@
+// Feature front-end on the device: what the reference gets from the Kaldi pipe
+// `apply-cmvn-sliding --norm-vars=false --center=true --cmn-window=300` in front of the network (tf_extract.py:63).
+//
+// Sliding-window mean normalisation [ext: Kaldi SlidingWindowCmn]: frame t is centred on the mean of a window of up to
+// `cmn_window` frames around t, shifted to stay inside [0, T); sums in double precision like Kaldi.  Two kernels over the
+// packed [total_frames, F] matrix: per-utterance, per-bin running sums (one thread per bin walks the frames; consecutive
+// threads read consecutive bins, so every step is one coalesced row), then one thread per element subtracts the window mean.
+#include "kernels.cuh"
+
+namespace svx {
+
+__global__ void __launch_bounds__(128) cmn_prefix_kernel(const float* __restrict__ feats, const int32_t* __restrict__ frame_off, double* csum,
+                                                         int F) {
+  const int u = blockIdx.x;
+  const int f = threadIdx.x;
+  if (f >= F) return;
+  const int t0 = frame_off[u], t1 = frame_off[u + 1];
+  // csum has one extra row per utterance: rows [t0 + u, t1 + u + 1)
+  double* c = csum + (static_cast<size_t>(t0) + u) * F + f;
+  const float* x = feats + static_cast<size_t>(t0) * F + f;
+  double acc = 0.0;
+  c[0] = 0.0;
+  for (int t = 0; t < t1 - t0; ++t) {
+    acc += static_cast<double>(x[static_cast<size_t>(t) * F]);
+    c[static_cast<size_t>(t + 1) * F] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256) cmn_apply_kernel(const float* __restrict__ feats, const int32_t* __restrict__ frame_off,
+                                                        const int32_t* __restrict__ utt_of_frame, const double* __restrict__ csum, float* out,
+                                                        long long total, int F, int window, int center) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total * F) return;
+  const long long row = idx / F;
+  const int f = static_cast<int>(idx - row * F);
+  const int u = utt_of_frame[row];
+  const int t0 = frame_off[u], T = frame_off[u + 1] - t0;
+  const int t = static_cast<int>(row - t0);
+  int ws, we;
+  if (center) { ws = t - window / 2; we = ws + window; } else { ws = t - window; we = t + 1; }
+  if (ws < 0) { we -= ws; ws = 0; }
+  if (!center && we > t + 1) we = t + 1;
+  if (we > T) { ws -= we - T; we = T; if (ws < 0) ws = 0; }
+  const double* c = csum + (static_cast<size_t>(t0) + u) * F + f;
+  const double mean = (c[static_cast<size_t>(we) * F] - c[static_cast<size_t>(ws) * F]) / static_cast<double>(we - ws);
+  out[idx] = static_cast<float>(static_cast<double>(feats[idx]) - mean);
+}
+
+__global__ void utt_of_frame_kernel(int32_t* utt_of_frame, long long total, const int32_t* frame_off, int n_utts) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int lo = 0, hi = n_utts - 1, ans = 0;
+  while (lo <= hi) {
+    const int mid = (lo + hi) >> 1;
+    if (frame_off[mid] <= i) { ans = mid; lo = mid + 1; } else { hi = mid - 1; }
+  }
+  utt_of_frame[i] = ans;
+}
+
+cudaError_t launch_cmn_sliding(const float* feats, float* out, const int32_t* frame_off_dev, int n_utts, long long total_frames, int F,
+                               int window, int center, double* csum_ws, int32_t* utt_ws, cudaStream_t st) {
+  if (n_utts <= 0 || total_frames <= 0) return cudaSuccess;
+  if (F > 128) return cudaErrorInvalidValue;
+  utt_of_frame_kernel<<<static_cast<unsigned>((total_frames + 255) / 256), 256, 0, st>>>(utt_ws, total_frames, frame_off_dev, n_utts);
+  cmn_prefix_kernel<<<n_utts, 128, 0, st>>>(feats, frame_off_dev, csum_ws, F);
+  const long long n = total_frames * F;
+  cmn_apply_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(feats, frame_off_dev, utt_ws, csum_ws, out, total_frames, F, window,
+                                                                          center);
+  return cudaGetLastError();
+}
+
+}  // namespace svx

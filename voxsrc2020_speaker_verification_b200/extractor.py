@@ -116,8 +116,18 @@ class Extractor:
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def extract(self, utterances: Sequence[np.ndarray]) -> np.ndarray:
-        """Host → host: list of [T_i, F] float32 matrices → [n, E] float32 (chunk rule applied)."""
+    def cmvn_sliding(self, feats_dev: torch.Tensor, frame_offsets: np.ndarray, cmn_window: int = 300, center: bool = True) -> torch.Tensor:
+        """In place on a CUDA tensor [total, F]: what ``apply-cmvn-sliding --norm-vars=false --center=true --cmn-window=300``
+        does in front of the network (reference tf_extract.py:63)."""
+        frame_offsets = np.ascontiguousarray(frame_offsets, dtype=np.int32)
+        lib.check(self._lib.svx_cmvn_sliding(ctypes.c_void_p(feats_dev.data_ptr()), ctypes.c_void_p(feats_dev.data_ptr()),
+                                             frame_offsets.ctypes.data_as(ctypes.c_void_p), frame_offsets.shape[0] - 1, self.feat_dim,
+                                             int(cmn_window), int(center), ctypes.c_void_p(self._stream())))
+        return feats_dev
+
+    def extract(self, utterances: Sequence[np.ndarray], cmvn: bool = False) -> np.ndarray:
+        """Host → host: list of [T_i, F] float32 matrices → [n, E] float32 (chunk rule applied).  ``cmvn``: apply the
+        sliding-window mean normalisation on the device first (raw FBANK in, as read from the feature ark)."""
         n = len(utterances)
         if n == 0:
             return np.zeros((0, self.embed_dim), np.float32)
@@ -135,7 +145,12 @@ class Extractor:
         stage = self._pinned_in.numpy()[: total * self.feat_dim].reshape(total, self.feat_dim)
         for i, u in enumerate(utterances):
             stage[offs[i]:offs[i + 1]] = u
-        self.extract_packed(self._pinned_in, offs, self._pinned_out)
+        if cmvn:
+            dev = self._pinned_in[: total * self.feat_dim].to(torch.device("cuda", self.device), non_blocking=True).view(total, self.feat_dim)
+            self.cmvn_sliding(dev, offs)
+            self.extract_packed(dev, offs, self._pinned_out)
+        else:
+            self.extract_packed(self._pinned_in, offs, self._pinned_out)
         return self._pinned_out.numpy()[: n * self.embed_dim].reshape(n, self.embed_dim).copy()
 
     def extract_packed(self, feats: torch.Tensor, frame_offsets: np.ndarray, out: torch.Tensor) -> None:
@@ -158,7 +173,7 @@ class Extractor:
             ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(self._stream())))
         return out
 
-    def extract_bucketed(self, utterances: Sequence[np.ndarray], max_frames: int = 60000) -> np.ndarray:
+    def extract_bucketed(self, utterances: Sequence[np.ndarray], max_frames: int = 60000, cmvn: bool = False) -> np.ndarray:
         """Length-bucketed batches (sorted by frame count, ≤ max_frames per launch sequence), results
         returned in the caller's order."""
         order = np.argsort([u.shape[0] for u in utterances], kind="stable")
@@ -171,7 +186,7 @@ class Extractor:
                 frames += utterances[idx].shape[0]
                 continue
             if batch:
-                out[batch] = self.extract([utterances[i] for i in batch])
+                out[batch] = self.extract([utterances[i] for i in batch], cmvn=cmvn)
             batch, frames = ([int(idx)], utterances[idx].shape[0]) if idx is not None else ([], 0)
         return out
 

@@ -36,13 +36,13 @@ def run(pb_file: str, expand_dim: int, rspec: str, wspec: str, precision: str = 
             nonlocal keys, mats, frames, n_done
             if not keys:
                 return
-            emb = ex.extract_bucketed(mats, max_frames=max_frames)
+            emb = ex.extract_bucketed(mats, max_frames=max_frames, cmvn=cmvn)   # sliding CMN runs on the device
             for k, e in zip(keys, emb):          # written in input order, like the reference
                 writer.write(k, e)
             n_done += len(keys)
             keys, mats, frames = [], [], 0
 
-        for key, mat in iter_features(rspec, cmvn):
+        for key, mat in iter_features(rspec, False):
             if mat.shape[0] < 25:
                 # the reference divides by zero here (tf_extract.py:102,111); fail as loudly
                 raise ZeroDivisionError("utterance %s has %d frames (< 25)" % (key, mat.shape[0]))
