@@ -7,6 +7,19 @@
 #include "umma.cuh"
 using namespace svx::ptx;
 
+template <int MT, int KS>
+__device__ __forceinline__ void issue_tap(uint64_t adesc0, uint64_t bdesc0, uint32_t d_tmem, uint32_t n_tile, uint32_t idesc, uint32_t first) {
+  constexpr uint32_t kSub16 = 64u * KS;     // sub-tiles 32 rows apart here so that 4 of them + shifts stay inside the operand area
+  if (elect_one()) {
+#pragma unroll
+    for (int j = 0; j < MT; ++j) {
+#pragma unroll
+      for (int k = 0; k < KS; ++k)
+        umma_f16(d_tmem + j * n_tile, adesc0 + (j * kSub16 + k * 2), bdesc0 + k * 2, idesc, k == 0 ? first : 1u);
+    }
+  }
+}
+
 template <int VARIANT>
 __global__ void __launch_bounds__(128, 1) k(int n, uint32_t row_bytes, int iters, int shift_rows, long long* out) {
   extern __shared__ uint8_t raw[];
@@ -33,6 +46,14 @@ __global__ void __launch_bounds__(128, 1) k(int n, uint32_t row_bytes, int iters
 #pragma unroll
         for (int u = 0; u < 8; ++u)
           if (elect_one()) umma_f16(tb, ad, bd, idesc, 1);
+      }
+    } else if (VARIANT == 2) {
+      int it = 0;
+      while (it < iters) {
+        for (int tap = 0; tap < 9; ++tap, it += 8) {
+          const uint32_t a_tap = a0 + (shift_rows + tap * 7) * row_bytes;
+          issue_tap<4, 2>(base + (a_tap >> 4), base + (b0 >> 4), tb, n <= 64 ? n : 64, idesc, 1u);
+        }
       }
     } else {
       int it = 0;
@@ -64,14 +85,15 @@ int main() {
   long long* d; cudaMalloc(&d, 16);
   cudaFuncSetAttribute(k<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  const int iters = 4096;
+  cudaFuncSetAttribute(k<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  const int iters = 4608;
   for (int grid : {148})
     for (uint32_t rb : {128u, 64u})
-      for (int n : {32, 64, 128, 256})
-        for (int variant : {0, 1})
-          for (int shift : {0, 3, 82}) {
+      for (int n : {32, 64})
+        for (int variant : {0, 2})
+          for (int shift : {0, 82}) {
             if (variant == 0) k<0><<<grid, 128, 200 * 1024>>>(n, rb, iters, shift, d);
-            else k<1><<<grid, 128, 200 * 1024>>>(n, rb, iters, shift, d);
+            else k<2><<<grid, 128, 200 * 1024>>>(n, rb, iters, shift, d);
             cudaError_t e = cudaDeviceSynchronize();
             long long h[2] = {0, 0};
             cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);

@@ -164,6 +164,7 @@ struct FlatConvParams {
   int taps;
   int tap_shift[kMaxTaps];
   int nkc, kbox, kpad;         // K boxes per tap, elements per box (64/32/16), nkc*kbox
+  int a_c_step;                // grouped conv (block-diagonal weights per n-tile): input-channel offset per n-tile; 0 for dense
   int n_tile, n_tiles;
   int a_stages, b_stages;
   uint32_t a_stage_bytes, b_item_bytes;
@@ -180,8 +181,8 @@ struct FlatConvParams {
   int boxes;                   // staging boxes per buffer = ceil(n_tile / box_ch)
   int slots;                   // epilogue slot ring depth PER WARPGROUP (each of the two epilogue warpgroups owns its ring)
   uint32_t slot_bytes;
-  uint8_t route_map[16];       // per global staging box (n0/box_ch + b): which output map it is stored through (0xff: none)
-  int32_t route_c[16];         //   and at which channel coordinate of that map
+  uint8_t route_map[32];       // per global staging box (n0/box_ch + b): which output map it is stored through (0xff: none)
+  int32_t route_c[32];         //   and at which channel coordinate of that map
   int pre_relu, post_relu;
   unsigned long long* trace;
   unsigned long long* dbg;     // host-mapped words: which barrier wait timed out (written before the trap)

@@ -231,7 +231,7 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
           mbar_expect_tx(&S.a_full[sa], a_tx);
           uint8_t* dst = a_smem + static_cast<size_t>(sa) * p.a_stage_bytes;
           for (int b = 0; b < p.a_boxes; ++b)
-            tma_load_2d(dst + static_cast<size_t>(b) * p.a_box_rows * row_bytes, &maps.a, &S.a_full[sa], kc * p.kbox,
+            tma_load_2d(dst + static_cast<size_t>(b) * p.a_box_rows * row_bytes, &maps.a, &S.a_full[sa], kc * p.kbox + n_blk * p.a_c_step,
                         p0 - p.halo + b * p.a_box_rows);
           if (!p.b_resident) {
             for (int tap = 0; tap < p.taps; ++tap, ++ib) {

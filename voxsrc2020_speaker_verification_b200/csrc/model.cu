@@ -428,6 +428,7 @@ int Model::upload_conv_weights(ConvDesc& c) {
     if (cin_g != cout_g || 32 % cin_g != 0) { set_last_error("unsupported grouped conv shape"); return 1; }
     grp_ntile = 32; grp_cstep = 32;
     c.kbox = 32; c.nkc = 1; c.kpad = 32; c.n_tile = 32;
+    c.no_staged = true;   // 32-channel n-tiles: the 2-D kernel's 64-channel store boxes would spill into the neighbouring tile
   } else {
     c.kbox = pick_kbox(c.cin);
     c.nkc = (c.cin + c.kbox - 1) / c.kbox;
@@ -605,7 +606,8 @@ int Model::plan_conv(ConvDesc& c) {
   c.use_umma = false;
   const int taps = c.kh * c.kw;
   auto mult8 = [](int v) { return v % 8 == 0; };
-  bool ok = c.split_w == 0 && c.groups == 1 && taps <= kMaxTaps && (c.stride == 1 || (c.stride == 2 && c.dil == 1)) && mult8(tin.C) && mult8(c.in.coff) &&
+  const bool grouped_ok = c.groups > 1 && c.n_tile == 32 && c.kbox == 32 && c.nkc == 1 && c.cin == c.cout && c.cin % 32 == 0;
+  bool ok = c.split_w == 0 && (c.groups == 1 || grouped_ok) && taps <= kMaxTaps && (c.stride == 1 || (c.stride == 2 && c.dil == 1)) && mult8(tin.C) && mult8(c.in.coff) &&
             mult8(c.cout) && mult8(e.out_C) && mult8(e.out_coff) && mult8(e.n_split) &&
             (!e.res || (mult8(e.res_C) && mult8(e.res_coff))) && (!e.outb || (mult8(e.outb_C) && mult8(e.outb_coff))) &&
             (!e.out2 || (mult8(e.out2_C) && mult8(e.out2_coff) && mult8(e.add2_C) && mult8(e.add2_coff)));
@@ -616,7 +618,7 @@ int Model::plan_conv(ConvDesc& c) {
   int w_box = 1;
   while (w_box < 128 && out_W % (w_box * 2) == 0) w_box *= 2;
   up.out_rows = 0; up.out_W = out_W; up.out_Wp = out_Wp; up.w_box = w_box; up.h_box = 128 / w_box; up.w_tiles = out_W / w_box;
-  up.taps = taps; up.nkc = c.nkc; up.kbox = c.kbox; up.a_c_step = 0; up.n_tile = c.n_tile; up.n_tiles = c.n_tiles;
+  up.taps = taps; up.nkc = c.nkc; up.kbox = c.kbox; up.a_c_step = c.groups > 1 ? 32 : 0; up.n_tile = c.n_tile; up.n_tiles = c.n_tiles;
   up.aux_mode = e.res ? 1 : (e.out2 ? 2 : 0);
   up.aux_boxes = up.aux_mode ? (c.n_tile + 63) / 64 : 0;
   up.aux_width = up.aux_mode == 1 ? e.n_split : (up.aux_mode == 2 ? c.cout : 0);
@@ -707,7 +709,11 @@ int Model::plan_flat(ConvDesc& c) {
   if (disabled) return 0;
   const ActTensor& tin = tensors_[c.in.id];
   const ActTensor& tout = tensors_[c.out.id];
-  if (c.groups != 1 || c.stride != 1 || tin.stage != tout.stage) return 0;
+  if (c.stride != 1 || tin.stage != tout.stage) return 0;
+  // grouped convs (DPN, 32 groups): n-tiles of 32 output channels with block-diagonal weights over their own 32 input channels
+  // (upload_conv_weights lays the weights out that way); each n-tile's CTA offsets its A loads by 32 channels
+  const bool grouped = c.groups > 1;
+  if (grouped && (c.n_tile != 32 || c.kbox != 32 || c.nkc != 1 || c.cin != c.cout || c.cin % 32 != 0)) return 0;
   const int taps = c.kh * c.kw;
   if (taps > kMaxTaps) return 0;
   const int Wp = stage_Wp_[tout.stage], W = stage_W_[tout.stage];
@@ -730,6 +736,7 @@ int Model::plan_flat(ConvDesc& c) {
   FlatConvParams fp;
   memset(&fp, 0, sizeof fp);
   fp.taps = taps; fp.nkc = c.nkc; fp.kbox = c.kbox; fp.kpad = c.kpad;
+  fp.a_c_step = grouped ? 32 : 0;
   int halo = 0;
   for (int t = 0; t < taps; ++t) {
     const int r = t / c.kw, s = t % c.kw;
@@ -776,7 +783,8 @@ int Model::plan_flat(ConvDesc& c) {
       if (!split && box_ch == 32 && n_tile > 32 && n_tile % 64 == 0) continue;   // 64-channel boxes are never worse there
       // routing of channels >= n_split
       if (!split && n_split < c.cout && n_split % box_ch != 0) continue;       // a staging box has exactly one destination
-      if ((N + box_ch - 1) / box_ch > 16) continue;                              // routing table size
+      if ((N + box_ch - 1) / box_ch > 32) continue;                              // routing table size
+      if (grouped && (n_tile != 32 || box_ch != 32)) continue;
       const int boxes = (n_tile + box_ch - 1) / box_ch;
       const uint32_t box_bytes = 128u * box_ch * 2u;
       const uint32_t slot_bytes = boxes * box_bytes * (aux_mode == 2 ? 2u : 1u);

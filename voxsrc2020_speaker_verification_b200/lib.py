@@ -7,7 +7,7 @@ import os
 from ctypes import POINTER, byref, c_char_p, c_float, c_int, c_int32, c_int64, c_longlong, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsvx.so")
+LIB_PATH = os.environ.get("SVX_LIB") or os.path.join(HERE, "libsvx.so")   # SVX_LIB: debug override (A/B of two builds)
 
 PRECISION_FP16, PRECISION_BF16 = 0, 1
 
