@@ -1133,16 +1133,21 @@ static int grow(float** p, size_t* have, size_t need) {
 }
 
 int Model::run_segments(const float* d_feats, const int32_t* h_frame_off, int n_seg, float* d_out, cudaStream_t st) {
+  if (n_seg <= 0) { launches_ = 0; return 0; }
+  std::vector<int> starts(n_seg), lens(n_seg);
+  for (int i = 0; i < n_seg; ++i) { starts[i] = h_frame_off[i]; lens[i] = h_frame_off[i + 1] - h_frame_off[i]; }
+  return run_segments_sl(d_feats, starts, lens, d_out, st);
+}
+
+int Model::run_segments_sl(const float* d_feats, const std::vector<int>& starts, const std::vector<int>& lens, float* d_out, cudaStream_t st) {
   if (!finalized_) { set_last_error("extractor not finalized"); return 1; }
   SVX_CUDA(cudaSetDevice(device_));
   launches_ = 0;
   if (!in_extract_) { ev_used_ = 0; conv_flops_ = 0.0; }
+  const int n_seg = static_cast<int>(starts.size());
   if (n_seg <= 0) return 0;
-  std::vector<int> starts(n_seg), lens(n_seg);
-  for (int i = 0; i < n_seg; ++i) {
-    starts[i] = h_frame_off[i]; lens[i] = h_frame_off[i + 1] - h_frame_off[i];
+  for (int i = 0; i < n_seg; ++i)
     if (lens[i] <= 0) { set_last_error("empty segment"); return 1; }
-  }
   // sub-batches bounded by workspace rows
   const int max_rows0 = 1 << 17;
   int i0 = 0;
@@ -1333,21 +1338,14 @@ int Model::extract(const float* feats, int feats_on_device, const int32_t* h_fra
     if (grow(&d_out_, &d_out_bytes_, static_cast<size_t>(n_utts) * E * 4)) { set_last_error("allocation failed"); return 1; }
     d_out = d_out_;
   }
-  // run_segments wants contiguous offsets; chunks of one utterance are contiguous except for dropped tails, so
-  // feed (start,len) pairs through a synthetic offset table per contiguous run.
+  // all chunks in one pass: segments are (first frame, length) pairs, so dropped tails leave no gaps to work around
   long long total_launches = 0;
   ev_used_ = 0; conv_flops_ = 0.0; in_extract_ = true;
   struct Guard { bool& f; ~Guard() { f = false; } } guard{in_extract_};
-  int s0 = 0;
-  while (s0 < n_seg) {
-    int s1 = s0 + 1;
-    while (s1 < n_seg && starts[s1] == starts[s1 - 1] + seg_len[s1 - 1]) ++s1;
-    std::vector<int32_t> offs(s1 - s0 + 1);
-    for (int i = s0; i < s1; ++i) offs[i - s0] = starts[i];
-    offs[s1 - s0] = starts[s1 - 1] + seg_len[s1 - 1];
-    if (run_segments(d_feats, offs.data(), s1 - s0, d_seg_emb_ + static_cast<size_t>(s0) * E, st)) return 1;
+  {
+    std::vector<int> st_i(starts.begin(), starts.end()), ln_i(seg_len.begin(), seg_len.end());
+    if (run_segments_sl(d_feats, st_i, ln_i, d_seg_emb_, st)) return 1;
     total_launches += launches_;
-    s0 = s1;
   }
   bool single = true;
   for (int u = 0; u < n_utts; ++u) if (utt_seg_off[u + 1] - utt_seg_off[u] != 1) { single = false; break; }

@@ -87,6 +87,8 @@ class Model {
   int set_option(const char* key, int value);
   // segments: contiguous [frame_off[i], frame_off[i+1]) rows of feats (device fp32 [total_frames, F])
   int run_segments(const float* d_feats, const int32_t* h_frame_off, int n_seg, float* d_out, cudaStream_t st);
+  // the same for segments given as (first frame, length) pairs, which need not be contiguous (chunk rule with dropped tails)
+  int run_segments_sl(const float* d_feats, const std::vector<int>& starts, const std::vector<int>& lens, float* d_out, cudaStream_t st);
   // utterances with the chunk rule; host or device feats/out
   int extract(const float* feats, int feats_on_device, const int32_t* h_frame_off, int n_utts, float* out, int out_on_device,
               cudaStream_t st);
