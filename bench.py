@@ -256,10 +256,21 @@ def main():
             hi = (rank + 1) * SCORE_TRIALS // world
             sc.trial_scores(x, i1[lo:hi], i2[lo:hi], mean, std)
         ms_score = timed(score_step, 3, 2)
+        ms_score_rows = None
+        if world > 1:       # the natural layout beside it: test rows sharded, cohort replicated, all-gather of [n, 2] statistics
+            def score_step_rows():
+                mean, std = svdist.rows_sharded_cohort_mean_std(sc, x, cohort, SCORE_TOPK)
+                lo = rank * SCORE_TRIALS // world
+                hi = (rank + 1) * SCORE_TRIALS // world
+                sc.trial_scores(x, i1[lo:hi], i2[lo:hi], mean, std)
+            ms_score_rows = timed(score_step_rows, 3, 2)
         score = {"value": SCORE_TRIALS / (ms_score / 3 * 1e-3), "unit": "trials/s", "ms_per_job": ms_score / 3,
                  "workload": "%d x %d-d test rows vs %d-speaker cohort, top-%d, %d trials%s" %
                              (SCORE_N, SCORE_D, SCORE_C, SCORE_TOPK, SCORE_TRIALS,
-                              "; cohort row-sharded, NCCL all-gather of per-rank top-k" if world > 1 else "")}
+                              "; cohort row-sharded, NCCL all-to-all of per-rank top-k candidates, merge on the owner of each test row" if world > 1 else "")}
+        if ms_score_rows is not None:
+            score["test_rows_sharded"] = {"value": SCORE_TRIALS / (ms_score_rows / 3 * 1e-3), "unit": "trials/s", "ms_per_job": ms_score_rows / 3,
+                                          "note": "natural layout: test rows sharded, cohort replicated, all-gather of the statistics"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

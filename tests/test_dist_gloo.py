@@ -20,6 +20,10 @@ class NumpyScorer:
             top = np.concatenate([top, np.full((top.shape[0], k - top.shape[1]), -1e30, np.float32)], 1)
         return torch.from_numpy(np.ascontiguousarray(top.astype(np.float32)))
 
+    def cohort_mean_std(self, test, cohort, k):
+        top = -np.sort(-(test.numpy() @ cohort.numpy().T), axis=1)[:, :k]
+        return torch.from_numpy(top.mean(1)), torch.from_numpy(top.std(1))
+
     def topk_stats(self, vals, k):
         top = -np.sort(-vals.numpy(), axis=1)[:, :k]
         return torch.from_numpy(top.mean(1)), torch.from_numpy(top.std(1))
@@ -33,9 +37,11 @@ def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     rng = np.random.default_rng(0)
-    x = torch.from_numpy(rng.standard_normal((50, 16)).astype(np.float32))
+    x = torch.from_numpy(rng.standard_normal((51, 16)).astype(np.float32))
     cohort = torch.from_numpy(rng.standard_normal((37, 16)).astype(np.float32))
     mean, std = svdist.sharded_cohort_mean_std(NumpyScorer(), x, cohort, 10)
+    mean2, std2 = svdist.rows_sharded_cohort_mean_std(NumpyScorer(), x, cohort, 10)
+    assert torch.allclose(mean, mean2, atol=1e-6) and torch.allclose(std, std2, atol=1e-6)
     # extraction side: every rank "extracts" its balanced share, then the embeddings are gathered
     lengths = [300, 25, 2999, 1000, 57, 640, 41]
     mine = svdist.balance_by_frames(lengths, world)[rank]
@@ -56,7 +62,7 @@ def test_world2_sharded_cohort_and_gather():
     [p.join(60) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
     rng = np.random.default_rng(0)
-    x = rng.standard_normal((50, 16)).astype(np.float32)
+    x = rng.standard_normal((51, 16)).astype(np.float32)
     cohort = rng.standard_normal((37, 16)).astype(np.float32)
     top = -np.sort(-(x @ cohort.T), axis=1)[:, :10]
     np.testing.assert_allclose(mean, top.mean(1), atol=1e-6)

@@ -245,8 +245,8 @@ __global__ void __launch_bounds__(kTopkThreads) topk_stats_kernel(const float* s
 // no memory.  The generic kernel above spends ~3000 instructions per thread re-reading shared memory and recomputing buckets;
 // this one ~800 (profiles/r01_score_launches.txt).  Same exact-selection logic: 2048 monotone buckets, 8-bit radix select
 // inside the bucket of the k-th largest, ties counted.
-constexpr int kVPT = 24;
-
+// kVPT values per thread: instantiated for 4 / 8 / 12 / 24 so that a cohort shard (or a merged candidate list) pays for its own size
+template <int kVPT>
 __global__ void __launch_bounds__(kTopkThreads, 3) topk_stats_reg_kernel(const float* __restrict__ scores, int ld, int c, int topk,
                                                                       float* mean_out, float* std_out, float* vals_out, int vals_ld) {
   __shared__ int hist[kBuckets];
@@ -405,8 +405,12 @@ cudaError_t launch_topk_stats(const float* scores, int ld, long long n_rows, int
                               float* vals_out, int vals_ld, cudaStream_t st) {
   if (n_rows <= 0) return cudaSuccess;
   static const bool no_reg = getenv("SVX_TOPK_GENERIC") != nullptr;   // debug switch
-  if (c <= kVPT * kTopkThreads && !no_reg) {
-    topk_stats_reg_kernel<<<static_cast<unsigned>(n_rows), kTopkThreads, 0, st>>>(scores, ld, c, topk, mean, stdv, vals_out, vals_ld);
+  if (c <= 24 * kTopkThreads && !no_reg) {
+    const unsigned g = static_cast<unsigned>(n_rows);
+    if (c <= 4 * kTopkThreads) topk_stats_reg_kernel<4><<<g, kTopkThreads, 0, st>>>(scores, ld, c, topk, mean, stdv, vals_out, vals_ld);
+    else if (c <= 8 * kTopkThreads) topk_stats_reg_kernel<8><<<g, kTopkThreads, 0, st>>>(scores, ld, c, topk, mean, stdv, vals_out, vals_ld);
+    else if (c <= 12 * kTopkThreads) topk_stats_reg_kernel<12><<<g, kTopkThreads, 0, st>>>(scores, ld, c, topk, mean, stdv, vals_out, vals_ld);
+    else topk_stats_reg_kernel<24><<<g, kTopkThreads, 0, st>>>(scores, ld, c, topk, mean, stdv, vals_out, vals_ld);
     return cudaGetLastError();
   }
   const size_t smem = static_cast<size_t>(c) * sizeof(float);

@@ -73,15 +73,57 @@ def sharded_cohort_mean_std(scorer, test: torch.Tensor, cohort: torch.Tensor, to
     """get_cohort_mean_std (snorm.py:83-110) with the cohort row-sharded over the ranks of ``group``.
 
     ``scorer`` provides cohort_topk_values(test, shard, k) → [n,k] and topk_stats(vals, k) → (mean, std);
-    every rank holds the full ``test`` and ``cohort`` (or at least its own slice of the cohort rows)."""
+    every rank holds the full ``test`` and ``cohort`` (or at least its own slice of the cohort rows).
+
+    Exchange: each rank keeps the per-row top-k candidates of ITS cohort slice for all test rows, then the candidate
+    lists are exchanged so that rank r receives, from every rank, the candidates of ITS slice of the test rows
+    (all-to-all over NVLink; on backends without all-to-all — gloo in the CPU tests — an all-gather followed by the
+    same row slice).  Each rank merges only its rows (top-k of the union of ``world`` lists) and a small all-gather
+    returns the [n] statistics to everyone, so neither the merge nor the received bytes grow with the world size."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     c = cohort.shape[0]
     k_eff = min(int(topk), c)
     lo, hi = shard_bounds(c, world)[rank]
     k_shard = max(1, min(k_eff, max(b - a for a, b in shard_bounds(c, world))))
-    vals = scorer.cohort_topk_values(test, cohort[lo:hi], k_shard)                 # [n, k_shard], padded with -1e30
+    vals = scorer.cohort_topk_values(test, cohort[lo:hi], k_shard).contiguous()    # [n, k_shard], padded with -1e30
     n, k = vals.shape
-    gathered = torch.empty((world * n, k), dtype=vals.dtype, device=vals.device)
-    dist.all_gather_into_tensor(gathered, vals.contiguous(), group=group)
-    return scorer.topk_stats(merge_candidates(gathered.view(world, n, k)), k_eff)
+    rows = shard_bounds(n, world)
+    r_lo, r_hi = rows[rank]
+    n_mine = r_hi - r_lo
+    if dist.get_backend(group) == "nccl":
+        recv = torch.empty((world * n_mine, k), dtype=vals.dtype, device=vals.device)
+        dist.all_to_all_single(recv, vals, output_split_sizes=[n_mine] * world, input_split_sizes=[b - a for a, b in rows], group=group)
+        mine = recv.view(world, n_mine, k)
+    else:
+        gathered = torch.empty((world * n, k), dtype=vals.dtype, device=vals.device)
+        dist.all_gather_into_tensor(gathered, vals, group=group)
+        mine = gathered.view(world, n, k)[:, r_lo:r_hi]
+    mean_r, std_r = scorer.topk_stats(merge_candidates(mine.contiguous()), k_eff)
+    # statistics of every row back to every rank (row slices differ by at most one row: padded to the longest)
+    return _allgather_rows(mean_r, std_r, rows, group)
+
+
+def _allgather_rows(mean_r: torch.Tensor, std_r: torch.Tensor, rows, group=None):
+    world = dist.get_world_size(group)
+    n_max = max(b - a for a, b in rows)
+    pad = torch.zeros((2, n_max), dtype=mean_r.dtype, device=mean_r.device)
+    pad[0, : mean_r.shape[0]] = mean_r
+    pad[1, : std_r.shape[0]] = std_r
+    out = torch.empty((world, 2, n_max), dtype=pad.dtype, device=pad.device)
+    dist.all_gather_into_tensor(out.view(world * 2, n_max), pad, group=group)
+    mean = torch.cat([out[r, 0, : b - a] for r, (a, b) in enumerate(rows)])
+    std = torch.cat([out[r, 1, : b - a] for r, (a, b) in enumerate(rows)])
+    return mean, std
+
+
+def rows_sharded_cohort_mean_std(scorer, test: torch.Tensor, cohort: torch.Tensor, topk: int, group=None):
+    """The natural layout: the TEST rows are sharded, the 6 MB cohort is replicated; every rank computes
+    the statistics of its own rows (``scorer.cohort_mean_std``) and one all-gather of 2 floats per row returns them to
+    everyone.  No candidate exchange at all — kept beside the cohort-sharded layout the north star names."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    rows = shard_bounds(test.shape[0], world)
+    lo, hi = rows[rank]
+    mean_r, std_r = scorer.cohort_mean_std(test[lo:hi], cohort, topk)
+    return _allgather_rows(mean_r, std_r, rows, group)
