@@ -5,6 +5,8 @@
 #include <string>
 
 #include "kernels.cuh"
+#include <cstdlib>
+
 #include "model.h"
 #include "umma.cuh"
 
@@ -228,7 +230,23 @@ static int cohort_pass(svx_scorer* h, const float* test_dev, int64_t n, const fl
   int n_tile = 256;
   while (n_tile > 16 && n_tile / 2 >= c) n_tile /= 2;
   const int c_pad = (c + n_tile - 1) / n_tile * n_tile;
-  const int block_rows = 4096;
+  // rows per pass: a whole number of waves of (128 x n_tile) tiles over the SMs, near 4096 rows (the fp32 score block then
+  // stays close to the L2 size); SVX_SCORE_BLOCK_ROWS overrides (debug)
+  static const int env_rows = getenv("SVX_SCORE_BLOCK_ROWS") ? atoi(getenv("SVX_SCORE_BLOCK_ROWS")) : 0;
+  int block_rows = 4096;
+  {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    const int n_tiles_ = c_pad / n_tile;
+    int best = 4096; double best_eff = 0.0;
+    for (int mt = 24; mt <= 40; ++mt) {
+      const long long tiles = static_cast<long long>(mt) * n_tiles_;
+      const double eff = static_cast<double>(tiles) / (static_cast<double>((tiles + sms - 1) / sms) * sms);
+      if (eff > best_eff + 1e-9) { best_eff = eff; best = mt * 128; }
+    }
+    block_rows = best;
+  }
+  if (env_rows >= 128) block_rows = env_rows / 128 * 128;
   if (grow_buf(&h->d_a, &h->a_bytes, static_cast<size_t>(block_rows) * K * 2)) return 1;
   if (grow_buf(&h->d_b, &h->b_bytes, static_cast<size_t>(c_pad) * K * 2)) return 1;
   if (grow_buf(&h->d_s, &h->s_bytes, static_cast<size_t>(block_rows) * c_pad * 4)) return 1;

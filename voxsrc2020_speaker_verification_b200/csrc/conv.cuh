@@ -184,6 +184,8 @@ struct FlatConvParams {
   uint8_t route_map[32];       // per global staging box (n0/box_ch + b): which output map it is stored through (0xff: none)
   int32_t route_c[32];         //   and at which channel coordinate of that map
   int pre_relu, post_relu;
+  int reverse;                 // walk the spans from the last pixel to the first: consecutive layers alternate, so a consumer starts on
+                               // the pixels its producer wrote last (still in the 126 MB L2)
   unsigned long long* trace;
   unsigned long long* dbg;     // host-mapped words: which barrier wait timed out (written before the trap)
 };

@@ -222,7 +222,7 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
       Tracer tr; tr.init(p.trace, 0);
       uint32_t ia = 0, ib = 0;
       for (int span = my_group; span < n_spans; span += groups) {
-        const int p0 = span * span_px;
+        const int p0 = (p.reverse ? n_spans - 1 - span : span) * span_px;
         tr.ev(1);
         S.prog[0] = ia;
         for (int kc = 0; kc < p.nkc; ++kc, ++ia) {
@@ -336,7 +336,7 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
       Tracer tr; tr.init(p.trace, 2);
       int ls = 0;
       for (int span = my_group; span < n_spans; span += groups, ++ls) {
-        const int p0 = span * span_px;
+        const int p0 = (p.reverse ? n_spans - 1 - span : span) * span_px;
         for (int j = 0; j < p.mt; ++j) {
           const uint32_t q = static_cast<uint32_t>(ls >> 1) * p.mt + j;      // sub-tile counter of the warpgroup that owns this span
           const int slot = (ls & 1) * p.slots + q % p.slots;
@@ -363,7 +363,7 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
       int prev_slot = -1;
       int ls = 0;
       for (int span = my_group; span < n_spans; span += groups, ++ls) {
-        const int p0 = span * span_px;
+        const int p0 = (p.reverse ? n_spans - 1 - span : span) * span_px;
         for (int j = 0; j < p.mt; ++j) {
           const uint32_t q = static_cast<uint32_t>(ls >> 1) * p.mt + j;
           const int slot = (ls & 1) * p.slots + q % p.slots;
@@ -408,7 +408,7 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
     int ls = 0;
     for (int span = my_group; span < n_spans; span += groups, ++ls) {
       if ((ls & 1) != wg) continue;
-      const long long p0 = static_cast<long long>(span) * span_px;
+      const long long p0 = static_cast<long long>(p.reverse ? n_spans - 1 - span : span) * span_px;
       uint32_t vm[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {

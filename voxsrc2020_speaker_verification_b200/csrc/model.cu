@@ -1070,8 +1070,19 @@ int Model::launch_conv(ConvDesc& c, cudaStream_t st) {
       c.fp.P = static_cast<long long>(out_rows) * stage_Wp_[out_stage];
       c.fp.trace = trace_dir ? d_trace : nullptr;
       c.fp.dbg = flat_dbg_words();
+      // walk the pixels in the opposite direction of the kernel that wrote the input: the consumer then starts on what is
+      // still in L2 (+0.6 % measured on the headline step)
+      static const bool no_rev = getenv("SVX_NO_REVERSE") != nullptr;   // debug switch
+      if (tensor_dir_.size() != tensors_.size()) tensor_dir_.assign(tensors_.size(), 0);
+      c.fp.reverse = no_rev ? 0 : 1 - tensor_dir_[c.in.id];
+      auto mark = [&](const TensorRef& r) { if (r.id >= 0) tensor_dir_[r.id] = c.fp.reverse; };
+      mark(c.out); mark(c.outb); mark(c.out2);
+      for (const TensorRef& r : c.split_out) mark(r);
       SVX_CUDA(launch_conv_flat(c.fp, c.fmaps, is_bf16_, st));
     } else {
+      if (tensor_dir_.size() != tensors_.size()) tensor_dir_.assign(tensors_.size(), 0);
+      tensor_dir_[c.out.id] = 0;
+      if (c.outb.id >= 0) tensor_dir_[c.outb.id] = 0;
       c.up.out_rows = out_rows;
       c.up.trace = trace_dir ? d_trace : nullptr;
       SVX_CUDA(launch_conv_umma(c.up, c.amaps, c.bmap, c.auxmap, c.omaps, is_bf16_, st));

@@ -126,6 +126,7 @@ class Model {
   std::vector<int> stage_Wp_;        // pixels per row in memory: W + 1 zero column for the 2-D networks, W for the TDNN
   std::vector<uint8_t*> d_pix_valid_;
   int force_no_flat_ = 0;
+  std::vector<int> tensor_dir_;       // per activation tensor: 1 if its last writer walked the pixels backwards
   std::vector<int> rows_cap_, rows_used_;
   int seg_cap_ = 0;
   // per stage device tables
