@@ -60,3 +60,54 @@ def test_tf_extract_cli_rejects_short_utterance(tmp_path):
     rspec = _write_feats(tmp_path, {"short": np.zeros((24, 40), np.float32)})
     with pytest.raises(ZeroDivisionError):    # tf_extract.py:102,111 divides by zero for < 25 frames
         tf_extract.main(["--pb-file", pb, "--expand-dim", "2", "--rspec", rspec, "--wspec", str(tmp_path / "x")])
+
+
+def test_eval_inference_model_pipeline(tmp_path):
+    """eval_inference_model.sh stand-in on a miniature data directory: per-GPU scp shards in, concatenated arks and
+    cosine_/snorm_ score files out, scores equal to the score oracle fed with the oracle's embeddings."""
+    from oracle import score_oracle
+    from voxsrc2020_speaker_verification_b200 import eval_inference_model
+    cfg = arch.get_config("tdnn")
+    params = net_oracle.init_params(cfg, 40, seed=4321)
+    pb = str(tmp_path / "model.pb")
+    pb_loader.write_pb(pb, params, cfg, 40)
+    rng = np.random.default_rng(11)
+    data = tmp_path / "data"
+    feats = {}
+    for ds, spk, per in (("voxceleb2_dev", 5, 3), ("voxceleb1", 4, 2)):
+        d = data / ds / "1-split"
+        d.mkdir(parents=True)
+        ark = str(data / ds / "raw.ark")
+        with open(ark, "wb") as fa, open(str(d / "feats.1.scp"), "w") as fs, open(str(data / ds / "spk2utt"), "w") as fu:
+            for s in range(spk):
+                utts = []
+                for u in range(per):
+                    key = "%s_id%02d/u%d.wav" % (ds[-4:], s, u)
+                    m = (rng.standard_normal((int(rng.integers(40, 90)), 40)) + s).astype(np.float32)
+                    off = kaldi_ark.write_mat(fa, m, key)
+                    fs.write("%s %s:%d\n" % (key, ark, off))
+                    feats[key] = m
+                    utts.append(key)
+                fu.write("%s_id%02d %s\n" % (ds[-4:], s, " ".join(utts)))
+    test_keys = [k for k in feats if k.startswith("leb1")]
+    (data / "voxceleb1_trials").mkdir()
+    with open(str(data / "voxceleb1_trials" / "list_test_T.txt"), "w") as f:
+        for i in range(12):
+            a, b = rng.choice(len(test_keys), 2, replace=False)
+            f.write("%d %s %s\n" % (i % 2, test_keys[a], test_keys[b]))
+    assert eval_inference_model.main([pb, "2", "--data-root", str(data), "--num-gpus", "1", "--topk", "3"]) == 0
+    out = str(tmp_path / "model_embeddings" / "voxceleb1")
+    got = [ln.split() for ln in open(os.path.join(out, "snorm_T.txt"))]
+    cos = [ln.split() for ln in open(os.path.join(out, "cosine_T.txt"))]
+    assert len(got) == 12 and len(cos) == 12
+    # oracle: embeddings of the CMN-normalised features, then the reference scoring restatement
+    emb = {k: net_oracle.extract_utterance(cfg, params, kaldi_ark.apply_cmvn_sliding(m)) for k, m in feats.items()}
+    test = score_oracle.normalise_xvectors({k: emb[k] for k in test_keys})
+    spk2utt = score_oracle.read_spk2utt(str(data / "voxceleb2_dev" / "spk2utt"))
+    cohort = score_oracle.read_speaker_xvector(score_oracle.normalise_xvectors({k: v for k, v in emb.items() if k.startswith("_dev")}), spk2utt)
+    mean, std = score_oracle.get_cohort_mean_std(test, cohort, 3)
+    for (a, b, s), (_, _, c) in zip(got, cos):
+        want_c = float(np.dot(test[a], test[b]))
+        want_s = 0.5 * ((want_c - mean[a]) / std[a] + (want_c - mean[b]) / std[b])
+        assert abs(float(c) - want_c) < 1e-3
+        assert abs(float(s) - want_s) < 5e-2 * max(1.0, abs(want_s))      # std over 3 cohort scores amplifies the embedding tolerance
