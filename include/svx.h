@@ -97,6 +97,13 @@ int svx_extractor_conv_time(svx_extractor* h, double* ms, double* flops);
 int svx_cmvn_sliding(const float* feats_dev, float* out_dev, const int32_t* frame_offsets_host, int n_utts, int feat_dim,
                      int cmn_window, int center, void* cuda_stream);
 
+/* Kaldi CompressedMatrix ('CM ') records → fp32 [total_frames, feat_dim] on the device, bit-identical to
+ * kaldi_io._read_compressed_mat (kaldi_io.py:471-504).  blob_dev: the records' payloads back to back, each starting at its
+ * global header {min f32, range f32, rows i32, cols i32} (i.e. right after the "CM " token); record_offsets_host[i] = byte
+ * offset of record i in the blob; frame_offsets_host: int32 [n + 1] cumulative row counts. */
+int svx_decode_compressed(const uint8_t* blob_dev, const int64_t* record_offsets_host, const int32_t* frame_offsets_host, int n_records,
+                          int feat_dim, float* out_dev, void* cuda_stream);
+
 /* ---- scoring: replaces the NumPy body of tensorflow/snorm.py.  All pointers are device pointers. */
 typedef struct svx_scorer svx_scorer;
 int svx_scorer_create(int device, svx_scorer** out);

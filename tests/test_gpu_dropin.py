@@ -111,3 +111,56 @@ def test_eval_inference_model_pipeline(tmp_path):
         want_s = 0.5 * ((want_c - mean[a]) / std[a] + (want_c - mean[b]) / std[b])
         assert abs(float(c) - want_c) < 1e-3
         assert abs(float(s) - want_s) < 5e-2 * max(1.0, abs(want_s))      # std over 3 cohort scores amplifies the embedding tolerance
+
+
+def test_compressed_matrix_decode_on_device_is_bit_exact(golden_dir):
+    """svx_decode_compressed on the reference-written 'CM ' ark vs the matrices the reference's own kaldi_io decoded from it
+    (tests/golden/io/ref_feats.npz, generated by oracle/gen_golden.py from /root/reference/tensorflow/kaldi_io.py)."""
+    from voxsrc2020_speaker_verification_b200.extractor import Extractor
+    g = os.path.join(golden_dir, "io")
+    ref = np.load(os.path.join(g, "ref_feats.npz"))
+    recs = list(kaldi_ark.read_mat_ark_raw(os.path.join(g, "feats_cm.ark")))
+    assert recs and all(kind == "CM " for _, kind, _, _, _ in recs)
+    cfg = arch.get_config("tdnn")
+    for feat_dim in sorted({c for _, _, _, _, c in recs}):          # the fixture mixes 40- and 80-bin matrices
+        group = [r for r in recs if r[4] == feat_dim]
+        ex = Extractor("tdnn", feat_dim).load_params(net_oracle.init_params(cfg, feat_dim, seed=1, calib_frames=32, calib_batch=2))
+        dev = ex.decode_compressed([p for _, _, p, _, _ in group], [r for _, _, _, r, _ in group]).cpu().numpy()
+        row = 0
+        for key, _, _, rows, cols in group:
+            want = ref["cm:" + key]
+            assert want.shape == (rows, cols)
+            np.testing.assert_array_equal(dev[row:row + rows], want)
+            row += rows
+
+
+def test_tf_extract_cli_on_compressed_ark(tmp_path):
+    """Compressed ('CM ') FBANK in: records are decoded, mean-normalised and embedded on the device; the result must equal the
+    oracle run on the host-decoded, host-normalised matrices."""
+    import struct
+    from voxsrc2020_speaker_verification_b200 import tf_extract
+    cfg = arch.get_config("tdnn")
+    params = net_oracle.init_params(cfg, 40, seed=4321)
+    pb = str(tmp_path / "tdnn.pb")
+    pb_loader.write_pb(pb, params, cfg, 40)
+    rng = np.random.default_rng(8)
+    ark, scp = str(tmp_path / "cm.ark"), str(tmp_path / "feats.1.scp")
+    keys = []
+    with open(ark, "wb") as fa, open(scp, "w") as fs:
+        for i, rows in enumerate((64, 33, 410)):
+            key = "id%d/x.wav" % i
+            keys.append(key)
+            fa.write((key + " ").encode())
+            off = fa.tell()
+            heads = np.sort(rng.integers(0, 65536, (40, 4)), axis=1).astype("<u2")       # any sorted percentiles are a valid header
+            fa.write(b"\0BCM " + struct.pack("<ffii", -12.5, 30.0, rows, 40) + heads.tobytes() +
+                     rng.integers(0, 256, (40, rows)).astype(np.uint8).tobytes())
+            fs.write("%s %s:%d\n" % (key, ark, off))
+    wspec = str(tmp_path / "xv")
+    assert tf_extract.main(["--pb-file", pb, "--expand-dim", "2", "--rspec", scp[:-4], "--wspec", wspec]) == 0
+    got = dict(kaldi_ark.read_vec_flt_ark(wspec + ".ark"))
+    assert list(got) == keys
+    for key, m in kaldi_ark.read_mat_scp(scp):
+        want = net_oracle.extract_utterance(cfg, params, kaldi_ark.apply_cmvn_sliding(np.asarray(m, np.float32)))
+        cos = float(np.dot(got[key], want) / np.linalg.norm(got[key]) / np.linalg.norm(want))
+        assert cos >= 0.9999, (key, cos)

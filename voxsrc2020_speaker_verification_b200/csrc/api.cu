@@ -177,6 +177,27 @@ int svx_cmvn_sliding(const float* feats_dev, float* out_dev, const int32_t* fram
   return 0;
 }
 
+int svx_decode_compressed(const uint8_t* blob_dev, const int64_t* record_offsets_host, const int32_t* frame_offsets_host, int n_records,
+                          int feat_dim, float* out_dev, void* cuda_stream) {
+  if (!blob_dev || !record_offsets_host || !frame_offsets_host || !out_dev) { set_last_error("null argument"); return 1; }
+  if (n_records <= 0) return 0;
+  if (feat_dim <= 0) { set_last_error("feat_dim must be positive"); return 1; }
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const long long total = frame_offsets_host[n_records];
+  long long* d_rec = nullptr; int32_t* d_off = nullptr; int32_t* d_utt = nullptr;
+  static_assert(sizeof(long long) == sizeof(int64_t), "offset width");
+  API_CUDA(cudaMallocAsync(&d_rec, static_cast<size_t>(n_records) * 8, st));
+  API_CUDA(cudaMallocAsync(&d_off, static_cast<size_t>(n_records + 1) * 4, st));
+  API_CUDA(cudaMallocAsync(&d_utt, static_cast<size_t>(total > 0 ? total : 1) * 4, st));
+  API_CUDA(cudaMemcpyAsync(d_rec, record_offsets_host, static_cast<size_t>(n_records) * 8, cudaMemcpyHostToDevice, st));
+  API_CUDA(cudaMemcpyAsync(d_off, frame_offsets_host, static_cast<size_t>(n_records + 1) * 4, cudaMemcpyHostToDevice, st));
+  cudaError_t e = launch_cm_decode(blob_dev, d_rec, d_off, n_records, total, feat_dim, out_dev, d_utt, st);
+  cudaFreeAsync(d_rec, st); cudaFreeAsync(d_off, st); cudaFreeAsync(d_utt, st);
+  API_CUDA(e);
+  API_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
 int svx_l2norm_rows(const float* in_dev, float* out_dev, int64_t n, int d, void* cuda_stream) {
   if (!in_dev || !out_dev) { set_last_error("null argument"); return 1; }
   API_CUDA(launch_l2norm_rows(in_dev, out_dev, n, d, static_cast<cudaStream_t>(cuda_stream)));

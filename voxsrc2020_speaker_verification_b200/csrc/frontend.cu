@@ -70,3 +70,50 @@ cudaError_t launch_cmn_sliding(const float* feats, float* out, const int32_t* fr
 }
 
 }  // namespace svx
+
+// ---------------------------------------------------------------------------------------------------------
+// Kaldi CompressedMatrix ('CM ') decode on the device: the format `copy-feats --compress=true` writes for the prepared FBANK
+// (reference prepare_data.sh:68-69) and kaldi_io._read_compressed_mat reads (kaldi_io.py:471-504).  Per record: global header
+// {min f32, range f32, rows i32, cols i32}, per column 4 x uint16 percentiles (0, 25, 75, 100), then uint8 data column-major.
+// The arithmetic follows kaldi_io.py operation by operation in fp32 without contraction, so the result is bit-identical.
+namespace svx {
+
+__global__ void __launch_bounds__(256) cm_decode_kernel(const uint8_t* __restrict__ blob, const long long* __restrict__ rec_off,
+                                                        const int32_t* __restrict__ frame_off, const int32_t* __restrict__ utt_of_frame,
+                                                        float* out, long long total, int cols) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total * cols) return;
+  const long long row = idx / cols;
+  const int c = static_cast<int>(idx - row * cols);
+  const int u = utt_of_frame[row];
+  const int r = static_cast<int>(row - frame_off[u]);
+  const int rows = frame_off[u + 1] - frame_off[u];
+  const uint8_t* rec = blob + rec_off[u];
+  float gmin, grange;
+  memcpy(&gmin, rec, 4); memcpy(&grange, rec + 4, 4);
+  const uint8_t* ch = rec + 16 + static_cast<size_t>(c) * 8;
+  float p[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const unsigned short q = static_cast<unsigned short>(ch[2 * i] | (ch[2 * i + 1] << 8));
+    p[i] = __fadd_rn(__fmul_rn(__fmul_rn(static_cast<float>(q), grange), 1.52590218966964e-05f), gmin);     // kaldi_io.py:480-483
+  }
+  const uint8_t b = rec[16 + static_cast<size_t>(cols) * 8 + static_cast<size_t>(c) * rows + r];
+  const float d = static_cast<float>(b);
+  float v;
+  if (b <= 64) v = __fadd_rn(p[0], __fmul_rn(__fdiv_rn(__fsub_rn(p[1], p[0]), 64.f), d));                        // kaldi_io.py:497-503
+  else if (b > 192) v = __fadd_rn(p[2], __fmul_rn(__fdiv_rn(__fsub_rn(p[3], p[2]), 63.f), __fsub_rn(d, 192.f)));
+  else v = __fadd_rn(p[1], __fmul_rn(__fdiv_rn(__fsub_rn(p[2], p[1]), 128.f), __fsub_rn(d, 64.f)));
+  out[idx] = v;
+}
+
+cudaError_t launch_cm_decode(const uint8_t* blob, const long long* rec_off_dev, const int32_t* frame_off_dev, int n_utts, long long total_frames,
+                             int cols, float* out, int32_t* utt_ws, cudaStream_t st) {
+  if (n_utts <= 0 || total_frames <= 0) return cudaSuccess;
+  utt_of_frame_kernel<<<static_cast<unsigned>((total_frames + 255) / 256), 256, 0, st>>>(utt_ws, total_frames, frame_off_dev, n_utts);
+  const long long n = total_frames * cols;
+  cm_decode_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(blob, rec_off_dev, frame_off_dev, utt_ws, out, total_frames, cols);
+  return cudaGetLastError();
+}
+
+}  // namespace svx

@@ -35,6 +35,9 @@ cudaError_t launch_chunk_combine(const float* seg_emb, const int32_t* utt_seg_of
 cudaError_t launch_cmn_sliding(const float* feats, float* out, const int32_t* frame_off_dev, int n_utts, long long total_frames, int F,
                                int window, int center, double* csum_ws, int32_t* utt_ws, cudaStream_t st);
 
+cudaError_t launch_cm_decode(const uint8_t* blob, const long long* rec_off_dev, const int32_t* frame_off_dev, int n_utts, long long total_frames,
+                             int cols, float* out, int32_t* utt_ws, cudaStream_t st);
+
 // scoring
 cudaError_t launch_l2norm_rows(const float* in, float* out, long long n, int d, cudaStream_t st);
 cudaError_t launch_split3(const float* in, __nv_bfloat16* out, long long n, long long n_pad, int d, int cohort_side, cudaStream_t st);

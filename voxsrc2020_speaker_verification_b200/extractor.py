@@ -125,6 +125,21 @@ class Extractor:
                                              int(cmn_window), int(center), ctypes.c_void_p(self._stream())))
         return feats_dev
 
+    def decode_compressed(self, payloads: Sequence[bytes], rows: Sequence[int]) -> torch.Tensor:
+        """Kaldi 'CM ' records (payloads from ``kaldi_ark.read_mat_raw``) → CUDA fp32 [sum(rows), F], decoded on the device
+        bit-identically to kaldi_io._read_compressed_mat (reference kaldi_io.py:471-504)."""
+        n = len(payloads)
+        rec_off = np.zeros(n, np.int64)
+        np.cumsum([len(p) for p in payloads[:-1]], out=rec_off[1:])
+        offs = np.zeros(n + 1, np.int32)
+        np.cumsum(np.asarray(rows, np.int64), out=offs[1:])
+        blob = torch.frombuffer(bytearray(b"".join(payloads)), dtype=torch.uint8).to(torch.device("cuda", self.device))
+        out = torch.empty((int(offs[-1]), self.feat_dim), dtype=torch.float32, device=blob.device)
+        lib.check(self._lib.svx_decode_compressed(ctypes.c_void_p(blob.data_ptr()), rec_off.ctypes.data_as(ctypes.c_void_p),
+                                                  offs.ctypes.data_as(ctypes.c_void_p), n, self.feat_dim, ctypes.c_void_p(out.data_ptr()),
+                                                  ctypes.c_void_p(self._stream())))
+        return out
+
     def extract(self, utterances: Sequence[np.ndarray], cmvn: bool = False) -> np.ndarray:
         """Host → host: list of [T_i, F] float32 matrices → [n, E] float32 (chunk rule applied).  ``cmvn``: apply the
         sliding-window mean normalisation on the device first (raw FBANK in, as read from the feature ark)."""

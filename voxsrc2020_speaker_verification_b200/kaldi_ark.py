@@ -113,6 +113,35 @@ def read_mat(fd: BinaryIO) -> np.ndarray:
     return np.frombuffer(buf, dtype=dt).reshape(rows, cols)
 
 
+def read_mat_raw(fd: BinaryIO):
+    """Like ``read_mat`` but leaves 'CM ' records undecoded for the device decoder (svx_decode_compressed):
+    returns ('CM ', payload bytes starting at the global header, rows, cols) or ('dense', ndarray)."""
+    flag = _read_exact(fd, 2)
+    if flag != b"\0B":
+        raise UnknownMatrixHeader("only binary Kaldi matrices are supported, got %r" % flag)
+    header = _read_exact(fd, 3).decode("latin1")
+    if header == "CM ":
+        head = _read_exact(fd, 16)
+        _, _, rows, cols = struct.unpack("<ffii", head)
+        return "CM ", head + _read_exact(fd, cols * 8 + cols * rows), rows, cols
+    fd.seek(-5, 1)
+    m = read_mat(fd)
+    return "dense", m, m.shape[0], m.shape[1]
+
+
+def read_mat_ark_raw(path_or_fd):
+    """(key, kind, payload, rows, cols) for every record of a matrix ark (see ``read_mat_raw``)."""
+    fd, own = _open(path_or_fd)
+    try:
+        key = _read_key(fd)
+        while key:
+            yield (key,) + read_mat_raw(fd)
+            key = _read_key(fd)
+    finally:
+        if own:
+            fd.close()
+
+
 def read_mat_ark(path_or_fd) -> Iterator[Tuple[str, np.ndarray]]:
     """(key, matrix) pairs of a matrix ark, in file order (kaldi_io.py:367-385)."""
     fd, own = _open(path_or_fd)
@@ -157,6 +186,23 @@ def read_mat_scp(path: str) -> Iterator[Tuple[str, np.ndarray]]:
             if off is not None:
                 cur_fd.seek(off)
             yield key, read_mat(cur_fd)
+    finally:
+        if cur_fd is not None:
+            cur_fd.close()
+
+
+def read_mat_scp_raw(path: str):
+    """(key, kind, payload, rows, cols) addressed by a script file; 'CM ' records stay compressed (see ``read_mat_raw``)."""
+    cur_path, cur_fd = None, None
+    try:
+        for key, rx, off in read_scp(path):
+            if rx != cur_path:
+                if cur_fd is not None:
+                    cur_fd.close()
+                cur_fd, cur_path = open(rx, "rb"), rx
+            if off is not None:
+                cur_fd.seek(off)
+            yield (key,) + read_mat_raw(cur_fd)
     finally:
         if cur_fd is not None:
             cur_fd.close()

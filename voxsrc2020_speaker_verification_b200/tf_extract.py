@@ -11,9 +11,11 @@ CUDA_VISIBLE_DEVICES as in eval_inference_model.sh:29-36.
 from __future__ import annotations
 
 import argparse
+import io
 import sys
 
 import numpy as np
+import torch
 
 from . import kaldi_ark
 from .extractor import Extractor
@@ -30,29 +32,59 @@ def run(pb_file: str, expand_dim: int, rspec: str, wspec: str, precision: str = 
     ex = Extractor.from_pb(pb_file, expand_dim, device=device, precision=precision, model_id=model_id, feat_dim=feat_dim)
     n_done = 0
     with kaldi_ark.VectorArkScpWriter(wspec) as writer:
-        keys, mats, frames = [], [], 0
+        keys, recs, frames = [], [], 0
 
         def flush():
-            nonlocal keys, mats, frames, n_done
+            nonlocal keys, recs, frames, n_done
             if not keys:
                 return
-            emb = ex.extract_bucketed(mats, max_frames=max_frames, cmvn=cmvn)   # sliding CMN runs on the device
+            if all(kind == "CM " for kind, _, _ in recs):
+                emb = extract_compressed(ex, recs, max_frames, cmvn)      # decode + CMN + network, all on the device
+            else:
+                mats = [kaldi_ark._decode_compressed(io.BytesIO(p), "CM ") if kind == "CM " else np.asarray(p, np.float32)
+                        for kind, p, _ in recs]
+                emb = ex.extract_bucketed(mats, max_frames=max_frames, cmvn=cmvn)   # sliding CMN runs on the device
             for k, e in zip(keys, emb):          # written in input order, like the reference
                 writer.write(k, e)
             n_done += len(keys)
-            keys, mats, frames = [], [], 0
+            keys, recs, frames = [], [], 0
 
-        for key, mat in iter_features(rspec, False):
-            if mat.shape[0] < 25:
+        for key, kind, payload, rows, cols in kaldi_ark.read_mat_scp_raw(rspec + ".scp"):
+            if rows < 25:
                 # the reference divides by zero here (tf_extract.py:102,111); fail as loudly
-                raise ZeroDivisionError("utterance %s has %d frames (< 25)" % (key, mat.shape[0]))
+                raise ZeroDivisionError("utterance %s has %d frames (< 25)" % (key, rows))
             keys.append(key)
-            mats.append(mat)
-            frames += mat.shape[0]
+            recs.append((kind, payload, rows))
+            frames += rows
             if frames >= 4 * max_frames:
                 flush()
         flush()
     return n_done
+
+
+def extract_compressed(ex: Extractor, recs, max_frames: int, cmvn: bool) -> np.ndarray:
+    """Compressed FBANK records → embeddings without a host-side decode: length-sorted groups of ≤ max_frames frames are
+    decoded (svx_decode_compressed), mean-normalised (svx_cmvn_sliding) and embedded on the device."""
+    order = np.argsort([r for _, _, r in recs], kind="stable")
+    out = np.zeros((len(recs), ex.embed_dim), np.float32)
+    group, frames = [], 0
+    for idx in list(order) + [None]:
+        if idx is not None and (not group or frames + recs[idx][2] <= max_frames):
+            group.append(int(idx))
+            frames += recs[idx][2]
+            continue
+        if group:
+            rows = [recs[i][2] for i in group]
+            dev = ex.decode_compressed([recs[i][1] for i in group], rows)
+            offs = np.zeros(len(group) + 1, np.int32)
+            np.cumsum(rows, out=offs[1:])
+            if cmvn:
+                ex.cmvn_sliding(dev, offs)
+            res = torch.empty((len(group), ex.embed_dim), dtype=torch.float32, device=dev.device)
+            ex.extract_packed(dev, offs, res)
+            out[group] = res.cpu().numpy()
+        group, frames = ([int(idx)], recs[idx][2]) if idx is not None else ([], 0)
+    return out
 
 
 def main(argv=None) -> int:
