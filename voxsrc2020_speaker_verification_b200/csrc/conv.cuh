@@ -170,6 +170,8 @@ struct FlatConvParams {
   uint32_t a_stage_bytes, b_item_bytes;
   int b_resident;
   uint32_t idesc, sbo, layout_type, tmem_cols;
+  int pair;                    // 1: CTA pairs (cta_group::2, M = 256): even/odd CTAs of a cluster take consecutive spans, each holds half of B
+  int b_rows;                  // weight rows this CTA loads per item: n_tile, or n_tile/2 in pair mode
   // epilogue
   const float* scale; const float* shift;
   int n_valid;                 // real output channels

@@ -21,6 +21,7 @@
 //            second output (x_{i+1} + o_i) -> swizzled smem boxes (in place over the aux tile)
 // The epilogue body is specialised at compile time on <aux mode, pre-ReLU, post-ReLU>; the previous generic
 // body cost ~35 SASS instructions per output value and bounded every 1x1 conv.
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -127,15 +128,24 @@ __device__ __forceinline__ void epi8(const uint32_t* r, uint32_t sc, uint32_t sh
 // All MMAs of one filter tap: MT sub-tiles x KS K-steps, fully unrolled so that every descriptor is the tap's base
 // (one value) plus a compile-time constant.  A generic loop costs ~150 cycles of issue per MMA (descriptor arithmetic in
 // vector registers + 5 R2UR each, tools/microbench/mma_rate.cu) against 16-64 cycles of tensor-pipe time.
-template <int MT, int KS>
+template <int MT, int KS, bool pair>
 __device__ __forceinline__ void issue_tap(uint64_t adesc0, uint64_t bdesc0, uint32_t d_tmem, uint32_t n_tile, uint32_t idesc, uint32_t first) {
   constexpr uint32_t kSub16 = 256u * KS;      // (128 rows x 32*KS bytes) >> 4
   if (elect_one()) {      // one elected region for the whole tap: the R2UR traffic of consecutive MMAs overlaps
+    if constexpr (pair) {           // M = 256 across the CTA pair: the same descriptors address both CTAs' shared memory
 #pragma unroll
-    for (int j = 0; j < MT; ++j) {
+      for (int j = 0; j < MT; ++j) {
 #pragma unroll
-      for (int k = 0; k < KS; ++k)
-        umma_f16(d_tmem + j * n_tile, adesc0 + (j * kSub16 + k * 2), bdesc0 + k * 2, idesc, k == 0 ? first : 1u);
+        for (int k = 0; k < KS; ++k)
+          umma_f16_2cta(d_tmem + j * n_tile, adesc0 + (j * kSub16 + k * 2), bdesc0 + k * 2, idesc, k == 0 ? first : 1u);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < MT; ++j) {
+#pragma unroll
+        for (int k = 0; k < KS; ++k)
+          umma_f16(d_tmem + j * n_tile, adesc0 + (j * kSub16 + k * 2), bdesc0 + k * 2, idesc, k == 0 ? first : 1u);
+      }
     }
   }
 }
@@ -145,6 +155,7 @@ struct Smem {
   uint64_t slot_full[kRing], slot_empty[kRing], slot_ready[kRing];
   uint64_t tmem_full[2], tmem_empty[2];
   uint64_t bres_bar;
+  uint64_t pa_full[kRing], pb_full[kRing], pbres_bar;   // pair mode, leader CTA: the peer's A stage / weight item / resident weights landed
   uint32_t tmem_slot;
   volatile uint32_t prog[16];   // debug: progress of each role (warp), dumped by wait_dbg on a timeout
 };
@@ -152,7 +163,9 @@ static_assert(sizeof(Smem) <= 1024, "barrier block");
 
 }  // namespace
 
-template <typename T, int AUX, bool PRE, bool POST>
+// PAIR is a template parameter because a kernel that contains cta_group::2 instructions can only be launched as a cluster
+// (a plain launch of such a binary fails with "cluster misconfiguration").
+template <typename T, int AUX, bool PRE, bool POST, bool PAIR>
 __global__ void __launch_bounds__(kFlatThreads, 1)
 conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant__ FlatMaps maps) {
   extern __shared__ uint8_t smem_raw[];
@@ -170,9 +183,18 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
   const int lane = threadIdx.x & 31;
   const int span_px = p.mt * 128;
   const int n_spans = static_cast<int>((p.P + span_px - 1) / span_px);
-  const int groups = gridDim.x / p.n_tiles;
-  const int my_group = blockIdx.x / p.n_tiles;
-  const int n_blk = blockIdx.x % p.n_tiles;
+  // pair mode: CTAs (2i, 2i+1) of a cluster form one unit that takes two consecutive spans per step (rank r takes span 2u + r)
+  constexpr bool pair = PAIR;
+  uint32_t rank = 0u;
+  if constexpr (pair) rank = cluster_ctarank();
+  const int sstride = pair ? 2 : 1;
+  const int unit_id = pair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int n_cta_units = pair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int n_units = (n_spans + sstride - 1) / sstride;
+  const int n_spans_all = n_units * sstride;          // includes the phantom span of an odd count (fully masked, loads zero-filled)
+  const int groups = n_cta_units / p.n_tiles;
+  const int my_group = unit_id / p.n_tiles;
+  const int n_blk = unit_id % p.n_tiles;
   const int n0 = n_blk * p.n_tile;
   const uint32_t row_bytes = static_cast<uint32_t>(p.kbox) * 2u;
   const uint32_t box_bytes = 128u * static_cast<uint32_t>(p.box_ch) * 2u;
@@ -187,18 +209,24 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
       mbar_init(&S.b_full[i], 1); mbar_init(&S.b_empty[i], 1);
       mbar_init(&S.slot_full[i], 1); mbar_init(&S.slot_empty[i], 1); mbar_init(&S.slot_ready[i], 128);
     }
-    for (int b = 0; b < 2; ++b) { mbar_init(&S.tmem_full[b], 1); mbar_init(&S.tmem_empty[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&S.tmem_full[b], 1); mbar_init(&S.tmem_empty[b], pair ? 8 : 4); }   // pair: both CTAs' epilogue warps
     mbar_init(&S.bres_bar, 1);
+    for (int i = 0; i < kRing; ++i) { mbar_init(&S.pa_full[i], 1); mbar_init(&S.pb_full[i], 1); }
+    mbar_init(&S.pbres_bar, 1);
     fence_barrier_init();
     if (p.b_resident) {     // weights are static: fetch them before the dependency wait
-      const uint32_t bb = static_cast<uint32_t>(p.n_tile) * row_bytes;
+      const uint32_t bb = static_cast<uint32_t>(p.b_rows) * row_bytes;
       mbar_expect_tx(&S.bres_bar, bb * total_items);
       for (int kc = 0; kc < p.nkc; ++kc)
         for (int tap = 0; tap < p.taps; ++tap)
-          tma_load_2d(b_smem + static_cast<size_t>(kc * p.taps + tap) * p.b_item_bytes, &maps.b, &S.bres_bar, tap * p.kpad + kc * p.kbox, n0);
+          tma_load_2d(b_smem + static_cast<size_t>(kc * p.taps + tap) * p.b_item_bytes, &maps.b, &S.bres_bar, tap * p.kpad + kc * p.kbox,
+                      n0 + static_cast<int>(rank) * p.b_rows);
     }
   }
-  if (warp == 1) { tmem_alloc(&S.tmem_slot, p.tmem_cols); tmem_relinquish(); }
+  if (warp == 1) {
+    if constexpr (pair) { tmem_alloc_2cta(&S.tmem_slot, p.tmem_cols); tmem_relinquish_2cta(); }
+    else { tmem_alloc(&S.tmem_slot, p.tmem_cols); tmem_relinquish(); }
+  }
   for (int i = threadIdx.x; i < p.n_tile; i += kFlatThreads) {
     const int c = n0 + i;
     s_scale[i] = (p.scale && c < p.n_valid) ? p.scale[c] : 1.f;
@@ -206,6 +234,7 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (pair) cluster_sync_all();        // the peer's barriers are initialised before anything arrives on them remotely
   tc_fence_after();
   const uint32_t tmem_base = S.tmem_slot;
   // Programmatic dependent launch: the next conv's CTAs may be scheduled as soon as SMs free up and run their own prologue
@@ -217,12 +246,13 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
   if (warp == 0) {
     // ------------------------------------------------------------------ producer: A spans + weights
     if (lane == 0) {
-      const uint32_t b_box_bytes = static_cast<uint32_t>(p.n_tile) * row_bytes;
+      const uint32_t b_box_bytes = static_cast<uint32_t>(p.b_rows) * row_bytes;
       const uint32_t a_tx = static_cast<uint32_t>(p.a_boxes) * p.a_box_rows * row_bytes;
       Tracer tr; tr.init(p.trace, 0);
       uint32_t ia = 0, ib = 0;
-      for (int span = my_group; span < n_spans; span += groups) {
-        const int p0 = (p.reverse ? n_spans - 1 - span : span) * span_px;
+      for (int unit = my_group; unit < n_units; unit += groups) {
+        const int span = unit * sstride + static_cast<int>(rank);
+        const int p0 = (p.reverse ? n_spans_all - 1 - span : span) * span_px;
         tr.ev(1);
         S.prog[0] = ia;
         for (int kc = 0; kc < p.nkc; ++kc, ++ia) {
@@ -238,7 +268,8 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
               const int sb = ib % p.b_stages;
               wait_dbg(&S.b_empty[sb], ((ib / p.b_stages) & 1) ^ 1, p.dbg, 0x02, sb, ib, S.prog);
               mbar_expect_tx(&S.b_full[sb], b_box_bytes);
-              tma_load_2d(b_smem + static_cast<size_t>(sb) * p.b_item_bytes, &maps.b, &S.b_full[sb], tap * p.kpad + kc * p.kbox, n0);
+              tma_load_2d(b_smem + static_cast<size_t>(sb) * p.b_item_bytes, &maps.b, &S.b_full[sb], tap * p.kpad + kc * p.kbox,
+                          n0 + static_cast<int>(rank) * p.b_rows);
             }
           }
         }
@@ -250,45 +281,44 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
     // The whole warp runs the loop CONVERGED and computes the descriptors (uniform values → uniform registers); only the
     // tcgen05 instructions themselves sit under the elected-lane branch.  Computing them inside an `if (lane == 0)` region
     // made ptxas wrap every UTCHMMA in an ELECT / 5x R2UR.BROADCAST waterfall: ~200 ns per MMA whatever its shape.
+    //
+    // Pair mode: the leader (cluster rank 0) issues M = 256 MMAs that read both CTAs' shared memory and write both CTAs'
+    // TMEM; its commits multicast to both CTAs' barriers.  The peer's warp 1 is a relay: it walks the same ring positions and
+    // forwards "my A stage / weight item landed" to the leader's pa_full / pb_full barriers.
     const int ksteps = p.kbox >> 4;
-    if (p.b_resident) wait_dbg(&S.bres_bar, 0, p.dbg, 0x10, 0, 0, S.prog);
+    const bool relay = pair && rank == 1;
+    if (p.b_resident) {
+      wait_dbg(&S.bres_bar, 0, p.dbg, 0x10, 0, 0, S.prog);
+      if constexpr (pair) {
+        if (relay) { if (elect_one()) mbar_arrive_remote(&S.pbres_bar, 0); }
+        else wait_dbg(&S.pbres_bar, 0, p.dbg, 0x14, 0, 0, S.prog);
+      }
+    }
     const uint64_t desc_base = make_kmajor_desc(0, p.sbo, p.layout_type);
     const uint32_t a_base = smem_u32(a_smem), b_base = smem_u32(b_smem);
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
     const int mtks = (p.mt << 4) | ksteps;
-    const bool jmajor = false;   // sub-tile-major issue order measured slower (62 vs 50 ns per MMA): per-call overhead dominates
     Tracer tr; tr.init(lane == 0 ? p.trace : nullptr, 1);
     uint32_t ia = 0, ib = 0;
     int ls = 0;
-    for (int span = my_group; span < n_spans; span += groups, ++ls) {
+    for (int unit = my_group; unit < n_units; unit += groups, ++ls) {
       const int buf = ls & 1;
       tr.ev(1);
       if (lane == 0) S.prog[1] = ls;
-      wait_dbg(&S.tmem_empty[buf], ((ls >> 1) & 1) ^ 1, p.dbg, 0x11, buf, ls, S.prog);
+      if (!relay) wait_dbg(&S.tmem_empty[buf], ((ls >> 1) & 1) ^ 1, p.dbg, 0x11, buf, ls, S.prog);
       tr.ev(2);
       tc_fence_after();
       const uint32_t d_tmem = tb + static_cast<uint32_t>(buf * p.mt * p.n_tile);
       for (int kc = 0; kc < p.nkc; ++kc, ++ia) {
         const int sa = ia % p.a_stages;
-        wait_dbg(&S.a_full[sa], (ia / p.a_stages) & 1, p.dbg, 0x12, sa, ia, S.prog);
+        const uint32_t a_par = (ia / p.a_stages) & 1;
+        wait_dbg(&S.a_full[sa], a_par, p.dbg, 0x12, sa, ia, S.prog);
+        if constexpr (pair) {
+          if (relay) { if (elect_one()) mbar_arrive_remote(&S.pa_full[sa], 0); }
+          else wait_dbg(&S.pa_full[sa], a_par, p.dbg, 0x15, sa, ia, S.prog);
+        }
         if (kc == 0) tr.ev(3);
         const uint32_t a_addr = a_base + static_cast<uint32_t>(sa) * p.a_stage_bytes;
-        if (p.b_resident && p.mt > 1 && jmajor) {
-          // resident weights: any order is legal; sub-tile-major keeps each accumulator's MMAs back to back
-          tc_fence_after();
-          const uint32_t nt = static_cast<uint32_t>(p.n_tile);
-          for (int j = 0; j < p.mt; ++j) {
-            for (int tap = 0; tap < p.taps; ++tap) {
-              const uint32_t b_addr = b_base + static_cast<uint32_t>(kc * p.taps + tap) * p.b_item_bytes;
-              const uint32_t a_tap = a_addr + static_cast<uint32_t>(p.halo + p.tap_shift[tap] + j * 128) * row_bytes;
-              const uint32_t first = (kc == 0 && tap == 0) ? 0u : 1u;
-              const uint64_t adesc0 = desc_base + (a_tap >> 4), bdesc0 = desc_base + (b_addr >> 4);
-              if (ksteps == 4) issue_tap<1, 4>(adesc0, bdesc0, d_tmem + j * nt, nt, p.idesc, first);
-              else if (ksteps == 2) issue_tap<1, 2>(adesc0, bdesc0, d_tmem + j * nt, nt, p.idesc, first);
-              else issue_tap<1, 1>(adesc0, bdesc0, d_tmem + j * nt, nt, p.idesc, first);
-            }
-          }
-        } else
         for (int tap = 0; tap < p.taps; ++tap) {
           uint32_t b_addr;
           int sb = 0;
@@ -296,31 +326,42 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
             b_addr = b_base + static_cast<uint32_t>(kc * p.taps + tap) * p.b_item_bytes;
           } else {
             sb = ib % p.b_stages;
-            wait_dbg(&S.b_full[sb], (ib / p.b_stages) & 1, p.dbg, 0x13, sb, ib, S.prog);
+            const uint32_t b_par = (ib / p.b_stages) & 1;
+            wait_dbg(&S.b_full[sb], b_par, p.dbg, 0x13, sb, ib, S.prog);
+            if constexpr (pair) {
+              if (relay) { if (elect_one()) mbar_arrive_remote(&S.pb_full[sb], 0); }
+              else wait_dbg(&S.pb_full[sb], b_par, p.dbg, 0x16, sb, ib, S.prog);
+            }
             b_addr = b_base + static_cast<uint32_t>(sb) * p.b_item_bytes;
             ++ib;
           }
+          if (relay) continue;
           tc_fence_after();
           const uint32_t a_tap = a_addr + static_cast<uint32_t>(p.halo + p.tap_shift[tap]) * row_bytes;
           const uint32_t first = (kc == 0 && tap == 0) ? 0u : 1u;
           const uint64_t adesc0 = desc_base + (a_tap >> 4), bdesc0 = desc_base + (b_addr >> 4);   // smem < 256 KB: no carry out of the field
           const uint32_t nt = static_cast<uint32_t>(p.n_tile);
           switch (mtks) {
-            case 0x11: issue_tap<1, 1>(adesc0, bdesc0, d_tmem, nt, p.idesc, first); break;
-            case 0x12: issue_tap<1, 2>(adesc0, bdesc0, d_tmem, nt, p.idesc, first); break;
-            case 0x14: issue_tap<1, 4>(adesc0, bdesc0, d_tmem, nt, p.idesc, first); break;
-            case 0x21: issue_tap<2, 1>(adesc0, bdesc0, d_tmem, nt, p.idesc, first); break;
-            case 0x22: issue_tap<2, 2>(adesc0, bdesc0, d_tmem, nt, p.idesc, first); break;
-            case 0x24: issue_tap<2, 4>(adesc0, bdesc0, d_tmem, nt, p.idesc, first); break;
-            case 0x41: issue_tap<4, 1>(adesc0, bdesc0, d_tmem, nt, p.idesc, first); break;
-            case 0x42: issue_tap<4, 2>(adesc0, bdesc0, d_tmem, nt, p.idesc, first); break;
-            default:   issue_tap<4, 4>(adesc0, bdesc0, d_tmem, nt, p.idesc, first); break;
+            case 0x11: issue_tap<1, 1, PAIR>(adesc0, bdesc0, d_tmem, nt, p.idesc, first); break;
+            case 0x12: issue_tap<1, 2, PAIR>(adesc0, bdesc0, d_tmem, nt, p.idesc, first); break;
+            case 0x14: issue_tap<1, 4, PAIR>(adesc0, bdesc0, d_tmem, nt, p.idesc, first); break;
+            case 0x21: issue_tap<2, 1, PAIR>(adesc0, bdesc0, d_tmem, nt, p.idesc, first); break;
+            case 0x22: issue_tap<2, 2, PAIR>(adesc0, bdesc0, d_tmem, nt, p.idesc, first); break;
+            case 0x24: issue_tap<2, 4, PAIR>(adesc0, bdesc0, d_tmem, nt, p.idesc, first); break;
+            case 0x41: issue_tap<4, 1, PAIR>(adesc0, bdesc0, d_tmem, nt, p.idesc, first); break;
+            case 0x42: issue_tap<4, 2, PAIR>(adesc0, bdesc0, d_tmem, nt, p.idesc, first); break;
+            default:   issue_tap<4, 4, PAIR>(adesc0, bdesc0, d_tmem, nt, p.idesc, first); break;
           }
-          if (!p.b_resident && elect_one()) umma_commit(&S.b_empty[sb]);
+          if (!p.b_resident && elect_one()) { if constexpr (pair) umma_commit_2cta(&S.b_empty[sb]); else umma_commit(&S.b_empty[sb]); }
         }
-        if (elect_one()) {
-          umma_commit(&S.a_empty[sa]);
-          if (kc == p.nkc - 1) umma_commit(&S.tmem_full[buf]);
+        if (!relay && elect_one()) {
+          if constexpr (pair) {
+            umma_commit_2cta(&S.a_empty[sa]);
+            if (kc == p.nkc - 1) umma_commit_2cta(&S.tmem_full[buf]);
+          } else {
+            umma_commit(&S.a_empty[sa]);
+            if (kc == p.nkc - 1) umma_commit(&S.tmem_full[buf]);
+          }
         }
       }
       tr.ev(4);
@@ -335,8 +376,9 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
       const uint32_t buf_off = AUX == 2 ? static_cast<uint32_t>(p.boxes) * box_bytes : 0u;
       Tracer tr; tr.init(p.trace, 2);
       int ls = 0;
-      for (int span = my_group; span < n_spans; span += groups, ++ls) {
-        const int p0 = (p.reverse ? n_spans - 1 - span : span) * span_px;
+      for (int unit = my_group; unit < n_units; unit += groups, ++ls) {
+        const int span = unit * sstride + static_cast<int>(rank);
+        const int p0 = (p.reverse ? n_spans_all - 1 - span : span) * span_px;
         for (int j = 0; j < p.mt; ++j) {
           const uint32_t q = static_cast<uint32_t>(ls >> 1) * p.mt + j;      // sub-tile counter of the warpgroup that owns this span
           const int slot = (ls & 1) * p.slots + q % p.slots;
@@ -362,8 +404,9 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
       const uint32_t slot_base = smem_u32(slot_smem);
       int prev_slot = -1;
       int ls = 0;
-      for (int span = my_group; span < n_spans; span += groups, ++ls) {
-        const int p0 = (p.reverse ? n_spans - 1 - span : span) * span_px;
+      for (int unit = my_group; unit < n_units; unit += groups, ++ls) {
+        const int span = unit * sstride + static_cast<int>(rank);
+        const int p0 = (p.reverse ? n_spans_all - 1 - span : span) * span_px;
         for (int j = 0; j < p.mt; ++j) {
           const uint32_t q = static_cast<uint32_t>(ls >> 1) * p.mt + j;
           const int slot = (ls & 1) * p.slots + q % p.slots;
@@ -406,9 +449,10 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
     const uint32_t bufB_off = static_cast<uint32_t>(p.boxes) * box_bytes;
     Tracer tr; tr.init((q4 == 0 && lane == 0) ? p.trace : nullptr, 4 + wg);
     int ls = 0;
-    for (int span = my_group; span < n_spans; span += groups, ++ls) {
+    for (int unit = my_group; unit < n_units; unit += groups, ++ls) {
+        const int span = unit * sstride + static_cast<int>(rank);
       if ((ls & 1) != wg) continue;
-      const long long p0 = static_cast<long long>(p.reverse ? n_spans - 1 - span : span) * span_px;
+      const long long p0 = static_cast<long long>(p.reverse ? n_spans_all - 1 - span : span) * span_px;
       uint32_t vm[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -462,7 +506,11 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
         if (j == p.mt - 1) {              // all accumulators of this span are in registers / smem: hand TMEM back
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&S.tmem_empty[wg]);
+          if (lane == 0) {
+            bool done = false;
+            if constexpr (pair) { if (rank == 1) { mbar_arrive_remote(&S.tmem_empty[wg], 0); done = true; } }
+            if (!done) mbar_arrive(&S.tmem_empty[wg]);
+          }
         }
         if (lane == 0) S.prog[warp] = 0x30000u | q;
         fence_proxy_async();              // generic-proxy writes of this thread → visible to the TMA store
@@ -473,7 +521,8 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+  if constexpr (pair) cluster_sync_all();        // the leader's MMAs read the peer's shared memory: nobody leaves before everybody is done
+  if (warp == 1) { if constexpr (pair) tmem_dealloc_2cta(tmem_base, p.tmem_cols); else tmem_dealloc(tmem_base, p.tmem_cols); }
 }
 
 size_t conv_flat_smem_bytes(const FlatConvParams& p) {
@@ -485,7 +534,9 @@ static int g_flat_sms = 0;
 
 template <typename T, int AUX, bool PRE, bool POST>
 static cudaError_t set_attr() {
-  return cudaFuncSetAttribute(conv_flat_kernel<T, AUX, PRE, POST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(conv_flat_kernel<T, AUX, PRE, POST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(conv_flat_kernel<T, AUX, PRE, POST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 
 template <typename T>
@@ -517,12 +568,27 @@ static cudaError_t launch_typed(const FlatConvParams& p, const FlatMaps& maps, d
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = grid; cfg.blockDim = dim3(kFlatThreads, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (p.pair) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (!no_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr; cfg.numAttrs = na;
   cudaError_t le = cudaSuccess;
-#define SVX_FLAT(AUX, PRE, POST) le = cudaLaunchKernelEx(&cfg, conv_flat_kernel<T, AUX, PRE, POST>, p, maps)
+  static const bool launch_log = getenv("SVX_LAUNCH_LOG") != nullptr;   // debug switch
+  if (launch_log)
+    fprintf(stderr, "conv_flat launch: grid %u smem %zu pair %d n_tiles %d n_tile %d mt %d P %lld aux %d\n", grid.x, smem, p.pair, p.n_tiles, p.n_tile, p.mt,
+            p.P, p.aux_mode);
+#define SVX_FLAT(AUX, PRE, POST)                                                                       \
+  le = p.pair ? cudaLaunchKernelEx(&cfg, conv_flat_kernel<T, AUX, PRE, POST, true>, p, maps)          \
+              : cudaLaunchKernelEx(&cfg, conv_flat_kernel<T, AUX, PRE, POST, false>, p, maps)
   if (p.aux_mode == 0) {
     if (p.pre_relu && !p.post_relu) SVX_FLAT(0, true, false);
     else if (!p.pre_relu && p.post_relu) SVX_FLAT(0, false, true);
@@ -536,7 +602,11 @@ static cudaError_t launch_typed(const FlatConvParams& p, const FlatMaps& maps, d
     SVX_FLAT(2, false, true);
   }
 #undef SVX_FLAT
-  if (le != cudaSuccess) return le;
+  if (le != cudaSuccess) {
+    fprintf(stderr, "conv_flat launch failed: grid %u block %d smem %zu pair %d n_tiles %d n_tile %d mt %d\n", grid.x, kFlatThreads, smem, p.pair, p.n_tiles,
+            p.n_tile, p.mt);
+    return le;
+  }
   return cudaGetLastError();
 }
 
@@ -544,10 +614,12 @@ cudaError_t launch_conv_flat(const FlatConvParams& p, const FlatMaps& maps, int 
   if (p.P <= 0) return cudaSuccess;
   const long long n_spans = (p.P + p.mt * 128 - 1) / (p.mt * 128);
   const int sms = g_flat_sms > 0 ? g_flat_sms : 148;
-  long long groups = sms / p.n_tiles;
+  const int per_unit = p.pair ? 2 : 1;                                   // CTAs per scheduling unit
+  const long long n_units = (n_spans + per_unit - 1) / per_unit;
+  long long groups = (sms / per_unit) / p.n_tiles;
   if (groups < 1) groups = 1;
-  if (groups > n_spans) groups = n_spans;
-  dim3 grid(static_cast<unsigned>(groups * p.n_tiles), 1, 1);
+  if (groups > n_units) groups = n_units;
+  dim3 grid(static_cast<unsigned>(groups * p.n_tiles * per_unit), 1, 1);
   const size_t smem = conv_flat_smem_bytes(p);
   return is_bf16 ? launch_typed<__nv_bfloat16>(p, maps, grid, smem, stream) : launch_typed<__half>(p, maps, grid, smem, stream);
 }

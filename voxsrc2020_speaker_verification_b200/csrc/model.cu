@@ -771,6 +771,10 @@ int Model::plan_flat(ConvDesc& c) {
   }
   static const int env_maxmt = getenv("SVX_FLAT_MAXMT") ? atoi(getenv("SVX_FLAT_MAXMT")) : 4;          // debug switches
   static const bool plan_log = getenv("SVX_PLAN_LOG") != nullptr;
+  // CTA pairs (cta_group::2): worth it where the weights dominate shared memory or are streamed — total K (taps x channels) at or
+  // above a threshold; SVX_PAIR_MIN_K overrides (0 = every layer, huge = never)
+  static const int pair_min_k = getenv("SVX_PAIR_MIN_K") ? atoi(getenv("SVX_PAIR_MIN_K")) : (1 << 30);
+  const bool use_pair = !grouped && taps * c.kpad >= pair_min_k;
   const int ksteps = c.kbox / 16;
   bool found = false;
   double best = 1e30;
@@ -788,7 +792,8 @@ int Model::plan_flat(ConvDesc& c) {
       const int boxes = (n_tile + box_ch - 1) / box_ch;
       const uint32_t box_bytes = 128u * box_ch * 2u;
       const uint32_t slot_bytes = boxes * box_bytes * (aux_mode == 2 ? 2u : 1u);
-      const uint32_t b_item = static_cast<uint32_t>(round_up(n_tile * static_cast<int>(row_bytes), 1024));
+      const int b_rows_cta = use_pair ? n_tile / 2 : n_tile;                    // pair mode: each CTA of the pair holds half of the weights
+      const uint32_t b_item = static_cast<uint32_t>(round_up(b_rows_cta * static_cast<int>(row_bytes), 1024));
       const int items = taps * c.nkc;
       const long long b_total = static_cast<long long>(items) * b_item;
       for (int mt : {4, 2, 1}) {
@@ -813,7 +818,7 @@ int Model::plan_flat(ConvDesc& c) {
           // ---- cost per 128 output pixels (cycles)
           const double halo_ovh = 1.0 + 2.0 * halo / (mt * 128.0);
           const double a_rows = static_cast<double>(n_tiles) * c.nkc * 128.0 * halo_ovh;
-          const double b_rows = b_res ? 0.0 : static_cast<double>(n_tiles) * items * n_tile / mt;
+          const double b_rows = b_res ? 0.0 : static_cast<double>(n_tiles) * items * b_rows_cta / mt;
           const int aux_boxes = aux_mode ? boxes : 0;
           const double aux_rows = static_cast<double>(n_tiles) * aux_boxes * 128.0;
           const double st_rows = static_cast<double>(n_tiles) * boxes * 128.0 * (aux_mode == 2 ? 2.0 : 1.0);
@@ -876,7 +881,9 @@ int Model::plan_flat(ConvDesc& c) {
   while (tc < 2u * fp.mt * fp.n_tile) tc *= 2;
   if (tc > 512) return 0;
   fp.tmem_cols = tc;
-  fp.idesc = ptx::make_idesc_f16(is_bf16_ ? 1u : 0u, 128u, static_cast<uint32_t>(fp.n_tile));
+  fp.pair = use_pair ? 1 : 0;
+  fp.b_rows = use_pair ? fp.n_tile / 2 : fp.n_tile;
+  fp.idesc = ptx::make_idesc_f16(is_bf16_ ? 1u : 0u, use_pair ? 256u : 128u, static_cast<uint32_t>(fp.n_tile));
 
   // tensor maps over the flat pixel sequence
   const size_t esz = 2;
@@ -897,7 +904,7 @@ int Model::plan_flat(ConvDesc& c) {
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(taps) * c.kpad, static_cast<uint64_t>(c.n_pad)};
     const uint64_t str[1] = {static_cast<uint64_t>(taps) * c.kpad * esz};
-    const uint32_t box[2] = {static_cast<uint32_t>(c.kbox), static_cast<uint32_t>(fp.n_tile)};
+    const uint32_t box[2] = {static_cast<uint32_t>(c.kbox), static_cast<uint32_t>(fp.b_rows)};
     if (encode_tmap(&fm.b, is_bf16_, c.d_wgt, 2, dims, str, box, row_bytes)) return 1;
   }
   // L2 promotion widens every TMA request to the promotion size; on a narrow channel slice of a wider row that
