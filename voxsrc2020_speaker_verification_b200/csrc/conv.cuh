@@ -180,7 +180,8 @@ struct FlatConvParams {
   const uint8_t* pix_valid;    // [P_cap] 1 = pixel belongs to a segment and is not the zero column
   int aux_mode;                // 0 none, 1 residual added before post-ReLU (in place), 2 second output = v + add2
   int box_ch;                  // channels per staging box: 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B)
-  int boxes;                   // staging boxes per buffer = ceil(n_tile / box_ch)
+  int boxes;                   // staging boxes per buffer = ceil(part_cols / box_ch)
+  int n_parts, part_cols;      // a slot holds part_cols = n_tile / n_parts columns: 256-wide tiles go through the slots in two halves
   int slots;                   // epilogue slot ring depth PER WARPGROUP (each of the two epilogue warpgroups owns its ring)
   uint32_t slot_bytes;
   uint8_t route_map[32];       // per global staging box (n0/box_ch + b): which output map it is stored through (0xff: none)

@@ -182,6 +182,7 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int span_px = p.mt * 128;
+  const int n_parts = PAIR ? p.n_parts : 1;   // column parts exist only in pair mode (folds away otherwise)
   const int n_spans = static_cast<int>((p.P + span_px - 1) / span_px);
   // pair mode: CTAs (2i, 2i+1) of a cluster form one unit that takes two consecutive spans per step (rank r takes span 2u + r)
   constexpr bool pair = PAIR;
@@ -370,19 +371,20 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
     // ------------------------------------------------------------------ aux producer (residual / add2 tiles)
     if (AUX != 0 && lane == 0) {
       const int aux_hi = AUX == 1 ? p.n_res : p.n_valid;
-      int nb = 0;
-      for (int b = 0; b < p.boxes; ++b)
-        if (n0 + b * p.box_ch < aux_hi) ++nb;
       const uint32_t buf_off = AUX == 2 ? static_cast<uint32_t>(p.boxes) * box_bytes : 0u;
       Tracer tr; tr.init(p.trace, 2);
       int ls = 0;
       for (int unit = my_group; unit < n_units; unit += groups, ++ls) {
         const int span = unit * sstride + static_cast<int>(rank);
         const int p0 = (p.reverse ? n_spans_all - 1 - span : span) * span_px;
-        for (int j = 0; j < p.mt; ++j) {
-          const uint32_t q = static_cast<uint32_t>(ls >> 1) * p.mt + j;      // sub-tile counter of the warpgroup that owns this span
+        for (int jh = 0; jh < p.mt * n_parts; ++jh) {
+          const int j = jh / n_parts, cb = n0 + (jh % n_parts) * p.part_cols;   // sub-tile, first channel of this column part
+          const uint32_t q = static_cast<uint32_t>(ls >> 1) * (p.mt * n_parts) + jh;   // slot counter of the warpgroup that owns this span
           const int slot = (ls & 1) * p.slots + q % p.slots;
-          S.prog[2] = (ls << 8) | j;
+          S.prog[2] = (ls << 8) | jh;
+          int nb = 0;
+          for (int b = 0; b < p.boxes; ++b)
+            if (cb + b * p.box_ch < aux_hi) ++nb;
           tr.ev(1);
           wait_dbg(&S.slot_empty[slot], ((q / p.slots) & 1) ^ 1, p.dbg, 0x21, slot, q, S.prog);
           tr.ev(2);
@@ -390,7 +392,7 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
             mbar_expect_tx(&S.slot_full[slot], static_cast<uint32_t>(nb) * box_bytes);
             uint8_t* dst = slot_smem + static_cast<size_t>(slot) * p.slot_bytes + buf_off;
             for (int b = 0; b < nb; ++b)
-              tma_load_2d(dst + static_cast<size_t>(b) * box_bytes, &maps.aux, &S.slot_full[slot], n0 + b * p.box_ch, p0 + j * 128);
+              tma_load_2d(dst + static_cast<size_t>(b) * box_bytes, &maps.aux, &S.slot_full[slot], cb + b * p.box_ch, p0 + j * 128);
           } else {
             mbar_arrive(&S.slot_full[slot]);
           }
@@ -407,19 +409,20 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
       for (int unit = my_group; unit < n_units; unit += groups, ++ls) {
         const int span = unit * sstride + static_cast<int>(rank);
         const int p0 = (p.reverse ? n_spans_all - 1 - span : span) * span_px;
-        for (int j = 0; j < p.mt; ++j) {
-          const uint32_t q = static_cast<uint32_t>(ls >> 1) * p.mt + j;
+        for (int jh = 0; jh < p.mt * n_parts; ++jh) {
+          const int j = jh / n_parts, cb = n0 + (jh % n_parts) * p.part_cols;
+          const uint32_t q = static_cast<uint32_t>(ls >> 1) * (p.mt * n_parts) + jh;
           const int slot = (ls & 1) * p.slots + q % p.slots;
-          S.prog[3] = (ls << 8) | j;
+          S.prog[3] = (ls << 8) | jh;
           wait_dbg(&S.slot_ready[slot], (q / p.slots) & 1, p.dbg, 0x31, slot, q, S.prog);
           tr.ev(1);
           const uint32_t bufA = slot_base + static_cast<uint32_t>(slot) * p.slot_bytes;
           const uint32_t bufB = bufA + static_cast<uint32_t>(p.boxes) * box_bytes;
           const int px = p0 + j * 128;
           for (int b = 0; b < p.boxes; ++b) {
-            const int cg = n0 + b * p.box_ch;
+            const int cg = cb + b * p.box_ch;
             if (cg >= p.n_valid) break;
-            const int gb = n_blk * p.boxes + b;
+            const int gb = cg / p.box_ch;           // global staging box (tiles and parts start on box boundaries)
             if (p.route_map[gb] != 0xff) tma_store_2d(&maps.o[p.route_map[gb]], bufA + b * box_bytes, p.route_c[gb], px);
             if (AUX == 2) tma_store_2d(&maps.o2, bufB + b * box_bytes, cg, px);
           }
@@ -465,9 +468,10 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
       tr.ev(2);
       tc_fence_after();
 #pragma unroll 1
-      for (int j = 0; j < p.mt; ++j) {
-        const uint32_t q = static_cast<uint32_t>(ls >> 1) * p.mt + j;   // this warpgroup's own sub-tile counter: its slot ring is private,
-        const int slot = wg * p.slots + q % p.slots;                      // so a parity wait is never more than one phase ahead
+      for (int jh = 0; jh < p.mt * n_parts; ++jh) {
+        const int j = jh / n_parts, cpart = (jh % n_parts) * p.part_cols;   // sub-tile, first tile-local column of this part
+        const uint32_t q = static_cast<uint32_t>(ls >> 1) * (p.mt * n_parts) + jh;   // this warpgroup's own slot counter: its ring is
+        const int slot = wg * p.slots + q % p.slots;                                     // private, so a parity wait is never > 1 phase ahead
         const uint32_t u = q / p.slots;
         if (lane == 0) S.prog[warp] = 0x20000u | q;
         if (AUX != 0) wait_dbg(&S.slot_full[slot], u & 1, p.dbg, 0x42, slot, q, S.prog);
@@ -477,33 +481,36 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
         const uint32_t vmask = j == 0 ? vm[0] : j == 1 ? vm[1] : j == 2 ? vm[2] : vm[3];
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>((wg * p.mt + j) * p.n_tile);
         uint32_t ra[16], rb[16];
-        tmem_ld16(taddr, ra);
+        const int c_end = cpart + p.part_cols;
+        tmem_ld16(taddr + cpart, ra);
 #pragma unroll 1
-        for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
+        for (int c0 = cpart; c0 < c_end; c0 += 32) {
           tmem_ld_wait();
-          if (c0 + 16 < p.n_tile) tmem_ld16(taddr + c0 + 16, rb);
+          if (c0 + 16 < c_end) tmem_ld16(taddr + c0 + 16, rb);
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             const int cl = c0 + g * 8, cg = n0 + cl;
             if (cg < p.n_valid && (cg & p.grp_mask) < p.grp_w) {
-              const uint32_t ua = bufA + (static_cast<uint32_t>(cl) >> bsh) * box_bytes + ((((static_cast<uint32_t>(cl) & bmask) >> 3) << 4) ^ row_xor);
+              const uint32_t cs = static_cast<uint32_t>(cl - cpart);   // column inside the slot
+              const uint32_t ua = bufA + (cs >> bsh) * box_bytes + ((((cs & bmask) >> 3) << 4) ^ row_xor);
               epi8<T, AUX, PRE, POST>(ra + g * 8, sc_base + cl * 4, sh_base + cl * 4, ua, ua + bufB_off, cg < p.n_res, vmask);
             }
           }
-          if (c0 + 16 < p.n_tile) {
+          if (c0 + 16 < c_end) {
             tmem_ld_wait();
-            if (c0 + 32 < p.n_tile) tmem_ld16(taddr + c0 + 32, ra);
+            if (c0 + 32 < c_end) tmem_ld16(taddr + c0 + 32, ra);
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
               const int cl = c0 + 16 + g * 8, cg = n0 + cl;
               if (cg < p.n_valid && (cg & p.grp_mask) < p.grp_w) {
-                const uint32_t ua = bufA + (static_cast<uint32_t>(cl) >> bsh) * box_bytes + ((((static_cast<uint32_t>(cl) & bmask) >> 3) << 4) ^ row_xor);
+                const uint32_t cs = static_cast<uint32_t>(cl - cpart);   // column inside the slot
+              const uint32_t ua = bufA + (cs >> bsh) * box_bytes + ((((cs & bmask) >> 3) << 4) ^ row_xor);
                 epi8<T, AUX, PRE, POST>(rb + g * 8, sc_base + cl * 4, sh_base + cl * 4, ua, ua + bufB_off, cg < p.n_res, vmask);
               }
             }
           }
         }
-        if (j == p.mt - 1) {              // all accumulators of this span are in registers / smem: hand TMEM back
+        if (jh == p.mt * n_parts - 1) {   // all accumulators of this span are in registers / smem: hand TMEM back
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {

@@ -789,7 +789,10 @@ int Model::plan_flat(ConvDesc& c) {
       if (!split && n_split < c.cout && n_split % box_ch != 0) continue;       // a staging box has exactly one destination
       if ((N + box_ch - 1) / box_ch > 32) continue;                              // routing table size
       if (grouped && (n_tile != 32 || box_ch != 32)) continue;
-      const int boxes = (n_tile + box_ch - 1) / box_ch;
+      // pair mode: a slot holds at most 128 columns, wider tiles pass through the slots in two column parts
+      const int n_parts = (use_pair && n_tile > 128 && n_tile % (2 * box_ch) == 0) ? 2 : 1;   // (slower than one wide slot without pairing)
+      const int part_cols = n_tile / n_parts;
+      const int boxes = (part_cols + box_ch - 1) / box_ch;
       const uint32_t box_bytes = 128u * box_ch * 2u;
       const uint32_t slot_bytes = boxes * box_bytes * (aux_mode == 2 ? 2u : 1u);
       const int b_rows_cta = use_pair ? n_tile / 2 : n_tile;                    // pair mode: each CTA of the pair holds half of the weights
@@ -834,7 +837,7 @@ int Model::plan_flat(ConvDesc& c) {
           auto t_lat = [&]() {
             return load_bytes * 3000.0 / static_cast<double>(static_cast<long long>(a_stages) * a_stage + static_cast<long long>(b_stages) * b_item);
           };
-          auto t_slot = [&]() { return static_cast<double>(n_tiles) * (aux_mode ? 7600.0 : 2900.0) / (2.0 * slots); };
+          auto t_slot = [&]() { return static_cast<double>(n_tiles) * n_parts * (aux_mode ? 7600.0 : 2900.0) / (2.0 * slots); };
           for (;;) {   // grow whichever ring currently bounds the tile, while it fits
             const double tl = t_lat(), ts = t_slot();
             if (std::max(tl, ts) <= t_fixed) break;
@@ -867,6 +870,7 @@ int Model::plan_flat(ConvDesc& c) {
             fp.mt = mt; fp.a_box_rows = a_box_rows; fp.a_boxes = a_boxes; fp.n_tile = n_tile; fp.n_tiles = n_tiles;
             fp.a_stages = a_stages; fp.b_stages = b_stages; fp.a_stage_bytes = a_stage; fp.b_item_bytes = b_item;
             fp.b_resident = b_res; fp.box_ch = box_ch; fp.boxes = boxes; fp.slots = slots; fp.slot_bytes = slot_bytes;
+            fp.n_parts = n_parts; fp.part_cols = part_cols;
             found = true;
           }
         }
