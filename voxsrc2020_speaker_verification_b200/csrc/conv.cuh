@@ -190,6 +190,7 @@ struct FlatConvParams {
   int reverse;                 // walk the spans from the last pixel to the first: consecutive layers alternate, so a consumer starts on
                                // the pixels its producer wrote last (still in the 126 MB L2)
   unsigned long long* trace;
+  int knock;                   // debug timing experiments only (SVX_FLAT_KNOCK): 1 skip epilogue math, 2 skip stores, 4 skip aux loads, 8 skip tcgen05.ld
   unsigned long long* dbg;     // host-mapped words: which barrier wait timed out (written before the trap)
 };
 struct FlatMaps { CUtensorMap a, b, aux, o2, o[8]; };   // o2: second output of aux mode 2

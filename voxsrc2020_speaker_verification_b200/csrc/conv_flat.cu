@@ -59,6 +59,14 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// Timing experiments only (tools/build_knock.sh builds a second library with -DSVX_KNOCK): parts of the pipeline can be
+// switched off at run time to see what the MMA phase costs without them.  The production build compiles these out.
+#ifdef SVX_KNOCK
+#define KNOCK(bit) ((p.knock & (bit)) != 0)
+#else
+#define KNOCK(bit) false
+#endif
+
 // Bounded wait that says which barrier starved before trapping: code = role*16 + barrier kind, a = ring index, b = counter.
 // On a timeout the thread also copies the CTA's 16 role progress words (prog) so the host can see where every role stood.
 __device__ __forceinline__ void wait_dbg(uint64_t* bar, uint32_t parity, unsigned long long* dbg, int code, int a, unsigned b,
@@ -125,27 +133,46 @@ __device__ __forceinline__ void epi8(const uint32_t* r, uint32_t sc, uint32_t sh
   }
 }
 
+// tcgen05.mma with the shared-memory descriptors given as {low word, common high word}: the high word (SBO, version, swizzle
+// mode) is the same for every operand of a launch, the low word is (address >> 4) | LBO, so all per-MMA descriptor arithmetic is
+// one 32-bit add.
+template <bool pair>
+__device__ __forceinline__ void umma_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (pair) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}\n"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(hi)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}\n"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(hi)
+        : "memory");
+  }
+}
+
 // All MMAs of one filter tap: MT sub-tiles x KS K-steps, fully unrolled so that every descriptor is the tap's base
 // (one value) plus a compile-time constant.  A generic loop costs ~150 cycles of issue per MMA (descriptor arithmetic in
 // vector registers + 5 R2UR each, tools/microbench/mma_rate.cu) against 16-64 cycles of tensor-pipe time.
 template <int MT, int KS, bool pair>
-__device__ __forceinline__ void issue_tap(uint64_t adesc0, uint64_t bdesc0, uint32_t d_tmem, uint32_t n_tile, uint32_t idesc, uint32_t first) {
+__device__ __forceinline__ void issue_tap(uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t d_tmem, uint32_t n_tile, uint32_t idesc, uint32_t first,
+                                          int knock = 0) {
   constexpr uint32_t kSub16 = 256u * KS;      // (128 rows x 32*KS bytes) >> 4
   if (elect_one()) {      // one elected region for the whole tap: the R2UR traffic of consecutive MMAs overlaps
-    if constexpr (pair) {           // M = 256 across the CTA pair: the same descriptors address both CTAs' shared memory
 #pragma unroll
-      for (int j = 0; j < MT; ++j) {
+    for (int j = 0; j < MT; ++j) {
 #pragma unroll
-        for (int k = 0; k < KS; ++k)
-          umma_f16_2cta(d_tmem + j * n_tile, adesc0 + (j * kSub16 + k * 2), bdesc0 + k * 2, idesc, k == 0 ? first : 1u);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < MT; ++j) {
-#pragma unroll
-        for (int k = 0; k < KS; ++k)
-          umma_f16(d_tmem + j * n_tile, adesc0 + (j * kSub16 + k * 2), bdesc0 + k * 2, idesc, k == 0 ? first : 1u);
-      }
+      for (int k = 0; k < KS; ++k)
+#ifdef SVX_KNOCK
+        if (!(knock & 32))
+#endif
+        umma_lo<pair>(d_tmem + j * n_tile, a_lo + (j * kSub16 + k * 2), b_lo + k * 2, hi, idesc, k == 0 ? first : 1u);
     }
   }
 }
@@ -157,9 +184,106 @@ struct Smem {
   uint64_t bres_bar;
   uint64_t pa_full[kRing], pb_full[kRing], pbres_bar;   // pair mode, leader CTA: the peer's A stage / weight item / resident weights landed
   uint32_t tmem_slot;
+  uint32_t tapoff16[12];        // ((halo + tap_shift[tap]) * row_bytes) >> 4: descriptor displacement of each filter tap
   volatile uint32_t prog[16];   // debug: progress of each role (warp), dumped by wait_dbg on a timeout
 };
 static_assert(sizeof(Smem) <= 1024, "barrier block");
+
+// MMA issuer role (warp 1), one instantiation per <sub-tiles per span, K-steps per box>.
+// The whole warp runs the loop CONVERGED and computes the descriptors (uniform values); only the tcgen05 instructions
+// themselves sit under the elected-lane branch.  Computing them inside an `if (lane == 0)` region made ptxas wrap every
+// UTCHMMA in an ELECT / 5x R2UR.BROADCAST waterfall: ~200 ns per MMA whatever its shape.
+//
+// Pair mode: the leader (cluster rank 0) issues M = 256 MMAs that read both CTAs' shared memory and write both CTAs'
+// TMEM; its commits multicast to both CTAs' barriers.  The peer's warp 1 is a relay: it walks the same ring positions and
+// forwards "my A stage / weight item landed" to the leader's pa_full / pb_full barriers.
+template <int MT, int KS, bool PAIR>
+__device__ __forceinline__ void mma_role(const FlatConvParams& p, Smem& S, uint32_t tb, uint32_t a_base, uint32_t b_base, int my_group, int n_units,
+                                         int groups, uint32_t rank, int lane, Tracer& tr) {
+  constexpr bool pair = PAIR;
+  const bool relay = pair && rank == 1;
+  if (p.b_resident) {
+    wait_dbg(&S.bres_bar, 0, p.dbg, 0x10, 0, 0, S.prog);
+    if constexpr (pair) {
+      if (relay) { if (elect_one()) mbar_arrive_remote(&S.pbres_bar, 0); }
+      else wait_dbg(&S.pbres_bar, 0, p.dbg, 0x14, 0, 0, S.prog);
+    }
+  }
+  const uint64_t desc_base = make_kmajor_desc(0, p.sbo, p.layout_type);
+  const uint32_t hi = static_cast<uint32_t>(desc_base >> 32);
+  const uint32_t lo0 = static_cast<uint32_t>(desc_base);           // LBO field; the address field is added below (smem < 256 KB: no carry out of it)
+  const uint32_t a_lo_base = lo0 + (a_base >> 4), b_lo_base = lo0 + (b_base >> 4);
+  const uint32_t a_stage16 = p.a_stage_bytes >> 4, b_item16 = p.b_item_bytes >> 4;
+  const uint32_t nt = static_cast<uint32_t>(p.n_tile);
+  const uint32_t idesc = p.idesc;
+  const int taps = p.taps, nkc = p.nkc;
+  const bool b_res = p.b_resident != 0;
+  uint32_t ia = 0, ib = 0;
+  int ls = 0;
+  for (int unit = my_group; unit < n_units; unit += groups, ++ls) {
+    const int buf = ls & 1;
+    tr.ev(1);
+    if (lane == 0) S.prog[1] = ls;
+    if (!relay) wait_dbg(&S.tmem_empty[buf], ((ls >> 1) & 1) ^ 1, p.dbg, 0x11, buf, ls, S.prog);
+    tr.ev(2);
+    const uint32_t d_tmem = tb + static_cast<uint32_t>(buf * MT) * nt;
+    uint32_t first = 0u;
+    for (int kc = 0; kc < nkc; ++kc, ++ia) {
+      const int sa = ia % p.a_stages;
+      const uint32_t a_par = (ia / p.a_stages) & 1;
+      uint32_t toff = S.tapoff16[0];                       // fetched before the wait: off the critical path
+      wait_dbg(&S.a_full[sa], a_par, p.dbg, 0x12, sa, ia, S.prog);
+      if constexpr (pair) {
+        if (relay) { if (elect_one()) mbar_arrive_remote(&S.pa_full[sa], 0); }
+        else wait_dbg(&S.pa_full[sa], a_par, p.dbg, 0x15, sa, ia, S.prog);
+      }
+      if (kc == 0) tr.ev(3);
+      tc_fence_after();
+      const uint32_t a_lo = a_lo_base + static_cast<uint32_t>(sa) * a_stage16;
+      if (b_res) {
+        if (!relay) {
+          uint32_t b_lo = b_lo_base + static_cast<uint32_t>(kc * taps) * b_item16;
+#pragma unroll 1
+          for (int tap = 0; tap < taps; ++tap, b_lo += b_item16) {
+            const uint32_t toff_next = S.tapoff16[tap + 1];   // next tap's displacement loads while this tap issues
+            issue_tap<MT, KS, PAIR>(a_lo + toff, b_lo, hi, d_tmem, nt, idesc, first, p.knock);
+            first = 1u;
+            toff = toff_next;
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int tap = 0; tap < taps; ++tap, ++ib) {
+          const int sb = ib % p.b_stages;
+          const uint32_t b_par = (ib / p.b_stages) & 1;
+          const uint32_t toff_next = S.tapoff16[tap + 1];
+          wait_dbg(&S.b_full[sb], b_par, p.dbg, 0x13, sb, ib, S.prog);
+          if constexpr (pair) {
+            if (relay) { if (elect_one()) mbar_arrive_remote(&S.pb_full[sb], 0); }
+            else wait_dbg(&S.pb_full[sb], b_par, p.dbg, 0x16, sb, ib, S.prog);
+          }
+          if (!relay) {
+            tc_fence_after();
+            issue_tap<MT, KS, PAIR>(a_lo + toff, b_lo_base + static_cast<uint32_t>(sb) * b_item16, hi, d_tmem, nt, idesc, first, p.knock);
+            first = 1u;
+            if (elect_one()) { if constexpr (pair) umma_commit_2cta(&S.b_empty[sb]); else umma_commit(&S.b_empty[sb]); }
+          }
+          toff = toff_next;
+        }
+      }
+      if (!relay && elect_one()) {
+        if constexpr (pair) {
+          umma_commit_2cta(&S.a_empty[sa]);
+          if (kc == nkc - 1) umma_commit_2cta(&S.tmem_full[buf]);
+        } else {
+          umma_commit(&S.a_empty[sa]);
+          if (kc == nkc - 1) umma_commit(&S.tmem_full[buf]);
+        }
+      }
+    }
+    tr.ev(4);
+  }
+}
 
 }  // namespace
 
@@ -214,6 +338,7 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
     mbar_init(&S.bres_bar, 1);
     for (int i = 0; i < kRing; ++i) { mbar_init(&S.pa_full[i], 1); mbar_init(&S.pb_full[i], 1); }
     mbar_init(&S.pbres_bar, 1);
+    for (int t = 0; t < 12; ++t) S.tapoff16[t] = t < p.taps ? (static_cast<uint32_t>(p.halo + p.tap_shift[t]) * row_bytes) >> 4 : 0u;
     fence_barrier_init();
     if (p.b_resident) {     // weights are static: fetch them before the dependency wait
       const uint32_t bb = static_cast<uint32_t>(p.b_rows) * row_bytes;
@@ -279,93 +404,22 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    // The whole warp runs the loop CONVERGED and computes the descriptors (uniform values → uniform registers); only the
-    // tcgen05 instructions themselves sit under the elected-lane branch.  Computing them inside an `if (lane == 0)` region
-    // made ptxas wrap every UTCHMMA in an ELECT / 5x R2UR.BROADCAST waterfall: ~200 ns per MMA whatever its shape.
-    //
-    // Pair mode: the leader (cluster rank 0) issues M = 256 MMAs that read both CTAs' shared memory and write both CTAs'
-    // TMEM; its commits multicast to both CTAs' barriers.  The peer's warp 1 is a relay: it walks the same ring positions and
-    // forwards "my A stage / weight item landed" to the leader's pa_full / pb_full barriers.
     const int ksteps = p.kbox >> 4;
-    const bool relay = pair && rank == 1;
-    if (p.b_resident) {
-      wait_dbg(&S.bres_bar, 0, p.dbg, 0x10, 0, 0, S.prog);
-      if constexpr (pair) {
-        if (relay) { if (elect_one()) mbar_arrive_remote(&S.pbres_bar, 0); }
-        else wait_dbg(&S.pbres_bar, 0, p.dbg, 0x14, 0, 0, S.prog);
-      }
-    }
-    const uint64_t desc_base = make_kmajor_desc(0, p.sbo, p.layout_type);
-    const uint32_t a_base = smem_u32(a_smem), b_base = smem_u32(b_smem);
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
-    const int mtks = (p.mt << 4) | ksteps;
     Tracer tr; tr.init(lane == 0 ? p.trace : nullptr, 1);
-    uint32_t ia = 0, ib = 0;
-    int ls = 0;
-    for (int unit = my_group; unit < n_units; unit += groups, ++ls) {
-      const int buf = ls & 1;
-      tr.ev(1);
-      if (lane == 0) S.prog[1] = ls;
-      if (!relay) wait_dbg(&S.tmem_empty[buf], ((ls >> 1) & 1) ^ 1, p.dbg, 0x11, buf, ls, S.prog);
-      tr.ev(2);
-      tc_fence_after();
-      const uint32_t d_tmem = tb + static_cast<uint32_t>(buf * p.mt * p.n_tile);
-      for (int kc = 0; kc < p.nkc; ++kc, ++ia) {
-        const int sa = ia % p.a_stages;
-        const uint32_t a_par = (ia / p.a_stages) & 1;
-        wait_dbg(&S.a_full[sa], a_par, p.dbg, 0x12, sa, ia, S.prog);
-        if constexpr (pair) {
-          if (relay) { if (elect_one()) mbar_arrive_remote(&S.pa_full[sa], 0); }
-          else wait_dbg(&S.pa_full[sa], a_par, p.dbg, 0x15, sa, ia, S.prog);
-        }
-        if (kc == 0) tr.ev(3);
-        const uint32_t a_addr = a_base + static_cast<uint32_t>(sa) * p.a_stage_bytes;
-        for (int tap = 0; tap < p.taps; ++tap) {
-          uint32_t b_addr;
-          int sb = 0;
-          if (p.b_resident) {
-            b_addr = b_base + static_cast<uint32_t>(kc * p.taps + tap) * p.b_item_bytes;
-          } else {
-            sb = ib % p.b_stages;
-            const uint32_t b_par = (ib / p.b_stages) & 1;
-            wait_dbg(&S.b_full[sb], b_par, p.dbg, 0x13, sb, ib, S.prog);
-            if constexpr (pair) {
-              if (relay) { if (elect_one()) mbar_arrive_remote(&S.pb_full[sb], 0); }
-              else wait_dbg(&S.pb_full[sb], b_par, p.dbg, 0x16, sb, ib, S.prog);
-            }
-            b_addr = b_base + static_cast<uint32_t>(sb) * p.b_item_bytes;
-            ++ib;
-          }
-          if (relay) continue;
-          tc_fence_after();
-          const uint32_t a_tap = a_addr + static_cast<uint32_t>(p.halo + p.tap_shift[tap]) * row_bytes;
-          const uint32_t first = (kc == 0 && tap == 0) ? 0u : 1u;
-          const uint64_t adesc0 = desc_base + (a_tap >> 4), bdesc0 = desc_base + (b_addr >> 4);   // smem < 256 KB: no carry out of the field
-          const uint32_t nt = static_cast<uint32_t>(p.n_tile);
-          switch (mtks) {
-            case 0x11: issue_tap<1, 1, PAIR>(adesc0, bdesc0, d_tmem, nt, p.idesc, first); break;
-            case 0x12: issue_tap<1, 2, PAIR>(adesc0, bdesc0, d_tmem, nt, p.idesc, first); break;
-            case 0x14: issue_tap<1, 4, PAIR>(adesc0, bdesc0, d_tmem, nt, p.idesc, first); break;
-            case 0x21: issue_tap<2, 1, PAIR>(adesc0, bdesc0, d_tmem, nt, p.idesc, first); break;
-            case 0x22: issue_tap<2, 2, PAIR>(adesc0, bdesc0, d_tmem, nt, p.idesc, first); break;
-            case 0x24: issue_tap<2, 4, PAIR>(adesc0, bdesc0, d_tmem, nt, p.idesc, first); break;
-            case 0x41: issue_tap<4, 1, PAIR>(adesc0, bdesc0, d_tmem, nt, p.idesc, first); break;
-            case 0x42: issue_tap<4, 2, PAIR>(adesc0, bdesc0, d_tmem, nt, p.idesc, first); break;
-            default:   issue_tap<4, 4, PAIR>(adesc0, bdesc0, d_tmem, nt, p.idesc, first); break;
-          }
-          if (!p.b_resident && elect_one()) { if constexpr (pair) umma_commit_2cta(&S.b_empty[sb]); else umma_commit(&S.b_empty[sb]); }
-        }
-        if (!relay && elect_one()) {
-          if constexpr (pair) {
-            umma_commit_2cta(&S.a_empty[sa]);
-            if (kc == p.nkc - 1) umma_commit_2cta(&S.tmem_full[buf]);
-          } else {
-            umma_commit(&S.a_empty[sa]);
-            if (kc == p.nkc - 1) umma_commit(&S.tmem_full[buf]);
-          }
-        }
-      }
-      tr.ev(4);
+    // The shape switch sits OUTSIDE the loops: inside the tap loop its jump-table load, the indexed constant loads of the tap
+    // shifts and the 64-bit descriptor arithmetic formed one serial dependent chain of ~500 cycles per tap in this single warp
+    // (knock-out measurement, profiles/r01_knockout_issue_loop.txt) — more than the MMAs of a narrow tap take to execute.
+    switch ((p.mt << 4) | ksteps) {
+      case 0x11: mma_role<1, 1, PAIR>(p, S, tb, smem_u32(a_smem), smem_u32(b_smem), my_group, n_units, groups, rank, lane, tr); break;
+      case 0x12: mma_role<1, 2, PAIR>(p, S, tb, smem_u32(a_smem), smem_u32(b_smem), my_group, n_units, groups, rank, lane, tr); break;
+      case 0x14: mma_role<1, 4, PAIR>(p, S, tb, smem_u32(a_smem), smem_u32(b_smem), my_group, n_units, groups, rank, lane, tr); break;
+      case 0x21: mma_role<2, 1, PAIR>(p, S, tb, smem_u32(a_smem), smem_u32(b_smem), my_group, n_units, groups, rank, lane, tr); break;
+      case 0x22: mma_role<2, 2, PAIR>(p, S, tb, smem_u32(a_smem), smem_u32(b_smem), my_group, n_units, groups, rank, lane, tr); break;
+      case 0x24: mma_role<2, 4, PAIR>(p, S, tb, smem_u32(a_smem), smem_u32(b_smem), my_group, n_units, groups, rank, lane, tr); break;
+      case 0x41: mma_role<4, 1, PAIR>(p, S, tb, smem_u32(a_smem), smem_u32(b_smem), my_group, n_units, groups, rank, lane, tr); break;
+      case 0x42: mma_role<4, 2, PAIR>(p, S, tb, smem_u32(a_smem), smem_u32(b_smem), my_group, n_units, groups, rank, lane, tr); break;
+      default:   mma_role<4, 4, PAIR>(p, S, tb, smem_u32(a_smem), smem_u32(b_smem), my_group, n_units, groups, rank, lane, tr); break;
     }
   } else if (warp == 2) {
     // ------------------------------------------------------------------ aux producer (residual / add2 tiles)
@@ -388,7 +442,7 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
           tr.ev(1);
           wait_dbg(&S.slot_empty[slot], ((q / p.slots) & 1) ^ 1, p.dbg, 0x21, slot, q, S.prog);
           tr.ev(2);
-          if (nb > 0) {
+          if (nb > 0 && !KNOCK(4)) {
             mbar_expect_tx(&S.slot_full[slot], static_cast<uint32_t>(nb) * box_bytes);
             uint8_t* dst = slot_smem + static_cast<size_t>(slot) * p.slot_bytes + buf_off;
             for (int b = 0; b < nb; ++b)
@@ -421,7 +475,7 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
           const int px = p0 + j * 128;
           for (int b = 0; b < p.boxes; ++b) {
             const int cg = cb + b * p.box_ch;
-            if (cg >= p.n_valid) break;
+            if (cg >= p.n_valid || KNOCK(2)) break;
             const int gb = cg / p.box_ch;           // global staging box (tiles and parts start on box boundaries)
             if (p.route_map[gb] != 0xff) tma_store_2d(&maps.o[p.route_map[gb]], bufA + b * box_bytes, p.route_c[gb], px);
             if (AUX == 2) tma_store_2d(&maps.o2, bufB + b * box_bytes, cg, px);
@@ -482,15 +536,15 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>((wg * p.mt + j) * p.n_tile);
         uint32_t ra[16], rb[16];
         const int c_end = cpart + p.part_cols;
-        tmem_ld16(taddr + cpart, ra);
+        if (!KNOCK(8)) tmem_ld16(taddr + cpart, ra);
 #pragma unroll 1
         for (int c0 = cpart; c0 < c_end; c0 += 32) {
           tmem_ld_wait();
-          if (c0 + 16 < c_end) tmem_ld16(taddr + c0 + 16, rb);
+          if (c0 + 16 < c_end && !KNOCK(8)) tmem_ld16(taddr + c0 + 16, rb);
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             const int cl = c0 + g * 8, cg = n0 + cl;
-            if (cg < p.n_valid && (cg & p.grp_mask) < p.grp_w) {
+            if (cg < p.n_valid && (cg & p.grp_mask) < p.grp_w && !KNOCK(1)) {
               const uint32_t cs = static_cast<uint32_t>(cl - cpart);   // column inside the slot
               const uint32_t ua = bufA + (cs >> bsh) * box_bytes + ((((cs & bmask) >> 3) << 4) ^ row_xor);
               epi8<T, AUX, PRE, POST>(ra + g * 8, sc_base + cl * 4, sh_base + cl * 4, ua, ua + bufB_off, cg < p.n_res, vmask);
@@ -498,11 +552,11 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
           }
           if (c0 + 16 < c_end) {
             tmem_ld_wait();
-            if (c0 + 32 < c_end) tmem_ld16(taddr + c0 + 32, ra);
+            if (c0 + 32 < c_end && !KNOCK(8)) tmem_ld16(taddr + c0 + 32, ra);
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
               const int cl = c0 + 16 + g * 8, cg = n0 + cl;
-              if (cg < p.n_valid && (cg & p.grp_mask) < p.grp_w) {
+              if (cg < p.n_valid && (cg & p.grp_mask) < p.grp_w && !KNOCK(1)) {
                 const uint32_t cs = static_cast<uint32_t>(cl - cpart);   // column inside the slot
               const uint32_t ua = bufA + (cs >> bsh) * box_bytes + ((((cs & bmask) >> 3) << 4) ^ row_xor);
                 epi8<T, AUX, PRE, POST>(rb + g * 8, sc_base + cl * 4, sh_base + cl * 4, ua, ua + bufB_off, cg < p.n_res, vmask);

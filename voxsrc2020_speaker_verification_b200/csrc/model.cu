@@ -1081,6 +1081,7 @@ int Model::launch_conv(ConvDesc& c, cudaStream_t st) {
       c.fp.P = static_cast<long long>(out_rows) * stage_Wp_[out_stage];
       c.fp.trace = trace_dir ? d_trace : nullptr;
       c.fp.dbg = flat_dbg_words();
+      { static const char* kn = getenv("SVX_FLAT_KNOCK"); c.fp.knock = kn ? atoi(kn) : 0; }
       // walk the pixels in the opposite direction of the kernel that wrote the input: the consumer then starts on what is
       // still in L2 (+0.6 % measured on the headline step)
       static const bool no_rev = getenv("SVX_NO_REVERSE") != nullptr;   // debug switch
