@@ -190,6 +190,14 @@ struct FlatConvParams {
   int reverse;                 // walk the spans from the last pixel to the first: consecutive layers alternate, so a consumer starts on
                                // the pixels its producer wrote last (still in the 126 MB L2)
   unsigned long long* trace;
+  // direct epilogue (narrow tiles, n_tile <= 64, one destination): the epilogue threads read the aux tile and write the outputs
+  // with their own 16-byte global accesses (a thread owns a pixel = one contiguous channel run), no slots, no TMA for them.
+  // With 64-byte rows the TMA engine's ~2.5 ns per box ROW made the aux loads + stores the bound of every narrow 3x3 conv.
+  int direct;
+  long long P_cap;             // pixels allocated (stores/loads of the direct epilogue are clipped here, like the tensor maps clip)
+  uint8_t* d_out; uint32_t d_out_pitch;        // primary output slice (first channel of the slice), bytes per pixel
+  uint8_t* d_out2; uint32_t d_out2_pitch;      // second output (aux mode 2)
+  const uint8_t* d_aux; uint32_t d_aux_pitch;  // residual (aux mode 1) / add2 (aux mode 2)
   int knock;                   // debug timing experiments only (SVX_FLAT_KNOCK): 1 skip epilogue math, 2 skip stores, 4 skip aux loads, 8 skip tcgen05.ld
   unsigned long long* dbg;     // host-mapped words: which barrier wait timed out (written before the trap)
 };

@@ -133,6 +133,43 @@ __device__ __forceinline__ void epi8(const uint32_t* r, uint32_t sc, uint32_t sh
   }
 }
 
+// 256-bit global accesses (sm_100: LDG/STG.256): one full 32-byte sector per lane, half the LSU requests of two 128-bit ones.
+__device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+
+// The same 8 channels with the aux values already in registers and the results written straight to global memory.
+template <typename T, int AUX, bool PRE, bool POST>
+__device__ __forceinline__ void epi8_direct(const uint32_t* r, uint32_t sc, uint32_t sh, const uint4& ax, uint4& o, uint4& o2, uint32_t vmask) {
+  const float4 s0 = lds_f4(sc), s1 = lds_f4(sc + 16), b0 = lds_f4(sh), b1 = lds_f4(sh + 16);
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    v[j] = __uint_as_float(r[j]);
+    if (PRE) v[j] = fmaxf(v[j], 0.f);
+  }
+  v[0] = fmaf(v[0], s0.x, b0.x); v[1] = fmaf(v[1], s0.y, b0.y); v[2] = fmaf(v[2], s0.z, b0.z); v[3] = fmaf(v[3], s0.w, b0.w);
+  v[4] = fmaf(v[4], s1.x, b1.x); v[5] = fmaf(v[5], s1.y, b1.y); v[6] = fmaf(v[6], s1.z, b1.z); v[7] = fmaf(v[7], s1.w, b1.w);
+  float2 a0, a1, a2, a3;
+  if (AUX != 0) { a0 = TypeOps<T>::unpack2(ax.x); a1 = TypeOps<T>::unpack2(ax.y); a2 = TypeOps<T>::unpack2(ax.z); a3 = TypeOps<T>::unpack2(ax.w); }
+  if (AUX == 1) { v[0] += a0.x; v[1] += a0.y; v[2] += a1.x; v[3] += a1.y; v[4] += a2.x; v[5] += a2.y; v[6] += a3.x; v[7] += a3.y; }
+  if (POST) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+  o.x = TypeOps<T>::pack2(v[0], v[1]) & vmask; o.y = TypeOps<T>::pack2(v[2], v[3]) & vmask;
+  o.z = TypeOps<T>::pack2(v[4], v[5]) & vmask; o.w = TypeOps<T>::pack2(v[6], v[7]) & vmask;
+  if (AUX == 2) {
+    o2.x = TypeOps<T>::pack2(v[0] + a0.x, v[1] + a0.y) & vmask; o2.y = TypeOps<T>::pack2(v[2] + a1.x, v[3] + a1.y) & vmask;
+    o2.z = TypeOps<T>::pack2(v[4] + a2.x, v[5] + a2.y) & vmask; o2.w = TypeOps<T>::pack2(v[6] + a3.x, v[7] + a3.y) & vmask;
+  }
+}
+
 // tcgen05.mma with the shared-memory descriptors given as {low word, common high word}: the high word (SBO, version, swizzle
 // mode) is the same for every operand of a launch, the low word is (address >> 4) | LBO, so all per-MMA descriptor arithmetic is
 // one 32-bit add.
@@ -423,7 +460,7 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
     }
   } else if (warp == 2) {
     // ------------------------------------------------------------------ aux producer (residual / add2 tiles)
-    if (AUX != 0 && lane == 0) {
+    if (AUX != 0 && lane == 0 && !p.direct) {
       const int aux_hi = AUX == 1 ? p.n_res : p.n_valid;
       const uint32_t buf_off = AUX == 2 ? static_cast<uint32_t>(p.boxes) * box_bytes : 0u;
       Tracer tr; tr.init(p.trace, 2);
@@ -455,7 +492,7 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
     }
   } else if (warp == 3) {
     // ------------------------------------------------------------------ store issuer
-    if (lane == 0) {
+    if (lane == 0 && !p.direct) {
       Tracer tr; tr.init(p.trace, 3);
       const uint32_t slot_base = smem_u32(slot_smem);
       int prev_slot = -1;
@@ -506,6 +543,89 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
     const uint32_t bufB_off = static_cast<uint32_t>(p.boxes) * box_bytes;
     Tracer tr; tr.init((q4 == 0 && lane == 0) ? p.trace : nullptr, 4 + wg);
     int ls = 0;
+    if (p.direct) {
+      // ---- direct epilogue: this thread's pixel is one contiguous channel run in every tensor it touches
+      const int ngrp = (min(p.n_tile, p.n_valid - n0) + 7) >> 3;       // 8-channel groups of this n-tile (<= 8)
+      const uint8_t* aux_base = p.d_aux + static_cast<size_t>(n0) * 2;
+      uint8_t* out_base = p.d_out + static_cast<size_t>(n0) * 2;
+      uint8_t* out2_base = p.d_out2 + static_cast<size_t>(n0) * 2;
+      const bool aux32 = AUX != 0 && ((reinterpret_cast<uintptr_t>(aux_base) | p.d_aux_pitch) & 31u) == 0;     // 32-byte aligned pixel runs
+      const bool out32 = ((reinterpret_cast<uintptr_t>(out_base) | p.d_out_pitch) & 31u) == 0;
+      const bool out2_32 = AUX == 2 && ((reinterpret_cast<uintptr_t>(out2_base) | p.d_out2_pitch) & 31u) == 0;
+      uint4 ax[8], nx[8];
+#pragma unroll
+      for (int g = 0; g < 8; ++g) ax[g] = nx[g] = make_uint4(0, 0, 0, 0);
+      auto load_aux = [&](const uint4* src, uint4 (&d)[8]) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (2 * q + 1 < ngrp && aux32) ldg256(src + 2 * q, d[2 * q], d[2 * q + 1]);
+          else {
+            if (2 * q < ngrp) d[2 * q] = __ldg(src + 2 * q);
+            if (2 * q + 1 < ngrp) d[2 * q + 1] = __ldg(src + 2 * q + 1);
+          }
+        }
+      };
+      for (int unit = my_group; unit < n_units; unit += groups, ++ls) {
+        const int span = unit * sstride + static_cast<int>(rank);
+        if ((ls & 1) != wg) continue;
+        const long long p0 = static_cast<long long>(p.reverse ? n_spans_all - 1 - span : span) * span_px;
+        uint32_t vm[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const long long pp = p0 + j * 128 + m;
+          vm[j] = (j < p.mt && pp < p.P && p.pix_valid[pp]) ? 0xffffffffu : 0u;
+        }
+        if (AUX != 0 && p0 + m < p.P_cap) {        // aux values of sub-tile 0: in flight while the MMAs of this span finish
+          load_aux(reinterpret_cast<const uint4*>(aux_base + static_cast<size_t>(p0 + m) * p.d_aux_pitch), ax);
+        }
+        tr.ev(1);
+        if (lane == 0) S.prog[warp] = 0x10000u | (static_cast<uint32_t>(ls) << 4);
+        wait_dbg(&S.tmem_full[wg], (ls >> 1) & 1, p.dbg, 0x41, wg, ls, S.prog);
+        tr.ev(2);
+        tc_fence_after();
+#pragma unroll 1
+        for (int j = 0; j < p.mt; ++j) {
+          const long long pp = p0 + j * 128 + m;
+          const bool inb = pp < p.P_cap;
+          if (AUX != 0 && j + 1 < p.mt && pp + 128 < p.P_cap) {   // next sub-tile's aux values load under this one's arithmetic
+            load_aux(reinterpret_cast<const uint4*>(aux_base + static_cast<size_t>(pp + 128) * p.d_aux_pitch), nx);
+          }
+          const uint32_t vmask = j == 0 ? vm[0] : j == 1 ? vm[1] : j == 2 ? vm[2] : vm[3];
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>((wg * p.mt + j) * p.n_tile);
+          uint4* o1 = reinterpret_cast<uint4*>(out_base + static_cast<size_t>(pp) * p.d_out_pitch);
+          uint4* o2 = reinterpret_cast<uint4*>(out2_base + static_cast<size_t>(pp) * p.d_out2_pitch);
+          uint32_t ra[16];
+          tr.ev(3);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (2 * q < ngrp) {
+              tmem_ld16(taddr + q * 16, ra);
+              tmem_ld_wait();
+              if (inb && !KNOCK(1)) {
+                uint4 va, vb, wa, wb;
+                epi8_direct<T, AUX, PRE, POST>(ra, sc_base + q * 64, sh_base + q * 64, ax[2 * q], va, wa, vmask);
+                if (2 * q + 1 < ngrp) {
+                  epi8_direct<T, AUX, PRE, POST>(ra + 8, sc_base + q * 64 + 32, sh_base + q * 64 + 32, ax[2 * q + 1], vb, wb, vmask);
+                  if (out32) stg256(o1 + 2 * q, va, vb); else { o1[2 * q] = va; o1[2 * q + 1] = vb; }
+                  if (AUX == 2) { if (out2_32) stg256(o2 + 2 * q, wa, wb); else { o2[2 * q] = wa; o2[2 * q + 1] = wb; } }
+                } else {
+                  o1[2 * q] = va;
+                  if (AUX == 2) o2[2 * q] = wa;
+                }
+              }
+            }
+          }
+          if (j == p.mt - 1) {              // all accumulators of this span have been read: hand TMEM back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.tmem_empty[wg]);
+          }
+#pragma unroll
+          for (int g = 0; g < 8; ++g) ax[g] = nx[g];
+          tr.ev(4);
+        }
+      }
+    } else
     for (int unit = my_group; unit < n_units; unit += groups, ++ls) {
         const int span = unit * sstride + static_cast<int>(rank);
       if ((ls & 1) != wg) continue;

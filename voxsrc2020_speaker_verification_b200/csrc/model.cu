@@ -776,6 +776,9 @@ int Model::plan_flat(ConvDesc& c) {
   static const int pair_min_k = getenv("SVX_PAIR_MIN_K") ? atoi(getenv("SVX_PAIR_MIN_K")) : (1 << 30);
   const bool use_pair = !grouped && taps * c.kpad >= pair_min_k;
   const int ksteps = c.kbox / 16;
+  // direct epilogue (global accesses from the epilogue threads instead of slots + TMA) for narrow single-destination tiles
+  static const bool no_direct = getenv("SVX_NO_DIRECT") != nullptr;   // debug switch
+  const bool direct_ok = !no_direct && !split && n_split == c.cout && !use_pair && c.outb.id < 0;
   bool found = false;
   double best = 1e30;
   for (int n_tile : cands) {
@@ -794,7 +797,8 @@ int Model::plan_flat(ConvDesc& c) {
       const int part_cols = n_tile / n_parts;
       const int boxes = (part_cols + box_ch - 1) / box_ch;
       const uint32_t box_bytes = 128u * box_ch * 2u;
-      const uint32_t slot_bytes = boxes * box_bytes * (aux_mode == 2 ? 2u : 1u);
+      const bool direct = direct_ok && n_tile <= 64 && (n_tiles == 1 || grouped);   // several n-tiles would re-read A per 64 channels
+      const uint32_t slot_bytes = direct ? 0u : boxes * box_bytes * (aux_mode == 2 ? 2u : 1u);
       const int b_rows_cta = use_pair ? n_tile / 2 : n_tile;                    // pair mode: each CTA of the pair holds half of the weights
       const uint32_t b_item = static_cast<uint32_t>(round_up(b_rows_cta * static_cast<int>(row_bytes), 1024));
       const int items = taps * c.nkc;
@@ -822,9 +826,9 @@ int Model::plan_flat(ConvDesc& c) {
           const double halo_ovh = 1.0 + 2.0 * halo / (mt * 128.0);
           const double a_rows = static_cast<double>(n_tiles) * c.nkc * 128.0 * halo_ovh;
           const double b_rows = b_res ? 0.0 : static_cast<double>(n_tiles) * items * b_rows_cta / mt;
-          const int aux_boxes = aux_mode ? boxes : 0;
+          const int aux_boxes = (aux_mode && !direct) ? boxes : 0;
           const double aux_rows = static_cast<double>(n_tiles) * aux_boxes * 128.0;
-          const double st_rows = static_cast<double>(n_tiles) * boxes * 128.0 * (aux_mode == 2 ? 2.0 : 1.0);
+          const double st_rows = direct ? 0.0 : static_cast<double>(n_tiles) * boxes * 128.0 * (aux_mode == 2 ? 2.0 : 1.0);
           const double t_req = (a_rows + b_rows + aux_rows) * 5.6;
           const double t_st = st_rows * 4.6;
           const double load_bytes = (a_rows + b_rows) * row_bytes;
@@ -837,7 +841,7 @@ int Model::plan_flat(ConvDesc& c) {
           auto t_lat = [&]() {
             return load_bytes * 3000.0 / static_cast<double>(static_cast<long long>(a_stages) * a_stage + static_cast<long long>(b_stages) * b_item);
           };
-          auto t_slot = [&]() { return static_cast<double>(n_tiles) * n_parts * (aux_mode ? 7600.0 : 2900.0) / (2.0 * slots); };
+          auto t_slot = [&]() { return direct ? 0.0 : static_cast<double>(n_tiles) * n_parts * (aux_mode ? 7600.0 : 2900.0) / (2.0 * slots); };
           for (;;) {   // grow whichever ring currently bounds the tile, while it fits
             const double tl = t_lat(), ts = t_slot();
             if (std::max(tl, ts) <= t_fixed) break;
@@ -871,6 +875,7 @@ int Model::plan_flat(ConvDesc& c) {
             fp.a_stages = a_stages; fp.b_stages = b_stages; fp.a_stage_bytes = a_stage; fp.b_item_bytes = b_item;
             fp.b_resident = b_res; fp.box_ch = box_ch; fp.boxes = boxes; fp.slots = slots; fp.slot_bytes = slot_bytes;
             fp.n_parts = n_parts; fp.part_cols = part_cols;
+            fp.direct = direct ? 1 : 0;
             found = true;
           }
         }
@@ -878,8 +883,8 @@ int Model::plan_flat(ConvDesc& c) {
     }
   }
   if (found && plan_log)
-    fprintf(stderr, "plan %dx%d cin %d cout %d aux %d: n_tile %d x%d box %d mt %d bres %d a_st %d b_st %d slots %d score %.0f\n", c.kh, c.kw, c.cin,
-            c.cout, aux_mode, fp.n_tile, fp.n_tiles, fp.box_ch, fp.mt, fp.b_resident, fp.a_stages, fp.b_stages, fp.slots, best);
+    fprintf(stderr, "plan %dx%d cin %d cout %d aux %d: n_tile %d x%d box %d mt %d bres %d a_st %d b_st %d slots %d direct %d score %.0f\n", c.kh, c.kw, c.cin,
+            c.cout, aux_mode, fp.n_tile, fp.n_tiles, fp.box_ch, fp.mt, fp.b_resident, fp.a_stages, fp.b_stages, fp.slots, fp.direct, best);
   if (!found) return 0;
   uint32_t tc = 32;
   while (tc < 2u * fp.mt * fp.n_tile) tc *= 2;
@@ -966,6 +971,19 @@ int Model::plan_flat(ConvDesc& c) {
     if (ta.stage != tout.stage || t2.stage != tout.stage) return 0;
     if (slice_map(&fm.aux, ta, c.add2.coff, c.cout)) return 1;
     if (slice_map(&fm.o2, t2, c.out2.coff, c.cout)) return 1;
+  }
+  fp.P_cap = static_cast<long long>(P_cap);
+  if (fp.direct) {
+    fp.d_out = static_cast<uint8_t*>(tout.ptr) + static_cast<size_t>(c.out.coff) * esz; fp.d_out_pitch = static_cast<uint32_t>(tout.C * esz);
+    if (aux_mode == 1) {
+      const ActTensor& tr = tensors_[c.res.id];
+      fp.d_aux = static_cast<const uint8_t*>(tr.ptr) + static_cast<size_t>(c.res.coff) * esz; fp.d_aux_pitch = static_cast<uint32_t>(tr.C * esz);
+    } else if (aux_mode == 2) {
+      const ActTensor& ta = tensors_[c.add2.id];
+      const ActTensor& t2 = tensors_[c.out2.id];
+      fp.d_aux = static_cast<const uint8_t*>(ta.ptr) + static_cast<size_t>(c.add2.coff) * esz; fp.d_aux_pitch = static_cast<uint32_t>(ta.C * esz);
+      fp.d_out2 = static_cast<uint8_t*>(t2.ptr) + static_cast<size_t>(c.out2.coff) * esz; fp.d_out2_pitch = static_cast<uint32_t>(t2.C * esz);
+    }
   }
   if (conv_flat_smem_bytes(fp) > 227 * 1024) return 0;
   c.fp = fp;
