@@ -97,11 +97,12 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* feats, cons
   }
   __syncthreads();
   const int groups = Cpad >> 3;
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long total = static_cast<long long>(rows) * F * groups;
+  // 32-bit index arithmetic (the launcher guarantees rows * F * groups < 2^31): the 64-bit divisions cost more than the conv
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned total = static_cast<unsigned>(rows) * F * groups;
   if (idx >= total) return;
   const int g = static_cast<int>(idx % groups);
-  const long long pix = idx / groups;
+  const unsigned pix = idx / groups;
   const int f = static_cast<int>(pix % F);
   const int row = static_cast<int>(pix / F);
   const int seg = seg_of_row[row];
@@ -140,6 +141,7 @@ cudaError_t launch_stem_conv(const float* feats, const int32_t* seg_frame_off, c
                              int rows, int F, int Wp, int C, int Cpad, int is_bf16, cudaStream_t st) {
   const long long total = static_cast<long long>(rows) * F * (Cpad / 8);
   if (total <= 0) return cudaSuccess;
+  if (total >= (1LL << 31)) return cudaErrorInvalidValue;   // stage-0 capacity is 2^17 rows: far below
   const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
   const size_t smem = 11 * Cpad * sizeof(float);
   if (is_bf16)
@@ -430,12 +432,12 @@ cudaError_t launch_att_pool(const void* x, const void* logits, int C, int W, int
 // Split-K: grid = (E/128, n-tiles of 8, K-splits); each thread owns one output column for 8 segments and
 // streams its slice of Wf with coalesced loads into a partial-sum slab; a second kernel adds the slabs in a
 // fixed order (bit-reproducible, no atomics).
-constexpr int kFcRows = 8;
-constexpr int kFcKChunk = 512;
+constexpr int kFcRows = 32;     // rows per block: every weight element is used 32 times from a register
+constexpr int kFcKChunk = 256;  // 32 x 256 floats of pooled statistics = 32 KB of shared memory
 
 __global__ void __launch_bounds__(128) fc_kernel(const float* __restrict__ pooled, const float* __restrict__ Wf, float* partial, int n,
                                                  int D, int E) {
-  __shared__ float sp[kFcRows][kFcKChunk];
+  __shared__ __align__(16) float sp[kFcRows][kFcKChunk];
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   const int n0 = blockIdx.y * kFcRows;
   const int d0 = blockIdx.z * kFcKChunk;
@@ -450,10 +452,20 @@ __global__ void __launch_bounds__(128) fc_kernel(const float* __restrict__ poole
 #pragma unroll
   for (int r = 0; r < kFcRows; ++r) acc[r] = 0.f;
   const float* wp = Wf + static_cast<size_t>(d0) * E + e;
-  for (int d = 0; d < dn; ++d) {
+  int d = 0;
+  for (; d + 4 <= dn; d += 4) {     // same summation order as the scalar loop (d ascending), 4 weights per iteration
+    const float w0 = wp[static_cast<size_t>(d) * E], w1 = wp[static_cast<size_t>(d + 1) * E];
+    const float w2 = wp[static_cast<size_t>(d + 2) * E], w3 = wp[static_cast<size_t>(d + 3) * E];
+#pragma unroll
+    for (int r = 0; r < kFcRows; ++r) {
+      const float4 x = *reinterpret_cast<const float4*>(&sp[r][d]);   // broadcast read
+      acc[r] = fmaf(x.w, w3, fmaf(x.z, w2, fmaf(x.y, w1, fmaf(x.x, w0, acc[r]))));
+    }
+  }
+  for (; d < dn; ++d) {
     const float w = wp[static_cast<size_t>(d) * E];
 #pragma unroll
-    for (int r = 0; r < kFcRows; ++r) acc[r] += sp[r][d] * w;
+    for (int r = 0; r < kFcRows; ++r) acc[r] = fmaf(sp[r][d], w, acc[r]);
   }
   float* po = partial + static_cast<size_t>(blockIdx.z) * n * E;
 #pragma unroll
