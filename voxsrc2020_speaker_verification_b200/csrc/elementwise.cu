@@ -97,49 +97,73 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* feats, cons
   }
   __syncthreads();
   const int groups = Cpad >> 3;
-  // 32-bit index arithmetic (the launcher guarantees rows * F * groups < 2^31): the 64-bit divisions cost more than the conv
+  // One thread = 8 consecutive feature columns x 8 output channels: its 72 weights live in registers and the 3 x 10 input
+  // window is loaded once for the 8 pixels.  32-bit index arithmetic (the launcher guarantees the count fits).
+  const int nch = (F + 7) >> 3;
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned total = static_cast<unsigned>(rows) * F * groups;
+  const unsigned total = static_cast<unsigned>(rows) * nch * groups;
   if (idx >= total) return;
   const int g = static_cast<int>(idx % groups);
-  const unsigned pix = idx / groups;
-  const int f = static_cast<int>(pix % F);
-  const int row = static_cast<int>(pix / F);
+  const unsigned chunk = idx / groups;
+  const int f0 = static_cast<int>(chunk % nch) * 8;
+  const int row = static_cast<int>(chunk / nch);
   const int seg = seg_of_row[row];
-  float v[8];
+  T* orow = out + (static_cast<size_t>(row) * Wp + f0) * Cpad + g * 8;
+  if (seg < 0) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) v[j] = 0.f;
-  if (seg >= 0) {
-    const int t = row - seg_row_off[seg];
-    const int T_ = seg_h[seg];
-    const float* base = feats + static_cast<size_t>(seg_frame_off[seg]) * F;
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int tt = t + r - 1;
-      if (tt < 0 || tt >= T_) continue;
-#pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const int ff = f + s - 1;
-        if (ff < 0 || ff >= F) continue;
-        const float x = base[static_cast<size_t>(tt) * F + ff];
-        const float* wk = sw + (r * 3 + s) * Cpad + g * 8;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] += x * wk[j];
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j] * sw[9 * Cpad + g * 8 + j] + sw[10 * Cpad + g * 8 + j], 0.f);
+    for (int p = 0; p < 8; ++p)
+      if (f0 + p < F) *reinterpret_cast<uint4*>(orow + static_cast<size_t>(p) * Cpad) = make_uint4(0, 0, 0, 0);
+    return;
   }
-  uint4 o;
-  o.x = TypeOps<T>::pack2(v[0], v[1]); o.y = TypeOps<T>::pack2(v[2], v[3]);
-  o.z = TypeOps<T>::pack2(v[4], v[5]); o.w = TypeOps<T>::pack2(v[6], v[7]);
-  *reinterpret_cast<uint4*>(out + (static_cast<size_t>(row) * Wp + f) * Cpad + g * 8) = o;
+  float w[9][8], sc[8], sh[8];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const float4 a = *reinterpret_cast<const float4*>(sw + k * Cpad + g * 8), b4 = *reinterpret_cast<const float4*>(sw + k * Cpad + g * 8 + 4);
+    w[k][0] = a.x; w[k][1] = a.y; w[k][2] = a.z; w[k][3] = a.w; w[k][4] = b4.x; w[k][5] = b4.y; w[k][6] = b4.z; w[k][7] = b4.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = sw[9 * Cpad + g * 8 + j]; sh[j] = sw[10 * Cpad + g * 8 + j]; }
+  const int t = row - seg_row_off[seg];
+  const int T_ = seg_h[seg];
+  const float* base = feats + static_cast<size_t>(seg_frame_off[seg]) * F;
+  float x[3][10];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int tt = t + r - 1;
+    const bool rok = tt >= 0 && tt < T_;
+#pragma unroll
+    for (int q = 0; q < 10; ++q) {
+      const int ff = f0 + q - 1;
+      x[r][q] = (rok && ff >= 0 && ff < F) ? __ldg(base + static_cast<size_t>(tt) * F + ff) : 0.f;
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    if (f0 + p >= F) break;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int s_ = 0; s_ < 3; ++s_) {
+        const float xv = x[r][p + s_];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaf(xv, w[r * 3 + s_][j], v[j]);
+      }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f);
+    uint4 o;
+    o.x = TypeOps<T>::pack2(v[0], v[1]); o.y = TypeOps<T>::pack2(v[2], v[3]);
+    o.z = TypeOps<T>::pack2(v[4], v[5]); o.w = TypeOps<T>::pack2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(orow + static_cast<size_t>(p) * Cpad) = o;
+  }
 }
 
 cudaError_t launch_stem_conv(const float* feats, const int32_t* seg_frame_off, const int32_t* seg_row_off, const int32_t* seg_h,
                              const int32_t* seg_of_row, const float* w9, const float* scale, const float* shift, void* out,
                              int rows, int F, int Wp, int C, int Cpad, int is_bf16, cudaStream_t st) {
-  const long long total = static_cast<long long>(rows) * F * (Cpad / 8);
+  const long long total = static_cast<long long>(rows) * ((F + 7) / 8) * (Cpad / 8);
   if (total <= 0) return cudaSuccess;
   if (total >= (1LL << 31)) return cudaErrorInvalidValue;   // stage-0 capacity is 2^17 rows: far below
   const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
