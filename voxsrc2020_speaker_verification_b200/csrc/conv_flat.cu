@@ -58,6 +58,14 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// 1-D bulk copies (no tensor map, no rows): a 128-pixel tile of a DENSE planar tensor is one contiguous run in global memory.
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_store_1d(void* gdst, uint32_t smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes) : "memory");
+}
 
 // Timing experiments only (tools/build_knock.sh builds a second library with -DSVX_KNOCK): parts of the pipeline can be
 // switched off at run time to see what the MMA phase costs without them.  The production build compiles these out.
@@ -105,7 +113,7 @@ __device__ __forceinline__ void epi8(const uint32_t* r, uint32_t sc, uint32_t sh
   const float4 s0 = lds_f4(sc), s1 = lds_f4(sc + 16), b0 = lds_f4(sh), b1 = lds_f4(sh + 16);
   uint4 ax = make_uint4(0, 0, 0, 0);
   if (AUX == 1) { if (res_here) ax = lds_u4(ua); }
-  if (AUX == 2) ax = lds_u4(ub);
+  if (AUX >= 2) ax = lds_u4(ub);
   float v[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -125,7 +133,7 @@ __device__ __forceinline__ void epi8(const uint32_t* r, uint32_t sc, uint32_t sh
   o.x = TypeOps<T>::pack2(v[0], v[1]) & vmask; o.y = TypeOps<T>::pack2(v[2], v[3]) & vmask;
   o.z = TypeOps<T>::pack2(v[4], v[5]) & vmask; o.w = TypeOps<T>::pack2(v[6], v[7]) & vmask;
   sts_u4(ua, o);
-  if (AUX == 2) {   // second output = v + add2, in place over the add2 tile
+  if (AUX >= 2) {   // second output = v + add2, in place over the add2 tile
     uint4 o2;
     o2.x = TypeOps<T>::pack2(v[0] + a0.x, v[1] + a0.y) & vmask; o2.y = TypeOps<T>::pack2(v[2] + a1.x, v[3] + a1.y) & vmask;
     o2.z = TypeOps<T>::pack2(v[4] + a2.x, v[5] + a2.y) & vmask; o2.w = TypeOps<T>::pack2(v[6] + a3.x, v[7] + a3.y) & vmask;
@@ -164,7 +172,7 @@ __device__ __forceinline__ void epi8_direct(const uint32_t* r, uint32_t sc, uint
   }
   o.x = TypeOps<T>::pack2(v[0], v[1]) & vmask; o.y = TypeOps<T>::pack2(v[2], v[3]) & vmask;
   o.z = TypeOps<T>::pack2(v[4], v[5]) & vmask; o.w = TypeOps<T>::pack2(v[6], v[7]) & vmask;
-  if (AUX == 2) {
+  if (AUX >= 2) {
     o2.x = TypeOps<T>::pack2(v[0] + a0.x, v[1] + a0.y) & vmask; o2.y = TypeOps<T>::pack2(v[2] + a1.x, v[3] + a1.y) & vmask;
     o2.z = TypeOps<T>::pack2(v[4] + a2.x, v[5] + a2.y) & vmask; o2.w = TypeOps<T>::pack2(v[6] + a3.x, v[7] + a3.y) & vmask;
   }
@@ -365,7 +373,7 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
     prefetch_tmap(&maps.a); prefetch_tmap(&maps.b);
     if (AUX) prefetch_tmap(&maps.aux);
     prefetch_tmap(&maps.o[0]);
-    if (AUX == 2) prefetch_tmap(&maps.o2);
+    if (AUX >= 2) prefetch_tmap(&maps.o2);
     for (int i = 0; i < kRing; ++i) {
       mbar_init(&S.a_full[i], 1); mbar_init(&S.a_empty[i], 1);
       mbar_init(&S.b_full[i], 1); mbar_init(&S.b_empty[i], 1);
@@ -462,7 +470,7 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
     // ------------------------------------------------------------------ aux producer (residual / add2 tiles)
     if (AUX != 0 && lane == 0 && !p.direct) {
       const int aux_hi = AUX == 1 ? p.n_res : p.n_valid;
-      const uint32_t buf_off = AUX == 2 ? static_cast<uint32_t>(p.boxes) * box_bytes : 0u;
+      const uint32_t buf_off = AUX >= 2 ? static_cast<uint32_t>(p.boxes) * box_bytes : 0u;
       Tracer tr; tr.init(p.trace, 2);
       int ls = 0;
       for (int unit = my_group; unit < n_units; unit += groups, ++ls) {
@@ -479,7 +487,12 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
           tr.ev(1);
           wait_dbg(&S.slot_empty[slot], ((q / p.slots) & 1) ^ 1, p.dbg, 0x21, slot, q, S.prog);
           tr.ev(2);
-          if (nb > 0 && !KNOCK(4)) {
+          if (AUX == 3 && !KNOCK(4)) {       // add2 tile of a dense planar tensor: one contiguous run, no rows
+            const uint32_t bytes = 128u * p.d_aux_pitch;
+            mbar_expect_tx(&S.slot_full[slot], bytes);
+            bulk_load_1d(slot_smem + static_cast<size_t>(slot) * p.slot_bytes + buf_off, p.d_aux + static_cast<size_t>(p0 + j * 128) * p.d_aux_pitch, bytes,
+                         &S.slot_full[slot]);
+          } else if (nb > 0 && !KNOCK(4)) {
             mbar_expect_tx(&S.slot_full[slot], static_cast<uint32_t>(nb) * box_bytes);
             uint8_t* dst = slot_smem + static_cast<size_t>(slot) * p.slot_bytes + buf_off;
             for (int b = 0; b < nb; ++b)
@@ -517,6 +530,7 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
             if (p.route_map[gb] != 0xff) tma_store_2d(&maps.o[p.route_map[gb]], bufA + b * box_bytes, p.route_c[gb], px);
             if (AUX == 2) tma_store_2d(&maps.o2, bufB + b * box_bytes, cg, px);
           }
+          if (AUX == 3 && !KNOCK(2)) bulk_store_1d(p.d_out2 + static_cast<size_t>(px) * p.d_out2_pitch, bufB, 128u * p.d_out2_pitch);
           bulk_commit();
           if (p.slots == 1) {             // a single slot per warpgroup cannot stay held until the next commit
             bulk_wait_read<0>(); mbar_arrive(&S.slot_empty[slot]);
@@ -551,7 +565,7 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
       uint8_t* out2_base = p.d_out2 + static_cast<size_t>(n0) * 2;
       const bool aux32 = AUX != 0 && ((reinterpret_cast<uintptr_t>(aux_base) | p.d_aux_pitch) & 31u) == 0;     // 32-byte aligned pixel runs
       const bool out32 = ((reinterpret_cast<uintptr_t>(out_base) | p.d_out_pitch) & 31u) == 0;
-      const bool out2_32 = AUX == 2 && ((reinterpret_cast<uintptr_t>(out2_base) | p.d_out2_pitch) & 31u) == 0;
+      const bool out2_32 = AUX >= 2 && ((reinterpret_cast<uintptr_t>(out2_base) | p.d_out2_pitch) & 31u) == 0;
       uint4 ax[8], nx[8];
 #pragma unroll
       for (int g = 0; g < 8; ++g) ax[g] = nx[g] = make_uint4(0, 0, 0, 0);
@@ -607,10 +621,10 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
                 if (2 * q + 1 < ngrp) {
                   epi8_direct<T, AUX, PRE, POST>(ra + 8, sc_base + q * 64 + 32, sh_base + q * 64 + 32, ax[2 * q + 1], vb, wb, vmask);
                   if (out32) stg256(o1 + 2 * q, va, vb); else { o1[2 * q] = va; o1[2 * q + 1] = vb; }
-                  if (AUX == 2) { if (out2_32) stg256(o2 + 2 * q, wa, wb); else { o2[2 * q] = wa; o2[2 * q + 1] = wb; } }
+                  if (AUX >= 2) { if (out2_32) stg256(o2 + 2 * q, wa, wb); else { o2[2 * q] = wa; o2[2 * q + 1] = wb; } }
                 } else {
                   o1[2 * q] = va;
-                  if (AUX == 2) o2[2 * q] = wa;
+                  if (AUX >= 2) o2[2 * q] = wa;
                 }
               }
             }
@@ -652,6 +666,8 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
         else wait_dbg(&S.slot_empty[slot], (u & 1) ^ 1, p.dbg, 0x43, slot, q, S.prog);
         tr.ev(3);
         const uint32_t bufA = slot_base + static_cast<uint32_t>(slot) * p.slot_bytes + row_off;
+        // AUX 3: the add2 / out2 tile is the linear image [128 pixels][pitch] of a dense planar tensor (48-byte rows: conflict-free)
+        const uint32_t linB = slot_base + static_cast<uint32_t>(slot) * p.slot_bytes + bufB_off + static_cast<uint32_t>(m) * p.d_aux_pitch;
         const uint32_t vmask = j == 0 ? vm[0] : j == 1 ? vm[1] : j == 2 ? vm[2] : vm[3];
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>((wg * p.mt + j) * p.n_tile);
         uint32_t ra[16], rb[16];
@@ -667,7 +683,7 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
             if (cg < p.n_valid && (cg & p.grp_mask) < p.grp_w && !KNOCK(1)) {
               const uint32_t cs = static_cast<uint32_t>(cl - cpart);   // column inside the slot
               const uint32_t ua = bufA + (cs >> bsh) * box_bytes + ((((cs & bmask) >> 3) << 4) ^ row_xor);
-              epi8<T, AUX, PRE, POST>(ra + g * 8, sc_base + cl * 4, sh_base + cl * 4, ua, ua + bufB_off, cg < p.n_res, vmask);
+              epi8<T, AUX, PRE, POST>(ra + g * 8, sc_base + cl * 4, sh_base + cl * 4, ua, AUX == 3 ? linB + (cs >> 3) * 16u : ua + bufB_off, cg < p.n_res, vmask);
             }
           }
           if (c0 + 16 < c_end) {
@@ -679,7 +695,7 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
               if (cg < p.n_valid && (cg & p.grp_mask) < p.grp_w && !KNOCK(1)) {
                 const uint32_t cs = static_cast<uint32_t>(cl - cpart);   // column inside the slot
               const uint32_t ua = bufA + (cs >> bsh) * box_bytes + ((((cs & bmask) >> 3) << 4) ^ row_xor);
-                epi8<T, AUX, PRE, POST>(rb + g * 8, sc_base + cl * 4, sh_base + cl * 4, ua, ua + bufB_off, cg < p.n_res, vmask);
+                epi8<T, AUX, PRE, POST>(rb + g * 8, sc_base + cl * 4, sh_base + cl * 4, ua, AUX == 3 ? linB + (cs >> 3) * 16u : ua + bufB_off, cg < p.n_res, vmask);
               }
             }
           }
@@ -729,6 +745,7 @@ static cudaError_t init_type() {
   if ((e = set_attr<T, 1, false, false>()) != cudaSuccess) return e;
   if ((e = set_attr<T, 1, false, true>()) != cudaSuccess) return e;
   if ((e = set_attr<T, 2, false, true>()) != cudaSuccess) return e;
+  if ((e = set_attr<T, 3, false, true>()) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
@@ -780,7 +797,7 @@ static cudaError_t launch_typed(const FlatConvParams& p, const FlatMaps& maps, d
     if (p.post_relu) SVX_FLAT(1, false, true); else SVX_FLAT(1, false, false);
   } else {
     if (p.pre_relu || !p.post_relu) return cudaErrorInvalidValue;
-    SVX_FLAT(2, false, true);
+    if (p.lin) SVX_FLAT(3, false, true); else SVX_FLAT(2, false, true);
   }
 #undef SVX_FLAT
   if (le != cudaSuccess) {

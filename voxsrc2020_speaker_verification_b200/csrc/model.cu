@@ -779,6 +779,16 @@ int Model::plan_flat(ConvDesc& c) {
   // direct epilogue (global accesses from the epilogue threads instead of slots + TMA) for narrow single-destination tiles
   static const bool no_direct = getenv("SVX_NO_DIRECT") != nullptr;   // debug switch
   const bool direct_ok = !no_direct && !split && n_split == c.cout && !use_pair && c.outb.id < 0;
+  // aux mode 2 over dense planar tensors: the add2 / out2 tiles are contiguous runs -> 1-D bulk copies instead of 128 rows each
+  // (measured: no gain — 14 354 vs 14 458 emb/s with it on the stage-3 3x3 convs, and none on stages 1-2 against 2-D TMA tiles —
+  // so it is opt-in: SVX_LIN=1)
+  static const bool use_lin = getenv("SVX_LIN") != nullptr;   // debug switch
+  bool lin_ok = false;
+  if (use_lin && aux_mode == 2 && !use_pair && !split) {
+    const ActTensor& ta = tensors_[c.add2.id];
+    const ActTensor& t2 = tensors_[c.out2.id];
+    lin_ok = ta.C == c.cout && t2.C == c.cout && c.add2.coff == 0 && c.out2.coff == 0 && (c.cout * 2) % 16 == 0;
+  }
   bool found = false;
   double best = 1e30;
   for (int n_tile : cands) {
@@ -798,7 +808,9 @@ int Model::plan_flat(ConvDesc& c) {
       const int boxes = (part_cols + box_ch - 1) / box_ch;
       const uint32_t box_bytes = 128u * box_ch * 2u;
       const bool direct = direct_ok && n_tile <= 64 && (n_tiles == 1 || grouped);   // several n-tiles would re-read A per 64 channels
-      const uint32_t slot_bytes = direct ? 0u : boxes * box_bytes * (aux_mode == 2 ? 2u : 1u);
+      const bool lin = lin_ok && !direct && n_tiles == 1;
+      const uint32_t slot_bytes = direct ? 0u : lin ? boxes * box_bytes + static_cast<uint32_t>(round_up(128 * c.cout * 2, 1024))
+                                                    : boxes * box_bytes * (aux_mode == 2 ? 2u : 1u);
       const int b_rows_cta = use_pair ? n_tile / 2 : n_tile;                    // pair mode: each CTA of the pair holds half of the weights
       const uint32_t b_item = static_cast<uint32_t>(round_up(b_rows_cta * static_cast<int>(row_bytes), 1024));
       const int items = taps * c.nkc;
@@ -826,9 +838,9 @@ int Model::plan_flat(ConvDesc& c) {
           const double halo_ovh = 1.0 + 2.0 * halo / (mt * 128.0);
           const double a_rows = static_cast<double>(n_tiles) * c.nkc * 128.0 * halo_ovh;
           const double b_rows = b_res ? 0.0 : static_cast<double>(n_tiles) * items * b_rows_cta / mt;
-          const int aux_boxes = (aux_mode && !direct) ? boxes : 0;
+          const int aux_boxes = (aux_mode && !direct && !lin) ? boxes : 0;
           const double aux_rows = static_cast<double>(n_tiles) * aux_boxes * 128.0;
-          const double st_rows = direct ? 0.0 : static_cast<double>(n_tiles) * boxes * 128.0 * (aux_mode == 2 ? 2.0 : 1.0);
+          const double st_rows = direct ? 0.0 : static_cast<double>(n_tiles) * boxes * 128.0 * ((aux_mode == 2 && !lin) ? 2.0 : 1.0);
           const double t_req = (a_rows + b_rows + aux_rows) * 5.6;
           const double t_st = st_rows * 4.6;
           const double load_bytes = (a_rows + b_rows) * row_bytes;
@@ -875,7 +887,7 @@ int Model::plan_flat(ConvDesc& c) {
             fp.a_stages = a_stages; fp.b_stages = b_stages; fp.a_stage_bytes = a_stage; fp.b_item_bytes = b_item;
             fp.b_resident = b_res; fp.box_ch = box_ch; fp.boxes = boxes; fp.slots = slots; fp.slot_bytes = slot_bytes;
             fp.n_parts = n_parts; fp.part_cols = part_cols;
-            fp.direct = direct ? 1 : 0;
+            fp.direct = direct ? 1 : 0; fp.lin = lin ? 1 : 0;
             found = true;
           }
         }
@@ -883,8 +895,8 @@ int Model::plan_flat(ConvDesc& c) {
     }
   }
   if (found && plan_log)
-    fprintf(stderr, "plan %dx%d cin %d cout %d aux %d: n_tile %d x%d box %d mt %d bres %d a_st %d b_st %d slots %d direct %d score %.0f\n", c.kh, c.kw, c.cin,
-            c.cout, aux_mode, fp.n_tile, fp.n_tiles, fp.box_ch, fp.mt, fp.b_resident, fp.a_stages, fp.b_stages, fp.slots, fp.direct, best);
+    fprintf(stderr, "plan %dx%d cin %d cout %d aux %d: n_tile %d x%d box %d mt %d bres %d a_st %d b_st %d slots %d direct %d lin %d score %.0f\n", c.kh, c.kw, c.cin,
+            c.cout, aux_mode, fp.n_tile, fp.n_tiles, fp.box_ch, fp.mt, fp.b_resident, fp.a_stages, fp.b_stages, fp.slots, fp.direct, fp.lin, best);
   if (!found) return 0;
   uint32_t tc = 32;
   while (tc < 2u * fp.mt * fp.n_tile) tc *= 2;
@@ -973,7 +985,7 @@ int Model::plan_flat(ConvDesc& c) {
     if (slice_map(&fm.o2, t2, c.out2.coff, c.cout)) return 1;
   }
   fp.P_cap = static_cast<long long>(P_cap);
-  if (fp.direct) {
+  if (fp.direct || fp.lin) {
     fp.d_out = static_cast<uint8_t*>(tout.ptr) + static_cast<size_t>(c.out.coff) * esz; fp.d_out_pitch = static_cast<uint32_t>(tout.C * esz);
     if (aux_mode == 1) {
       const ActTensor& tr = tensors_[c.res.id];
