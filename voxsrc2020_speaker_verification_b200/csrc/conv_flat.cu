@@ -505,7 +505,7 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
     }
   } else if (warp == 3) {
     // ------------------------------------------------------------------ store issuer
-    if (lane == 0 && !p.direct) {
+    if (lane == 0 && p.direct != 1) {
       Tracer tr; tr.init(p.trace, 3);
       const uint32_t slot_base = smem_u32(slot_smem);
       int prev_slot = -1;
@@ -526,6 +526,7 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
           for (int b = 0; b < p.boxes; ++b) {
             const int cg = cb + b * p.box_ch;
             if (cg >= p.n_valid || KNOCK(2)) break;
+            if (p.direct == 2) { tma_store_2d(&maps.o2, bufA + b * box_bytes, cg, px); continue; }   // hybrid: only out2 goes through the slot
             const int gb = cg / p.box_ch;           // global staging box (tiles and parts start on box boundaries)
             if (p.route_map[gb] != 0xff) tma_store_2d(&maps.o[p.route_map[gb]], bufA + b * box_bytes, p.route_c[gb], px);
             if (AUX == 2) tma_store_2d(&maps.o2, bufB + b * box_bytes, cg, px);
@@ -608,6 +609,13 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>((wg * p.mt + j) * p.n_tile);
           uint4* o1 = reinterpret_cast<uint4*>(out_base + static_cast<size_t>(pp) * p.d_out_pitch);
           uint4* o2 = reinterpret_cast<uint4*>(out2_base + static_cast<size_t>(pp) * p.d_out2_pitch);
+          // hybrid (direct == 2): the second output is staged in a slot and leaves by TMA (scattered STG rows cost ~2.5x a TMA
+          // row, profiles/r01_microbench_tma_rate.txt), the aux values and the primary output stay on the LSU
+          const bool hybrid = AUX >= 2 && p.direct == 2;
+          const uint32_t qs = static_cast<uint32_t>(ls >> 1) * p.mt + j;
+          const int slot = wg * p.slots + qs % p.slots;
+          const uint32_t slotA = slot_base + static_cast<uint32_t>(slot) * p.slot_bytes + row_off;
+          if (hybrid) wait_dbg(&S.slot_empty[slot], ((qs / p.slots) & 1) ^ 1, p.dbg, 0x43, slot, qs, S.prog);
           uint32_t ra[16];
           tr.ev(3);
 #pragma unroll
@@ -621,10 +629,21 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
                 if (2 * q + 1 < ngrp) {
                   epi8_direct<T, AUX, PRE, POST>(ra + 8, sc_base + q * 64 + 32, sh_base + q * 64 + 32, ax[2 * q + 1], vb, wb, vmask);
                   if (out32) stg256(o1 + 2 * q, va, vb); else { o1[2 * q] = va; o1[2 * q + 1] = vb; }
-                  if (AUX >= 2) { if (out2_32) stg256(o2 + 2 * q, wa, wb); else { o2[2 * q] = wa; o2[2 * q + 1] = wb; } }
+                  if (AUX >= 2) {
+                    if (hybrid) {
+                      const uint32_t c0s = q * 16u, c1s = q * 16u + 8u;
+                      sts_u4(slotA + (c0s >> bsh) * box_bytes + ((((c0s & bmask) >> 3) << 4) ^ row_xor), wa);
+                      sts_u4(slotA + (c1s >> bsh) * box_bytes + ((((c1s & bmask) >> 3) << 4) ^ row_xor), wb);
+                    } else if (out2_32) stg256(o2 + 2 * q, wa, wb);
+                    else { o2[2 * q] = wa; o2[2 * q + 1] = wb; }
+                  }
                 } else {
                   o1[2 * q] = va;
-                  if (AUX >= 2) o2[2 * q] = wa;
+                  if (AUX >= 2) {
+                    const uint32_t c0s = q * 16u;
+                    if (hybrid) sts_u4(slotA + (c0s >> bsh) * box_bytes + ((((c0s & bmask) >> 3) << 4) ^ row_xor), wa);
+                    else o2[2 * q] = wa;
+                  }
                 }
               }
             }
@@ -633,6 +652,10 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.tmem_empty[wg]);
+          }
+          if (hybrid) {
+            fence_proxy_async();              // generic-proxy writes of this thread -> visible to the TMA store
+            mbar_arrive(&S.slot_ready[slot]);
           }
 #pragma unroll
           for (int g = 0; g < 8; ++g) ax[g] = nx[g];

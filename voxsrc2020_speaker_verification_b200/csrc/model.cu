@@ -808,8 +808,10 @@ int Model::plan_flat(ConvDesc& c) {
       const int boxes = (part_cols + box_ch - 1) / box_ch;
       const uint32_t box_bytes = 128u * box_ch * 2u;
       const bool direct = direct_ok && n_tile <= 64 && (n_tiles == 1 || grouped);   // several n-tiles would re-read A per 64 channels
+      static const bool no_hybrid = getenv("SVX_NO_HYBRID") != nullptr;   // debug switch
+      const bool hybrid = direct && aux_mode == 2 && !no_hybrid;          // out2 through a slot + TMA, aux and out1 on the LSU
       const bool lin = lin_ok && !direct && n_tiles == 1;
-      const uint32_t slot_bytes = direct ? 0u : lin ? boxes * box_bytes + static_cast<uint32_t>(round_up(128 * c.cout * 2, 1024))
+      const uint32_t slot_bytes = hybrid ? boxes * box_bytes : direct ? 0u : lin ? boxes * box_bytes + static_cast<uint32_t>(round_up(128 * c.cout * 2, 1024))
                                                     : boxes * box_bytes * (aux_mode == 2 ? 2u : 1u);
       const int b_rows_cta = use_pair ? n_tile / 2 : n_tile;                    // pair mode: each CTA of the pair holds half of the weights
       const uint32_t b_item = static_cast<uint32_t>(round_up(b_rows_cta * static_cast<int>(row_bytes), 1024));
@@ -840,7 +842,7 @@ int Model::plan_flat(ConvDesc& c) {
           const double b_rows = b_res ? 0.0 : static_cast<double>(n_tiles) * items * b_rows_cta / mt;
           const int aux_boxes = (aux_mode && !direct && !lin) ? boxes : 0;
           const double aux_rows = static_cast<double>(n_tiles) * aux_boxes * 128.0;
-          const double st_rows = direct ? 0.0 : static_cast<double>(n_tiles) * boxes * 128.0 * ((aux_mode == 2 && !lin) ? 2.0 : 1.0);
+          const double st_rows = hybrid ? static_cast<double>(n_tiles) * boxes * 128.0 : direct ? 0.0 : static_cast<double>(n_tiles) * boxes * 128.0 * ((aux_mode == 2 && !lin) ? 2.0 : 1.0);
           const double t_req = (a_rows + b_rows + aux_rows) * 5.6;
           const double t_st = st_rows * 4.6;
           const double load_bytes = (a_rows + b_rows) * row_bytes;
@@ -853,7 +855,7 @@ int Model::plan_flat(ConvDesc& c) {
           auto t_lat = [&]() {
             return load_bytes * 3000.0 / static_cast<double>(static_cast<long long>(a_stages) * a_stage + static_cast<long long>(b_stages) * b_item);
           };
-          auto t_slot = [&]() { return direct ? 0.0 : static_cast<double>(n_tiles) * n_parts * (aux_mode ? 7600.0 : 2900.0) / (2.0 * slots); };
+          auto t_slot = [&]() { return (direct && !hybrid) ? 0.0 : static_cast<double>(n_tiles) * n_parts * (aux_mode ? 7600.0 : 2900.0) / (2.0 * slots); };
           for (;;) {   // grow whichever ring currently bounds the tile, while it fits
             const double tl = t_lat(), ts = t_slot();
             if (std::max(tl, ts) <= t_fixed) break;
@@ -887,7 +889,7 @@ int Model::plan_flat(ConvDesc& c) {
             fp.a_stages = a_stages; fp.b_stages = b_stages; fp.a_stage_bytes = a_stage; fp.b_item_bytes = b_item;
             fp.b_resident = b_res; fp.box_ch = box_ch; fp.boxes = boxes; fp.slots = slots; fp.slot_bytes = slot_bytes;
             fp.n_parts = n_parts; fp.part_cols = part_cols;
-            fp.direct = direct ? 1 : 0; fp.lin = lin ? 1 : 0;
+            fp.direct = hybrid ? 2 : direct ? 1 : 0; fp.lin = lin ? 1 : 0;
             found = true;
           }
         }
