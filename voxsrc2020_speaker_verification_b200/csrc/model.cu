@@ -825,9 +825,13 @@ int Model::plan_flat(ConvDesc& c) {
         const int a_box_rows = round_up((a_rows_min + a_boxes - 1) / a_boxes, 8);
         const uint32_t a_stage = static_cast<uint32_t>(round_up(a_boxes * a_box_rows * static_cast<int>(row_bytes), 1024));
         for (int b_res : {1, 0}) {
-          if (b_res && b_total > 96 * 1024) continue;
+          static const long long bres_max = getenv("SVX_BRES_MAX") ? atoll(getenv("SVX_BRES_MAX")) : 64 * 1024;   // tuning knobs; resident weights above 64 KB starve the A ring (measured +1.2 % against 96 KB)
+          static const double lat_cyc = getenv("SVX_LAT_CYC") ? atof(getenv("SVX_LAT_CYC")) : 3000.0;
+          static const double slot_scale = getenv("SVX_SLOT_SCALE") ? atof(getenv("SVX_SLOT_SCALE")) : 1.0;
+          if (b_res && b_total > bres_max) continue;
           if (!b_res && items < 2) continue;
-          int a_stages = 2, b_stages = b_res ? 0 : 2, slots = 2;               // slots: per warpgroup (2: convert j+1 while j is stored)
+          static const int slots0 = getenv("SVX_SLOTS0") ? atoi(getenv("SVX_SLOTS0")) : 2;
+          int a_stages = 2, b_stages = b_res ? 0 : 2, slots = slots0;               // slots: per warpgroup (2: convert j+1 while j is stored)
           long long left = budget - (b_res ? b_total : 2LL * b_item) - 2LL * a_stage - 2LL * slots * slot_bytes;
           if (left < 0) { slots = 1; left += 2LL * slot_bytes; }
           if (left < 0) continue;
@@ -853,9 +857,9 @@ int Model::plan_flat(ConvDesc& c) {
           // latency terms shrink with ring depth: loads in flight against ~1.5 us, and slots held ~4 us with an aux tile
           // (prefetch → conversion → store read), ~1.5 us without (profiles/r01_trace_flat_*.txt); 2*slots are in flight
           auto t_lat = [&]() {
-            return load_bytes * 3000.0 / static_cast<double>(static_cast<long long>(a_stages) * a_stage + static_cast<long long>(b_stages) * b_item);
+            return load_bytes * lat_cyc / static_cast<double>(static_cast<long long>(a_stages) * a_stage + static_cast<long long>(b_stages) * b_item);
           };
-          auto t_slot = [&]() { return (direct && !hybrid) ? 0.0 : static_cast<double>(n_tiles) * n_parts * (aux_mode ? 7600.0 : 2900.0) / (2.0 * slots); };
+          auto t_slot = [&]() { return (direct && !hybrid) ? 0.0 : static_cast<double>(n_tiles) * n_parts * (aux_mode ? 7600.0 : 2900.0) * slot_scale / (2.0 * slots); };
           for (;;) {   // grow whichever ring currently bounds the tile, while it fits
             const double tl = t_lat(), ts = t_slot();
             if (std::max(tl, ts) <= t_fixed) break;
@@ -874,6 +878,8 @@ int Model::plan_flat(ConvDesc& c) {
           }
           // the model is optimistic about overlap: when shared memory is left over, take a second slot per warpgroup (convert
           // j+1 while j is being stored), a third A stage, and a third slot for aux tiles
+          static const int a_min = getenv("SVX_A_MIN") ? atoi(getenv("SVX_A_MIN")) : 3;
+          while (a_stages < a_min && a_min > 3 && left >= a_stage) { ++a_stages; left -= a_stage; }
           if (slots < 2 && left >= 2LL * slot_bytes) { ++slots; left -= 2LL * slot_bytes; }
           if (a_stages < 3 && left >= a_stage) { ++a_stages; left -= a_stage; }
           if (aux_mode && slots < 3 && left >= 2LL * slot_bytes) { ++slots; left -= 2LL * slot_bytes; }
