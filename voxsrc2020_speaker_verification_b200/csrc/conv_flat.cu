@@ -565,8 +565,9 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
       uint8_t* out_base = p.d_out + static_cast<size_t>(n0) * 2;
       uint8_t* out2_base = p.d_out2 + static_cast<size_t>(n0) * 2;
       const bool aux32 = AUX != 0 && ((reinterpret_cast<uintptr_t>(aux_base) | p.d_aux_pitch) & 31u) == 0;     // 32-byte aligned pixel runs
-      const bool out32 = ((reinterpret_cast<uintptr_t>(out_base) | p.d_out_pitch) & 31u) == 0;
-      const bool out2_32 = AUX >= 2 && ((reinterpret_cast<uintptr_t>(out2_base) | p.d_out2_pitch) & 31u) == 0;
+      // 256-bit accesses only for runs that are whole sectors: a 48-byte run as 32 + 16 bytes measured slower than 3 x 16 (345 vs 322 us)
+      const bool out32 = (ngrp & 1) == 0 && ((reinterpret_cast<uintptr_t>(out_base) | p.d_out_pitch) & 31u) == 0;
+      const bool out2_32 = AUX >= 2 && (ngrp & 1) == 0 && ((reinterpret_cast<uintptr_t>(out2_base) | p.d_out2_pitch) & 31u) == 0;
       uint4 ax[8], nx[8];
 #pragma unroll
       for (int g = 0; g < 8; ++g) ax[g] = nx[g] = make_uint4(0, 0, 0, 0);
