@@ -170,6 +170,7 @@ struct FlatConvParams {
   uint32_t a_stage_bytes, b_item_bytes;
   int b_resident;
   uint32_t idesc, sbo, layout_type, tmem_cols;
+  int tmem_bufs, tmem_bufs_log2;   // accumulator buffers in TMEM (2 or 4): with 4 an epilogue warpgroup may lag a whole span behind the MMAs
   int pair;                    // 1: CTA pairs (cta_group::2, M = 256): even/odd CTAs of a cluster take consecutive spans, each holds half of B
   int b_rows;                  // weight rows this CTA loads per item: n_tile, or n_tile/2 in pair mode
   // epilogue

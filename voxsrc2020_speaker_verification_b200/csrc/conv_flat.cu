@@ -225,7 +225,7 @@ __device__ __forceinline__ void issue_tap(uint32_t a_lo, uint32_t b_lo, uint32_t
 struct Smem {
   uint64_t a_full[kRing], a_empty[kRing], b_full[kRing], b_empty[kRing];
   uint64_t slot_full[kRing], slot_empty[kRing], slot_ready[kRing];
-  uint64_t tmem_full[2], tmem_empty[2];
+  uint64_t tmem_full[4], tmem_empty[4];   // accumulator buffers: 2, or 4 when 4 * mt * n_tile columns fit (p.tmem_bufs)
   uint64_t bres_bar;
   uint64_t pa_full[kRing], pb_full[kRing], pbres_bar;   // pair mode, leader CTA: the peer's A stage / weight item / resident weights landed
   uint32_t tmem_slot;
@@ -266,10 +266,10 @@ __device__ __forceinline__ void mma_role(const FlatConvParams& p, Smem& S, uint3
   uint32_t ia = 0, ib = 0;
   int ls = 0;
   for (int unit = my_group; unit < n_units; unit += groups, ++ls) {
-    const int buf = ls & 1;
+    const int buf = ls & (p.tmem_bufs - 1);       // span ls -> buffer ls mod bufs; warpgroup ls & 1 reads it (buffers wg, wg + 2)
     tr.ev(1);
     if (lane == 0) S.prog[1] = ls;
-    if (!relay) wait_dbg(&S.tmem_empty[buf], ((ls >> 1) & 1) ^ 1, p.dbg, 0x11, buf, ls, S.prog);
+    if (!relay) wait_dbg(&S.tmem_empty[buf], ((ls >> p.tmem_bufs_log2) & 1) ^ 1, p.dbg, 0x11, buf, ls, S.prog);
     tr.ev(2);
     const uint32_t d_tmem = tb + static_cast<uint32_t>(buf * MT) * nt;
     uint32_t first = 0u;
@@ -379,7 +379,7 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
       mbar_init(&S.b_full[i], 1); mbar_init(&S.b_empty[i], 1);
       mbar_init(&S.slot_full[i], 1); mbar_init(&S.slot_empty[i], 1); mbar_init(&S.slot_ready[i], 128);
     }
-    for (int b = 0; b < 2; ++b) { mbar_init(&S.tmem_full[b], 1); mbar_init(&S.tmem_empty[b], pair ? 8 : 4); }   // pair: both CTAs' epilogue warps
+    for (int b = 0; b < 4; ++b) { mbar_init(&S.tmem_full[b], 1); mbar_init(&S.tmem_empty[b], pair ? 8 : 4); }   // pair: both CTAs' epilogue warps
     mbar_init(&S.bres_bar, 1);
     for (int i = 0; i < kRing; ++i) { mbar_init(&S.pa_full[i], 1); mbar_init(&S.pb_full[i], 1); }
     mbar_init(&S.pbres_bar, 1);
@@ -596,7 +596,8 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
         }
         tr.ev(1);
         if (lane == 0) S.prog[warp] = 0x10000u | (static_cast<uint32_t>(ls) << 4);
-        wait_dbg(&S.tmem_full[wg], (ls >> 1) & 1, p.dbg, 0x41, wg, ls, S.prog);
+        const int tb_i = ls & (p.tmem_bufs - 1);
+        wait_dbg(&S.tmem_full[tb_i], (ls >> p.tmem_bufs_log2) & 1, p.dbg, 0x41, wg, ls, S.prog);
         tr.ev(2);
         tc_fence_after();
 #pragma unroll 1
@@ -607,7 +608,7 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
             load_aux(reinterpret_cast<const uint4*>(aux_base + static_cast<size_t>(pp + 128) * p.d_aux_pitch), nx);
           }
           const uint32_t vmask = j == 0 ? vm[0] : j == 1 ? vm[1] : j == 2 ? vm[2] : vm[3];
-          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>((wg * p.mt + j) * p.n_tile);
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>((tb_i * p.mt + j) * p.n_tile);
           uint4* o1 = reinterpret_cast<uint4*>(out_base + static_cast<size_t>(pp) * p.d_out_pitch);
           uint4* o2 = reinterpret_cast<uint4*>(out2_base + static_cast<size_t>(pp) * p.d_out2_pitch);
           // hybrid (direct == 2): the second output is staged in a slot and leaves by TMA (scattered STG rows cost ~2.5x a TMA
@@ -652,7 +653,7 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
           if (j == p.mt - 1) {              // all accumulators of this span have been read: hand TMEM back
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&S.tmem_empty[wg]);
+            if (lane == 0) mbar_arrive(&S.tmem_empty[tb_i]);
           }
           if (hybrid) {
             fence_proxy_async();              // generic-proxy writes of this thread -> visible to the TMA store
@@ -676,7 +677,8 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
       }
       tr.ev(1);
       if (lane == 0) S.prog[warp] = 0x10000u | (static_cast<uint32_t>(ls) << 4);
-      wait_dbg(&S.tmem_full[wg], (ls >> 1) & 1, p.dbg, 0x41, wg, ls, S.prog);
+      const int tb_i = ls & (p.tmem_bufs - 1);
+      wait_dbg(&S.tmem_full[tb_i], (ls >> p.tmem_bufs_log2) & 1, p.dbg, 0x41, wg, ls, S.prog);
       tr.ev(2);
       tc_fence_after();
 #pragma unroll 1
@@ -693,7 +695,7 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
         // AUX 3: the add2 / out2 tile is the linear image [128 pixels][pitch] of a dense planar tensor (48-byte rows: conflict-free)
         const uint32_t linB = slot_base + static_cast<uint32_t>(slot) * p.slot_bytes + bufB_off + static_cast<uint32_t>(m) * p.d_aux_pitch;
         const uint32_t vmask = j == 0 ? vm[0] : j == 1 ? vm[1] : j == 2 ? vm[2] : vm[3];
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>((wg * p.mt + j) * p.n_tile);
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>((tb_i * p.mt + j) * p.n_tile);
         uint32_t ra[16], rb[16];
         const int c_end = cpart + p.part_cols;
         if (!KNOCK(8)) tmem_ld16(taddr + cpart, ra);
@@ -729,8 +731,8 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
           __syncwarp();
           if (lane == 0) {
             bool done = false;
-            if constexpr (pair) { if (rank == 1) { mbar_arrive_remote(&S.tmem_empty[wg], 0); done = true; } }
-            if (!done) mbar_arrive(&S.tmem_empty[wg]);
+            if constexpr (pair) { if (rank == 1) { mbar_arrive_remote(&S.tmem_empty[tb_i], 0); done = true; } }
+            if (!done) mbar_arrive(&S.tmem_empty[tb_i]);
           }
         }
         if (lane == 0) S.prog[warp] = 0x30000u | q;

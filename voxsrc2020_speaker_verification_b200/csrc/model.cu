@@ -908,8 +908,13 @@ int Model::plan_flat(ConvDesc& c) {
     fprintf(stderr, "plan %dx%d cin %d cout %d aux %d: n_tile %d x%d box %d mt %d bres %d a_st %d b_st %d slots %d direct %d lin %d score %.0f\n", c.kh, c.kw, c.cin,
             c.cout, aux_mode, fp.n_tile, fp.n_tiles, fp.box_ch, fp.mt, fp.b_resident, fp.a_stages, fp.b_stages, fp.slots, fp.direct, fp.lin, best);
   if (!found) return 0;
+  // TMEM buffers: the epilogue of span s releases its accumulators only after its last sub-tile, so with 2 buffers the MMAs of
+  // span s+2 wait for it; 4 buffers (when they fit in 512 columns) take that wait off the critical path
+  static const bool no_tb4 = getenv("SVX_NO_TMEM4") != nullptr;   // debug switch
+  const int bufs = (!no_tb4 && !use_pair && 4 * fp.mt * fp.n_tile <= 512) ? 4 : 2;
+  fp.tmem_bufs = bufs; fp.tmem_bufs_log2 = bufs == 4 ? 2 : 1;
   uint32_t tc = 32;
-  while (tc < 2u * fp.mt * fp.n_tile) tc *= 2;
+  while (tc < static_cast<uint32_t>(bufs) * fp.mt * fp.n_tile) tc *= 2;
   if (tc > 512) return 0;
   fp.tmem_cols = tc;
   fp.pair = use_pair ? 1 : 0;
