@@ -200,7 +200,7 @@ struct FlatConvParams {
   uint8_t* d_out; uint32_t d_out_pitch;        // primary output slice (first channel of the slice), bytes per pixel
   uint8_t* d_out2; uint32_t d_out2_pitch;      // second output (aux mode 2)
   const uint8_t* d_aux; uint32_t d_aux_pitch;  // residual (aux mode 1) / add2 (aux mode 2)
-  int knock;                   // debug timing experiments only (SVX_FLAT_KNOCK): 1 skip epilogue math, 2 skip stores, 4 skip aux loads, 8 skip tcgen05.ld
+  int knock;                   // debug timing experiments only (SVX_FLAT_KNOCK): 1 skip epilogue math, 2 skip TMA stores, 4 skip aux loads, 8 skip tcgen05.ld, 32 skip the MMAs, 64 skip the direct epilogue's primary stores
   unsigned long long* dbg;     // host-mapped words: which barrier wait timed out (written before the trap)
 };
 struct FlatMaps { CUtensorMap a, b, aux, o2, o[8]; };   // o2: second output of aux mode 2

@@ -630,7 +630,8 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
                 epi8_direct<T, AUX, PRE, POST>(ra, sc_base + q * 64, sh_base + q * 64, ax[2 * q], va, wa, vmask);
                 if (2 * q + 1 < ngrp) {
                   epi8_direct<T, AUX, PRE, POST>(ra + 8, sc_base + q * 64 + 32, sh_base + q * 64 + 32, ax[2 * q + 1], vb, wb, vmask);
-                  if (out32) stg256(o1 + 2 * q, va, vb); else { o1[2 * q] = va; o1[2 * q + 1] = vb; }
+                  if (KNOCK(64)) { if (va.x == 0x12345u) o1[0] = va; }     // timing experiment: arithmetic kept, stores dropped
+                  else if (out32) stg256(o1 + 2 * q, va, vb); else { o1[2 * q] = va; o1[2 * q + 1] = vb; }
                   if (AUX >= 2) {
                     if (hybrid) {
                       const uint32_t c0s = q * 16u, c1s = q * 16u + 8u;
@@ -640,7 +641,7 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
                     else { o2[2 * q] = wa; o2[2 * q + 1] = wb; }
                   }
                 } else {
-                  o1[2 * q] = va;
+                  if (KNOCK(64)) { if (va.x == 0x12345u) o1[0] = va; } else o1[2 * q] = va;
                   if (AUX >= 2) {
                     const uint32_t c0s = q * 16u;
                     if (hybrid) sts_u4(slotA + (c0s >> bsh) * box_bytes + ((((c0s & bmask) >> 3) << 4) ^ row_xor), wa);
