@@ -561,12 +561,13 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
     if (p.direct) {
       // ---- direct epilogue: this thread's pixel is one contiguous channel run in every tensor it touches
       const int ngrp = (min(p.n_tile, p.n_valid - n0) + 7) >> 3;       // 8-channel groups of this n-tile (<= 8)
+      const int ngrp1 = (min(p.n_tile, p.n_store - n0) + 7) >> 3;      // groups written to the primary output (pad groups: zeros)
       const uint8_t* aux_base = p.d_aux + static_cast<size_t>(n0) * 2;
       uint8_t* out_base = p.d_out + static_cast<size_t>(n0) * 2;
       uint8_t* out2_base = p.d_out2 + static_cast<size_t>(n0) * 2;
       const bool aux32 = AUX != 0 && ((reinterpret_cast<uintptr_t>(aux_base) | p.d_aux_pitch) & 31u) == 0;     // 32-byte aligned pixel runs
       // 256-bit accesses only for runs that are whole sectors: a 48-byte run as 32 + 16 bytes measured slower than 3 x 16 (345 vs 322 us)
-      const bool out32 = (ngrp & 1) == 0 && ((reinterpret_cast<uintptr_t>(out_base) | p.d_out_pitch) & 31u) == 0;
+      const bool out32 = (ngrp1 & 1) == 0 && ((reinterpret_cast<uintptr_t>(out_base) | p.d_out_pitch) & 31u) == 0;
       const bool out2_32 = AUX >= 2 && (ngrp & 1) == 0 && ((reinterpret_cast<uintptr_t>(out2_base) | p.d_out2_pitch) & 31u) == 0;
       uint4 ax[8], nx[8];
 #pragma unroll
@@ -622,31 +623,24 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
           tr.ev(3);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            if (2 * q < ngrp) {
+            if (2 * q < ngrp1) {
               tmem_ld16(taddr + q * 16, ra);
               tmem_ld_wait();
               if (inb && !KNOCK(1)) {
-                uint4 va, vb, wa, wb;
+                const bool two1 = 2 * q + 1 < ngrp1, one2 = 2 * q < ngrp, two2 = 2 * q + 1 < ngrp;   // groups of out1 / of aux + out2
+                uint4 va, vb = make_uint4(0, 0, 0, 0), wa, wb = make_uint4(0, 0, 0, 0);
                 epi8_direct<T, AUX, PRE, POST>(ra, sc_base + q * 64, sh_base + q * 64, ax[2 * q], va, wa, vmask);
-                if (2 * q + 1 < ngrp) {
-                  epi8_direct<T, AUX, PRE, POST>(ra + 8, sc_base + q * 64 + 32, sh_base + q * 64 + 32, ax[2 * q + 1], vb, wb, vmask);
-                  if (KNOCK(64)) { if (va.x == 0x12345u) o1[0] = va; }     // timing experiment: arithmetic kept, stores dropped
-                  else if (out32) stg256(o1 + 2 * q, va, vb); else { o1[2 * q] = va; o1[2 * q + 1] = vb; }
-                  if (AUX >= 2) {
-                    if (hybrid) {
-                      const uint32_t c0s = q * 16u, c1s = q * 16u + 8u;
-                      sts_u4(slotA + (c0s >> bsh) * box_bytes + ((((c0s & bmask) >> 3) << 4) ^ row_xor), wa);
-                      sts_u4(slotA + (c1s >> bsh) * box_bytes + ((((c1s & bmask) >> 3) << 4) ^ row_xor), wb);
-                    } else if (out2_32) stg256(o2 + 2 * q, wa, wb);
-                    else { o2[2 * q] = wa; o2[2 * q + 1] = wb; }
-                  }
-                } else {
-                  if (KNOCK(64)) { if (va.x == 0x12345u) o1[0] = va; } else o1[2 * q] = va;
-                  if (AUX >= 2) {
-                    const uint32_t c0s = q * 16u;
-                    if (hybrid) sts_u4(slotA + (c0s >> bsh) * box_bytes + ((((c0s & bmask) >> 3) << 4) ^ row_xor), wa);
-                    else o2[2 * q] = wa;
-                  }
+                if (two1) epi8_direct<T, AUX, PRE, POST>(ra + 8, sc_base + q * 64 + 32, sh_base + q * 64 + 32, ax[2 * q + 1], vb, wb, vmask);
+                if (KNOCK(64)) { if (va.x == 0x12345u) o1[0] = va; }     // timing experiment: arithmetic kept, stores dropped
+                else if (two1) { if (out32) stg256(o1 + 2 * q, va, vb); else { o1[2 * q] = va; o1[2 * q + 1] = vb; } }
+                else o1[2 * q] = va;
+                if (AUX >= 2) {
+                  if (hybrid) {
+                    const uint32_t c0s = q * 16u, c1s = q * 16u + 8u;
+                    if (one2) sts_u4(slotA + (c0s >> bsh) * box_bytes + ((((c0s & bmask) >> 3) << 4) ^ row_xor), wa);
+                    if (two2) sts_u4(slotA + (c1s >> bsh) * box_bytes + ((((c1s & bmask) >> 3) << 4) ^ row_xor), wb);
+                  } else if (two2) { if (out2_32) stg256(o2 + 2 * q, wa, wb); else { o2[2 * q] = wa; o2[2 * q + 1] = wb; } }
+                  else if (one2) o2[2 * q] = wa;
                 }
               }
             }

@@ -183,7 +183,13 @@ void Model::build_res2net() {
     std::vector<int> ms(S, -1), zs(S, -1);
     for (int i = 0; i + 1 < S; ++i) ms[i] = new_tensor(stage, w);
     for (int i = 1; i + 1 < S; ++i) zs[i] = new_tensor(stage, w);
-    const int y = new_tensor(stage, mid);
+    // The concat y keeps one slice per split.  When a slice (w channels) is not a whole number of 32-byte sectors, the slices are
+    // padded to wp channels and the direct epilogue WRITES the pad (zeros): a 48-byte slice of a 192-byte pixel row is otherwise
+    // stored as partial sectors that L2 read-fills from DRAM, which bounded the narrow 3x3 convs (profiles/r01_knockout_direct_stores.txt).
+    // conv3 then reads S*wp channels; the weight rows of the pad positions are zero.
+    static const bool no_ypad = getenv("SVX_NO_YPAD") != nullptr;   // debug switch
+    const int wp = (!no_ypad && w % 16 != 0) ? round_up(w, 16) : w;
+    const int y = new_tensor(stage, S * wp);
     const int mp = st == 2 ? new_tensor(in_stage, mid) : -1;
     int out_t = xa;
     for (int b = 0; b < cfg_.block_sizes[li]; ++b) {
@@ -208,7 +214,7 @@ void Model::build_res2net() {
         if (bstride == 1) {   // x_0..x_{S-2} to their planar tensors, the last split passes straight into the concat (:74-75)
           c.out = {y, 0}; c.split_w = w;
           for (int i = 0; i + 1 < S; ++i) c.split_out.push_back({ms[i], 0});
-          c.split_out.push_back({y, (S - 1) * w});
+          c.split_out.push_back({y, (S - 1) * wp});
         } else { c.out = {mp, 0}; }
         ops_.push_back(op);
       }
@@ -222,8 +228,9 @@ void Model::build_res2net() {
           c.bn_name = next_name(inner, hscope + "/", "batch_normalization");
           add_var(c.bn_name + "/moving_mean", {w}); add_var(c.bn_name + "/moving_variance", {w});
           c.kh = c.kw = 3; c.stride = bstride; c.ph = c.pw = 1; c.cin = w; c.cout = w; c.post_relu = 1;
-          c.out = {y, i * w};
+          c.out = {y, i * wp};
           if (bstride == 1) {
+            c.out_store = wp;
             c.in = {i == 0 ? ms[0] : zs[i], 0};
             if (i < S - 2) { c.out2 = {zs[i + 1], 0}; c.add2 = {ms[i + 1], 0}; }       // x_{i+1} + o_i (:65-66)
           } else {
@@ -232,7 +239,7 @@ void Model::build_res2net() {
           ops_.push_back(op);
         }
         if (bstride == 2) {   // last split: avg_pool 3x3/2 over the padded tensor (:76-77)
-          Op op; op.kind = OP_AVGPOOL; op.in = {mp, (S - 1) * w}; op.out = {y, (S - 1) * w}; op.C = w;
+          Op op; op.kind = OP_AVGPOOL; op.in = {mp, (S - 1) * w}; op.out = {y, (S - 1) * wp}; op.C = w;
           ops_.push_back(op);
         }
       }
@@ -241,7 +248,8 @@ void Model::build_res2net() {
         c.kernel_name = next_name(root, "", "conv2d") + "/kernel"; add_var(c.kernel_name, {1, 1, mid, cout});
         c.bn_name = next_name(root, "", "batch_normalization");
         add_var(c.bn_name + "/moving_mean", {cout}); add_var(c.bn_name + "/moving_variance", {cout});
-        c.in = {y, 0}; c.cin = mid; c.cout = cout; c.res = {shortcut, 0}; c.post_relu = 1; c.out = {out_t, 0};
+        c.in = {y, 0}; c.cin = S * wp; c.cout = cout; c.res = {shortcut, 0}; c.post_relu = 1; c.out = {out_t, 0};
+        if (wp != w) { c.in_gw = w; c.in_gwp = wp; }
         ops_.push_back(op);
       }
       cur = out_t; out_t = (out_t == xa) ? xb : xa; cin = cout;
@@ -420,7 +428,8 @@ static int pick_ntile(int cout, int max_multi) {
 int Model::upload_conv_weights(ConvDesc& c) {
   const HostTensor& k = host_[c.kernel_name];   // [kh,kw,cin_g,cout_total]
   const int taps = c.kh * c.kw;
-  const int cin_g = c.cin / c.groups, cout_g = c.cout / c.groups;
+  const int cin_tf = c.in_gw > 0 ? (c.cin / c.in_gwp) * c.in_gw : c.cin;   // input channels of the TF variable (padded concat: fewer than cin)
+  const int cin_g = cin_tf / c.groups, cout_g = c.cout / c.groups;
   const int cout_total = static_cast<int>(k.shape[3]);
   const bool grouped = c.groups > 1;
   int grp_ntile = 0, grp_cstep = 0;
@@ -456,7 +465,8 @@ int Model::upload_conv_weights(ConvDesc& c) {
     const int abase = grouped ? (n / grp_ntile) * grp_cstep : 0;
     for (int t = 0; t < taps; ++t)
       for (int ci = 0; ci < cin_g; ++ci) {
-        const int j = g * cin_g + ci - abase;     // position inside the k-box row
+        int j = g * cin_g + ci - abase;           // position inside the k-box row
+        if (c.in_gw > 0) j = (j / c.in_gw) * c.in_gwp + j % c.in_gw;
         w[static_cast<size_t>(gemm_row(n)) * K + static_cast<size_t>(t) * c.kpad + j] =
             k.data[(static_cast<size_t>(t) * cin_g + ci) * cout_total + c.kernel_out_off + n];
       }
@@ -1000,6 +1010,7 @@ int Model::plan_flat(ConvDesc& c) {
     if (slice_map(&fm.o2, t2, c.out2.coff, c.cout)) return 1;
   }
   fp.P_cap = static_cast<long long>(P_cap);
+  fp.n_store = (fp.direct && c.out_store > c.cout && fp.n_tiles == 1 && c.out_store <= fp.n_tile) ? c.out_store : N;
   if (fp.direct || fp.lin) {
     fp.d_out = static_cast<uint8_t*>(tout.ptr) + static_cast<size_t>(c.out.coff) * esz; fp.d_out_pitch = static_cast<uint32_t>(tout.C * esz);
     if (aux_mode == 1) {
@@ -1160,7 +1171,7 @@ int Model::launch_conv(ConvDesc& c, cudaStream_t st) {
       // algorithmic FLOPs: 2 * valid output pixels * taps * cin * cout (no padding waste counted)
       double pix = 0.0;
       for (int h : seg_h_host_[out_stage]) pix += static_cast<double>(h) * stage_W_[out_stage];
-      conv_flops_ += 2.0 * pix * c.kh * c.kw * (c.cin / c.groups) * c.cout;
+      conv_flops_ += 2.0 * pix * c.kh * c.kw * ((c.in_gw > 0 ? (c.cin / c.in_gwp) * c.in_gw : c.cin) / c.groups) * c.cout;
     }
   } else {
     c.sp.out_rows = out_rows;

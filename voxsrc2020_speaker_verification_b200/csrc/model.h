@@ -40,6 +40,10 @@ struct ConvDesc {
   int kh = 1, kw = 1, stride = 1, dil = 1, ph = 0, pw = 0, groups = 1, cout = 0;
   std::string kernel_name;            // TF variable holding the weights
   int kernel_out_off = 0;             // first output column of that variable (hierarchical conv split, res2net_model.py:54)
+  // input read from a concat whose slices are padded (in_gw real channels in every in_gwp): cin is the PADDED count, the weight
+  // rows of the pad positions are zero and the pad channels of the tensor hold zeros
+  int in_gw = 0, in_gwp = 0;
+  int out_store = 0;                  // channels the direct epilogue writes (>= cout: the pad of a padded concat slice is written as zeros)
   std::string bn_name;                // BN applied to the conv output ("" = none)
   int pre_relu = 0, post_relu = 0;
   TensorRef out; int n_split = -1;    // -1 → all channels to `out`
