@@ -195,6 +195,7 @@ struct FlatConvParams {
   // with their own 16-byte global accesses (a thread owns a pixel = one contiguous channel run), no slots, no TMA for them.
   // With 64-byte rows the TMA engine's ~2.5 ns per box ROW made the aux loads + stores the bound of every narrow 3x3 conv.
   int direct;
+  int n_store2;                // same for the aux tile and the second output (padded planar tensors)
   int n_store;                 // direct epilogue: channels written to the primary output (>= n_valid: zeros in the pad of a padded concat slice)
   int lin;                     // aux mode 2 with add2 / out2 as DENSE planar tensors: their 128-pixel tiles move as 1-D bulk copies (kernel AUX = 3)
   long long P_cap;             // pixels allocated (stores/loads of the direct epilogue are clipped here, like the tensor maps clip)

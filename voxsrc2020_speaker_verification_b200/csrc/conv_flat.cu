@@ -560,25 +560,25 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
     int ls = 0;
     if (p.direct) {
       // ---- direct epilogue: this thread's pixel is one contiguous channel run in every tensor it touches
-      const int ngrp = (min(p.n_tile, p.n_valid - n0) + 7) >> 3;       // 8-channel groups of this n-tile (<= 8)
       const int ngrp1 = (min(p.n_tile, p.n_store - n0) + 7) >> 3;      // groups written to the primary output (pad groups: zeros)
+      const int ngrp2 = (min(p.n_tile, p.n_store2 - n0) + 7) >> 3;     // groups of the aux tile / second output (padded planar tensors)
       const uint8_t* aux_base = p.d_aux + static_cast<size_t>(n0) * 2;
       uint8_t* out_base = p.d_out + static_cast<size_t>(n0) * 2;
       uint8_t* out2_base = p.d_out2 + static_cast<size_t>(n0) * 2;
       const bool aux32 = AUX != 0 && ((reinterpret_cast<uintptr_t>(aux_base) | p.d_aux_pitch) & 31u) == 0;     // 32-byte aligned pixel runs
       // 256-bit accesses only for runs that are whole sectors: a 48-byte run as 32 + 16 bytes measured slower than 3 x 16 (345 vs 322 us)
       const bool out32 = (ngrp1 & 1) == 0 && ((reinterpret_cast<uintptr_t>(out_base) | p.d_out_pitch) & 31u) == 0;
-      const bool out2_32 = AUX >= 2 && (ngrp & 1) == 0 && ((reinterpret_cast<uintptr_t>(out2_base) | p.d_out2_pitch) & 31u) == 0;
+      const bool out2_32 = AUX >= 2 && (ngrp2 & 1) == 0 && ((reinterpret_cast<uintptr_t>(out2_base) | p.d_out2_pitch) & 31u) == 0;
       uint4 ax[8], nx[8];
 #pragma unroll
       for (int g = 0; g < 8; ++g) ax[g] = nx[g] = make_uint4(0, 0, 0, 0);
       auto load_aux = [&](const uint4* src, uint4 (&d)[8]) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          if (2 * q + 1 < ngrp && aux32) ldg256(src + 2 * q, d[2 * q], d[2 * q + 1]);
+          if (2 * q + 1 < ngrp2 && aux32) ldg256(src + 2 * q, d[2 * q], d[2 * q + 1]);
           else {
-            if (2 * q < ngrp) d[2 * q] = __ldg(src + 2 * q);
-            if (2 * q + 1 < ngrp) d[2 * q + 1] = __ldg(src + 2 * q + 1);
+            if (2 * q < ngrp2) d[2 * q] = __ldg(src + 2 * q);
+            if (2 * q + 1 < ngrp2) d[2 * q + 1] = __ldg(src + 2 * q + 1);
           }
         }
       };
@@ -623,11 +623,11 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
           tr.ev(3);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            if (2 * q < ngrp1) {
+            if (2 * q < max(ngrp1, ngrp2)) {
               tmem_ld16(taddr + q * 16, ra);
               tmem_ld_wait();
               if (inb && !KNOCK(1)) {
-                const bool two1 = 2 * q + 1 < ngrp1, one2 = 2 * q < ngrp, two2 = 2 * q + 1 < ngrp;   // groups of out1 / of aux + out2
+                const bool two1 = 2 * q + 1 < ngrp1, one2 = 2 * q < ngrp2, two2 = 2 * q + 1 < ngrp2;   // groups of out1 / of aux + out2
                 uint4 va, vb = make_uint4(0, 0, 0, 0), wa, wb = make_uint4(0, 0, 0, 0);
                 epi8_direct<T, AUX, PRE, POST>(ra, sc_base + q * 64, sh_base + q * 64, ax[2 * q], va, wa, vmask);
                 if (two1) epi8_direct<T, AUX, PRE, POST>(ra + 8, sc_base + q * 64 + 32, sh_base + q * 64 + 32, ax[2 * q + 1], vb, wb, vmask);

@@ -181,8 +181,11 @@ void Model::build_res2net() {
     // [pixels, w] tensor each: a 3x3 then reads whole DRAM lines instead of a w-channel slice of every S*w-channel row
     // (measured 3.7-4.8x read amplification on the interleaved layout).  y (the concat, conv3's input) stays interleaved.
     std::vector<int> ms(S, -1), zs(S, -1);
-    for (int i = 0; i + 1 < S; ++i) ms[i] = new_tensor(stage, w);
-    for (int i = 1; i + 1 < S; ++i) zs[i] = new_tensor(stage, w);
+    static const bool no_ypad0 = getenv("SVX_NO_YPAD") != nullptr;   // debug switch (see wp below)
+    static const bool no_ppad = getenv("SVX_NO_PPAD") != nullptr;    // debug switch: planar tensors unpadded
+    const int wpp = (!no_ypad0 && !no_ppad && w % 16 != 0) ? round_up(w, 16) : w;   // planar split tensors: padded like the concat slices, pad WRITTEN
+    for (int i = 0; i + 1 < S; ++i) ms[i] = new_tensor(stage, wpp);
+    for (int i = 1; i + 1 < S; ++i) zs[i] = new_tensor(stage, wpp);
     // The concat y keeps one slice per split.  When a slice (w channels) is not a whole number of 32-byte sectors, the slices are
     // padded to wp channels and the direct epilogue WRITES the pad (zeros): a 48-byte slice of a 192-byte pixel row is otherwise
     // stored as partial sectors that L2 read-fills from DRAM, which bounded the narrow 3x3 convs (profiles/r01_knockout_direct_stores.txt).
@@ -212,7 +215,7 @@ void Model::build_res2net() {
         add_var(c.bn_name + "/moving_mean", {mid}); add_var(c.bn_name + "/moving_variance", {mid});
         c.in = {cur, 0}; c.cin = cin; c.cout = mid; c.post_relu = 1;
         if (bstride == 1) {   // x_0..x_{S-2} to their planar tensors, the last split passes straight into the concat (:74-75)
-          c.out = {y, 0}; c.split_w = w;
+          c.out = {y, 0}; c.split_w = w; c.split_store = wpp;
           for (int i = 0; i + 1 < S; ++i) c.split_out.push_back({ms[i], 0});
           c.split_out.push_back({y, (S - 1) * wp});
         } else { c.out = {mp, 0}; }
@@ -230,7 +233,7 @@ void Model::build_res2net() {
           c.kh = c.kw = 3; c.stride = bstride; c.ph = c.pw = 1; c.cin = w; c.cout = w; c.post_relu = 1;
           c.out = {y, i * wp};
           if (bstride == 1) {
-            c.out_store = wp;
+            c.out_store = wp; c.out2_store = wpp;
             c.in = {i == 0 ? ms[0] : zs[i], 0};
             if (i < S - 2) { c.out2 = {zs[i + 1], 0}; c.add2 = {ms[i + 1], 0}; }       // x_{i+1} + o_i (:65-66)
           } else {
@@ -762,7 +765,8 @@ int Model::plan_flat(ConvDesc& c) {
   fp.aux_mode = aux_mode; fp.pre_relu = c.pre_relu; fp.post_relu = c.post_relu;
   fp.n_res = aux_mode == 1 ? n_split : 0;
   fp.grp_mask = 0; fp.grp_w = 1;
-  if (split && (c.split_wp & (c.split_wp - 1)) == 0 && c.split_w < c.split_wp) { fp.grp_mask = c.split_wp - 1; fp.grp_w = c.split_w; }
+  const int split_store = (split && c.split_store > c.split_w && c.split_store <= c.split_wp) ? c.split_store : c.split_w;   // pad channels stored as zeros
+  if (split && (c.split_wp & (c.split_wp - 1)) == 0 && split_store < c.split_wp) { fp.grp_mask = c.split_wp - 1; fp.grp_w = split_store; }
 
   // Search over tile shapes with a small cost model (cycles per 128 output pixels, all n-tiles): tensor pipe (bounded by
   // operand reads from shared memory when N is small), TMA row requests (~5.6 cycles per box row per SM with every SM
@@ -938,12 +942,14 @@ int Model::plan_flat(ConvDesc& c) {
   FlatMaps& fm = c.fmaps;
   memset(&fm, 0, sizeof fm);
   {
-    const uint64_t dims[2] = {static_cast<uint64_t>(c.cin), P_cap};
+    // a padded planar tensor (pad channels hold zeros, the weight rows of the pad are zero) is read whole: dense rows, full L2 promotion
+    const int a_width = (c.in.coff == 0 && tin.C > c.cin && tin.C <= c.kpad && c.groups == 1) ? tin.C : c.cin;
+    const uint64_t dims[2] = {static_cast<uint64_t>(a_width), P_cap};
     const uint64_t str[1] = {static_cast<uint64_t>(tin.C) * esz};
     const uint32_t box[2] = {static_cast<uint32_t>(c.kbox), static_cast<uint32_t>(fp.a_box_rows)};
     static const int env_promo = getenv("SVX_L2_PROMO") ? atoi(getenv("SVX_L2_PROMO")) : -1;   // debug switch (see promo_for below)
     const int pitch = tin.C * 2, off = c.in.coff * 2, wb = c.cin * 2;
-    const int promo = env_promo >= 0 ? env_promo : (c.cin == tin.C) ? 128 : (pitch % 128 == 0 && off % 128 == 0 && wb % 128 == 0) ? 128
+    const int promo = env_promo >= 0 ? env_promo : (a_width == tin.C) ? 128 : (pitch % 128 == 0 && off % 128 == 0 && wb % 128 == 0) ? 128
                                                  : (pitch % 64 == 0 && off % 64 == 0 && wb % 64 == 0) ? 64 : 0;
     if (encode_tmap(&fm.a, is_bf16_, static_cast<uint8_t*>(tin.ptr) + static_cast<size_t>(c.in.coff) * esz, 2, dims, str, box, row_bytes, promo)) return 1;
   }
@@ -979,11 +985,11 @@ int Model::plan_flat(ConvDesc& c) {
     for (size_t i = 0; i < c.split_out.size(); ++i) {
       const ActTensor& ts = tensors_[c.split_out[i].id];
       if (ts.stage != tout.stage) return 0;
-      if (slice_map(&fm.o[i], ts, c.split_out[i].coff, c.split_w)) return 1;
+      if (slice_map(&fm.o[i], ts, c.split_out[i].coff, std::min(split_store, ts.C - c.split_out[i].coff))) return 1;
     }
     for (int gb = 0; gb < n_boxes_total; ++gb) {
       const int ch = gb * fp.box_ch, sidx = ch / c.split_wp, j0 = ch - sidx * c.split_wp;
-      if (j0 < c.split_w) { fp.route_map[gb] = static_cast<uint8_t>(sidx); fp.route_c[gb] = j0; }
+      if (j0 < split_store) { fp.route_map[gb] = static_cast<uint8_t>(sidx); fp.route_c[gb] = j0; }
     }
   } else {
     if (slice_map(&fm.o[0], tout, c.out.coff, n_split)) return 1;
@@ -1007,9 +1013,10 @@ int Model::plan_flat(ConvDesc& c) {
     const ActTensor& t2 = tensors_[c.out2.id];
     if (ta.stage != tout.stage || t2.stage != tout.stage) return 0;
     if (slice_map(&fm.aux, ta, c.add2.coff, c.cout)) return 1;
-    if (slice_map(&fm.o2, t2, c.out2.coff, c.cout)) return 1;
+    if (slice_map(&fm.o2, t2, c.out2.coff, (fp.direct == 2 && c.out2_store > c.cout && c.out2_store <= t2.C - c.out2.coff) ? c.out2_store : c.cout)) return 1;
   }
   fp.P_cap = static_cast<long long>(P_cap);
+  fp.n_store2 = (fp.direct && c.out2_store > c.cout && fp.n_tiles == 1 && c.out2_store <= fp.n_tile) ? c.out2_store : N;
   fp.n_store = (fp.direct && c.out_store > c.cout && fp.n_tiles == 1 && c.out_store <= fp.n_tile) ? c.out_store : N;
   if (fp.direct || fp.lin) {
     fp.d_out = static_cast<uint8_t*>(tout.ptr) + static_cast<size_t>(c.out.coff) * esz; fp.d_out_pitch = static_cast<uint32_t>(tout.C * esz);

@@ -43,6 +43,8 @@ struct ConvDesc {
   // input read from a concat whose slices are padded (in_gw real channels in every in_gwp): cin is the PADDED count, the weight
   // rows of the pad positions are zero and the pad channels of the tensor hold zeros
   int in_gw = 0, in_gwp = 0;
+  int split_store = 0;                // planar-split conv: channels stored per split (> split_w: destination tensors padded, pad written as zeros)
+  int out2_store = 0;                 // same for the second output / aux tile of the direct epilogue (padded planar tensors)
   int out_store = 0;                  // channels the direct epilogue writes (>= cout: the pad of a padded concat slice is written as zeros)
   std::string bn_name;                // BN applied to the conv output ("" = none)
   int pre_relu = 0, post_relu = 0;
