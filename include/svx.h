@@ -94,15 +94,19 @@ int svx_extractor_conv_time(svx_extractor* h, double* ms, double* flops);
 /* ---- front-end: replaces the Kaldi pipe `apply-cmvn-sliding --norm-vars=false --center=true --cmn-window=300 scp:... ark:- |`
  * that tf_extract.py:63 reads its features through.  feats/out: device fp32 [total_frames, feat_dim] (may alias),
  * frame_offsets_host: int32 [n_utts + 1].  Window mean in double precision, window shifted to stay inside the utterance. */
+/* center = 0 follows Kaldi's rule for causal windows: [t - cmn_window, t + 1), and while fewer than min_window frames have been
+ * seen the window ends at min_window (Kaldi's --min-cmn-window, default 100), so the first frames look ahead. */
 int svx_cmvn_sliding(const float* feats_dev, float* out_dev, const int32_t* frame_offsets_host, int n_utts, int feat_dim,
-                     int cmn_window, int center, void* cuda_stream);
+                     int cmn_window, int center, int min_window, void* cuda_stream);
 
 /* Kaldi CompressedMatrix ('CM ') records → fp32 [total_frames, feat_dim] on the device, bit-identical to
  * kaldi_io._read_compressed_mat (kaldi_io.py:471-504).  blob_dev: the records' payloads back to back, each starting at its
  * global header {min f32, range f32, rows i32, cols i32} (i.e. right after the "CM " token); record_offsets_host[i] = byte
  * offset of record i in the blob; frame_offsets_host: int32 [n + 1] cumulative row counts. */
-int svx_decode_compressed(const uint8_t* blob_dev, const int64_t* record_offsets_host, const int32_t* frame_offsets_host, int n_records,
-                          int feat_dim, float* out_dev, void* cuda_stream);
+/* Validated before anything is decoded: every record's own header must say rows = its frame_offsets slice and cols = feat_dim,
+ * and the record must end inside blob_bytes (a 40-dim ark fed to an 80-dim model fails here instead of decoding garbage). */
+int svx_decode_compressed(const uint8_t* blob_dev, int64_t blob_bytes, const int64_t* record_offsets_host,
+                          const int32_t* frame_offsets_host, int n_records, int feat_dim, float* out_dev, void* cuda_stream);
 
 /* ---- scoring: replaces the NumPy body of tensorflow/snorm.py.  All pointers are device pointers. */
 typedef struct svx_scorer svx_scorer;
@@ -110,9 +114,10 @@ int svx_scorer_create(int device, svx_scorer** out);
 int svx_scorer_destroy(svx_scorer* h);
 /* snorm.l2norm (snorm.py:23-25) applied per row, as read_xvector does on load (snorm.py:32). */
 int svx_l2norm_rows(const float* in_dev, float* out_dev, int64_t n, int d, void* cuda_stream);
-/* read_speaker_xvector (snorm.py:45-67): out[g] = mean of unit rows with group[i] == g (group[i] < 0: unused).
- * inv_count[g] = 1/|g|. */
-int svx_group_means(const float* unit_rows_dev, int64_t n, int d, const int32_t* group_dev, const float* inv_count_dev,
+/* read_speaker_xvector (snorm.py:45-67): out[g] = mean of the unit rows member_rows[group_offsets[g] .. group_offsets[g+1])
+ * (CSR; members in the order the reference appends them).  Sequential fp32 sum in that order, then a true divide by the
+ * count — what np.mean(matrix, axis=0) does (snorm.py:63) — so the result is deterministic and bit-identical to it. */
+int svx_group_means(const float* unit_rows_dev, int d, const int32_t* member_rows_dev, const int32_t* group_offsets_dev,
                     float* out_dev, int n_groups, void* cuda_stream);
 /* get_cohort_mean_std (snorm.py:83-110): for every test row, mean and population std of its topk largest dot
  * products with the cohort rows (whole cohort when topk > c). test [n,d] unit rows, cohort [c,d]. */

@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from oracle import net_oracle
+from oracle import cmn_oracle, net_oracle
 from voxsrc2020_speaker_verification_b200 import arch, kaldi_ark, pb_loader
 
 pytestmark = pytest.mark.gpu
@@ -46,7 +46,7 @@ def test_tf_extract_cli_end_to_end(tmp_path):
             np.testing.assert_array_equal(kaldi_ark.read_vec_flt(f), got[key])
     # values: the oracle on host-normalised features with the chunk rule (1130 frames → 1000 + 130)
     for key, m in utts.items():
-        want = net_oracle.extract_utterance(cfg, params, kaldi_ark.apply_cmvn_sliding(m))
+        want = net_oracle.extract_utterance(cfg, params, cmn_oracle.apply_cmvn_sliding(m))
         cos = float(np.dot(got[key], want) / np.linalg.norm(got[key]) / np.linalg.norm(want))
         assert cos >= 0.9999, (key, cos)
 
@@ -101,7 +101,7 @@ def test_eval_inference_model_pipeline(tmp_path):
     cos = [ln.split() for ln in open(os.path.join(out, "cosine_T.txt"))]
     assert len(got) == 12 and len(cos) == 12
     # oracle: embeddings of the CMN-normalised features, then the reference scoring restatement
-    emb = {k: net_oracle.extract_utterance(cfg, params, kaldi_ark.apply_cmvn_sliding(m)) for k, m in feats.items()}
+    emb = {k: net_oracle.extract_utterance(cfg, params, cmn_oracle.apply_cmvn_sliding(m)) for k, m in feats.items()}
     test = score_oracle.normalise_xvectors({k: emb[k] for k in test_keys})
     spk2utt = score_oracle.read_spk2utt(str(data / "voxceleb2_dev" / "spk2utt"))
     cohort = score_oracle.read_speaker_xvector(score_oracle.normalise_xvectors({k: v for k, v in emb.items() if k.startswith("_dev")}), spk2utt)
@@ -161,6 +161,43 @@ def test_tf_extract_cli_on_compressed_ark(tmp_path):
     got = dict(kaldi_ark.read_vec_flt_ark(wspec + ".ark"))
     assert list(got) == keys
     for key, m in kaldi_ark.read_mat_scp(scp):
-        want = net_oracle.extract_utterance(cfg, params, kaldi_ark.apply_cmvn_sliding(np.asarray(m, np.float32)))
+        want = net_oracle.extract_utterance(cfg, params, cmn_oracle.apply_cmvn_sliding(np.asarray(m, np.float32)))
         cos = float(np.dot(got[key], want) / np.linalg.norm(got[key]) / np.linalg.norm(want))
         assert cos >= 0.9999, (key, cos)
+
+
+def test_feature_dimension_mismatch_is_rejected(tmp_path, golden_dir):
+    """A 40-dim ark fed to an 80-dim model (or the reverse) must fail loudly on both paths — the dense one and the compressed one,
+    whose device decoder would otherwise index the column headers and the byte plane with the wrong width."""
+    from voxsrc2020_speaker_verification_b200 import lib, tf_extract
+    from voxsrc2020_speaker_verification_b200.extractor import Extractor
+    cfg = arch.get_config("tdnn")
+    params = net_oracle.init_params(cfg, 80, seed=4321, calib_frames=32, calib_batch=2)
+    pb = str(tmp_path / "tdnn80.pb")
+    pb_loader.write_pb(pb, params, cfg, 80)
+    g = os.path.join(golden_dir, "io")
+    recs = [r for r in kaldi_ark.read_mat_ark_raw(os.path.join(g, "feats_cm.ark")) if r[4] == 40]
+    assert recs
+    ex = Extractor("tdnn", 80).load_params(params)
+    with pytest.raises(ValueError):
+        ex.decode_compressed([p for _, _, p, _, _ in recs], [r for _, _, _, r, _ in recs])
+    # straight through the C ABI with a lying caller: the library checks every record's own header on the device
+    import ctypes
+    import torch
+    payloads, rows = [p for _, _, p, _, _ in recs], [r for _, _, _, r, _ in recs]
+    rec_off = np.zeros(len(payloads), np.int64)
+    np.cumsum([len(p) for p in payloads[:-1]], out=rec_off[1:])
+    offs = np.zeros(len(payloads) + 1, np.int32)
+    np.cumsum([r // 3 for r in rows], out=offs[1:])            # a third of the rows, so that rows x 80 fits the record: only the header is wrong
+    blob = torch.frombuffer(bytearray(b"".join(payloads)), dtype=torch.uint8).cuda()
+    out = torch.zeros((int(offs[-1]), 80), dtype=torch.float32, device="cuda")
+    L = lib.load()
+    st = L.svx_decode_compressed(ctypes.c_void_p(blob.data_ptr()), int(blob.numel()), rec_off.ctypes.data_as(ctypes.c_void_p),
+                                 offs.ctypes.data_as(ctypes.c_void_p), len(payloads), 80, ctypes.c_void_p(out.data_ptr()),
+                                 ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert st != 0 and b"header" in L.svx_last_error()
+    assert float(out.abs().sum()) == 0.0                        # nothing was decoded
+    # the CLI on an uncompressed 40-dim ark
+    rspec = _write_feats(tmp_path, {"a": np.zeros((30, 40), np.float32)})
+    with pytest.raises(ValueError):
+        tf_extract.main(["--pb-file", pb, "--expand-dim", "2", "--rspec", rspec, "--wspec", str(tmp_path / "xv")])

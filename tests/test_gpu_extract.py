@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import net_oracle
+from oracle import cmn_oracle, net_oracle
 from voxsrc2020_speaker_verification_b200 import arch
 
 pytestmark = pytest.mark.gpu
@@ -161,9 +161,9 @@ def test_full_size_properties():
 
 
 def test_cmvn_sliding_on_device_matches_host_restatement():
-    """svx_cmvn_sliding vs the NumPy restatement of Kaldi's apply-cmvn-sliding (reference tf_extract.py:63 pipe),
-    windows shorter and longer than the utterance, then end to end through extract(cmvn=True)."""
-    from voxsrc2020_speaker_verification_b200 import kaldi_ark
+    """svx_cmvn_sliding vs the CMN oracle (Kaldi's SlidingWindowCmn rule pinned by hand-computed vectors in
+    tests/test_oracle_cmn.py; reference tf_extract.py:63 pipe), windows shorter and longer than the utterance, the centred
+    mode the reference uses and the causal mode with min_window, then end to end through extract(cmvn=True)."""
     cfg, params, ex = model("tdnn", 40)
     rng = np.random.default_rng(17)
     lens = [1, 25, 149, 300, 301, 777]
@@ -173,8 +173,13 @@ def test_cmvn_sliding_on_device_matches_host_restatement():
     dev = torch.from_numpy(np.concatenate(utts, 0)).cuda()
     ex.cmvn_sliding(dev, offs)
     got = dev.cpu().numpy()
-    want = np.concatenate([kaldi_ark.apply_cmvn_sliding(u) for u in utts], 0)
+    want = np.concatenate([cmn_oracle.apply_cmvn_sliding(u) for u in utts], 0)
     np.testing.assert_allclose(got, want, rtol=0, atol=2e-6)
+    for window, min_window in ((300, 100), (100, 30)):          # causal windows: the first frames look ahead to min_window
+        dev = torch.from_numpy(np.concatenate(utts, 0)).cuda()
+        ex.cmvn_sliding(dev, offs, cmn_window=window, center=False, min_window=min_window)
+        want = np.concatenate([cmn_oracle.apply_cmvn_sliding(u, window, False, min_window) for u in utts], 0)
+        np.testing.assert_allclose(dev.cpu().numpy(), want, rtol=0, atol=2e-6)
     a = ex.extract(utts[1:], cmvn=True)
-    b = ex.extract([kaldi_ark.apply_cmvn_sliding(u) for u in utts[1:]])
+    b = ex.extract([cmn_oracle.apply_cmvn_sliding(u) for u in utts[1:]])
     np.testing.assert_allclose(a, b, atol=2e-4)

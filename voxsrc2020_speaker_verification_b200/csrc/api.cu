@@ -54,6 +54,17 @@ static int require_device(int device) {
   return 0;
 }
 
+// Every entry point that launches work runs on the device of its handle (or, without a handle, the device the caller's
+// stream belongs to = the caller's current device) and leaves the calling thread's current device as it found it.
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (device >= 0 && device != prev) cudaSetDevice(device);
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 template <typename P>
 static int grow_buf(P** p, size_t* have, size_t need) {
   if (need <= *have) return 0;
@@ -86,6 +97,7 @@ int svx_extractor_create(const svx_model_config* cfg, int device, int precision,
 
 int svx_extractor_destroy(svx_extractor* h) {
   if (!h) return 0;
+  DeviceGuard guard(h->model->device());
   delete h->model;
   delete h;
   return 0;
@@ -107,7 +119,11 @@ int svx_extractor_set_tensor(svx_extractor* h, const char* name, const float* da
   return h->model->set_tensor(name, data, ndim, shape);
 }
 
-int svx_extractor_finalize(svx_extractor* h) { if (!h) { set_last_error("null handle"); return 1; } return h->model->finalize(); }
+int svx_extractor_finalize(svx_extractor* h) {
+  if (!h) { set_last_error("null handle"); return 1; }
+  DeviceGuard guard(h->model->device());
+  return h->model->finalize();
+}
 int svx_extractor_embed_dim(svx_extractor* h) { return h ? h->model->embed_dim() : -1; }
 int svx_extractor_set_option(svx_extractor* h, const char* key, int value) {
   if (!h || !key) { set_last_error("null argument"); return 1; }
@@ -117,12 +133,14 @@ int svx_extractor_set_option(svx_extractor* h, const char* key, int value) {
 int svx_extractor_run_segments(svx_extractor* h, const float* feats_dev, const int32_t* frame_offsets_host, int n_segments,
                                float* out_dev, void* cuda_stream) {
   if (!h || !feats_dev || !frame_offsets_host || !out_dev) { set_last_error("null argument"); return 1; }
+  DeviceGuard guard(h->model->device());
   return h->model->run_segments(feats_dev, frame_offsets_host, n_segments, out_dev, static_cast<cudaStream_t>(cuda_stream));
 }
 
 int svx_extractor_extract(svx_extractor* h, const float* feats, int feats_on_device, const int32_t* frame_offsets_host, int n_utts,
                           float* out, int out_on_device, void* cuda_stream) {
   if (!h || !feats || !frame_offsets_host || !out) { set_last_error("null argument"); return 1; }
+  DeviceGuard guard(h->model->device());
   return h->model->extract(feats, feats_on_device, frame_offsets_host, n_utts, out, out_on_device,
                            static_cast<cudaStream_t>(cuda_stream));
 }
@@ -139,7 +157,7 @@ int svx_scorer_create(int device, svx_scorer** out) {
   if (!out) { set_last_error("null argument"); return 1; }
   *out = nullptr;
   if (require_device(device)) return 1;
-  API_CUDA(cudaSetDevice(device));
+  DeviceGuard guard(device);
   API_CUDA(conv_umma_init());
   svx_scorer* s = new svx_scorer();
   s->device = device;
@@ -149,17 +167,18 @@ int svx_scorer_create(int device, svx_scorer** out) {
 
 int svx_scorer_destroy(svx_scorer* h) {
   if (!h) return 0;
-  cudaSetDevice(h->device);
+  DeviceGuard guard(h->device);
   cudaFree(h->d_a); cudaFree(h->d_b); cudaFree(h->d_s);
   delete h;
   return 0;
 }
 
 int svx_cmvn_sliding(const float* feats_dev, float* out_dev, const int32_t* frame_offsets_host, int n_utts, int feat_dim, int cmn_window,
-                     int center, void* cuda_stream) {
+                     int center, int min_window, void* cuda_stream) {
   if (!feats_dev || !out_dev || !frame_offsets_host) { set_last_error("null argument"); return 1; }
   if (n_utts <= 0) return 0;
   if (feat_dim <= 0 || feat_dim > 128 || cmn_window <= 0) { set_last_error("feat_dim must be in 1..128 and cmn_window positive"); return 1; }
+  if (min_window <= 0 || min_window > cmn_window) { set_last_error("min_window must be in 1..cmn_window"); return 1; }
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   const long long total = frame_offsets_host[n_utts];
   for (int i = 0; i < n_utts; ++i)
@@ -170,31 +189,52 @@ int svx_cmvn_sliding(const float* feats_dev, float* out_dev, const int32_t* fram
   API_CUDA(cudaMallocAsync(&d_utt, static_cast<size_t>(total) * 4, st));
   API_CUDA(cudaMallocAsync(&d_csum, static_cast<size_t>(total + n_utts) * feat_dim * 8, st));
   API_CUDA(cudaMemcpyAsync(d_off, frame_offsets_host, static_cast<size_t>(n_utts + 1) * 4, cudaMemcpyHostToDevice, st));
-  cudaError_t e = launch_cmn_sliding(feats_dev, out_dev, d_off, n_utts, total, feat_dim, cmn_window, center, d_csum, d_utt, st);
+  cudaError_t e = launch_cmn_sliding(feats_dev, out_dev, d_off, n_utts, total, feat_dim, cmn_window, center, min_window, d_csum, d_utt, st);
   cudaFreeAsync(d_off, st); cudaFreeAsync(d_utt, st); cudaFreeAsync(d_csum, st);
   API_CUDA(e);
   API_CUDA(cudaStreamSynchronize(st));   // frame_offsets_host is the caller's buffer
   return 0;
 }
 
-int svx_decode_compressed(const uint8_t* blob_dev, const int64_t* record_offsets_host, const int32_t* frame_offsets_host, int n_records,
-                          int feat_dim, float* out_dev, void* cuda_stream) {
+int svx_decode_compressed(const uint8_t* blob_dev, int64_t blob_bytes, const int64_t* record_offsets_host, const int32_t* frame_offsets_host,
+                          int n_records, int feat_dim, float* out_dev, void* cuda_stream) {
   if (!blob_dev || !record_offsets_host || !frame_offsets_host || !out_dev) { set_last_error("null argument"); return 1; }
   if (n_records <= 0) return 0;
   if (feat_dim <= 0) { set_last_error("feat_dim must be positive"); return 1; }
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   const long long total = frame_offsets_host[n_records];
-  long long* d_rec = nullptr; int32_t* d_off = nullptr; int32_t* d_utt = nullptr;
+  // what can be checked on the host: every record (header + per-column percentiles + rows x cols bytes) fits between its
+  // offset and the next one; the headers themselves live on the device and are checked there (cm_check_kernel)
+  for (int i = 0; i < n_records; ++i) {
+    const long long rows = frame_offsets_host[i + 1] - frame_offsets_host[i];
+    const long long need = 16 + 8LL * feat_dim + rows * feat_dim;
+    const long long end = i + 1 < n_records ? record_offsets_host[i + 1] : blob_bytes;
+    if (rows <= 0 || record_offsets_host[i] < 0 || record_offsets_host[i] + need > end) {
+      set_last_error("compressed record " + std::to_string(i) + ": " + std::to_string(rows) + " rows x " + std::to_string(feat_dim) +
+                     " columns need " + std::to_string(need) + " bytes, the record has " + std::to_string(end - record_offsets_host[i]));
+      return 1;
+    }
+  }
+  long long* d_rec = nullptr; int32_t* d_off = nullptr; int32_t* d_utt = nullptr; int32_t* d_bad = nullptr;
+  API_CUDA(cudaMallocAsync(&d_bad, 4, st));
+  API_CUDA(cudaMemsetAsync(d_bad, 0x7f, 4, st));
   static_assert(sizeof(long long) == sizeof(int64_t), "offset width");
   API_CUDA(cudaMallocAsync(&d_rec, static_cast<size_t>(n_records) * 8, st));
   API_CUDA(cudaMallocAsync(&d_off, static_cast<size_t>(n_records + 1) * 4, st));
   API_CUDA(cudaMallocAsync(&d_utt, static_cast<size_t>(total > 0 ? total : 1) * 4, st));
   API_CUDA(cudaMemcpyAsync(d_rec, record_offsets_host, static_cast<size_t>(n_records) * 8, cudaMemcpyHostToDevice, st));
   API_CUDA(cudaMemcpyAsync(d_off, frame_offsets_host, static_cast<size_t>(n_records + 1) * 4, cudaMemcpyHostToDevice, st));
-  cudaError_t e = launch_cm_decode(blob_dev, d_rec, d_off, n_records, total, feat_dim, out_dev, d_utt, st);
-  cudaFreeAsync(d_rec, st); cudaFreeAsync(d_off, st); cudaFreeAsync(d_utt, st);
+  cudaError_t e = launch_cm_decode(blob_dev, d_rec, d_off, n_records, total, feat_dim, out_dev, d_utt, blob_bytes, d_bad, st);
+  int32_t bad = kCmNoBadRecord;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, st);
+  cudaFreeAsync(d_rec, st); cudaFreeAsync(d_off, st); cudaFreeAsync(d_utt, st); cudaFreeAsync(d_bad, st);
   API_CUDA(e);
   API_CUDA(cudaStreamSynchronize(st));
+  if (bad != kCmNoBadRecord) {
+    set_last_error("compressed record " + std::to_string(bad) + ": its header (rows, cols) does not match frame_offsets / feat_dim " +
+                   std::to_string(feat_dim) + " — nothing was decoded");
+    return 1;
+  }
   return 0;
 }
 
@@ -204,12 +244,11 @@ int svx_l2norm_rows(const float* in_dev, float* out_dev, int64_t n, int d, void*
   return 0;
 }
 
-int svx_group_means(const float* unit_rows_dev, int64_t n, int d, const int32_t* group_dev, const float* inv_count_dev,
-                    float* out_dev, int n_groups, void* cuda_stream) {
-  if (!unit_rows_dev || !group_dev || !inv_count_dev || !out_dev) { set_last_error("null argument"); return 1; }
-  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-  API_CUDA(cudaMemsetAsync(out_dev, 0, static_cast<size_t>(n_groups) * d * 4, st));
-  API_CUDA(launch_segment_mean(unit_rows_dev, n, d, group_dev, inv_count_dev, out_dev, n_groups, st));
+int svx_group_means(const float* unit_rows_dev, int d, const int32_t* member_rows_dev, const int32_t* group_offsets_dev, float* out_dev,
+                    int n_groups, void* cuda_stream) {
+  if (!unit_rows_dev || !member_rows_dev || !group_offsets_dev || !out_dev) { set_last_error("null argument"); return 1; }
+  if (d <= 0 || n_groups < 0) { set_last_error("bad group-mean shape"); return 1; }
+  API_CUDA(launch_group_mean(unit_rows_dev, d, member_rows_dev, group_offsets_dev, out_dev, n_groups, static_cast<cudaStream_t>(cuda_stream)));
   return 0;
 }
 
@@ -242,7 +281,7 @@ static int cohort_pass(svx_scorer* h, const float* test_dev, int64_t n, const fl
   if (c <= 0 || d <= 0 || topk <= 0) { set_last_error("cohort size, dimension and topk must be positive"); return 1; }
   if (d % 8 != 0) { set_last_error("embedding dimension must be a multiple of 8"); return 1; }
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-  API_CUDA(cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
   h->launches = 0;
   if (n <= 0) return 0;
   const int K = 3 * d;

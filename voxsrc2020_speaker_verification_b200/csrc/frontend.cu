@@ -2,7 +2,12 @@
 // `apply-cmvn-sliding --norm-vars=false --center=true --cmn-window=300` in front of the network (tf_extract.py:63).
 //
 // Sliding-window mean normalisation [ext: Kaldi SlidingWindowCmn]: frame t is centred on the mean of a window of up to
-// `cmn_window` frames around t, shifted to stay inside [0, T); sums in double precision like Kaldi.  Two kernels over the
+// `cmn_window` frames around t, shifted to stay inside [0, T); sums in double precision like Kaldi.  The window rule (the
+// oracle restates it frame by frame, oracle/cmn_oracle.py):
+//   center:     [t - W/2, t - W/2 + W);   otherwise: [t - W, t + 1)
+//   start < 0 → both ends move right by -start
+//   !center and end > t → end = max(t + 1, min_window)        (the first frames look ahead until min_window frames are seen)
+//   end > T → both ends move left by end - T, start clamped at 0  Two kernels over the
 // packed [total_frames, F] matrix: per-utterance, per-bin running sums (one thread per bin walks the frames; consecutive
 // threads read consecutive bins, so every step is one coalesced row), then one thread per element subtracts the window mean.
 #include "kernels.cuh"
@@ -28,7 +33,7 @@ __global__ void __launch_bounds__(128) cmn_prefix_kernel(const float* __restrict
 
 __global__ void __launch_bounds__(256) cmn_apply_kernel(const float* __restrict__ feats, const int32_t* __restrict__ frame_off,
                                                         const int32_t* __restrict__ utt_of_frame, const double* __restrict__ csum, float* out,
-                                                        long long total, int F, int window, int center) {
+                                                        long long total, int F, int window, int center, int min_window) {
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total * F) return;
   const long long row = idx / F;
@@ -39,7 +44,7 @@ __global__ void __launch_bounds__(256) cmn_apply_kernel(const float* __restrict_
   int ws, we;
   if (center) { ws = t - window / 2; we = ws + window; } else { ws = t - window; we = t + 1; }
   if (ws < 0) { we -= ws; ws = 0; }
-  if (!center && we > t + 1) we = t + 1;
+  if (!center && we > t) we = max(t + 1, min_window);
   if (we > T) { ws -= we - T; we = T; if (ws < 0) ws = 0; }
   const double* c = csum + (static_cast<size_t>(t0) + u) * F + f;
   const double mean = (c[static_cast<size_t>(we) * F] - c[static_cast<size_t>(ws) * F]) / static_cast<double>(we - ws);
@@ -58,14 +63,14 @@ __global__ void utt_of_frame_kernel(int32_t* utt_of_frame, long long total, cons
 }
 
 cudaError_t launch_cmn_sliding(const float* feats, float* out, const int32_t* frame_off_dev, int n_utts, long long total_frames, int F,
-                               int window, int center, double* csum_ws, int32_t* utt_ws, cudaStream_t st) {
+                               int window, int center, int min_window, double* csum_ws, int32_t* utt_ws, cudaStream_t st) {
   if (n_utts <= 0 || total_frames <= 0) return cudaSuccess;
   if (F > 128) return cudaErrorInvalidValue;
   utt_of_frame_kernel<<<static_cast<unsigned>((total_frames + 255) / 256), 256, 0, st>>>(utt_ws, total_frames, frame_off_dev, n_utts);
   cmn_prefix_kernel<<<n_utts, 128, 0, st>>>(feats, frame_off_dev, csum_ws, F);
   const long long n = total_frames * F;
   cmn_apply_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(feats, frame_off_dev, utt_ws, csum_ws, out, total_frames, F, window,
-                                                                          center);
+                                                                          center, min_window);
   return cudaGetLastError();
 }
 
@@ -80,11 +85,12 @@ namespace svx {
 
 __global__ void __launch_bounds__(256) cm_decode_kernel(const uint8_t* __restrict__ blob, const long long* __restrict__ rec_off,
                                                         const int32_t* __restrict__ frame_off, const int32_t* __restrict__ utt_of_frame,
-                                                        float* out, long long total, int cols) {
+                                                        float* out, long long total, int cols, const int32_t* __restrict__ bad) {
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total * cols) return;
   const long long row = idx / cols;
   const int c = static_cast<int>(idx - row * cols);
+  if (*bad != kCmNoBadRecord) return;                                // a record failed validation: nothing is decoded, the call reports it
   const int u = utt_of_frame[row];
   const int r = static_cast<int>(row - frame_off[u]);
   const int rows = frame_off[u + 1] - frame_off[u];
@@ -107,12 +113,31 @@ __global__ void __launch_bounds__(256) cm_decode_kernel(const uint8_t* __restric
   out[idx] = v;
 }
 
+// Every record's own header must agree with what the caller says about it: rows = its slice of frame_off, cols = the model's
+// feature dimension, and the record must end inside the blob.  *bad starts at kCmNoBadRecord and receives the
+// smallest offending record index.
+__global__ void cm_check_kernel(const uint8_t* __restrict__ blob, const long long* __restrict__ rec_off, const int32_t* __restrict__ frame_off,
+                                int n, int cols, long long blob_bytes, int32_t* bad) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n) return;
+  const long long off = rec_off[u];
+  const int rows = frame_off[u + 1] - frame_off[u];
+  bool ok = off >= 0 && rows > 0 && off + 16 <= blob_bytes;
+  if (ok) {
+    int32_t hr, hc;
+    memcpy(&hr, blob + off + 8, 4); memcpy(&hc, blob + off + 12, 4);
+    ok = hr == rows && hc == cols && off + 16 + 8LL * cols + static_cast<long long>(rows) * cols <= blob_bytes;
+  }
+  if (!ok) atomicMin(bad, u);
+}
+
 cudaError_t launch_cm_decode(const uint8_t* blob, const long long* rec_off_dev, const int32_t* frame_off_dev, int n_utts, long long total_frames,
-                             int cols, float* out, int32_t* utt_ws, cudaStream_t st) {
+                             int cols, float* out, int32_t* utt_ws, long long blob_bytes, int32_t* bad_record, cudaStream_t st) {
   if (n_utts <= 0 || total_frames <= 0) return cudaSuccess;
+  cm_check_kernel<<<(n_utts + 127) / 128, 128, 0, st>>>(blob, rec_off_dev, frame_off_dev, n_utts, cols, blob_bytes, bad_record);
   utt_of_frame_kernel<<<static_cast<unsigned>((total_frames + 255) / 256), 256, 0, st>>>(utt_ws, total_frames, frame_off_dev, n_utts);
   const long long n = total_frames * cols;
-  cm_decode_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(blob, rec_off_dev, frame_off_dev, utt_ws, out, total_frames, cols);
+  cm_decode_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(blob, rec_off_dev, frame_off_dev, utt_ws, out, total_frames, cols, bad_record);
   return cudaGetLastError();
 }
 

@@ -32,11 +32,12 @@ cudaError_t launch_chunk_combine(const float* seg_emb, const int32_t* utt_seg_of
                                  int E, cudaStream_t st);
 
 // front-end
+constexpr int32_t kCmNoBadRecord = 0x7f7f7f7f;   // cudaMemset(0x7f) pattern: no record failed validation
 cudaError_t launch_cmn_sliding(const float* feats, float* out, const int32_t* frame_off_dev, int n_utts, long long total_frames, int F,
-                               int window, int center, double* csum_ws, int32_t* utt_ws, cudaStream_t st);
+                               int window, int center, int min_window, double* csum_ws, int32_t* utt_ws, cudaStream_t st);
 
 cudaError_t launch_cm_decode(const uint8_t* blob, const long long* rec_off_dev, const int32_t* frame_off_dev, int n_utts, long long total_frames,
-                             int cols, float* out, int32_t* utt_ws, cudaStream_t st);
+                             int cols, float* out, int32_t* utt_ws, long long blob_bytes, int32_t* bad_record, cudaStream_t st);
 
 // scoring
 cudaError_t launch_l2norm_rows(const float* in, float* out, long long n, int d, cudaStream_t st);
@@ -45,7 +46,7 @@ cudaError_t launch_topk_stats(const float* scores, int ld, long long n_rows, int
                               float* vals_out, int vals_ld, cudaStream_t st);
 cudaError_t launch_trial_scores(const float* emb, int d, const int32_t* idx1, const int32_t* idx2, long long t, const float* mean,
                                 const float* stdv, float* cos_out, float* snorm_out, cudaStream_t st);
-cudaError_t launch_segment_mean(const float* unit_rows, long long n, int d, const int32_t* group, const float* inv_count,
-                                float* out, int n_groups, cudaStream_t st);
+cudaError_t launch_group_mean(const float* unit_rows, int d, const int32_t* member_rows, const int32_t* group_off, float* out, int n_groups,
+                              cudaStream_t st);
 
 }  // namespace svx

@@ -90,6 +90,7 @@ class Model {
   int set_tensor(const char* name, const float* data, int ndim, const int64_t* shape);
   int finalize();
   int embed_dim() const { return cfg_.embed_dim; }
+  int device() const { return device_; }
   int set_option(const char* key, int value);
   // segments: contiguous [frame_off[i], frame_off[i+1]) rows of feats (device fp32 [total_frames, F])
   int run_segments(const float* d_feats, const int32_t* h_frame_off, int n_seg, float* d_out, cudaStream_t st);

@@ -414,11 +414,9 @@ cudaError_t launch_topk_stats(const float* scores, int ld, long long n_rows, int
     return cudaGetLastError();
   }
   const size_t smem = static_cast<size_t>(c) * sizeof(float);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem > 48 * 1024) {   // the attribute is per device and the call is cheap: set it on whatever device is current
     cudaError_t e = cudaFuncSetAttribute(topk_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   topk_stats_kernel<<<static_cast<unsigned>(n_rows), kTopkThreads, smem, st>>>(scores, ld, c, topk, mean, stdv, vals_out, vals_ld);
   return cudaGetLastError();
@@ -465,22 +463,27 @@ cudaError_t launch_trial_scores(const float* emb, int d, const int32_t* idx1, co
 
 // ---------------------------------------------------------------------------------------------------------
 // Cohort / enrolment models (snorm.py:45-67): mean of the unit vectors of each group, not re-normalised.
-// out must be zeroed by the caller; inv_count[g] = 1/|group g|; group[i] < 0 → row i unused.
-__global__ void __launch_bounds__(256) segment_mean_kernel(const float* unit_rows, long long n, int d, const int32_t* group,
-                                                           const float* inv_count, float* out) {
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= n * d) return;
-  const long long row = idx / d;
-  const int g = group[row];
-  if (g < 0) return;
-  atomicAdd(out + static_cast<size_t>(g) * d + (idx - row * d), unit_rows[idx] * inv_count[g]);
+// Groups arrive as a CSR list (member_rows[group_off[g] .. group_off[g+1]) = rows of group g, in the order the reference's
+// dict iteration appends them).  One thread per (group, column) adds its members in that order and divides by the count:
+// the same sequential fp32 sum + true divide np.mean(matrix, axis=0) performs, so the result is run-to-run deterministic
+// and bit-identical to the reference (no atomics).  Consecutive threads read consecutive columns of a row: coalesced.
+__global__ void __launch_bounds__(256) group_mean_kernel(const float* __restrict__ unit_rows, int d, const int32_t* __restrict__ member_rows,
+                                                         const int32_t* __restrict__ group_off, float* out, int n_groups) {
+  const int g = blockIdx.x;
+  if (g >= n_groups) return;
+  const int lo = group_off[g], hi = group_off[g + 1];
+  for (int col = threadIdx.x; col < d; col += blockDim.x) {
+    float acc = 0.f;
+    for (int i = lo; i < hi; ++i) acc = __fadd_rn(acc, unit_rows[static_cast<size_t>(member_rows[i]) * d + col]);
+    out[static_cast<size_t>(g) * d + col] = hi > lo ? __fdiv_rn(acc, static_cast<float>(hi - lo)) : 0.f;
+  }
 }
 
-cudaError_t launch_segment_mean(const float* unit_rows, long long n, int d, const int32_t* group, const float* inv_count,
-                                float* out, int n_groups, cudaStream_t st) {
-  (void)n_groups;
-  if (n <= 0) return cudaSuccess;
-  segment_mean_kernel<<<static_cast<unsigned>((n * d + 255) / 256), 256, 0, st>>>(unit_rows, n, d, group, inv_count, out);
+cudaError_t launch_group_mean(const float* unit_rows, int d, const int32_t* member_rows, const int32_t* group_off, float* out, int n_groups,
+                              cudaStream_t st) {
+  if (n_groups <= 0) return cudaSuccess;
+  group_mean_kernel<<<static_cast<unsigned>(n_groups), d >= 256 ? 256 : (d > 32 ? (d + 31) / 32 * 32 : 32), 0, st>>>(unit_rows, d, member_rows,
+                                                                                                              group_off, out, n_groups);
   return cudaGetLastError();
 }
 

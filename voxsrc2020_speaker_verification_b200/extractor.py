@@ -116,26 +116,33 @@ class Extractor:
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def cmvn_sliding(self, feats_dev: torch.Tensor, frame_offsets: np.ndarray, cmn_window: int = 300, center: bool = True) -> torch.Tensor:
+    def cmvn_sliding(self, feats_dev: torch.Tensor, frame_offsets: np.ndarray, cmn_window: int = 300, center: bool = True,
+                     min_window: int = 100) -> torch.Tensor:
         """In place on a CUDA tensor [total, F]: what ``apply-cmvn-sliding --norm-vars=false --center=true --cmn-window=300``
-        does in front of the network (reference tf_extract.py:63)."""
+        does in front of the network (reference tf_extract.py:63).  ``min_window`` only matters for center=False
+        (Kaldi's --min-cmn-window)."""
         frame_offsets = np.ascontiguousarray(frame_offsets, dtype=np.int32)
         lib.check(self._lib.svx_cmvn_sliding(ctypes.c_void_p(feats_dev.data_ptr()), ctypes.c_void_p(feats_dev.data_ptr()),
                                              frame_offsets.ctypes.data_as(ctypes.c_void_p), frame_offsets.shape[0] - 1, self.feat_dim,
-                                             int(cmn_window), int(center), ctypes.c_void_p(self._stream())))
+                                             int(cmn_window), int(center), int(min(min_window, cmn_window)), ctypes.c_void_p(self._stream())))
         return feats_dev
 
     def decode_compressed(self, payloads: Sequence[bytes], rows: Sequence[int]) -> torch.Tensor:
         """Kaldi 'CM ' records (payloads from ``kaldi_ark.read_mat_raw``) → CUDA fp32 [sum(rows), F], decoded on the device
         bit-identically to kaldi_io._read_compressed_mat (reference kaldi_io.py:471-504)."""
         n = len(payloads)
+        for i, (p, r) in enumerate(zip(payloads, rows)):       # the record's own header: min f32, range f32, rows i32, cols i32
+            hr, hc = np.frombuffer(p, dtype="<i4", count=2, offset=8) if len(p) >= 16 else (-1, -1)
+            if hc != self.feat_dim or hr != r:
+                raise ValueError("compressed record %d is %d x %d, expected %d x %d (the model takes %d-dim features)"
+                                 % (i, hr, hc, r, self.feat_dim, self.feat_dim))
         rec_off = np.zeros(n, np.int64)
         np.cumsum([len(p) for p in payloads[:-1]], out=rec_off[1:])
         offs = np.zeros(n + 1, np.int32)
         np.cumsum(np.asarray(rows, np.int64), out=offs[1:])
         blob = torch.frombuffer(bytearray(b"".join(payloads)), dtype=torch.uint8).to(torch.device("cuda", self.device))
         out = torch.empty((int(offs[-1]), self.feat_dim), dtype=torch.float32, device=blob.device)
-        lib.check(self._lib.svx_decode_compressed(ctypes.c_void_p(blob.data_ptr()), rec_off.ctypes.data_as(ctypes.c_void_p),
+        lib.check(self._lib.svx_decode_compressed(ctypes.c_void_p(blob.data_ptr()), int(blob.numel()), rec_off.ctypes.data_as(ctypes.c_void_p),
                                                   offs.ctypes.data_as(ctypes.c_void_p), n, self.feat_dim, ctypes.c_void_p(out.data_ptr()),
                                                   ctypes.c_void_p(self._stream())))
         return out

@@ -299,27 +299,3 @@ class VectorArkScpWriter:
 
     def __exit__(self, *exc):
         self.close()
-
-
-# ------------------------------------------------------------------ sliding-window CMN
-def apply_cmvn_sliding(feats: np.ndarray, cmn_window: int = 300, center: bool = True) -> np.ndarray:
-    """``apply-cmvn-sliding --norm-vars=false --center=true --cmn-window=300`` (reference
-    tf_extract.py:63) [ext: Kaldi SlidingWindowCmn]: subtract the mean of a window of up to
-    ``cmn_window`` frames centred on t, shifted to stay inside [0, T); sums in double precision."""
-    t_total = feats.shape[0]
-    csum = np.concatenate([np.zeros((1, feats.shape[1]), np.float64), np.cumsum(feats.astype(np.float64), axis=0)])
-    t = np.arange(t_total)
-    if center:
-        ws = t - cmn_window // 2
-        we = ws + cmn_window
-    else:
-        ws = t - cmn_window
-        we = t + 1
-    shift = np.where(ws < 0, -ws, 0)
-    ws, we = ws + shift, we + shift
-    if not center:
-        we = np.minimum(we, t + 1)   # never look ahead
-    over = np.where(we > t_total, we - t_total, 0)
-    ws, we = np.maximum(ws - over, 0), we - over
-    mean = (csum[we] - csum[ws]) / (we - ws)[:, None]
-    return (feats.astype(np.float64) - mean).astype(np.float32)

@@ -45,12 +45,12 @@ SYMBOLS = {
     "svx_extractor_extract": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "svx_extractor_last_launches": (c_longlong, [c_void_p]),
     "svx_extractor_conv_time": (c_int, [c_void_p, POINTER(ctypes.c_double), POINTER(ctypes.c_double)]),
-    "svx_cmvn_sliding": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
-    "svx_decode_compressed": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "svx_cmvn_sliding": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "svx_decode_compressed": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "svx_scorer_create": (c_int, [c_int, POINTER(c_void_p)]),
     "svx_scorer_destroy": (c_int, [c_void_p]),
     "svx_l2norm_rows": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
-    "svx_group_means": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "svx_group_means": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "svx_asnorm_stats": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "svx_cohort_topk_values": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "svx_topk_stats": (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),

@@ -47,13 +47,19 @@ class Scorer:
         self.launches += 1
         return out
 
-    def group_means(self, unit_rows: torch.Tensor, group: torch.Tensor, n_groups: int) -> torch.Tensor:
-        """read_speaker_xvector (snorm.py:45-67): mean of the unit rows of each group, not re-normalised."""
-        counts = torch.bincount(group[group >= 0].to(torch.int64), minlength=n_groups).to(torch.float32)
-        inv = (1.0 / counts.clamp(min=1.0)).contiguous()
-        out = torch.empty((n_groups, unit_rows.shape[1]), dtype=torch.float32, device=unit_rows.device)
-        lib.check(self._lib.svx_group_means(_ptr(unit_rows.contiguous()), unit_rows.shape[0], unit_rows.shape[1],
-                                            _ptr(group.to(torch.int32).contiguous()), _ptr(inv), _ptr(out), n_groups, self._stream()))
+    def group_means(self, unit_rows: torch.Tensor, group, n_groups: int) -> torch.Tensor:
+        """read_speaker_xvector (snorm.py:45-67): mean of the unit rows of each group, not re-normalised.
+        ``group[i]`` = group of row i (< 0: unused).  Members are summed in row order (the order the reference appends
+        them) and divided by the count, like np.mean(matrix, axis=0): deterministic and bit-identical to it."""
+        g = np.asarray(group.cpu() if isinstance(group, torch.Tensor) else group, dtype=np.int64)
+        used = np.nonzero(g >= 0)[0]
+        order = used[np.argsort(g[used], kind="stable")].astype(np.int32)          # CSR: rows of group 0, then group 1, …
+        offs = np.zeros(n_groups + 1, np.int32)
+        np.cumsum(np.bincount(g[used], minlength=n_groups), out=offs[1:])
+        dv = unit_rows.device
+        out = torch.empty((n_groups, unit_rows.shape[1]), dtype=torch.float32, device=dv)
+        lib.check(self._lib.svx_group_means(_ptr(unit_rows.contiguous()), unit_rows.shape[1], _ptr(torch.from_numpy(order).to(dv)),
+                                            _ptr(torch.from_numpy(offs).to(dv)), _ptr(out), n_groups, self._stream()))
         self.launches += 1
         return out
 

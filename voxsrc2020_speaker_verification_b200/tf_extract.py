@@ -21,12 +21,6 @@ from . import kaldi_ark
 from .extractor import Extractor
 
 
-def iter_features(rspec: str, cmvn: bool = True):
-    for key, mat in kaldi_ark.read_mat_scp(rspec + ".scp"):
-        mat = np.asarray(mat, dtype=np.float32)
-        yield key, (kaldi_ark.apply_cmvn_sliding(mat) if cmvn else mat)
-
-
 def run(pb_file: str, expand_dim: int, rspec: str, wspec: str, precision: str = "fp16", device: int = 0,
         max_frames: int = 60000, cmvn: bool = True, model_id=None, feat_dim=None) -> int:
     ex = Extractor.from_pb(pb_file, expand_dim, device=device, precision=precision, model_id=model_id, feat_dim=feat_dim)
@@ -53,6 +47,8 @@ def run(pb_file: str, expand_dim: int, rspec: str, wspec: str, precision: str = 
             if rows < 25:
                 # the reference divides by zero here (tf_extract.py:102,111); fail as loudly
                 raise ZeroDivisionError("utterance %s has %d frames (< 25)" % (key, rows))
+            if cols != ex.feat_dim:
+                raise ValueError("utterance %s has %d-dim features, the model takes %d" % (key, cols, ex.feat_dim))
             keys.append(key)
             recs.append((kind, payload, rows))
             frames += rows
