@@ -58,6 +58,8 @@ typedef struct svx_model_config {
 typedef struct svx_extractor svx_extractor;
 
 int svx_version(void);
+/* bit 0: debug build (SVX_* environment switches compiled in); bit 1: the cta_group::2 instantiation of the flat conv kernel. */
+int svx_build_flags(void);
 const char* svx_last_error(void);
 
 /* ---- extractor: replaces the frozen graph `model/inputs:0 → model/outputs:0` that tf_extract.py:75-82 imports
@@ -85,6 +87,10 @@ int svx_extractor_run_segments(svx_extractor* h, const float* feats_dev, const i
  * Fails for utterances shorter than 25 frames (the reference divides by zero there). */
 int svx_extractor_extract(svx_extractor* h, const float* feats, int feats_on_device, const int32_t* frame_offsets_host,
                           int n_utts, float* out, int out_on_device, void* cuda_stream);
+/* Parity tooling: with a directory set, every op of the next runs writes its destination tensor there after it ran (one raw
+ * 16-bit NHWC file per op, name = op index, kind, tensor id, rows, row pitch, channels, channel offset, width); NULL / "" = off.
+ * tests/test_gpu_blocks.py feeds these to the oracle block by block. */
+int svx_extractor_set_dump_dir(svx_extractor* h, const char* dir);
 /* Number of kernels launched by the last run/extract call. */
 long long svx_extractor_last_launches(svx_extractor* h);
 /* With option "time_convs" = 1: summed device time (CUDA events on the launching stream) of the tensor-core conv

@@ -1,6 +1,8 @@
 """The alternative code paths of the flat conv kernel give the same embeddings as the default one.
 
-The library reads its debug switches once per process (static getenv), so every variant runs in its own subprocess:
+The switches exist only in the debug build of the library (libsvx_dbg.so, `python -m voxsrc2020_speaker_verification_b200.build
+--debug`; the production libsvx.so reads no environment variable), which the subprocess selects through SVX_LIB; the test is
+skipped when that build is not in the tree.  The switches are read once per process, so every variant runs in its own subprocess:
 the default path is covered by test_gpu_extract.py; here: unpadded concat / planar tensors (SVX_NO_YPAD), TMA-only epilogue (SVX_NO_DIRECT), two TMEM buffers (SVX_NO_TMEM4).
 All of them are checked against the CPU oracle with the tolerance of BASELINE.json (cosine >= 0.9999 per utterance).
 """
@@ -40,8 +42,12 @@ print("RESULT " + json.dumps({"cos": cos.tolist()}))
 @pytest.mark.parametrize("env", [{"SVX_NO_YPAD": "1"}, {"SVX_NO_DIRECT": "1"}, {"SVX_NO_TMEM4": "1"}],
                          ids=["unpadded_splits", "tma_epilogue", "two_tmem_buffers"])
 def test_variant_matches_oracle(env):
+    dbg = os.path.join(ROOT, "voxsrc2020_speaker_verification_b200", "libsvx_dbg.so")
+    if not os.path.exists(dbg):
+        pytest.skip("debug library not built")
     e = dict(os.environ)
     e.update(env)
+    e["SVX_LIB"] = dbg
     r = subprocess.run([sys.executable, "-c", SNIPPET], capture_output=True, text=True, env=e, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1]

@@ -10,6 +10,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libsvx.so")
+DBG_LIB_PATH = os.path.join(HERE, "libsvx_dbg.so")   # debug build: SVX_* environment switches, CTA-pair instantiation, 2 s watchdog
 SOURCES = ["conv_flat.cu", "conv_umma.cu", "conv_simple.cu", "elementwise.cu", "frontend.cu", "scoring.cu", "model.cu", "api.cu"]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
@@ -23,24 +24,28 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found; libsvx cannot be built")
 
 
-def _stale() -> bool:
-    if not os.path.exists(LIB_PATH):
+def _stale(lib_path: str = LIB_PATH) -> bool:
+    if not os.path.exists(lib_path):
         return True
-    t = os.path.getmtime(LIB_PATH)
+    t = os.path.getmtime(lib_path)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "svx.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
-        return LIB_PATH
+def build_library(force: bool = False, verbose: bool = False, debug: bool = False) -> str:
+    """``debug``: the library with the SVX_* tuning / knock-out switches compiled in (libsvx_dbg.so; select it with SVX_LIB=…).
+    The production libsvx.so reads no environment variable."""
+    lib_path = DBG_LIB_PATH if debug else LIB_PATH
+    if not force and not _stale(lib_path):
+        return lib_path
     nvcc = _nvcc()
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build_dbg" if debug else "build")
+    extra = ["-DSVX_DEBUG_SWITCHES", "-DSVX_ENABLE_PAIR", "-DSVX_WATCHDOG_MS=2000"] if debug else []
     os.makedirs(objdir, exist_ok=True)
 
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc] + ARCH_FLAGS + COMMON + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + ARCH_FLAGS + COMMON + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
@@ -52,13 +57,13 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc] + ARCH_FLAGS + ["-shared", "-o", LIB_PATH] + objs + ["-cudart", "static", "-Xlinker", "--no-undefined",
+    cmd = [nvcc] + ARCH_FLAGS + ["-shared", "-o", lib_path] + objs + ["-cudart", "static", "-Xlinker", "--no-undefined",
                                                                    "-ldl", "-lpthread", "-lrt"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv, debug="--debug" in sys.argv))

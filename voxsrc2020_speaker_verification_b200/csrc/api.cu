@@ -78,7 +78,18 @@ static int grow_buf(P** p, size_t* have, size_t need) {
 
 extern "C" {
 
-int svx_version(void) { return 100; }
+int svx_version(void) { return 200; }
+
+int svx_build_flags(void) {
+  int f = 0;
+#ifdef SVX_DEBUG_SWITCHES
+  f |= 1;
+#endif
+#ifdef SVX_ENABLE_PAIR
+  f |= 2;
+#endif
+  return f;
+}
 
 const char* svx_last_error(void) { return g_last_error.c_str(); }
 
@@ -143,6 +154,12 @@ int svx_extractor_extract(svx_extractor* h, const float* feats, int feats_on_dev
   DeviceGuard guard(h->model->device());
   return h->model->extract(feats, feats_on_device, frame_offsets_host, n_utts, out, out_on_device,
                            static_cast<cudaStream_t>(cuda_stream));
+}
+
+int svx_extractor_set_dump_dir(svx_extractor* h, const char* dir) {
+  if (!h) { set_last_error("null handle"); return 1; }
+  h->model->set_dump_dir(dir);
+  return 0;
 }
 
 long long svx_extractor_last_launches(svx_extractor* h) { return h ? h->model->last_launches() : -1; }
@@ -292,7 +309,7 @@ static int cohort_pass(svx_scorer* h, const float* test_dev, int64_t n, const fl
   const int c_pad = (c + n_tile - 1) / n_tile * n_tile;
   // rows per pass: a whole number of waves of (128 x n_tile) tiles over the SMs, near 4096 rows (the fp32 score block then
   // stays close to the L2 size); SVX_SCORE_BLOCK_ROWS overrides (debug)
-  static const int env_rows = getenv("SVX_SCORE_BLOCK_ROWS") ? atoi(getenv("SVX_SCORE_BLOCK_ROWS")) : 0;
+  static const int env_rows = dbg_env("SVX_SCORE_BLOCK_ROWS") ? atoi(dbg_env("SVX_SCORE_BLOCK_ROWS")) : 0;
   int block_rows = 4096;
   {
     int sms = 148;

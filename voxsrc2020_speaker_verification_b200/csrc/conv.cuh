@@ -10,8 +10,17 @@
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace svx {
+
+// Debug / tuning switches (SVX_* environment variables) exist only in the debug build (`build.py --debug` → libsvx_dbg.so,
+// -DSVX_DEBUG_SWITCHES); in the production library every one of them folds to "unset" at compile time.
+#ifdef SVX_DEBUG_SWITCHES
+inline const char* dbg_env(const char* name) { return getenv(name); }
+#else
+inline const char* dbg_env(const char*) { return nullptr; }
+#endif
 
 constexpr int kMaxTaps = 9;
 constexpr int kTraceEvents = 4096;

@@ -80,9 +80,14 @@ __device__ __forceinline__ void bulk_store_1d(void* gdst, uint32_t smem_src, uin
 __device__ __forceinline__ void wait_dbg(uint64_t* bar, uint32_t parity, unsigned long long* dbg, int code, int a, unsigned b,
                                          const volatile uint32_t* prog) {
   uint32_t spins = 0;
+  unsigned long long t0 = 0;
+  bool reported = false;
   while (!mbar_try_wait(bar, parity)) {
-    ++spins;
-    if (spins == (1u << 21) && dbg) {      // first report, then keep waiting so that every starved role can report
+    if ((++spins & 0x3fffu) != 0) continue;
+    const unsigned long long now = global_ns();       // wall-time watchdog (see umma.cuh): report after 2 s, trap after kWatchdogNs
+    if (t0 == 0) { t0 = now; continue; }
+    if (!reported && now - t0 > 2000000000ull && dbg) {      // first report, then keep waiting so that every starved role can report
+      reported = true;
       if ((threadIdx.x & 31) == 0 || (threadIdx.x >> 5) >= 4) {
         dbg[(blockIdx.x & 3) * 16 + (threadIdx.x >> 5)] = (static_cast<unsigned long long>(b) << 32) | (static_cast<unsigned long long>(blockIdx.x) << 16) |
                                                         (static_cast<unsigned long long>(a & 0xff) << 8) | static_cast<unsigned long long>(code & 0xff);
@@ -91,7 +96,7 @@ __device__ __forceinline__ void wait_dbg(uint64_t* bar, uint32_t parity, unsigne
         __threadfence_system();
       }
     }
-    if (spins > (1u << 23)) __trap();
+    if (now - t0 > kWatchdogNs) __trap();
   }
 }
 
@@ -750,11 +755,16 @@ size_t conv_flat_smem_bytes(const FlatConvParams& p) {
 
 static int g_flat_sms = 0;
 
+// The cta_group::2 instantiation (PAIR) is slower than single CTAs on every layer class as built, so the
+// production library does not carry it: -DSVX_ENABLE_PAIR compiles it back in for experiments.
 template <typename T, int AUX, bool PRE, bool POST>
 static cudaError_t set_attr() {
   cudaError_t e = cudaFuncSetAttribute(conv_flat_kernel<T, AUX, PRE, POST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+#ifdef SVX_ENABLE_PAIR
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(conv_flat_kernel<T, AUX, PRE, POST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  e = cudaFuncSetAttribute(conv_flat_kernel<T, AUX, PRE, POST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+#endif
+  return e;
 }
 
 template <typename T>
@@ -783,7 +793,7 @@ cudaError_t conv_flat_init() {
 
 template <typename T>
 static cudaError_t launch_typed(const FlatConvParams& p, const FlatMaps& maps, dim3 grid, size_t smem, cudaStream_t st) {
-  static const bool no_pdl = getenv("SVX_NO_PDL") != nullptr;   // debug switch
+  static const bool no_pdl = dbg_env("SVX_NO_PDL") != nullptr;   // debug switch
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = grid; cfg.blockDim = dim3(kFlatThreads, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
@@ -801,13 +811,18 @@ static cudaError_t launch_typed(const FlatConvParams& p, const FlatMaps& maps, d
   }
   cfg.attrs = attr; cfg.numAttrs = na;
   cudaError_t le = cudaSuccess;
-  static const bool launch_log = getenv("SVX_LAUNCH_LOG") != nullptr;   // debug switch
+  static const bool launch_log = dbg_env("SVX_LAUNCH_LOG") != nullptr;   // debug switch
   if (launch_log)
     fprintf(stderr, "conv_flat launch: grid %u smem %zu pair %d n_tiles %d n_tile %d mt %d P %lld aux %d\n", grid.x, smem, p.pair, p.n_tiles, p.n_tile, p.mt,
             p.P, p.aux_mode);
+#ifdef SVX_ENABLE_PAIR
 #define SVX_FLAT(AUX, PRE, POST)                                                                       \
   le = p.pair ? cudaLaunchKernelEx(&cfg, conv_flat_kernel<T, AUX, PRE, POST, true>, p, maps)          \
               : cudaLaunchKernelEx(&cfg, conv_flat_kernel<T, AUX, PRE, POST, false>, p, maps)
+#else
+  if (p.pair) return cudaErrorNotSupported;
+#define SVX_FLAT(AUX, PRE, POST) le = cudaLaunchKernelEx(&cfg, conv_flat_kernel<T, AUX, PRE, POST, false>, p, maps)
+#endif
   if (p.aux_mode == 0) {
     if (p.pre_relu && !p.post_relu) SVX_FLAT(0, true, false);
     else if (!p.pre_relu && p.post_relu) SVX_FLAT(0, false, true);

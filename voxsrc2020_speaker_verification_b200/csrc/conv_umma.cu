@@ -481,14 +481,14 @@ bool conv_umma_finish_params(UmmaConvParams& p) {
   // weights stay resident in shared memory when they are small (every layer of the two high-resolution stages)
   const long long b_total = static_cast<long long>(total_it) * p.b_stage_bytes;
   p.bres_bytes = 0;
-  static const bool no_bres = getenv("SVX_NO_BRES") != nullptr;   // debug switch
+  static const bool no_bres = dbg_env("SVX_NO_BRES") != nullptr;   // debug switch
   if (!no_bres && b_total <= 64 * 1024 && 225 * 1024 - fixed - b_total >= 4LL * p.a_stage_bytes)
     p.bres_bytes = static_cast<uint32_t>(b_total);
   const long long budget = 225 * 1024 - fixed - p.bres_bytes;
   long long stages = budget / static_cast<long long>(ring_stage_bytes(p));
   if (stages < 2) return false;
   if (stages > kMaxStages) stages = kMaxStages;
-  static const int env_stages = getenv("SVX_MAX_STAGES") ? atoi(getenv("SVX_MAX_STAGES")) : 0;   // debug switch
+  static const int env_stages = dbg_env("SVX_MAX_STAGES") ? atoi(dbg_env("SVX_MAX_STAGES")) : 0;   // debug switch
   if (env_stages >= 2 && stages > env_stages) stages = env_stages;
   p.stages = static_cast<int>(stages);
   uint32_t tc = 32;

@@ -77,8 +77,9 @@ int encode_tmap(CUtensorMap* m, int is_bf16, void* base, int rank, const uint64_
 
 // ------------------------------------------------------------------------------------------------ construction
 Model::Model(const svx_model_config& cfg, int device, int precision) : cfg_(cfg), device_(device), is_bf16_(precision == SVX_PRECISION_BF16) {
-  const char* fs = getenv("SVX_FORCE_SIMPLE");
+  const char* fs = dbg_env("SVX_FORCE_SIMPLE");
   if (fs && fs[0] == '1') force_simple_ = 1;
+  if (const char* dd = dbg_env("SVX_DUMP_DIR")) dump_dir_ = dd;
 }
 
 Model::~Model() {
@@ -181,8 +182,8 @@ void Model::build_res2net() {
     // [pixels, w] tensor each: a 3x3 then reads whole DRAM lines instead of a w-channel slice of every S*w-channel row
     // (measured 3.7-4.8x read amplification on the interleaved layout).  y (the concat, conv3's input) stays interleaved.
     std::vector<int> ms(S, -1), zs(S, -1);
-    static const bool no_ypad0 = getenv("SVX_NO_YPAD") != nullptr;   // debug switch (see wp below)
-    static const bool no_ppad = getenv("SVX_NO_PPAD") != nullptr;    // debug switch: planar tensors unpadded
+    static const bool no_ypad0 = dbg_env("SVX_NO_YPAD") != nullptr;   // debug switch (see wp below)
+    static const bool no_ppad = dbg_env("SVX_NO_PPAD") != nullptr;    // debug switch: planar tensors unpadded
     const int wpp = (!no_ypad0 && !no_ppad && w % 16 != 0) ? round_up(w, 16) : w;   // planar split tensors: padded like the concat slices, pad WRITTEN
     for (int i = 0; i + 1 < S; ++i) ms[i] = new_tensor(stage, wpp);
     for (int i = 1; i + 1 < S; ++i) zs[i] = new_tensor(stage, wpp);
@@ -190,7 +191,7 @@ void Model::build_res2net() {
     // padded to wp channels and the direct epilogue WRITES the pad (zeros): a 48-byte slice of a 192-byte pixel row is otherwise
     // stored as partial sectors that L2 read-fills from DRAM, which bounded the narrow 3x3 convs (profiles/r01_knockout_direct_stores.txt).
     // conv3 then reads S*wp channels; the weight rows of the pad positions are zero.
-    static const bool no_ypad = getenv("SVX_NO_YPAD") != nullptr;   // debug switch
+    static const bool no_ypad = dbg_env("SVX_NO_YPAD") != nullptr;   // debug switch
     const int wp = (!no_ypad && w % 16 != 0) ? round_up(w, 16) : w;
     const int y = new_tensor(stage, S * wp);
     const int mp = st == 2 ? new_tensor(in_stage, mid) : -1;
@@ -408,7 +409,7 @@ template <> __nv_bfloat16 host_cvt<__nv_bfloat16>(float v) { return __float2bflo
 // TMA issues one request per box row at a fixed ~1.75 ns whatever its width (profiles/r01_microbench_tma_rate.txt),
 // so the widest swizzle span that the slice fills at all is the cheapest; padded K only costs idle MMA cycles.
 static int pick_kbox(int cin) {
-  if (getenv("SVX_KBOX_OLD")) {   // debug switch: exact-fit boxes
+  if (dbg_env("SVX_KBOX_OLD")) {   // debug switch: exact-fit boxes
     if (cin % 64 == 0) return 64;
     if (cin % 32 == 0) return 32;
   }
@@ -636,7 +637,7 @@ int Model::plan_conv(ConvDesc& c) {
   up.aux_boxes = up.aux_mode ? (c.n_tile + 63) / 64 : 0;
   up.aux_width = up.aux_mode == 1 ? e.n_split : (up.aux_mode == 2 ? c.cout : 0);
   {   // debug switch: SVX_STAGED_MASK bit 1 plain, 2 split, 4 residual, 8 add2, 16 stride-2 (default all)
-    const char* mk = getenv("SVX_STAGED_MASK");
+    const char* mk = dbg_env("SVX_STAGED_MASK");
     const int mask = mk ? atoi(mk) : 63;
     int kind = up.aux_mode == 1 ? 4 : up.aux_mode == 2 ? 8 : (e.n_split < c.cout ? 2 : (c.cout % 64 == 0 ? 32 : 1));
     if (c.stride == 2 && !(mask & 16)) kind = 0;
@@ -718,7 +719,7 @@ int Model::plan_conv(ConvDesc& c) {
 // shared-memory budget (A span ring, weights resident or ringed, epilogue slots).  Leaves use_flat = false when the
 // layer does not qualify; the caller then plans the 2-D tiled kernel.
 int Model::plan_flat(ConvDesc& c) {
-  static const bool disabled = getenv("SVX_NO_FLAT") != nullptr;   // debug switch
+  static const bool disabled = dbg_env("SVX_NO_FLAT") != nullptr;   // debug switch
   if (disabled) return 0;
   const ActTensor& tin = tensors_[c.in.id];
   const ActTensor& tout = tensors_[c.out.id];
@@ -783,20 +784,25 @@ int Model::plan_flat(ConvDesc& c) {
     for (int t : {256, 192, 128, 64, 32})
       if (t < n16 && N % t == 0) cands.push_back(t);
   }
-  static const int env_maxmt = getenv("SVX_FLAT_MAXMT") ? atoi(getenv("SVX_FLAT_MAXMT")) : 4;          // debug switches
-  static const bool plan_log = getenv("SVX_PLAN_LOG") != nullptr;
+  static const int env_maxmt = dbg_env("SVX_FLAT_MAXMT") ? atoi(dbg_env("SVX_FLAT_MAXMT")) : 4;          // debug switches
+  static const bool plan_log = dbg_env("SVX_PLAN_LOG") != nullptr;
   // CTA pairs (cta_group::2): worth it where the weights dominate shared memory or are streamed — total K (taps x channels) at or
   // above a threshold; SVX_PAIR_MIN_K overrides (0 = every layer, huge = never)
-  static const int pair_min_k = getenv("SVX_PAIR_MIN_K") ? atoi(getenv("SVX_PAIR_MIN_K")) : (1 << 30);
+  static const int pair_min_k = dbg_env("SVX_PAIR_MIN_K") ? atoi(dbg_env("SVX_PAIR_MIN_K")) : (1 << 30);
+#ifdef SVX_ENABLE_PAIR
   const bool use_pair = !grouped && taps * c.kpad >= pair_min_k;
+#else
+  const bool use_pair = false;
+  (void)pair_min_k;
+#endif
   const int ksteps = c.kbox / 16;
   // direct epilogue (global accesses from the epilogue threads instead of slots + TMA) for narrow single-destination tiles
-  static const bool no_direct = getenv("SVX_NO_DIRECT") != nullptr;   // debug switch
+  static const bool no_direct = dbg_env("SVX_NO_DIRECT") != nullptr;   // debug switch
   const bool direct_ok = !no_direct && !split && n_split == c.cout && !use_pair && c.outb.id < 0;
   // aux mode 2 over dense planar tensors: the add2 / out2 tiles are contiguous runs -> 1-D bulk copies instead of 128 rows each
   // (measured: no gain — 14 354 vs 14 458 emb/s with it on the stage-3 3x3 convs, and none on stages 1-2 against 2-D TMA tiles —
   // so it is opt-in: SVX_LIN=1)
-  static const bool use_lin = getenv("SVX_LIN") != nullptr;   // debug switch
+  static const bool use_lin = dbg_env("SVX_LIN") != nullptr;   // debug switch
   bool lin_ok = false;
   if (use_lin && aux_mode == 2 && !use_pair && !split) {
     const ActTensor& ta = tensors_[c.add2.id];
@@ -822,7 +828,7 @@ int Model::plan_flat(ConvDesc& c) {
       const int boxes = (part_cols + box_ch - 1) / box_ch;
       const uint32_t box_bytes = 128u * box_ch * 2u;
       const bool direct = direct_ok && n_tile <= 64 && (n_tiles == 1 || grouped);   // several n-tiles would re-read A per 64 channels
-      static const bool no_hybrid = getenv("SVX_NO_HYBRID") != nullptr;   // debug switch
+      static const bool no_hybrid = dbg_env("SVX_NO_HYBRID") != nullptr;   // debug switch
       // out2 through a slot + TMA, aux and out1 on the LSU — where the pixel runs are not 32-byte multiples (24 channels); with
       // sector-aligned runs (48 channels) the 256-bit stores of the fully direct form are faster (118 vs 134 us in stage 2)
       const bool hybrid = direct && aux_mode == 2 && !no_hybrid && (c.cout * 2) % 32 != 0;
@@ -841,12 +847,12 @@ int Model::plan_flat(ConvDesc& c) {
         const int a_box_rows = round_up((a_rows_min + a_boxes - 1) / a_boxes, 8);
         const uint32_t a_stage = static_cast<uint32_t>(round_up(a_boxes * a_box_rows * static_cast<int>(row_bytes), 1024));
         for (int b_res : {1, 0}) {
-          static const long long bres_max = getenv("SVX_BRES_MAX") ? atoll(getenv("SVX_BRES_MAX")) : 64 * 1024;   // tuning knobs; resident weights above 64 KB starve the A ring (measured +1.2 % against 96 KB)
-          static const double lat_cyc = getenv("SVX_LAT_CYC") ? atof(getenv("SVX_LAT_CYC")) : 3000.0;
-          static const double slot_scale = getenv("SVX_SLOT_SCALE") ? atof(getenv("SVX_SLOT_SCALE")) : 1.0;
+          static const long long bres_max = dbg_env("SVX_BRES_MAX") ? atoll(dbg_env("SVX_BRES_MAX")) : 64 * 1024;   // tuning knobs; resident weights above 64 KB starve the A ring (measured +1.2 % against 96 KB)
+          static const double lat_cyc = dbg_env("SVX_LAT_CYC") ? atof(dbg_env("SVX_LAT_CYC")) : 3000.0;
+          static const double slot_scale = dbg_env("SVX_SLOT_SCALE") ? atof(dbg_env("SVX_SLOT_SCALE")) : 1.0;
           if (b_res && b_total > bres_max) continue;
           if (!b_res && items < 2) continue;
-          static const int slots0 = getenv("SVX_SLOTS0") ? atoi(getenv("SVX_SLOTS0")) : 2;
+          static const int slots0 = dbg_env("SVX_SLOTS0") ? atoi(dbg_env("SVX_SLOTS0")) : 2;
           int a_stages = 2, b_stages = b_res ? 0 : 2, slots = slots0;               // slots: per warpgroup (2: convert j+1 while j is stored)
           long long left = budget - (b_res ? b_total : 2LL * b_item) - 2LL * a_stage - 2LL * slots * slot_bytes;
           if (left < 0) { slots = 1; left += 2LL * slot_bytes; }
@@ -894,7 +900,7 @@ int Model::plan_flat(ConvDesc& c) {
           }
           // the model is optimistic about overlap: when shared memory is left over, take a second slot per warpgroup (convert
           // j+1 while j is being stored), a third A stage, and a third slot for aux tiles
-          static const int a_min = getenv("SVX_A_MIN") ? atoi(getenv("SVX_A_MIN")) : 3;
+          static const int a_min = dbg_env("SVX_A_MIN") ? atoi(dbg_env("SVX_A_MIN")) : 3;
           while (a_stages < a_min && a_min > 3 && left >= a_stage) { ++a_stages; left -= a_stage; }
           if (slots < 2 && left >= 2LL * slot_bytes) { ++slots; left -= 2LL * slot_bytes; }
           if (a_stages < 3 && left >= a_stage) { ++a_stages; left -= a_stage; }
@@ -924,7 +930,7 @@ int Model::plan_flat(ConvDesc& c) {
   if (!found) return 0;
   // TMEM buffers: the epilogue of span s releases its accumulators only after its last sub-tile, so with 2 buffers the MMAs of
   // span s+2 wait for it; 4 buffers (when they fit in 512 columns) take that wait off the critical path
-  static const bool no_tb4 = getenv("SVX_NO_TMEM4") != nullptr;   // debug switch
+  static const bool no_tb4 = dbg_env("SVX_NO_TMEM4") != nullptr;   // debug switch
   const int bufs = (!no_tb4 && !use_pair && 4 * fp.mt * fp.n_tile <= 512) ? 4 : 2;
   fp.tmem_bufs = bufs; fp.tmem_bufs_log2 = bufs == 4 ? 2 : 1;
   uint32_t tc = 32;
@@ -947,7 +953,7 @@ int Model::plan_flat(ConvDesc& c) {
     const uint64_t dims[2] = {static_cast<uint64_t>(a_width), P_cap};
     const uint64_t str[1] = {static_cast<uint64_t>(tin.C) * esz};
     const uint32_t box[2] = {static_cast<uint32_t>(c.kbox), static_cast<uint32_t>(fp.a_box_rows)};
-    static const int env_promo = getenv("SVX_L2_PROMO") ? atoi(getenv("SVX_L2_PROMO")) : -1;   // debug switch (see promo_for below)
+    static const int env_promo = dbg_env("SVX_L2_PROMO") ? atoi(dbg_env("SVX_L2_PROMO")) : -1;   // debug switch (see promo_for below)
     const int pitch = tin.C * 2, off = c.in.coff * 2, wb = c.cin * 2;
     const int promo = env_promo >= 0 ? env_promo : (a_width == tin.C) ? 128 : (pitch % 128 == 0 && off % 128 == 0 && wb % 128 == 0) ? 128
                                                  : (pitch % 64 == 0 && off % 64 == 0 && wb % 64 == 0) ? 64 : 0;
@@ -963,7 +969,7 @@ int Model::plan_flat(ConvDesc& c) {
   // multiplies the DRAM traffic (measured 3.7-4.8x on the 24-channel Res2Net splits), so promote only what the
   // slice geometry fills.
   auto promo_for = [&](const ActTensor& t, int coff, int width) -> int {
-    static const int env_promo = getenv("SVX_L2_PROMO") ? atoi(getenv("SVX_L2_PROMO")) : -1;   // debug switch
+    static const int env_promo = dbg_env("SVX_L2_PROMO") ? atoi(dbg_env("SVX_L2_PROMO")) : -1;   // debug switch
     if (env_promo >= 0) return env_promo;
     const int pitch = t.C * 2, off = coff * 2, wb = width * 2;
     if (width == t.C) return 128;                                  // dense tensor: every fetched byte is used
@@ -1129,7 +1135,7 @@ int Model::launch_conv(ConvDesc& c, cudaStream_t st) {
   const bool flat = c.use_flat && !force_simple_ && !force_no_flat_;
   const bool umma = !flat && c.use_umma && !force_simple_;
   if (flat || umma) {
-    static const char* trace_dir = getenv("SVX_TRACE_DIR");   // debug: per-launch event timeline of CTA 0
+    static const char* trace_dir = dbg_env("SVX_TRACE_DIR");   // debug: per-launch event timeline of CTA 0
     static unsigned long long* d_trace = nullptr;
     static int trace_idx = 0;
     if (trace_dir) {
@@ -1144,10 +1150,10 @@ int Model::launch_conv(ConvDesc& c, cudaStream_t st) {
       c.fp.P = static_cast<long long>(out_rows) * stage_Wp_[out_stage];
       c.fp.trace = trace_dir ? d_trace : nullptr;
       c.fp.dbg = flat_dbg_words();
-      { static const char* kn = getenv("SVX_FLAT_KNOCK"); c.fp.knock = kn ? atoi(kn) : 0; }
+      { static const char* kn = dbg_env("SVX_FLAT_KNOCK"); c.fp.knock = kn ? atoi(kn) : 0; }
       // walk the pixels in the opposite direction of the kernel that wrote the input: the consumer then starts on what is
       // still in L2 (+0.6 % measured on the headline step)
-      static const bool no_rev = getenv("SVX_NO_REVERSE") != nullptr;   // debug switch
+      static const bool no_rev = dbg_env("SVX_NO_REVERSE") != nullptr;   // debug switch
       if (tensor_dir_.size() != tensors_.size()) tensor_dir_.assign(tensors_.size(), 0);
       c.fp.reverse = no_rev ? 0 : 1 - tensor_dir_[c.in.id];
       auto mark = [&](const TensorRef& r) { if (r.id >= 0) tensor_dir_[r.id] = c.fp.reverse; };
@@ -1275,7 +1281,7 @@ int Model::run_segments_sl(const float* d_feats, const std::vector<int>& starts,
       set_last_error("allocation failed"); return 1;
     }
     int op_index = 0;
-    const char* dump_dir = getenv("SVX_DUMP_DIR");   // debug: raw dump of every op's destination tensor
+    const char* dump_dir = dump_dir_.empty() ? nullptr : dump_dir_.c_str();   // svx_extractor_set_dump_dir: raw dump of every op's destination tensor
     for (Op& op : ops_) {
       struct Dump {
         Model* m; Op& op; int idx; const char* dir; cudaStream_t st;
@@ -1332,7 +1338,7 @@ int Model::run_segments_sl(const float* d_feats, const std::vector<int>& starts,
         }
         default: break;
       }
-      static const bool sync_each = getenv("SVX_SYNC_EACH") != nullptr;   // debug: localise a failing launch
+      static const bool sync_each = dbg_env("SVX_SYNC_EACH") != nullptr;   // debug: localise a failing launch
       if (sync_each) {
         cudaError_t e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) {

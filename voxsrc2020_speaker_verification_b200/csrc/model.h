@@ -92,6 +92,7 @@ class Model {
   int embed_dim() const { return cfg_.embed_dim; }
   int device() const { return device_; }
   int set_option(const char* key, int value);
+  void set_dump_dir(const char* dir) { dump_dir_ = dir ? dir : ""; }
   // segments: contiguous [frame_off[i], frame_off[i+1]) rows of feats (device fp32 [total_frames, F])
   int run_segments(const float* d_feats, const int32_t* h_frame_off, int n_seg, float* d_out, cudaStream_t st);
   // the same for segments given as (first frame, length) pairs, which need not be contiguous (chunk rule with dropped tails)
@@ -122,6 +123,7 @@ class Model {
   int device_ = 0;
   int is_bf16_ = 0;
   int force_simple_ = 0;
+  std::string dump_dir_;              // non-empty: every op's destination tensor is written there after it ran (parity tests)
   bool finalized_ = false;
   std::vector<VarSpec> vars_;
   std::map<std::string, HostTensor> host_;

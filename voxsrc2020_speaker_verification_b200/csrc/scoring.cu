@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(kTopkThreads, 3) topk_stats_reg_kernel(const f
 cudaError_t launch_topk_stats(const float* scores, int ld, long long n_rows, int c, int topk, float* mean, float* stdv,
                               float* vals_out, int vals_ld, cudaStream_t st) {
   if (n_rows <= 0) return cudaSuccess;
-  static const bool no_reg = getenv("SVX_TOPK_GENERIC") != nullptr;   // debug switch
+  static const bool no_reg = dbg_env("SVX_TOPK_GENERIC") != nullptr;   // debug switch
   if (c <= 24 * kTopkThreads && !no_reg) {
     const unsigned g = static_cast<unsigned>(n_rows);
     if (c <= 4 * kTopkThreads) topk_stats_reg_kernel<4><<<g, kTopkThreads, 0, st>>>(scores, ld, c, topk, mean, stdv, vals_out, vals_ld);

@@ -49,11 +49,27 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded spin: a wrong descriptor must not hang the GPU box; after ~2^28 polls trap so the launch fails loudly.
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded wait: a wrong descriptor must not hang the GPU box.  The bound is WALL TIME (%globaltimer), not a spin count —
+// time-slicing with another process, a debugger or a profiler replay can stretch any number of polls — and it is generous:
+// no kernel of this library runs longer than a few milliseconds, the watchdog fires after kWatchdogNs of waiting on ONE barrier.
+#ifndef SVX_WATCHDOG_MS
+#define SVX_WATCHDOG_MS 20000
+#endif
+constexpr unsigned long long kWatchdogNs = static_cast<unsigned long long>(SVX_WATCHDOG_MS) * 1000 * 1000;
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
+  unsigned long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 28)) { __trap(); }
+    if ((++spins & 0x3fffu) == 0) {
+      const unsigned long long now = global_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > kWatchdogNs) __trap();
+    }
   }
 }
 

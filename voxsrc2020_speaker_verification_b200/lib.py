@@ -32,6 +32,7 @@ class ModelConfigStruct(ctypes.Structure):
 # every symbol include/svx.h declares: name → (restype, argtypes)
 SYMBOLS = {
     "svx_version": (c_int, []),
+    "svx_build_flags": (c_int, []),
     "svx_last_error": (c_char_p, []),
     "svx_extractor_create": (c_int, [POINTER(ModelConfigStruct), c_int, c_int, POINTER(c_void_p)]),
     "svx_extractor_destroy": (c_int, [c_void_p]),
@@ -43,6 +44,7 @@ SYMBOLS = {
     "svx_extractor_set_option": (c_int, [c_void_p, c_char_p, c_int]),
     "svx_extractor_run_segments": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "svx_extractor_extract": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    "svx_extractor_set_dump_dir": (c_int, [c_void_p, c_char_p]),
     "svx_extractor_last_launches": (c_longlong, [c_void_p]),
     "svx_extractor_conv_time": (c_int, [c_void_p, POINTER(ctypes.c_double), POINTER(ctypes.c_double)]),
     "svx_cmvn_sliding": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
