@@ -30,7 +30,8 @@ def test_every_declared_symbol_is_exported_and_bound(built):
     for n in names:
         assert hasattr(dll, n), "libsvx.so does not export %s" % n
     assert sorted(built.SYMBOLS) == names, "lib.py binds a different set of symbols than svx.h declares"
-    assert built.load().svx_version() == 100
+    assert built.load().svx_version() == 200
+    assert built.load().svx_build_flags() == 0        # production build: no environment switches, no CTA-pair instantiation
 
 
 def test_config_struct_matches_header(built):
