@@ -58,8 +58,8 @@ class Scorer:
         np.cumsum(np.bincount(g[used], minlength=n_groups), out=offs[1:])
         dv = unit_rows.device
         out = torch.empty((n_groups, unit_rows.shape[1]), dtype=torch.float32, device=dv)
-        lib.check(self._lib.svx_group_means(_ptr(unit_rows.contiguous()), unit_rows.shape[1], _ptr(torch.from_numpy(order).to(dv)),
-                                            _ptr(torch.from_numpy(offs).to(dv)), _ptr(out), n_groups, self._stream()))
+        rows_d, order_d, offs_d = unit_rows.contiguous(), torch.from_numpy(order).to(dv), torch.from_numpy(offs).to(dv)   # held until the launch
+        lib.check(self._lib.svx_group_means(_ptr(rows_d), rows_d.shape[1], _ptr(order_d), _ptr(offs_d), _ptr(out), n_groups, self._stream()))
         self.launches += 1
         return out
 
@@ -97,11 +97,11 @@ class Scorer:
     def trial_scores(self, emb: torch.Tensor, idx1: torch.Tensor, idx2: torch.Tensor, mean: Optional[torch.Tensor] = None,
                      std: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
         """get_cosine_score + get_asnorm1_score (snorm.py:113-131) for index-pair trials."""
-        emb = emb.contiguous()
+        emb, idx1, idx2 = emb.contiguous(), idx1.contiguous(), idx2.contiguous()      # named, so that they live until the launch
         t = idx1.shape[0]
         cos = torch.empty(t, dtype=torch.float32, device=emb.device)
         sn = torch.empty(t, dtype=torch.float32, device=emb.device) if mean is not None else None
-        lib.check(self._lib.svx_trial_scores(_ptr(emb), emb.shape[1], _ptr(idx1.contiguous()), _ptr(idx2.contiguous()), t,
+        lib.check(self._lib.svx_trial_scores(_ptr(emb), emb.shape[1], _ptr(idx1), _ptr(idx2), t,
                                              _ptr(mean), _ptr(std), _ptr(cos), _ptr(sn), self._stream()))
         self.launches += 1
         return cos, sn
