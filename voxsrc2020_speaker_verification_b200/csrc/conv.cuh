@@ -180,8 +180,10 @@ struct FlatConvParams {
   int b_resident;
   uint32_t idesc, sbo, layout_type, tmem_cols;
   int tmem_bufs, tmem_bufs_log2;   // accumulator buffers in TMEM (2 or 4): with 4 an epilogue warpgroup may lag a whole span behind the MMAs
-  int pair;                    // 1: CTA pairs (cta_group::2, M = 256): even/odd CTAs of a cluster take consecutive spans, each holds half of B
-  int b_rows;                  // weight rows this CTA loads per item: n_tile, or n_tile/2 in pair mode
+  int cn, cm;                  // multicast cluster cm x cn (1 x 1: none): cn CTAs share a span (A slices multicast), cm CTAs share an n-tile (weight slices multicast)
+  int a_slice_rows;            // rows of every A box this CTA loads (a_box_rows / cn)
+  int b_slice_rows;            // rows of every streamed weight item this CTA loads (n_tile / cm)
+  int b_rows;                  // weight rows per item (= n_tile)
   // epilogue
   const float* scale; const float* shift;
   int n_valid;                 // real output channels
@@ -216,6 +218,7 @@ struct FlatConvParams {
 };
 struct FlatMaps { CUtensorMap a, b, aux, o2, o[8]; };   // o2: second output of aux mode 2
 cudaError_t conv_flat_init();
+int conv_flat_max_clusters(int cluster_size);   // resident clusters of that many CTAs (one CTA per SM)
 size_t conv_flat_smem_bytes(const FlatConvParams& p);
 cudaError_t launch_conv_flat(const FlatConvParams& p, const FlatMaps& maps, int is_bf16, cudaStream_t stream);
 

@@ -186,31 +186,20 @@ __device__ __forceinline__ void epi8_direct(const uint32_t* r, uint32_t sc, uint
 // tcgen05.mma with the shared-memory descriptors given as {low word, common high word}: the high word (SBO, version, swizzle
 // mode) is the same for every operand of a launch, the low word is (address >> 4) | LBO, so all per-MMA descriptor arithmetic is
 // one 32-bit add.
-template <bool pair>
 __device__ __forceinline__ void umma_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
-  if constexpr (pair) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-        "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}\n"
-        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(hi)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-        "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}\n"
-        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(hi)
-        : "memory");
-  }
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(hi)
+      : "memory");
 }
 
 // All MMAs of one filter tap: MT sub-tiles x KS K-steps, fully unrolled so that every descriptor is the tap's base
 // (one value) plus a compile-time constant.  A generic loop costs ~150 cycles of issue per MMA (descriptor arithmetic in
 // vector registers + 5 R2UR each, tools/microbench/mma_rate.cu) against 16-64 cycles of tensor-pipe time.
-template <int MT, int KS, bool pair>
+template <int MT, int KS>
 __device__ __forceinline__ void issue_tap(uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t d_tmem, uint32_t n_tile, uint32_t idesc, uint32_t first,
                                           int knock = 0) {
   constexpr uint32_t kSub16 = 256u * KS;      // (128 rows x 32*KS bytes) >> 4
@@ -222,7 +211,7 @@ __device__ __forceinline__ void issue_tap(uint32_t a_lo, uint32_t b_lo, uint32_t
 #ifdef SVX_KNOCK
         if (!(knock & 32))
 #endif
-        umma_lo<pair>(d_tmem + j * n_tile, a_lo + (j * kSub16 + k * 2), b_lo + k * 2, hi, idesc, k == 0 ? first : 1u);
+        umma_lo(d_tmem + j * n_tile, a_lo + (j * kSub16 + k * 2), b_lo + k * 2, hi, idesc, k == 0 ? first : 1u);
     }
   }
 }
@@ -232,7 +221,6 @@ struct Smem {
   uint64_t slot_full[kRing], slot_empty[kRing], slot_ready[kRing];
   uint64_t tmem_full[4], tmem_empty[4];   // accumulator buffers: 2, or 4 when 4 * mt * n_tile columns fit (p.tmem_bufs)
   uint64_t bres_bar;
-  uint64_t pa_full[kRing], pb_full[kRing], pbres_bar;   // pair mode, leader CTA: the peer's A stage / weight item / resident weights landed
   uint32_t tmem_slot;
   uint32_t tapoff16[12];        // ((halo + tap_shift[tap]) * row_bytes) >> 4: descriptor displacement of each filter tap
   volatile uint32_t prog[16];   // debug: progress of each role (warp), dumped by wait_dbg on a timeout
@@ -244,21 +232,13 @@ static_assert(sizeof(Smem) <= 1024, "barrier block");
 // themselves sit under the elected-lane branch.  Computing them inside an `if (lane == 0)` region made ptxas wrap every
 // UTCHMMA in an ELECT / 5x R2UR.BROADCAST waterfall: ~200 ns per MMA whatever its shape.
 //
-// Pair mode: the leader (cluster rank 0) issues M = 256 MMAs that read both CTAs' shared memory and write both CTAs'
-// TMEM; its commits multicast to both CTAs' barriers.  The peer's warp 1 is a relay: it walks the same ring positions and
-// forwards "my A stage / weight item landed" to the leader's pa_full / pb_full barriers.
-template <int MT, int KS, bool PAIR>
+// Multicast clusters (MC): an A stage is filled by all cn CTAs that share the span and a streamed weight item by all cm CTAs
+// that share the n-tile, so a stage may be refilled only when every one of them has consumed it: the "empty" commits are
+// multicast to the same barrier in all CTAs of mask_a / mask_b (their barriers count cn / cm arrivals).
+template <int MT, int KS, bool MC>
 __device__ __forceinline__ void mma_role(const FlatConvParams& p, Smem& S, uint32_t tb, uint32_t a_base, uint32_t b_base, int my_group, int n_units,
-                                         int groups, uint32_t rank, int lane, Tracer& tr) {
-  constexpr bool pair = PAIR;
-  const bool relay = pair && rank == 1;
-  if (p.b_resident) {
-    wait_dbg(&S.bres_bar, 0, p.dbg, 0x10, 0, 0, S.prog);
-    if constexpr (pair) {
-      if (relay) { if (elect_one()) mbar_arrive_remote(&S.pbres_bar, 0); }
-      else wait_dbg(&S.pbres_bar, 0, p.dbg, 0x14, 0, 0, S.prog);
-    }
-  }
+                                         int groups, uint16_t mask_a, uint16_t mask_b, int lane, Tracer& tr) {
+  if (p.b_resident) wait_dbg(&S.bres_bar, 0, p.dbg, 0x10, 0, 0, S.prog);
   const uint64_t desc_base = make_kmajor_desc(0, p.sbo, p.layout_type);
   const uint32_t hi = static_cast<uint32_t>(desc_base >> 32);
   const uint32_t lo0 = static_cast<uint32_t>(desc_base);           // LBO field; the address field is added below (smem < 256 KB: no carry out of it)
@@ -274,7 +254,7 @@ __device__ __forceinline__ void mma_role(const FlatConvParams& p, Smem& S, uint3
     const int buf = ls & (p.tmem_bufs - 1);       // span ls -> buffer ls mod bufs; warpgroup ls & 1 reads it (buffers wg, wg + 2)
     tr.ev(1);
     if (lane == 0) S.prog[1] = ls;
-    if (!relay) wait_dbg(&S.tmem_empty[buf], ((ls >> p.tmem_bufs_log2) & 1) ^ 1, p.dbg, 0x11, buf, ls, S.prog);
+    wait_dbg(&S.tmem_empty[buf], ((ls >> p.tmem_bufs_log2) & 1) ^ 1, p.dbg, 0x11, buf, ls, S.prog);
     tr.ev(2);
     const uint32_t d_tmem = tb + static_cast<uint32_t>(buf * MT) * nt;
     uint32_t first = 0u;
@@ -283,23 +263,17 @@ __device__ __forceinline__ void mma_role(const FlatConvParams& p, Smem& S, uint3
       const uint32_t a_par = (ia / p.a_stages) & 1;
       uint32_t toff = S.tapoff16[0];                       // fetched before the wait: off the critical path
       wait_dbg(&S.a_full[sa], a_par, p.dbg, 0x12, sa, ia, S.prog);
-      if constexpr (pair) {
-        if (relay) { if (elect_one()) mbar_arrive_remote(&S.pa_full[sa], 0); }
-        else wait_dbg(&S.pa_full[sa], a_par, p.dbg, 0x15, sa, ia, S.prog);
-      }
       if (kc == 0) tr.ev(3);
       tc_fence_after();
       const uint32_t a_lo = a_lo_base + static_cast<uint32_t>(sa) * a_stage16;
       if (b_res) {
-        if (!relay) {
-          uint32_t b_lo = b_lo_base + static_cast<uint32_t>(kc * taps) * b_item16;
+        uint32_t b_lo = b_lo_base + static_cast<uint32_t>(kc * taps) * b_item16;
 #pragma unroll 1
-          for (int tap = 0; tap < taps; ++tap, b_lo += b_item16) {
-            const uint32_t toff_next = S.tapoff16[tap + 1];   // next tap's displacement loads while this tap issues
-            issue_tap<MT, KS, PAIR>(a_lo + toff, b_lo, hi, d_tmem, nt, idesc, first, p.knock);
-            first = 1u;
-            toff = toff_next;
-          }
+        for (int tap = 0; tap < taps; ++tap, b_lo += b_item16) {
+          const uint32_t toff_next = S.tapoff16[tap + 1];   // next tap's displacement loads while this tap issues
+          issue_tap<MT, KS>(a_lo + toff, b_lo, hi, d_tmem, nt, idesc, first, p.knock);
+          first = 1u;
+          toff = toff_next;
         }
       } else {
 #pragma unroll 1
@@ -308,27 +282,16 @@ __device__ __forceinline__ void mma_role(const FlatConvParams& p, Smem& S, uint3
           const uint32_t b_par = (ib / p.b_stages) & 1;
           const uint32_t toff_next = S.tapoff16[tap + 1];
           wait_dbg(&S.b_full[sb], b_par, p.dbg, 0x13, sb, ib, S.prog);
-          if constexpr (pair) {
-            if (relay) { if (elect_one()) mbar_arrive_remote(&S.pb_full[sb], 0); }
-            else wait_dbg(&S.pb_full[sb], b_par, p.dbg, 0x16, sb, ib, S.prog);
-          }
-          if (!relay) {
-            tc_fence_after();
-            issue_tap<MT, KS, PAIR>(a_lo + toff, b_lo_base + static_cast<uint32_t>(sb) * b_item16, hi, d_tmem, nt, idesc, first, p.knock);
-            first = 1u;
-            if (elect_one()) { if constexpr (pair) umma_commit_2cta(&S.b_empty[sb]); else umma_commit(&S.b_empty[sb]); }
-          }
+          tc_fence_after();
+          issue_tap<MT, KS>(a_lo + toff, b_lo_base + static_cast<uint32_t>(sb) * b_item16, hi, d_tmem, nt, idesc, first, p.knock);
+          first = 1u;
+          if (elect_one()) { if constexpr (MC) umma_commit_mc(&S.b_empty[sb], mask_b); else umma_commit(&S.b_empty[sb]); }
           toff = toff_next;
         }
       }
-      if (!relay && elect_one()) {
-        if constexpr (pair) {
-          umma_commit_2cta(&S.a_empty[sa]);
-          if (kc == nkc - 1) umma_commit_2cta(&S.tmem_full[buf]);
-        } else {
-          umma_commit(&S.a_empty[sa]);
-          if (kc == nkc - 1) umma_commit(&S.tmem_full[buf]);
-        }
+      if (elect_one()) {
+        if constexpr (MC) umma_commit_mc(&S.a_empty[sa], mask_a); else umma_commit(&S.a_empty[sa]);
+        if (kc == nkc - 1) umma_commit(&S.tmem_full[buf]);
       }
     }
     tr.ev(4);
@@ -337,9 +300,13 @@ __device__ __forceinline__ void mma_role(const FlatConvParams& p, Smem& S, uint3
 
 }  // namespace
 
-// PAIR is a template parameter because a kernel that contains cta_group::2 instructions can only be launched as a cluster
-// (a plain launch of such a binary fails with "cluster misconfiguration").
-template <typename T, int AUX, bool PRE, bool POST, bool PAIR>
+// MC (multicast clusters) is a template parameter so that the plain instantiation carries no cluster instruction at all and
+// launches without a cluster attribute.  In an MC launch a cluster is cm x cn CTAs (rank = im * cn + in): the cn CTAs of a row
+// work on the SAME span with different n-tiles, each loads 1/cn of every A stage and multicasts it to the row; the cm CTAs of a
+// column work on consecutive spans with the SAME n-tile, each loads 1/cm of every streamed weight item and multicasts it to the
+// column.  L2 reads per CTA drop to A/cn + B/cm — the L2 -> SM path (~6.5 TB/s for the whole chip, the same as HBM) is what
+// bounded the deep stages, where A was re-read once per n-tile and the weights once per span.
+template <typename T, int AUX, bool PRE, bool POST, bool MC>
 __global__ void __launch_bounds__(kFlatThreads, 1)
 conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant__ FlatMaps maps) {
   extern __shared__ uint8_t smem_raw[];
@@ -356,21 +323,28 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int span_px = p.mt * 128;
-  const int n_parts = PAIR ? p.n_parts : 1;   // column parts exist only in pair mode (folds away otherwise)
+  constexpr int n_parts = 1;
   const int n_spans = static_cast<int>((p.P + span_px - 1) / span_px);
-  // pair mode: CTAs (2i, 2i+1) of a cluster form one unit that takes two consecutive spans per step (rank r takes span 2u + r)
-  constexpr bool pair = PAIR;
+  // scheduling unit = one cluster (one CTA without MC): it takes cm consecutive spans per step (CTA row im takes span cm*u + im)
+  // and cn consecutive n-tiles (CTA column in); clusters are dealt over n_tiles/cn n-tile columns x `groups` span groups
+  const int cn = MC ? p.cn : 1, cm = MC ? p.cm : 1;
   uint32_t rank = 0u;
-  if constexpr (pair) rank = cluster_ctarank();
-  const int sstride = pair ? 2 : 1;
-  const int unit_id = pair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-  const int n_cta_units = pair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  if constexpr (MC) rank = cluster_ctarank();
+  const int in = static_cast<int>(rank) % cn, im = static_cast<int>(rank) / cn;
+  const int cluster_id = static_cast<int>(blockIdx.x) / (cn * cm);
+  const int n_clusters = static_cast<int>(gridDim.x) / (cn * cm);
+  const int n_cols = p.n_tiles / cn;
+  const int sstride = cm;
   const int n_units = (n_spans + sstride - 1) / sstride;
-  const int n_spans_all = n_units * sstride;          // includes the phantom span of an odd count (fully masked, loads zero-filled)
-  const int groups = n_cta_units / p.n_tiles;
-  const int my_group = unit_id / p.n_tiles;
-  const int n_blk = unit_id % p.n_tiles;
+  const int n_spans_all = n_units * sstride;          // includes phantom spans past the end (fully masked, loads zero-filled)
+  const int groups = n_clusters / n_cols;
+  const int my_group = cluster_id / n_cols;
+  const int n_blk = (cluster_id % n_cols) * cn + in;
   const int n0 = n_blk * p.n_tile;
+  // CTAs that receive the A slices this CTA loads (its row) and the weight slices it loads (its column)
+  const uint16_t mask_a = static_cast<uint16_t>(((1u << cn) - 1u) << (im * cn));
+  uint16_t mask_b = 0;
+  for (int j = 0; j < cm; ++j) mask_b |= static_cast<uint16_t>(1u << (j * cn + in));
   const uint32_t row_bytes = static_cast<uint32_t>(p.kbox) * 2u;
   const uint32_t box_bytes = 128u * static_cast<uint32_t>(p.box_ch) * 2u;
 
@@ -380,14 +354,12 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
     prefetch_tmap(&maps.o[0]);
     if (AUX >= 2) prefetch_tmap(&maps.o2);
     for (int i = 0; i < kRing; ++i) {
-      mbar_init(&S.a_full[i], 1); mbar_init(&S.a_empty[i], 1);
-      mbar_init(&S.b_full[i], 1); mbar_init(&S.b_empty[i], 1);
+      mbar_init(&S.a_full[i], 1); mbar_init(&S.a_empty[i], cn);     // a stage is free when every CTA of the row has consumed it
+      mbar_init(&S.b_full[i], 1); mbar_init(&S.b_empty[i], cm);     // a weight item when every CTA of the column has
       mbar_init(&S.slot_full[i], 1); mbar_init(&S.slot_empty[i], 1); mbar_init(&S.slot_ready[i], 128);
     }
-    for (int b = 0; b < 4; ++b) { mbar_init(&S.tmem_full[b], 1); mbar_init(&S.tmem_empty[b], pair ? 8 : 4); }   // pair: both CTAs' epilogue warps
+    for (int b = 0; b < 4; ++b) { mbar_init(&S.tmem_full[b], 1); mbar_init(&S.tmem_empty[b], 4); }
     mbar_init(&S.bres_bar, 1);
-    for (int i = 0; i < kRing; ++i) { mbar_init(&S.pa_full[i], 1); mbar_init(&S.pb_full[i], 1); }
-    mbar_init(&S.pbres_bar, 1);
     for (int t = 0; t < 12; ++t) S.tapoff16[t] = t < p.taps ? (static_cast<uint32_t>(p.halo + p.tap_shift[t]) * row_bytes) >> 4 : 0u;
     fence_barrier_init();
     if (p.b_resident) {     // weights are static: fetch them before the dependency wait
@@ -395,13 +367,11 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
       mbar_expect_tx(&S.bres_bar, bb * total_items);
       for (int kc = 0; kc < p.nkc; ++kc)
         for (int tap = 0; tap < p.taps; ++tap)
-          tma_load_2d(b_smem + static_cast<size_t>(kc * p.taps + tap) * p.b_item_bytes, &maps.b, &S.bres_bar, tap * p.kpad + kc * p.kbox,
-                      n0 + static_cast<int>(rank) * p.b_rows);
+          tma_load_2d(b_smem + static_cast<size_t>(kc * p.taps + tap) * p.b_item_bytes, &maps.b, &S.bres_bar, tap * p.kpad + kc * p.kbox, n0);
     }
   }
   if (warp == 1) {
-    if constexpr (pair) { tmem_alloc_2cta(&S.tmem_slot, p.tmem_cols); tmem_relinquish_2cta(); }
-    else { tmem_alloc(&S.tmem_slot, p.tmem_cols); tmem_relinquish(); }
+    tmem_alloc(&S.tmem_slot, p.tmem_cols); tmem_relinquish();
   }
   for (int i = threadIdx.x; i < p.n_tile; i += kFlatThreads) {
     const int c = n0 + i;
@@ -410,7 +380,7 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if constexpr (pair) cluster_sync_all();        // the peer's barriers are initialised before anything arrives on them remotely
+  if constexpr (MC) cluster_sync_all();          // the peers' barriers are initialised before anything arrives on them remotely
   tc_fence_after();
   const uint32_t tmem_base = S.tmem_slot;
   // Programmatic dependent launch: the next conv's CTAs may be scheduled as soon as SMs free up and run their own prologue
@@ -424,10 +394,15 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
     if (lane == 0) {
       const uint32_t b_box_bytes = static_cast<uint32_t>(p.b_rows) * row_bytes;
       const uint32_t a_tx = static_cast<uint32_t>(p.a_boxes) * p.a_box_rows * row_bytes;
+      // MC: this CTA loads rows [in * a_slice_rows, +a_slice_rows) of every A box and rows [im * b_slice_rows, +b_slice_rows) of
+      // every weight item, into the same offsets of every CTA of its row / column (the full barrier of each receiver, armed by
+      // its own producer for the whole stage, collects the bytes of all slices)
+      const uint32_t a_slice_off = static_cast<uint32_t>(in) * p.a_slice_rows * row_bytes;
+      const uint32_t b_slice_off = static_cast<uint32_t>(im) * p.b_slice_rows * row_bytes;
       Tracer tr; tr.init(p.trace, 0);
       uint32_t ia = 0, ib = 0;
       for (int unit = my_group; unit < n_units; unit += groups) {
-        const int span = unit * sstride + static_cast<int>(rank);
+        const int span = unit * sstride + im;
         const int p0 = (p.reverse ? n_spans_all - 1 - span : span) * span_px;
         tr.ev(1);
         S.prog[0] = ia;
@@ -436,16 +411,24 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
           wait_dbg(&S.a_empty[sa], ((ia / p.a_stages) & 1) ^ 1, p.dbg, 0x01, sa, ia, S.prog);
           mbar_expect_tx(&S.a_full[sa], a_tx);
           uint8_t* dst = a_smem + static_cast<size_t>(sa) * p.a_stage_bytes;
-          for (int b = 0; b < p.a_boxes; ++b)
-            tma_load_2d(dst + static_cast<size_t>(b) * p.a_box_rows * row_bytes, &maps.a, &S.a_full[sa], kc * p.kbox + n_blk * p.a_c_step,
-                        p0 - p.halo + b * p.a_box_rows);
+          for (int b = 0; b < p.a_boxes; ++b) {
+            if constexpr (MC)
+              tma_load_2d_mc(dst + static_cast<size_t>(b) * p.a_box_rows * row_bytes + a_slice_off, &maps.a, &S.a_full[sa],
+                             kc * p.kbox + n_blk * p.a_c_step, p0 - p.halo + b * p.a_box_rows + in * p.a_slice_rows, mask_a);
+            else
+              tma_load_2d(dst + static_cast<size_t>(b) * p.a_box_rows * row_bytes, &maps.a, &S.a_full[sa], kc * p.kbox + n_blk * p.a_c_step,
+                          p0 - p.halo + b * p.a_box_rows);
+          }
           if (!p.b_resident) {
             for (int tap = 0; tap < p.taps; ++tap, ++ib) {
               const int sb = ib % p.b_stages;
               wait_dbg(&S.b_empty[sb], ((ib / p.b_stages) & 1) ^ 1, p.dbg, 0x02, sb, ib, S.prog);
               mbar_expect_tx(&S.b_full[sb], b_box_bytes);
-              tma_load_2d(b_smem + static_cast<size_t>(sb) * p.b_item_bytes, &maps.b, &S.b_full[sb], tap * p.kpad + kc * p.kbox,
-                          n0 + static_cast<int>(rank) * p.b_rows);
+              if constexpr (MC)
+                tma_load_2d_mc(b_smem + static_cast<size_t>(sb) * p.b_item_bytes + b_slice_off, &maps.b, &S.b_full[sb], tap * p.kpad + kc * p.kbox,
+                               n0 + im * p.b_slice_rows, mask_b);
+              else
+                tma_load_2d(b_smem + static_cast<size_t>(sb) * p.b_item_bytes, &maps.b, &S.b_full[sb], tap * p.kpad + kc * p.kbox, n0);
             }
           }
         }
@@ -461,15 +444,15 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
     // shifts and the 64-bit descriptor arithmetic formed one serial dependent chain of ~500 cycles per tap in this single warp
     // (knock-out measurement, profiles/r01_knockout_issue_loop.txt) — more than the MMAs of a narrow tap take to execute.
     switch ((p.mt << 4) | ksteps) {
-      case 0x11: mma_role<1, 1, PAIR>(p, S, tb, smem_u32(a_smem), smem_u32(b_smem), my_group, n_units, groups, rank, lane, tr); break;
-      case 0x12: mma_role<1, 2, PAIR>(p, S, tb, smem_u32(a_smem), smem_u32(b_smem), my_group, n_units, groups, rank, lane, tr); break;
-      case 0x14: mma_role<1, 4, PAIR>(p, S, tb, smem_u32(a_smem), smem_u32(b_smem), my_group, n_units, groups, rank, lane, tr); break;
-      case 0x21: mma_role<2, 1, PAIR>(p, S, tb, smem_u32(a_smem), smem_u32(b_smem), my_group, n_units, groups, rank, lane, tr); break;
-      case 0x22: mma_role<2, 2, PAIR>(p, S, tb, smem_u32(a_smem), smem_u32(b_smem), my_group, n_units, groups, rank, lane, tr); break;
-      case 0x24: mma_role<2, 4, PAIR>(p, S, tb, smem_u32(a_smem), smem_u32(b_smem), my_group, n_units, groups, rank, lane, tr); break;
-      case 0x41: mma_role<4, 1, PAIR>(p, S, tb, smem_u32(a_smem), smem_u32(b_smem), my_group, n_units, groups, rank, lane, tr); break;
-      case 0x42: mma_role<4, 2, PAIR>(p, S, tb, smem_u32(a_smem), smem_u32(b_smem), my_group, n_units, groups, rank, lane, tr); break;
-      default:   mma_role<4, 4, PAIR>(p, S, tb, smem_u32(a_smem), smem_u32(b_smem), my_group, n_units, groups, rank, lane, tr); break;
+      case 0x11: mma_role<1, 1, MC>(p, S, tb, smem_u32(a_smem), smem_u32(b_smem), my_group, n_units, groups, mask_a, mask_b, lane, tr); break;
+      case 0x12: mma_role<1, 2, MC>(p, S, tb, smem_u32(a_smem), smem_u32(b_smem), my_group, n_units, groups, mask_a, mask_b, lane, tr); break;
+      case 0x14: mma_role<1, 4, MC>(p, S, tb, smem_u32(a_smem), smem_u32(b_smem), my_group, n_units, groups, mask_a, mask_b, lane, tr); break;
+      case 0x21: mma_role<2, 1, MC>(p, S, tb, smem_u32(a_smem), smem_u32(b_smem), my_group, n_units, groups, mask_a, mask_b, lane, tr); break;
+      case 0x22: mma_role<2, 2, MC>(p, S, tb, smem_u32(a_smem), smem_u32(b_smem), my_group, n_units, groups, mask_a, mask_b, lane, tr); break;
+      case 0x24: mma_role<2, 4, MC>(p, S, tb, smem_u32(a_smem), smem_u32(b_smem), my_group, n_units, groups, mask_a, mask_b, lane, tr); break;
+      case 0x41: mma_role<4, 1, MC>(p, S, tb, smem_u32(a_smem), smem_u32(b_smem), my_group, n_units, groups, mask_a, mask_b, lane, tr); break;
+      case 0x42: mma_role<4, 2, MC>(p, S, tb, smem_u32(a_smem), smem_u32(b_smem), my_group, n_units, groups, mask_a, mask_b, lane, tr); break;
+      default:   mma_role<4, 4, MC>(p, S, tb, smem_u32(a_smem), smem_u32(b_smem), my_group, n_units, groups, mask_a, mask_b, lane, tr); break;
     }
   } else if (warp == 2) {
     // ------------------------------------------------------------------ aux producer (residual / add2 tiles)
@@ -479,7 +462,7 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
       Tracer tr; tr.init(p.trace, 2);
       int ls = 0;
       for (int unit = my_group; unit < n_units; unit += groups, ++ls) {
-        const int span = unit * sstride + static_cast<int>(rank);
+        const int span = unit * sstride + im;
         const int p0 = (p.reverse ? n_spans_all - 1 - span : span) * span_px;
         for (int jh = 0; jh < p.mt * n_parts; ++jh) {
           const int j = jh / n_parts, cb = n0 + (jh % n_parts) * p.part_cols;   // sub-tile, first channel of this column part
@@ -516,7 +499,7 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
       int prev_slot = -1;
       int ls = 0;
       for (int unit = my_group; unit < n_units; unit += groups, ++ls) {
-        const int span = unit * sstride + static_cast<int>(rank);
+        const int span = unit * sstride + im;
         const int p0 = (p.reverse ? n_spans_all - 1 - span : span) * span_px;
         for (int jh = 0; jh < p.mt * n_parts; ++jh) {
           const int j = jh / n_parts, cb = n0 + (jh % n_parts) * p.part_cols;
@@ -588,7 +571,7 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
         }
       };
       for (int unit = my_group; unit < n_units; unit += groups, ++ls) {
-        const int span = unit * sstride + static_cast<int>(rank);
+        const int span = unit * sstride + im;
         if ((ls & 1) != wg) continue;
         const long long p0 = static_cast<long long>(p.reverse ? n_spans_all - 1 - span : span) * span_px;
         uint32_t vm[4];
@@ -666,7 +649,7 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
       }
     } else
     for (int unit = my_group; unit < n_units; unit += groups, ++ls) {
-        const int span = unit * sstride + static_cast<int>(rank);
+        const int span = unit * sstride + im;
       if ((ls & 1) != wg) continue;
       const long long p0 = static_cast<long long>(p.reverse ? n_spans_all - 1 - span : span) * span_px;
       uint32_t vm[4];
@@ -729,11 +712,7 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
         if (jh == p.mt * n_parts - 1) {   // all accumulators of this span are in registers / smem: hand TMEM back
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) {
-            bool done = false;
-            if constexpr (pair) { if (rank == 1) { mbar_arrive_remote(&S.tmem_empty[tb_i], 0); done = true; } }
-            if (!done) mbar_arrive(&S.tmem_empty[tb_i]);
-          }
+          if (lane == 0) mbar_arrive(&S.tmem_empty[tb_i]);
         }
         if (lane == 0) S.prog[warp] = 0x30000u | q;
         fence_proxy_async();              // generic-proxy writes of this thread → visible to the TMA store
@@ -744,8 +723,8 @@ conv_flat_kernel(const __grid_constant__ FlatConvParams p, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if constexpr (pair) cluster_sync_all();        // the leader's MMAs read the peer's shared memory: nobody leaves before everybody is done
-  if (warp == 1) { if constexpr (pair) tmem_dealloc_2cta(tmem_base, p.tmem_cols); else tmem_dealloc(tmem_base, p.tmem_cols); }
+  if constexpr (MC) cluster_sync_all();          // peers multicast into this CTA's shared memory and arrive on its barriers: nobody leaves early
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
 size_t conv_flat_smem_bytes(const FlatConvParams& p) {
@@ -755,16 +734,11 @@ size_t conv_flat_smem_bytes(const FlatConvParams& p) {
 
 static int g_flat_sms = 0;
 
-// The cta_group::2 instantiation (PAIR) is slower than single CTAs on every layer class as built, so the
-// production library does not carry it: -DSVX_ENABLE_PAIR compiles it back in for experiments.
 template <typename T, int AUX, bool PRE, bool POST>
 static cudaError_t set_attr() {
   cudaError_t e = cudaFuncSetAttribute(conv_flat_kernel<T, AUX, PRE, POST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-#ifdef SVX_ENABLE_PAIR
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(conv_flat_kernel<T, AUX, PRE, POST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-#endif
-  return e;
+  return cudaFuncSetAttribute(conv_flat_kernel<T, AUX, PRE, POST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 
 template <typename T>
@@ -791,17 +765,43 @@ cudaError_t conv_flat_init() {
   return cudaDeviceGetAttribute(&g_flat_sms, cudaDevAttrMultiProcessorCount, dev);
 }
 
+// How many clusters of `cs` CTAs (one CTA per SM: every plan uses most of the shared memory) can be resident at once: clusters
+// never straddle a GPC, so this is less than SMs / cs when the GPCs' SM counts are not multiples of cs.  Queried once per size.
+template <typename T>
+static int max_clusters(int cs, size_t smem) {
+  static int cache[17] = {0};
+  if (cs < 1 || cs > 16) return 0;
+  if (cache[cs] > 0) return cache[cs];
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(static_cast<unsigned>(cs * 64), 1, 1); cfg.blockDim = dim3(kFlatThreads, 1, 1); cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(cs); attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, conv_flat_kernel<T, 0, false, true, true>, &cfg) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    n = (g_flat_sms > 0 ? g_flat_sms : 148) / cs * 3 / 4;      // conservative guess
+  }
+  cache[cs] = n;
+  return n;
+}
+
+int conv_flat_max_clusters(int cluster_size) { return max_clusters<__half>(cluster_size, 200 * 1024); }
+
 template <typename T>
 static cudaError_t launch_typed(const FlatConvParams& p, const FlatMaps& maps, dim3 grid, size_t smem, cudaStream_t st) {
   static const bool no_pdl = dbg_env("SVX_NO_PDL") != nullptr;   // debug switch
+  const bool mc = p.cn * p.cm > 1;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = grid; cfg.blockDim = dim3(kFlatThreads, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr[2];
   int na = 0;
-  if (p.pair) {
+  if (mc) {
     attr[na].id = cudaLaunchAttributeClusterDimension;
-    attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    attr[na].val.clusterDim.x = static_cast<unsigned>(p.cn * p.cm); attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
     ++na;
   }
   if (!no_pdl) {
@@ -813,16 +813,11 @@ static cudaError_t launch_typed(const FlatConvParams& p, const FlatMaps& maps, d
   cudaError_t le = cudaSuccess;
   static const bool launch_log = dbg_env("SVX_LAUNCH_LOG") != nullptr;   // debug switch
   if (launch_log)
-    fprintf(stderr, "conv_flat launch: grid %u smem %zu pair %d n_tiles %d n_tile %d mt %d P %lld aux %d\n", grid.x, smem, p.pair, p.n_tiles, p.n_tile, p.mt,
-            p.P, p.aux_mode);
-#ifdef SVX_ENABLE_PAIR
+    fprintf(stderr, "conv_flat launch: grid %u smem %zu cluster %dx%d n_tiles %d n_tile %d mt %d P %lld aux %d\n", grid.x, smem, p.cm, p.cn, p.n_tiles,
+            p.n_tile, p.mt, p.P, p.aux_mode);
 #define SVX_FLAT(AUX, PRE, POST)                                                                       \
-  le = p.pair ? cudaLaunchKernelEx(&cfg, conv_flat_kernel<T, AUX, PRE, POST, true>, p, maps)          \
-              : cudaLaunchKernelEx(&cfg, conv_flat_kernel<T, AUX, PRE, POST, false>, p, maps)
-#else
-  if (p.pair) return cudaErrorNotSupported;
-#define SVX_FLAT(AUX, PRE, POST) le = cudaLaunchKernelEx(&cfg, conv_flat_kernel<T, AUX, PRE, POST, false>, p, maps)
-#endif
+  le = mc ? cudaLaunchKernelEx(&cfg, conv_flat_kernel<T, AUX, PRE, POST, true>, p, maps)              \
+          : cudaLaunchKernelEx(&cfg, conv_flat_kernel<T, AUX, PRE, POST, false>, p, maps)
   if (p.aux_mode == 0) {
     if (p.pre_relu && !p.post_relu) SVX_FLAT(0, true, false);
     else if (!p.pre_relu && p.post_relu) SVX_FLAT(0, false, true);
@@ -837,8 +832,8 @@ static cudaError_t launch_typed(const FlatConvParams& p, const FlatMaps& maps, d
   }
 #undef SVX_FLAT
   if (le != cudaSuccess) {
-    fprintf(stderr, "conv_flat launch failed: grid %u block %d smem %zu pair %d n_tiles %d n_tile %d mt %d\n", grid.x, kFlatThreads, smem, p.pair, p.n_tiles,
-            p.n_tile, p.mt);
+    fprintf(stderr, "conv_flat launch failed: grid %u block %d smem %zu cluster %dx%d n_tiles %d n_tile %d mt %d\n", grid.x, kFlatThreads, smem, p.cm, p.cn,
+            p.n_tiles, p.n_tile, p.mt);
     return le;
   }
   return cudaGetLastError();
@@ -848,13 +843,15 @@ cudaError_t launch_conv_flat(const FlatConvParams& p, const FlatMaps& maps, int 
   if (p.P <= 0) return cudaSuccess;
   const long long n_spans = (p.P + p.mt * 128 - 1) / (p.mt * 128);
   const int sms = g_flat_sms > 0 ? g_flat_sms : 148;
-  const int per_unit = p.pair ? 2 : 1;                                   // CTAs per scheduling unit
-  const long long n_units = (n_spans + per_unit - 1) / per_unit;
-  long long groups = (sms / per_unit) / p.n_tiles;
+  const size_t smem = conv_flat_smem_bytes(p);
+  const int cs = p.cn * p.cm;                                            // CTAs per scheduling unit (cluster)
+  const int n_cols = p.n_tiles / p.cn;                                   // clusters per span group
+  const long long n_units = (n_spans + p.cm - 1) / p.cm;
+  const int unit_cap = cs > 1 ? (is_bf16 ? max_clusters<__nv_bfloat16>(cs, smem) : max_clusters<__half>(cs, smem)) : sms;
+  long long groups = unit_cap / n_cols;
   if (groups < 1) groups = 1;
   if (groups > n_units) groups = n_units;
-  dim3 grid(static_cast<unsigned>(groups * p.n_tiles * per_unit), 1, 1);
-  const size_t smem = conv_flat_smem_bytes(p);
+  dim3 grid(static_cast<unsigned>(groups * n_cols * cs), 1, 1);
   return is_bf16 ? launch_typed<__nv_bfloat16>(p, maps, grid, smem, stream) : launch_typed<__half>(p, maps, grid, smem, stream);
 }
 

@@ -786,25 +786,26 @@ int Model::plan_flat(ConvDesc& c) {
   }
   static const int env_maxmt = dbg_env("SVX_FLAT_MAXMT") ? atoi(dbg_env("SVX_FLAT_MAXMT")) : 4;          // debug switches
   static const bool plan_log = dbg_env("SVX_PLAN_LOG") != nullptr;
-  // CTA pairs (cta_group::2): worth it where the weights dominate shared memory or are streamed — total K (taps x channels) at or
-  // above a threshold; SVX_PAIR_MIN_K overrides (0 = every layer, huge = never)
-  static const int pair_min_k = dbg_env("SVX_PAIR_MIN_K") ? atoi(dbg_env("SVX_PAIR_MIN_K")) : (1 << 30);
-#ifdef SVX_ENABLE_PAIR
-  const bool use_pair = !grouped && taps * c.kpad >= pair_min_k;
-#else
-  const bool use_pair = false;
-  (void)pair_min_k;
-#endif
+  // Multicast clusters cm x cn (conv_flat.cu): cn CTAs share a span (A slices multicast across the n-tiles), cm CTAs share an
+  // n-tile (streamed weight slices multicast across spans).  The cost model below charges the L2 row requests once per cluster;
+  // SVX_MC_CN / SVX_MC_CM force a shape.
+  // MEASURED (profiles/r02_multicast_clusters.txt): no shape is faster than single CTAs on any layer — A multicast x2 / x4 costs
+  // +6 % / +13 % on the deep 1x1 convs, weight multicast the same — so the bytes a CTA RECEIVES (~45-50 GB/s per SM with all
+  // SMs pulling), not the L2 reads, bound those layers; clusters are therefore opt-in (SVX_MC=1, debug build only).
+  static const bool no_mc = dbg_env("SVX_MC") == nullptr;
+  static const int force_cn = dbg_env("SVX_MC_CN") ? atoi(dbg_env("SVX_MC_CN")) : 0;
+  static const int force_cm = dbg_env("SVX_MC_CM") ? atoi(dbg_env("SVX_MC_CM")) : 0;
+  static const double mc_penalty = dbg_env("SVX_MC_PENALTY") ? atof(dbg_env("SVX_MC_PENALTY")) : 1.05;   // lockstep of the cluster's CTAs
   const int ksteps = c.kbox / 16;
   // direct epilogue (global accesses from the epilogue threads instead of slots + TMA) for narrow single-destination tiles
   static const bool no_direct = dbg_env("SVX_NO_DIRECT") != nullptr;   // debug switch
-  const bool direct_ok = !no_direct && !split && n_split == c.cout && !use_pair && c.outb.id < 0;
+  const bool direct_ok = !no_direct && !split && n_split == c.cout && c.outb.id < 0;
   // aux mode 2 over dense planar tensors: the add2 / out2 tiles are contiguous runs -> 1-D bulk copies instead of 128 rows each
   // (measured: no gain — 14 354 vs 14 458 emb/s with it on the stage-3 3x3 convs, and none on stages 1-2 against 2-D TMA tiles —
   // so it is opt-in: SVX_LIN=1)
   static const bool use_lin = dbg_env("SVX_LIN") != nullptr;   // debug switch
   bool lin_ok = false;
-  if (use_lin && aux_mode == 2 && !use_pair && !split) {
+  if (use_lin && aux_mode == 2 && !split) {
     const ActTensor& ta = tensors_[c.add2.id];
     const ActTensor& t2 = tensors_[c.out2.id];
     lin_ok = ta.C == c.cout && t2.C == c.cout && c.add2.coff == 0 && c.out2.coff == 0 && (c.cout * 2) % 16 == 0;
@@ -822,9 +823,8 @@ int Model::plan_flat(ConvDesc& c) {
       if (!split && n_split < c.cout && n_split % box_ch != 0) continue;       // a staging box has exactly one destination
       if ((N + box_ch - 1) / box_ch > 32) continue;                              // routing table size
       if (grouped && (n_tile != 32 || box_ch != 32)) continue;
-      // pair mode: a slot holds at most 128 columns, wider tiles pass through the slots in two column parts
-      const int n_parts = (use_pair && n_tile > 128 && n_tile % (2 * box_ch) == 0) ? 2 : 1;   // (slower than one wide slot without pairing)
-      const int part_cols = n_tile / n_parts;
+      const int n_parts = 1;
+      const int part_cols = n_tile;
       const int boxes = (part_cols + box_ch - 1) / box_ch;
       const uint32_t box_bytes = 128u * box_ch * 2u;
       const bool direct = direct_ok && n_tile <= 64 && (n_tiles == 1 || grouped);   // several n-tiles would re-read A per 64 channels
@@ -835,18 +835,31 @@ int Model::plan_flat(ConvDesc& c) {
       const bool lin = lin_ok && !direct && n_tiles == 1;
       const uint32_t slot_bytes = hybrid ? boxes * box_bytes : direct ? 0u : lin ? boxes * box_bytes + static_cast<uint32_t>(round_up(128 * c.cout * 2, 1024))
                                                     : boxes * box_bytes * (aux_mode == 2 ? 2u : 1u);
-      const int b_rows_cta = use_pair ? n_tile / 2 : n_tile;                    // pair mode: each CTA of the pair holds half of the weights
+      const int b_rows_cta = n_tile;
       const uint32_t b_item = static_cast<uint32_t>(round_up(b_rows_cta * static_cast<int>(row_bytes), 1024));
       const int items = taps * c.nkc;
       const long long b_total = static_cast<long long>(items) * b_item;
       for (int mt : {4, 2, 1}) {
         if (mt > env_maxmt) continue;
         if (mt * n_tile > 256) continue;
+        for (int cn : {1, 2, 4, 8})
+        for (int cm : {1, 2, 4}) {
+        if (cn * cm > 8) continue;
+        if (cn * cm > 1 && (no_mc || grouped || direct)) continue;
+        if (force_cn > 0 && n_tiles % force_cn == 0 && !grouped && !direct && cn != force_cn) continue;
+        if (force_cm > 0 && !grouped && !direct && cm != force_cm) continue;
+        if (n_tiles % cn != 0) continue;
+        if (n_tile % (8 * cm) != 0) continue;                       // weight slices are whole 8-row swizzle atoms
         const int a_rows_min = mt * 128 + 2 * halo;
         const int a_boxes = (a_rows_min + 255) / 256;
-        const int a_box_rows = round_up((a_rows_min + a_boxes - 1) / a_boxes, 8);
+        const int a_box_rows = round_up((a_rows_min + a_boxes - 1) / a_boxes, 8 * cn);   // ... and so are the A slices
+        if (a_box_rows > 256) continue;
         const uint32_t a_stage = static_cast<uint32_t>(round_up(a_boxes * a_box_rows * static_cast<int>(row_bytes), 1024));
+        // clusters never straddle a GPC: fewer CTAs fit than there are SMs (conv_flat_max_clusters), which the cost pays for
+        const int cs = cn * cm;
+        const double sm_frac = cs == 1 ? 1.0 : std::min(1.0, static_cast<double>(conv_flat_max_clusters(cs)) * cs / 148.0);
         for (int b_res : {1, 0}) {
+          if (cm > 1 && b_res) continue;                            // resident weights are loaded once: nothing to share
           static const long long bres_max = dbg_env("SVX_BRES_MAX") ? atoll(dbg_env("SVX_BRES_MAX")) : 64 * 1024;   // tuning knobs; resident weights above 64 KB starve the A ring (measured +1.2 % against 96 KB)
           static const double lat_cyc = dbg_env("SVX_LAT_CYC") ? atof(dbg_env("SVX_LAT_CYC")) : 3000.0;
           static const double slot_scale = dbg_env("SVX_SLOT_SCALE") ? atof(dbg_env("SVX_SLOT_SCALE")) : 1.0;
@@ -864,14 +877,15 @@ int Model::plan_flat(ConvDesc& c) {
           }
           // ---- cost per 128 output pixels (cycles)
           const double halo_ovh = 1.0 + 2.0 * halo / (mt * 128.0);
-          const double a_rows = static_cast<double>(n_tiles) * c.nkc * 128.0 * halo_ovh;
-          const double b_rows = b_res ? 0.0 : static_cast<double>(n_tiles) * items * b_rows_cta / mt;
+          const double a_rows_cta = static_cast<double>(n_tiles) * c.nkc * 128.0 * halo_ovh;       // rows every CTA receives
+          const double b_rows_rcv = b_res ? 0.0 : static_cast<double>(n_tiles) * items * b_rows_cta / mt;
+          const double a_rows = a_rows_cta / cn, b_rows = b_rows_rcv / cm;                           // rows requested from L2
           const int aux_boxes = (aux_mode && !direct && !lin) ? boxes : 0;
           const double aux_rows = static_cast<double>(n_tiles) * aux_boxes * 128.0;
           const double st_rows = hybrid ? static_cast<double>(n_tiles) * boxes * 128.0 : direct ? 0.0 : static_cast<double>(n_tiles) * boxes * 128.0 * ((aux_mode == 2 && !lin) ? 2.0 : 1.0);
           const double t_req = (a_rows + b_rows + aux_rows) * 5.6;
           const double t_st = st_rows * 4.6;
-          const double load_bytes = (a_rows + b_rows) * row_bytes;
+          const double load_bytes = (a_rows_cta + b_rows_rcv) * row_bytes;
           const double mma_cyc = std::max(n_tile / 2.0, (4096.0 + n_tile * 32.0) / 128.0) + 6.0;
           const double t_mma = static_cast<double>(n_tiles) * items * ksteps * mma_cyc;
           const double t_epi = static_cast<double>(n_tiles) * (n_tile / 16.0) * 150.0;
@@ -906,40 +920,43 @@ int Model::plan_flat(ConvDesc& c) {
           if (a_stages < 3 && left >= a_stage) { ++a_stages; left -= a_stage; }
           if (aux_mode && slots < 3 && left >= 2LL * slot_bytes) { ++slots; left -= 2LL * slot_bytes; }
           if (!b_res && b_stages < 4 && b_stages < items && left >= b_item) { ++b_stages; left -= b_item; }
-          const double score = std::max(t_fixed, std::max(t_lat(), t_slot())) + 0.01 * n_tiles - 0.001 * mt + (b_res ? 0.0 : 0.005);
+          const double score = std::max(t_fixed, std::max(t_lat(), t_slot())) / sm_frac * (cs > 1 ? mc_penalty : 1.0) + 0.01 * n_tiles - 0.001 * mt +
+                               (b_res ? 0.0 : 0.005);
           const double t_latv = t_lat(), t_slotv = t_slot();
           if (plan_log)
-            fprintf(stderr, "  cand n_tile %d box %d mt %d bres %d a_st %d b_st %d slots %d: req %.0f st %.0f lat %.0f mma %.0f epi %.0f slot %.0f -> %.0f\n", n_tile,
-                    box_ch, mt, b_res, a_stages, b_stages, slots, t_req, t_st, t_latv, t_mma, t_epi, t_slotv, score);
+            fprintf(stderr, "  cand n_tile %d box %d mt %d cl %dx%d bres %d a_st %d b_st %d slots %d: req %.0f st %.0f lat %.0f mma %.0f epi %.0f slot %.0f -> %.0f\n", n_tile,
+                    box_ch, mt, cm, cn, b_res, a_stages, b_stages, slots, t_req, t_st, t_latv, t_mma, t_epi, t_slotv, score);
           if (score < best) {
             best = score;
             fp.mt = mt; fp.a_box_rows = a_box_rows; fp.a_boxes = a_boxes; fp.n_tile = n_tile; fp.n_tiles = n_tiles;
             fp.a_stages = a_stages; fp.b_stages = b_stages; fp.a_stage_bytes = a_stage; fp.b_item_bytes = b_item;
             fp.b_resident = b_res; fp.box_ch = box_ch; fp.boxes = boxes; fp.slots = slots; fp.slot_bytes = slot_bytes;
             fp.n_parts = n_parts; fp.part_cols = part_cols;
+            fp.cn = cn; fp.cm = cm; fp.a_slice_rows = a_box_rows / cn; fp.b_slice_rows = n_tile / cm;
             fp.direct = hybrid ? 2 : direct ? 1 : 0; fp.lin = lin ? 1 : 0;
             found = true;
           }
+        }
         }
       }
     }
   }
   if (found && plan_log)
-    fprintf(stderr, "plan %dx%d cin %d cout %d aux %d: n_tile %d x%d box %d mt %d bres %d a_st %d b_st %d slots %d direct %d lin %d score %.0f\n", c.kh, c.kw, c.cin,
-            c.cout, aux_mode, fp.n_tile, fp.n_tiles, fp.box_ch, fp.mt, fp.b_resident, fp.a_stages, fp.b_stages, fp.slots, fp.direct, fp.lin, best);
+    fprintf(stderr, "plan %dx%d cin %d cout %d aux %d: n_tile %d x%d box %d mt %d cluster %dx%d bres %d a_st %d b_st %d slots %d direct %d lin %d score %.0f\n", c.kh,
+            c.kw, c.cin, c.cout, aux_mode, fp.n_tile, fp.n_tiles, fp.box_ch, fp.mt, fp.cm, fp.cn, fp.b_resident, fp.a_stages, fp.b_stages, fp.slots, fp.direct,
+            fp.lin, best);
   if (!found) return 0;
   // TMEM buffers: the epilogue of span s releases its accumulators only after its last sub-tile, so with 2 buffers the MMAs of
   // span s+2 wait for it; 4 buffers (when they fit in 512 columns) take that wait off the critical path
   static const bool no_tb4 = dbg_env("SVX_NO_TMEM4") != nullptr;   // debug switch
-  const int bufs = (!no_tb4 && !use_pair && 4 * fp.mt * fp.n_tile <= 512) ? 4 : 2;
+  const int bufs = (!no_tb4 && 4 * fp.mt * fp.n_tile <= 512) ? 4 : 2;
   fp.tmem_bufs = bufs; fp.tmem_bufs_log2 = bufs == 4 ? 2 : 1;
   uint32_t tc = 32;
   while (tc < static_cast<uint32_t>(bufs) * fp.mt * fp.n_tile) tc *= 2;
   if (tc > 512) return 0;
   fp.tmem_cols = tc;
-  fp.pair = use_pair ? 1 : 0;
-  fp.b_rows = use_pair ? fp.n_tile / 2 : fp.n_tile;
-  fp.idesc = ptx::make_idesc_f16(is_bf16_ ? 1u : 0u, use_pair ? 256u : 128u, static_cast<uint32_t>(fp.n_tile));
+  fp.b_rows = fp.n_tile;
+  fp.idesc = ptx::make_idesc_f16(is_bf16_ ? 1u : 0u, 128u, static_cast<uint32_t>(fp.n_tile));
 
   // tensor maps over the flat pixel sequence
   const size_t esz = 2;
@@ -952,7 +969,7 @@ int Model::plan_flat(ConvDesc& c) {
     const int a_width = (c.in.coff == 0 && tin.C > c.cin && tin.C <= c.kpad && c.groups == 1) ? tin.C : c.cin;
     const uint64_t dims[2] = {static_cast<uint64_t>(a_width), P_cap};
     const uint64_t str[1] = {static_cast<uint64_t>(tin.C) * esz};
-    const uint32_t box[2] = {static_cast<uint32_t>(c.kbox), static_cast<uint32_t>(fp.a_box_rows)};
+    const uint32_t box[2] = {static_cast<uint32_t>(c.kbox), static_cast<uint32_t>(fp.a_slice_rows)};      // one load per (box, cluster column)
     static const int env_promo = dbg_env("SVX_L2_PROMO") ? atoi(dbg_env("SVX_L2_PROMO")) : -1;   // debug switch (see promo_for below)
     const int pitch = tin.C * 2, off = c.in.coff * 2, wb = c.cin * 2;
     const int promo = env_promo >= 0 ? env_promo : (a_width == tin.C) ? 128 : (pitch % 128 == 0 && off % 128 == 0 && wb % 128 == 0) ? 128
@@ -962,7 +979,7 @@ int Model::plan_flat(ConvDesc& c) {
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(taps) * c.kpad, static_cast<uint64_t>(c.n_pad)};
     const uint64_t str[1] = {static_cast<uint64_t>(taps) * c.kpad * esz};
-    const uint32_t box[2] = {static_cast<uint32_t>(c.kbox), static_cast<uint32_t>(fp.b_rows)};
+    const uint32_t box[2] = {static_cast<uint32_t>(c.kbox), static_cast<uint32_t>(fp.b_resident ? fp.b_rows : fp.b_slice_rows)};
     if (encode_tmap(&fm.b, is_bf16_, c.d_wgt, 2, dims, str, box, row_bytes)) return 1;
   }
   // L2 promotion widens every TMA request to the promotion size; on a narrow channel slice of a wider row that
@@ -1107,11 +1124,13 @@ int Model::layout_segments(const std::vector<int>& seg_len) {
 // launch on the launching stream; bench.py divides the algorithmic FLOPs of those launches by this.
 int Model::conv_time(double* ms, double* flops) {
   double total = 0.0;
+  static const bool print_each = dbg_env("SVX_CONV_TIMES") != nullptr;   // debug build: one line per conv launch
   for (size_t i = 0; i + 1 < ev_used_; i += 2) {
     float t = 0.f;
     SVX_CUDA(cudaEventSynchronize(events_[i + 1]));
     SVX_CUDA(cudaEventElapsedTime(&t, events_[i], events_[i + 1]));
     total += t;
+    if (print_each && i / 2 < conv_labels_.size()) fprintf(stderr, "convtime %3zu %8.1f us  %s\n", i / 2, t * 1e3, conv_labels_[i / 2].c_str());
   }
   *ms = total; *flops = conv_flops_;
   return 0;
@@ -1184,7 +1203,16 @@ int Model::launch_conv(ConvDesc& c, cudaStream_t st) {
       // algorithmic FLOPs: 2 * valid output pixels * taps * cin * cout (no padding waste counted)
       double pix = 0.0;
       for (int h : seg_h_host_[out_stage]) pix += static_cast<double>(h) * stage_W_[out_stage];
-      conv_flops_ += 2.0 * pix * c.kh * c.kw * ((c.in_gw > 0 ? (c.cin / c.in_gwp) * c.in_gw : c.cin) / c.groups) * c.cout;
+      const double fl = 2.0 * pix * c.kh * c.kw * ((c.in_gw > 0 ? (c.cin / c.in_gwp) * c.in_gw : c.cin) / c.groups) * c.cout;
+      conv_flops_ += fl;
+      if (conv_labels_.size() < ev_used_ / 2) {
+        char lb[256];
+        snprintf(lb, sizeof lb, "stage %d %dx%d s%d g%d cin %4d cout %4d aux %d %s n_tile %3d x%d mt %d bres %d a_st %d b_st %d slots %d direct %d  %.1f GFLOP", out_stage,
+                 c.kh, c.kw, c.stride, c.groups, c.cin, c.cout, flat ? c.fp.aux_mode : c.up.aux_mode, flat ? "flat" : "umma", flat ? c.fp.n_tile : c.up.n_tile,
+                 flat ? c.fp.n_tiles : c.up.n_tiles, flat ? c.fp.mt : 1, flat ? c.fp.b_resident : (c.up.bres_bytes != 0), flat ? c.fp.a_stages : c.up.stages,
+                 flat ? c.fp.b_stages : 0, flat ? c.fp.slots : 0, flat ? c.fp.direct : 0, fl * 1e-9);
+        conv_labels_.push_back(lb);
+      }
     }
   } else {
     c.sp.out_rows = out_rows;
@@ -1235,7 +1263,7 @@ int Model::run_segments_sl(const float* d_feats, const std::vector<int>& starts,
   if (!finalized_) { set_last_error("extractor not finalized"); return 1; }
   SVX_CUDA(cudaSetDevice(device_));
   launches_ = 0;
-  if (!in_extract_) { ev_used_ = 0; conv_flops_ = 0.0; }
+  if (!in_extract_) { ev_used_ = 0; conv_flops_ = 0.0; conv_labels_.clear(); }
   const int n_seg = static_cast<int>(starts.size());
   if (n_seg <= 0) return 0;
   for (int i = 0; i < n_seg; ++i)
@@ -1432,7 +1460,7 @@ int Model::extract(const float* feats, int feats_on_device, const int32_t* h_fra
   }
   // all chunks in one pass: segments are (first frame, length) pairs, so dropped tails leave no gaps to work around
   long long total_launches = 0;
-  ev_used_ = 0; conv_flops_ = 0.0; in_extract_ = true;
+  ev_used_ = 0; conv_flops_ = 0.0; conv_labels_.clear(); in_extract_ = true;
   struct Guard { bool& f; ~Guard() { f = false; } } guard{in_extract_};
   {
     std::vector<int> st_i(starts.begin(), starts.end()), ln_i(seg_len.begin(), seg_len.end());

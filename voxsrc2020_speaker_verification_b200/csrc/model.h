@@ -165,6 +165,7 @@ class Model {
   long long launches_ = 0;
   int time_convs_ = 0; bool in_extract_ = false;
   std::vector<cudaEvent_t> events_; size_t ev_used_ = 0; double conv_flops_ = 0.0;
+  std::vector<std::string> conv_labels_;   // one per timed conv launch (shape and plan), printed by the debug build
   std::vector<std::vector<int>> seg_h_host_, seg_off_host_;
 };
 
