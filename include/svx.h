@@ -141,6 +141,11 @@ int svx_topk_stats(const float* vals_dev, int ld, int64_t n, int m, int topk, fl
 int svx_trial_scores(const float* emb_dev, int d, const int32_t* idx1_dev, const int32_t* idx2_dev, int64_t n_trials,
                      const float* mean_dev, const float* std_dev, float* cos_dev, float* snorm_dev, void* cuda_stream);
 long long svx_scorer_last_launches(svx_scorer* h);
+/* "fused" = 0 routes svx_asnorm_stats / svx_cohort_topk_values through the unfused kernels (GEMM → score block → per-row select);
+ * the default (1) is the fused kernel, which never writes the scores (shapes it does not take fall back on their own). */
+int svx_scorer_set_option(svx_scorer* h, const char* key, int value);
+/* How many rows of the last statistics call the fused kernel finished itself and how many it handed to the unfused kernels. */
+int svx_scorer_last_path(svx_scorer* h, long long* fused_rows, long long* fallback_rows);
 
 #ifdef __cplusplus
 }

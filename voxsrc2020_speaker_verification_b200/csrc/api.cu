@@ -1,5 +1,6 @@
 // C ABI (include/svx.h): handle management, error reporting, and the scorer that strings the scoring kernels
 // together (cohort GEMM on tcgen05 → exact top-k statistics → trial gather).
+#include <cmath>
 #include <cstring>
 #include <new>
 #include <string>
@@ -26,6 +27,15 @@ struct svx_scorer {
   __nv_bfloat16* d_a = nullptr; size_t a_bytes = 0;     // split test block [block_rows, 3d]
   __nv_bfloat16* d_b = nullptr; size_t b_bytes = 0;     // split cohort [c_pad, 3d]
   float* d_s = nullptr; size_t s_bytes = 0;             // score block [block_rows, c_pad]
+  // fused path (asnorm_fused.cu): split operands [rows_pad, 2*dp] and the rows handed back to the unfused path
+  __nv_bfloat16* d_a2 = nullptr; size_t a2_bytes = 0;
+  __nv_bfloat16* d_b2 = nullptr; size_t b2_bytes = 0;
+  int* d_flag = nullptr; size_t flag_bytes = 0;          // [0] = count, [1..] = row indices
+  float* d_fx = nullptr; size_t fx_bytes = 0;            // gathered flagged rows, then their results
+  float* d_fr = nullptr; size_t fr_bytes = 0;
+  int sms = 148;
+  int use_fused = 1;                                     // option "fused" (svx_scorer_set_option)
+  long long fused_rows = 0, fallback_rows = 0;           // of the last call
 };
 
 #define API_CUDA(expr)                                                                           \
@@ -176,8 +186,10 @@ int svx_scorer_create(int device, svx_scorer** out) {
   if (require_device(device)) return 1;
   DeviceGuard guard(device);
   API_CUDA(conv_umma_init());
+  API_CUDA(asnorm_fused_init());
   svx_scorer* s = new svx_scorer();
   s->device = device;
+  cudaDeviceGetAttribute(&s->sms, cudaDevAttrMultiProcessorCount, device);
   *out = s;
   return 0;
 }
@@ -186,6 +198,7 @@ int svx_scorer_destroy(svx_scorer* h) {
   if (!h) return 0;
   DeviceGuard guard(h->device);
   cudaFree(h->d_a); cudaFree(h->d_b); cudaFree(h->d_s);
+  cudaFree(h->d_a2); cudaFree(h->d_b2); cudaFree(h->d_flag); cudaFree(h->d_fx); cudaFree(h->d_fr);
   delete h;
   return 0;
 }
@@ -271,6 +284,22 @@ int svx_group_means(const float* unit_rows_dev, int d, const int32_t* member_row
 
 static int cohort_pass(svx_scorer* h, const float* test_dev, int64_t n, const float* cohort_dev, int c, int d, int topk,
                        float* mean_dev, float* std_dev, float* vals_dev, void* cuda_stream);
+static int cohort_pass_unfused(svx_scorer* h, const float* test_dev, int64_t n, const float* cohort_dev, int c, int d, int topk,
+                               float* mean_dev, float* std_dev, float* vals_dev, int vals_ld, cudaStream_t st);
+
+int svx_scorer_set_option(svx_scorer* h, const char* key, int value) {
+  if (!h || !key) { set_last_error("null argument"); return 1; }
+  if (!strcmp(key, "fused")) { h->use_fused = value; return 0; }
+  set_last_error(std::string("unknown scorer option: ") + key);
+  return 1;
+}
+
+int svx_scorer_last_path(svx_scorer* h, long long* fused_rows, long long* fallback_rows) {
+  if (!h) { set_last_error("null handle"); return 1; }
+  if (fused_rows) *fused_rows = h->fused_rows;
+  if (fallback_rows) *fallback_rows = h->fallback_rows;
+  return 0;
+}
 
 int svx_asnorm_stats(svx_scorer* h, const float* test_dev, int64_t n, const float* cohort_dev, int c, int d, int topk,
                      float* mean_dev, float* std_dev, void* cuda_stream) {
@@ -293,12 +322,90 @@ int svx_topk_stats(const float* vals_dev, int ld, int64_t n, int m, int topk, fl
 
 }  // extern "C"
 
+// z with P(Z > z) = q for a standard normal Z (bisection on erfc): where the k-th largest of c roughly-normal scores sits.
+static double normal_upper_quantile(double q) {
+  double lo = -8.0, hi = 8.0;
+  for (int i = 0; i < 80; ++i) {
+    const double mid = 0.5 * (lo + hi);
+    if (0.5 * std::erfc(mid / std::sqrt(2.0)) > q) lo = mid; else hi = mid;
+  }
+  return 0.5 * (lo + hi);
+}
+
 static int cohort_pass(svx_scorer* h, const float* test_dev, int64_t n, const float* cohort_dev, int c, int d, int topk,
                        float* mean_dev, float* std_dev, float* vals_dev, void* cuda_stream) {
   if (c <= 0 || d <= 0 || topk <= 0) { set_last_error("cohort size, dimension and topk must be positive"); return 1; }
   if (d % 8 != 0) { set_last_error("embedding dimension must be a multiple of 8"); return 1; }
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   DeviceGuard guard(h->device);
+  h->launches = 0; h->fused_rows = 0; h->fallback_rows = 0;
+  if (n <= 0) return 0;
+  // The fused kernel takes the shapes it was built for: operand resident in shared memory (d <= 256), a threshold well inside the
+  // cohort (k <= c/3) and a cohort large enough for the first 128 scores to be a sample (c >= 1024).  Everything else — and any
+  // row the fused kernel hands back — goes through the unfused kernels.
+  static const bool env_unfused = dbg_env("SVX_SCORE_UNFUSED") != nullptr;   // debug switch
+  const bool fused_ok = h->use_fused && !env_unfused && d <= 256 && c >= 1024 && static_cast<long long>(topk) * 3 <= c && n <= (1LL << 30);
+  if (!fused_ok) return cohort_pass_unfused(h, test_dev, n, cohort_dev, c, d, topk, mean_dev, std_dev, vals_dev, topk, st);
+
+  const int dp = (d + 63) / 64 * 64;
+  const long long n_pad = (n + 127) / 128 * 128;
+  const int c_pad = (c + 127) / 128 * 128;
+  if (grow_buf(&h->d_a2, &h->a2_bytes, static_cast<size_t>(n_pad) * 2 * dp * 2)) return 1;
+  if (grow_buf(&h->d_b2, &h->b2_bytes, static_cast<size_t>(c_pad) * 2 * dp * 2)) return 1;
+  if (grow_buf(&h->d_flag, &h->flag_bytes, (static_cast<size_t>(n) + 1) * 4)) return 1;
+  API_CUDA(launch_split2(test_dev, h->d_a2, n, n_pad, d, dp, st));
+  API_CUDA(launch_split2(cohort_dev, h->d_b2, c, c_pad, d, dp, st));
+  API_CUDA(cudaMemsetAsync(h->d_flag, 0, 4, st));
+  AsnormFusedParams fp;
+  memset(&fp, 0, sizeof fp);
+  fp.n_rows = static_cast<int>(n); fp.c = c; fp.n_row_blocks = static_cast<int>(n_pad / 128); fp.n_tiles = c_pad / 128;
+  fp.dp = dp; fp.kboxes = dp / 64; fp.topk = topk;
+  const double zq = normal_upper_quantile(static_cast<double>(topk) / c);
+  fp.z_lo = static_cast<float>(zq - 1.0); fp.z_hi = static_cast<float>(zq + 2.2);
+  fp.nb = 96; fp.cap = 28;                    // candidates per epilogue group: the shared-memory plan is then exactly 227 KB at d = 256
+  fp.mean = mean_dev; fp.stdv = std_dev; fp.vals = vals_dev; fp.vals_ld = topk;
+  fp.flag_count = h->d_flag; fp.flag_rows = h->d_flag + 1;
+  fp.stages = 8;
+  { static const char* kn = dbg_env("SVX_ASNORM_KNOCK"); fp.knock = kn ? atoi(kn) : 0; }
+  while (fp.stages > 2 && asnorm_fused_smem_bytes(fp) > 227 * 1024) --fp.stages;
+  if (asnorm_fused_smem_bytes(fp) > 227 * 1024) { set_last_error("fused cohort statistics: shared-memory plan does not fit"); return 1; }
+  CUtensorMap ma, mb;
+  {
+    const uint64_t adims[2] = {static_cast<uint64_t>(2 * dp), static_cast<uint64_t>(n_pad)};
+    const uint64_t bdims[2] = {static_cast<uint64_t>(2 * dp), static_cast<uint64_t>(c_pad)};
+    const uint64_t str[1] = {static_cast<uint64_t>(2 * dp) * 2};
+    const uint32_t box[2] = {64u, 128u};
+    if (encode_tmap(&ma, 1, h->d_a2, 2, adims, str, box, 128)) return 1;
+    if (encode_tmap(&mb, 1, h->d_b2, 2, bdims, str, box, 128)) return 1;
+  }
+  API_CUDA(launch_asnorm_fused(fp, ma, mb, h->sms, st));
+  h->launches += 3;
+  // rows the fused kernel could not finish (threshold bin outside its histogram, or overfull): usually none
+  int n_flag = 0;
+  API_CUDA(cudaMemcpyAsync(&n_flag, h->d_flag, 4, cudaMemcpyDeviceToHost, st));
+  API_CUDA(cudaStreamSynchronize(st));
+  h->fused_rows = n - n_flag; h->fallback_rows = n_flag;
+  if (n_flag > 0) {
+    const int w = vals_dev ? topk : 2;
+    if (grow_buf(&h->d_fx, &h->fx_bytes, static_cast<size_t>(n_flag) * d * 4)) return 1;
+    if (grow_buf(&h->d_fr, &h->fr_bytes, static_cast<size_t>(n_flag) * (w + 2) * 4)) return 1;
+    API_CUDA(launch_gather_rows(test_dev, h->d_flag + 1, n_flag, d, h->d_fx, st));
+    float* fm = h->d_fr; float* fs = h->d_fr + n_flag; float* fv = h->d_fr + 2 * static_cast<size_t>(n_flag);
+    const long long l0 = h->launches;
+    if (cohort_pass_unfused(h, h->d_fx, n_flag, cohort_dev, c, d, topk, mean_dev ? fm : nullptr, std_dev ? fs : nullptr,
+                            vals_dev ? fv : nullptr, topk, st)) return 1;
+    h->launches += l0;
+    if (mean_dev) API_CUDA(launch_scatter_rows(fm, h->d_flag + 1, n_flag, 1, mean_dev, 1, st));
+    if (std_dev) API_CUDA(launch_scatter_rows(fs, h->d_flag + 1, n_flag, 1, std_dev, 1, st));
+    if (vals_dev) API_CUDA(launch_scatter_rows(fv, h->d_flag + 1, n_flag, topk, vals_dev, topk, st));
+    h->launches += 4;
+  }
+  return 0;
+}
+
+static int cohort_pass_unfused(svx_scorer* h, const float* test_dev, int64_t n, const float* cohort_dev, int c, int d, int topk,
+                               float* mean_dev, float* std_dev, float* vals_dev, int vals_ld, cudaStream_t st) {
+  (void)vals_ld;
   h->launches = 0;
   if (n <= 0) return 0;
   const int K = 3 * d;

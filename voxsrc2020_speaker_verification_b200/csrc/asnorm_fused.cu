@@ -1,0 +1,403 @@
+// Fused cohort statistics for AS-norm (reference tensorflow/snorm.py:83-110, get_cohort_mean_std): for every test row the mean and
+// population std of its top-k dot products with the cohort, WITHOUT ever writing the score matrix.
+//
+//   S[r, j] = <x_r, c_j>  as one tcgen05 GEMM over split-bf16 operands, x = xh + xl, c = ch + cl (bf16 each):
+//             xh.ch + xl.ch + xh.cl  (fp32 accumulation in TMEM, ~2^-16 relative error per product — the same three terms, in the
+//             same order, as the unfused path, which is pinned to the reference's golden vectors)
+//
+// One persistent CTA per SM owns 128 test rows at a time.  Their split operand ([hi | lo], 2 x Dp bf16 per row, <= 128 KB) stays
+// RESIDENT in shared memory while the cohort streams through a TMA ring in tiles of 128 cohort rows, TWICE:
+//   pass 0  epilogue thread r (one per test row, reading its accumulator row from TMEM) bins every score into a per-row histogram
+//           in shared memory; the bin range is centred on where the k-th largest is expected: mean + z * std of the row's first 128
+//           scores, z from the normal quantile of k/c.  After the pass the thread walks its bins from the top and finds the bin b*
+//           that holds the k-th largest, the count above it and how many of b*'s members are needed.
+//   pass 1  the GEMM runs again (same instruction sequence -> bit-identical scores); scores above b* are accumulated (sum and sum
+//           of squares in double), the members of b* are collected in a short per-row list, and the thread finally picks the
+//           largest `need` of them.  Exact for ties: only the VALUES of the top-k multiset matter.
+// A row whose threshold bin falls outside the histogram range or holds more than `cap` scores is reported through flag_rows and
+// finished by the unfused kernels (api.cu) — correctness never depends on the score distribution, only the speed does.
+//
+// Roles (384 threads): warp 0 TMA producer, warp 1 tcgen05.mma issuer (two 128-column accumulator buffers in TMEM, so the MMAs of
+// tile t+1 overlap the epilogue of tile t), warps 4-7 / 8-11 two epilogue warpgroups on alternating tiles (warp & 3 = TMEM lane quarter).  All histogram / list words of a row
+// live at word index == row (mod 128): every epilogue thread touches only its own words, bank = lane, no synchronisation.
+//
+// Bounds: per tile of 128 cohort rows the CTA ingests 2 * Dp * 128 * 2 B (128 KB at D = 256) for 12 * Dp/64 MMAs of
+// 128x128x16 (48 at D = 256, 3072 tensor cycles): with ~45-50 GB/s of TMA ingest per SM when every SM pulls from L2 the kernel is
+// ingest-bound at ~2.7 us per tile and pass.
+#include <cstdio>
+#include <cstring>
+
+#include "kernels.cuh"
+#include "umma.cuh"
+
+namespace svx {
+
+using namespace ptx;
+
+namespace {
+
+constexpr int kThreads = 384;
+constexpr int kMaxStages = 8;
+constexpr uint32_t kBoxBytes = 128u * 128u;   // 128 rows x 64 bf16
+constexpr float kPad = -1e30f;
+
+struct Bars {
+  uint64_t a_full, a_empty;
+  uint64_t b_full[kMaxStages], b_empty[kMaxStages];
+  uint64_t t_full[2], t_empty[2];
+  uint32_t tmem_slot;
+};
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ void red_add_u32(uint32_t addr, uint32_t v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+
+}  // namespace
+
+template <bool VALS>
+__global__ void __launch_bounds__(kThreads, 1)
+asnorm_fused_kernel(const __grid_constant__ AsnormFusedParams p, const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  Bars& B = *reinterpret_cast<Bars*>(smem);
+  const int kb_n = p.kboxes;                                   // 64-element K boxes per operand half (hi or lo)
+  uint8_t* a_smem = smem + 1024;                               // [2 * kb_n] boxes: hi[0..kb_n), lo[0..kb_n)
+  uint8_t* b_smem = a_smem + static_cast<size_t>(2 * kb_n) * kBoxBytes;
+  uint8_t* aux = b_smem + static_cast<size_t>(p.stages) * kBoxBytes;   // per-row histogram (pass 0) / candidate list (pass 1), [word][128 rows]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int items = 2 * kb_n;                                   // ring items per cohort tile: hi[0], lo[0], hi[1], lo[1], ...
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_a); prefetch_tmap(&map_b);
+    mbar_init(&B.a_full, 1); mbar_init(&B.a_empty, 1);
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(&B.b_full[s], 1); mbar_init(&B.b_empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&B.t_full[b], 1); mbar_init(&B.t_empty[b], 4); }      // the 4 warps of the group that owns the buffer
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(&B.tmem_slot, 256); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = B.tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      int lb = 0;
+      for (int rb = blockIdx.x; rb < p.n_row_blocks; rb += gridDim.x, ++lb) {
+        mbar_wait(&B.a_empty, (lb & 1) ^ 1);                   // the MMAs of the previous row block have read the resident operand
+        mbar_expect_tx(&B.a_full, static_cast<uint32_t>(2 * kb_n) * kBoxBytes);
+        for (int h = 0; h < 2; ++h)
+          for (int kb = 0; kb < kb_n; ++kb)
+            tma_load_2d(a_smem + static_cast<size_t>(h * kb_n + kb) * kBoxBytes, &map_a, &B.a_full, h * p.dp + kb * 64, rb * 128);
+        for (int pass = 0; pass < 2; ++pass)
+          for (int t = 0; t < p.n_tiles; ++t)
+            for (int j = 0; j < items; ++j, ++it) {
+              const int s = it % p.stages;
+              mbar_wait(&B.b_empty[s], ((it / p.stages) & 1) ^ 1);
+              mbar_expect_tx(&B.b_full[s], kBoxBytes);
+              tma_load_2d(b_smem + static_cast<size_t>(s) * kBoxBytes, &map_b, &B.b_full[s], (j & 1) * p.dp + (j >> 1) * 64, t * 128);
+            }
+      }
+    }
+  } else if (warp == 1) {
+    // descriptors as {32-bit low word, common high word}, computed by the converged warp; only the tcgen05 instructions sit under
+    // the elected lane, unrolled with compile-time offsets (64-bit descriptor arithmetic inside the elected region costs ~200 ns
+    // per MMA: the first build of this kernel spent 13 us per tile on 48 MMAs)
+    const uint64_t dbase = make_kmajor_desc(0, 1024u, 2u);      // SWIZZLE_128B, 8-row groups 1024 B apart
+    const uint32_t hi = static_cast<uint32_t>(dbase >> 32);
+    const uint32_t lo0 = static_cast<uint32_t>(dbase);
+    const uint32_t idesc = make_idesc_f16(1u, 128u, 128u);      // bf16 operands, fp32 accumulate, M = N = 128
+    const uint32_t a_lo0 = lo0 + (smem_u32(a_smem) >> 4), b_lo0 = lo0 + (smem_u32(b_smem) >> 4);
+    constexpr uint32_t kBox16 = kBoxBytes >> 4;
+    uint32_t it = 0, tt = 0;
+    int lb = 0;
+    for (int rb = blockIdx.x; rb < p.n_row_blocks; rb += gridDim.x, ++lb) {
+      mbar_wait(&B.a_full, lb & 1);
+      for (int pass = 0; pass < 2; ++pass)
+        for (int t = 0; t < p.n_tiles; ++t, ++tt) {
+          const int buf = tt & 1;
+          mbar_wait(&B.t_empty[buf], ((tt >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * 128);
+#pragma unroll 1
+          for (int kb = 0; kb < kb_n; ++kb) {
+            const uint32_t ah = a_lo0 + static_cast<uint32_t>(kb) * kBox16, al = a_lo0 + static_cast<uint32_t>(kb_n + kb) * kBox16;
+            {                                                     // cohort hi box: xh.ch then xl.ch
+              const int s = it % p.stages;
+              mbar_wait(&B.b_full[s], (it / p.stages) & 1);
+              tc_fence_after();
+              const uint32_t bd = b_lo0 + static_cast<uint32_t>(s) * kBox16;
+              const uint32_t first = kb != 0 ? 1u : 0u;
+              if (elect_one()) {
+                if (!(p.knock & 4)) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_lo(d_tmem, ah + 2 * k, bd + 2 * k, hi, idesc, k == 0 ? first : 1u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_lo(d_tmem, al + 2 * k, bd + 2 * k, hi, idesc, 1u);
+                }
+                umma_commit(&B.b_empty[s]);
+              }
+              __syncwarp();
+              ++it;
+            }
+            {                                                     // cohort lo box: xh.cl
+              const int s = it % p.stages;
+              mbar_wait(&B.b_full[s], (it / p.stages) & 1);
+              tc_fence_after();
+              const uint32_t bd = b_lo0 + static_cast<uint32_t>(s) * kBox16;
+              if (elect_one()) {
+                if (!(p.knock & 4)) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_lo(d_tmem, ah + 2 * k, bd + 2 * k, hi, idesc, 1u);
+                }
+                umma_commit(&B.b_empty[s]);
+                if (kb == kb_n - 1) umma_commit(&B.t_full[buf]);
+              }
+              __syncwarp();
+              ++it;
+            }
+          }
+        }
+      if (elect_one()) umma_commit(&B.a_empty);                  // every MMA that reads this row block's operand has retired
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    // Two epilogue warpgroups: group g takes the tiles whose accumulator buffer is g (even / odd tiles), so every test row has two
+    // threads that share its histogram (shared-memory atomics) and keep private partial sums and candidate lists; group 0
+    // computes the bin range from the row block's first tile and finishes the row.  Three named barriers per row block.
+    const int g = (warp - 4) >> 2;
+    const int q4 = warp & 3;
+    const int row = q4 * 32 + lane;
+    const uint32_t aux_row = smem_u32(aux) + static_cast<uint32_t>(row) * 4u;     // word w of this row: aux_row + w * 512
+    const int nb = p.nb, cap = p.cap;                            // cap: candidates per GROUP; list words [g * cap, g * cap + cap)
+    const uint32_t list_row = aux_row + static_cast<uint32_t>(g * cap) * 512u;
+    const uint32_t part_row = aux_row + static_cast<uint32_t>(2 * cap) * 512u;   // 8 words: range (pass 0), then group 1's partial results
+    const uint32_t trash_row = part_row + 8u * 512u + static_cast<uint32_t>(g) * 512u;   // where the unconditional stores of unselected scores go
+    const int k = p.topk;
+    uint32_t tt = 0;
+    for (int rb = blockIdx.x; rb < p.n_row_blocks; rb += gridDim.x) {
+      const long long grow = static_cast<long long>(rb) * 128 + row;
+      float off = 0.f, scale = 0.f;
+      int bstar = -2, need = 0, above = 0;
+      bool bad = false;
+      double dsum = 0.0, dsq = 0.0;
+      int cnt = 0, pos = 0;
+      float* vo = (VALS && p.vals && grow < p.n_rows) ? p.vals + grow * p.vals_ld : nullptr;
+      for (int pass = 0; pass < 2; ++pass) {
+        for (int t = 0; t < p.n_tiles; ++t, ++tt) {
+          const int buf = tt & 1;
+          if (pass == 0 && t == 1 && g == 1) {                    // group 1's first tile: the range is published, the histogram zeroed
+            named_bar_sync(1, 256);
+            off = __uint_as_float(lds_u32(part_row)); scale = __uint_as_float(lds_u32(part_row + 512u));
+          }
+          if (buf != g) continue;
+          mbar_wait(&B.t_full[buf], (tt >> 1) & 1);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>(buf * 128);
+          const int nvalid = min(128, p.c - t * 128);            // cohort rows past c are zero padding
+          uint32_t r[16];
+          if (pass == 0 && t == 0) {
+            // bin range from the statistics of the first tile's scores (a 128-score sample of this row)
+            float s1 = 0.f, s2 = 0.f;
+            for (int c0 = 0; c0 < 128; c0 += 16) {
+              tmem_ld16(taddr + c0, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (c0 + i < nvalid) { const float v = __uint_as_float(r[i]); s1 += v; s2 = fmaf(v, v, s2); }
+            }
+            const float inv = 1.f / static_cast<float>(nvalid);
+            const float mu = s1 * inv;
+            const float sd = sqrtf(fmaxf(s2 * inv - mu * mu, 1e-30f));
+            const float lo = mu + p.z_lo * sd;
+            scale = static_cast<float>(nb) / ((p.z_hi - p.z_lo) * sd);
+            off = -lo * scale;
+            for (int w = 0; w < (nb >> 1); ++w) sts_u32(aux_row + w * 512, 0u);
+            sts_u32(part_row, __float_as_uint(off)); sts_u32(part_row + 512u, __float_as_uint(scale));
+            named_bar_sync(1, 256);
+          }
+          // Branch-free over the 16 scores of a TMEM load: with few epilogue warps per scheduler nothing hides the latency of a
+          // per-score branch chain (compare -> convert -> address -> atomic), which cost ~85-160 cycles per score in the first
+          // build; here the 16 chains are independent instruction streams and the atomics / list stores are predicated.
+          for (int c0 = 0; c0 < 128; c0 += 16) {
+            if (c0 >= nvalid || (p.knock & 1)) break;
+            tmem_ld16(taddr + c0, r);
+            tmem_ld_wait();
+            if ((p.knock & 2) || ((p.knock & 8) && pass == 0) || ((p.knock & 16) && pass == 1)) continue;
+            int bin[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float tb = fmaf(__uint_as_float(r[i]), scale, off);
+              const int b = min(nb - 1, __float2int_rz(tb));
+              bin[i] = (tb >= 0.f && c0 + i < nvalid) ? b : -1;
+            }
+            if (pass == 0) {
+              // no predication at all (ptxas turns a predicated atomic into a branch region, ~40 cycles of convergence-barrier
+              // latency per score with nothing to hide it): scores outside the range add to a trash word of this row instead
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                red_add_u32(bin[i] >= 0 ? aux_row + static_cast<uint32_t>(bin[i] >> 1) * 512u : trash_row, (bin[i] & 1) ? 65536u : 1u);
+            } else {
+              float s16 = 0.f, q16 = 0.f;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float v = __uint_as_float(r[i]);
+                const bool gt = bin[i] > bstar;
+                const float vs = gt ? v : 0.f;
+                s16 += vs;
+                q16 = fmaf(vs, vs, q16);
+                // (cohort-sharded layout only) the selected scores themselves: group 0 fills the row from the front, group 1 from
+                // position above-1 backwards — together they write exactly `above` scores
+                if constexpr (VALS) { if (vo != nullptr && gt && pos < above) vo[g == 0 ? pos : above - 1 - pos] = v; }
+                pos += gt ? 1 : 0;
+                const bool eq = bin[i] == bstar;
+                sts_u32((eq && cnt < cap) ? list_row + static_cast<uint32_t>(cnt) * 512u : trash_row, r[i]);   // unconditional store, see above
+                cnt += eq ? 1 : 0;
+              }
+              dsum += static_cast<double>(s16);                            // <= 16 fp32 terms per partial sum, the running sums in double
+              dsq += static_cast<double>(q16);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&B.t_empty[buf]);
+        }
+        if (pass == 0) {
+          __threadfence_block();
+          named_bar_sync(1, 256);                                 // both groups' atomics have landed
+          // walk the bins from the top: b* holds the k-th largest score (both threads of a row find the same one)
+          int cum = 0;
+          bstar = -1;
+          for (int b = nb - 1; b >= 0; --b) {
+            const uint32_t w = lds_u32(aux_row + static_cast<uint32_t>(b >> 1) * 512u);
+            const int h = static_cast<int>((b & 1) ? (w >> 16) : (w & 0xffffu));
+            if (cum + h >= k) { bstar = b; need = k - cum; above = cum; bad = h > 2 * cap; break; }
+            cum += h;
+          }
+          if (bstar < 0) bad = true;                              // fewer than k scores inside the bin range
+          if (bad) bstar = 1 << 30;                               // pass 1 then selects nothing for this row
+          named_bar_sync(1, 256);                                 // everybody has read the histogram: its words become the lists
+        }
+      }
+      if (g == 1) {                                               // hand this group's part to group 0
+        sts_u32(part_row + 2 * 512u, static_cast<uint32_t>(cnt)); sts_u32(part_row + 3 * 512u, static_cast<uint32_t>(pos));
+        const unsigned long long a = __double_as_longlong(dsum), b = __double_as_longlong(dsq);
+        sts_u32(part_row + 4 * 512u, static_cast<uint32_t>(a)); sts_u32(part_row + 5 * 512u, static_cast<uint32_t>(a >> 32));
+        sts_u32(part_row + 6 * 512u, static_cast<uint32_t>(b)); sts_u32(part_row + 7 * 512u, static_cast<uint32_t>(b >> 32));
+      }
+      named_bar_sync(1, 256);
+      if (g == 0 && !p.knock) {
+        const int cnt1 = static_cast<int>(lds_u32(part_row + 2 * 512u)), pos1 = static_cast<int>(lds_u32(part_row + 3 * 512u));
+        dsum += __longlong_as_double(static_cast<long long>(lds_u32(part_row + 4 * 512u)) | (static_cast<long long>(lds_u32(part_row + 5 * 512u)) << 32));
+        dsq += __longlong_as_double(static_cast<long long>(lds_u32(part_row + 6 * 512u)) | (static_cast<long long>(lds_u32(part_row + 7 * 512u)) << 32));
+        if (!bad && (cnt > cap || cnt1 > cap || pos + pos1 != above || cnt + cnt1 < need)) bad = true;
+        if (grow < p.n_rows) {
+          if (bad) {
+            const int slot = atomicAdd(p.flag_count, 1);
+            p.flag_rows[slot] = static_cast<int>(grow);
+          } else {
+            // the `need` largest members of the threshold bin: group 1's candidates are appended to group 0's, then a partial
+            // selection sort over this row's list words
+            for (int j = 0; j < cnt1; ++j) sts_u32(aux_row + static_cast<uint32_t>(cnt + j) * 512u, lds_u32(aux_row + static_cast<uint32_t>(cap + j) * 512u));
+            const int total = cnt + cnt1;
+            for (int i = 0; i < need; ++i) {
+              int best = i;
+              float bv = __uint_as_float(lds_u32(aux_row + static_cast<uint32_t>(i) * 512u));
+              const float first_v = bv;
+              for (int j = i + 1; j < total; ++j) {
+                const float v = __uint_as_float(lds_u32(aux_row + static_cast<uint32_t>(j) * 512u));
+                if (v > bv) { bv = v; best = j; }
+              }
+              if (best != i) sts_u32(aux_row + static_cast<uint32_t>(best) * 512u, __float_as_uint(first_v));
+              dsum += static_cast<double>(bv);
+              dsq = fma(static_cast<double>(bv), static_cast<double>(bv), dsq);
+              if (vo) vo[above + i] = bv;
+            }
+            if (vo)
+              for (int i = k; i < p.vals_ld; ++i) vo[i] = kPad;
+            const double mean = dsum / static_cast<double>(k);
+            const double var = dsq / static_cast<double>(k) - mean * mean;
+            if (p.mean) p.mean[grow] = static_cast<float>(mean);
+            if (p.stdv) p.stdv[grow] = static_cast<float>(sqrt(var > 0.0 ? var : 0.0));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
+// fp32 -> split bf16 rows [hi(dp) | lo(dp)], zero padded to dp columns and n_pad rows.
+__global__ void __launch_bounds__(256) split2_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n, long long n_pad,
+                                                     int d, int dp) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= n_pad * dp) return;
+  const long long row = idx / dp;
+  const int j = static_cast<int>(idx - row * dp);
+  const float v = (row < n && j < d) ? in[row * d + j] : 0.f;
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+  out[row * (2LL * dp) + j] = hi;
+  out[row * (2LL * dp) + dp + j] = lo;
+}
+
+cudaError_t launch_split2(const float* in, __nv_bfloat16* out, long long n, long long n_pad, int d, int dp, cudaStream_t st) {
+  const long long total = n_pad * dp;
+  if (total <= 0) return cudaSuccess;
+  split2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(in, out, n, n_pad, d, dp);
+  return cudaGetLastError();
+}
+
+size_t asnorm_fused_smem_bytes(const AsnormFusedParams& p) {
+  const size_t list_words = static_cast<size_t>(2 * p.cap + 10);       // two candidate lists + the partial-result words + two trash words
+  const size_t aux_words = list_words > static_cast<size_t>(p.nb / 2) ? list_words : static_cast<size_t>(p.nb / 2);
+  return 1024 + 1024 + static_cast<size_t>(2 * p.kboxes + p.stages) * kBoxBytes + aux_words * 512;
+}
+
+cudaError_t asnorm_fused_init() {
+  cudaError_t e = cudaFuncSetAttribute(asnorm_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(asnorm_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+
+cudaError_t launch_asnorm_fused(const AsnormFusedParams& p, const CUtensorMap& map_a, const CUtensorMap& map_b, int sms, cudaStream_t st) {
+  if (p.n_row_blocks <= 0) return cudaSuccess;
+  const int grid = p.n_row_blocks < sms ? p.n_row_blocks : sms;
+  if (p.vals) asnorm_fused_kernel<true><<<grid, kThreads, asnorm_fused_smem_bytes(p), st>>>(p, map_a, map_b);
+  else asnorm_fused_kernel<false><<<grid, kThreads, asnorm_fused_smem_bytes(p), st>>>(p, map_a, map_b);
+  return cudaGetLastError();
+}
+
+// gather / scatter of the rows the fused kernel handed back
+__global__ void gather_rows_kernel(const float* __restrict__ in, const int* __restrict__ rows, int n, int d, float* __restrict__ out) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(n) * d) return;
+  const int i = static_cast<int>(idx / d), j = static_cast<int>(idx - static_cast<long long>(i) * d);
+  out[idx] = in[static_cast<long long>(rows[i]) * d + j];
+}
+__global__ void scatter_rows_kernel(const float* __restrict__ in, const int* __restrict__ rows, int n, int d, float* __restrict__ out, int out_ld) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(n) * d) return;
+  const int i = static_cast<int>(idx / d), j = static_cast<int>(idx - static_cast<long long>(i) * d);
+  out[static_cast<long long>(rows[i]) * out_ld + j] = in[idx];
+}
+cudaError_t launch_gather_rows(const float* in, const int* rows, int n, int d, float* out, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  gather_rows_kernel<<<static_cast<unsigned>((static_cast<long long>(n) * d + 255) / 256), 256, 0, st>>>(in, rows, n, d, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_scatter_rows(const float* in, const int* rows, int n, int d, float* out, int out_ld, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  scatter_rows_kernel<<<static_cast<unsigned>((static_cast<long long>(n) * d + 255) / 256), 256, 0, st>>>(in, rows, n, d, out, out_ld);
+  return cudaGetLastError();
+}
+
+}  // namespace svx

@@ -183,19 +183,6 @@ __device__ __forceinline__ void epi8_direct(const uint32_t* r, uint32_t sc, uint
   }
 }
 
-// tcgen05.mma with the shared-memory descriptors given as {low word, common high word}: the high word (SBO, version, swizzle
-// mode) is the same for every operand of a launch, the low word is (address >> 4) | LBO, so all per-MMA descriptor arithmetic is
-// one 32-bit add.
-__device__ __forceinline__ void umma_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-      "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}\n"
-      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(hi)
-      : "memory");
-}
-
 // All MMAs of one filter tap: MT sub-tiles x KS K-steps, fully unrolled so that every descriptor is the tap's base
 // (one value) plus a compile-time constant.  A generic loop costs ~150 cycles of issue per MMA (descriptor arithmetic in
 // vector registers + 5 R2UR each, tools/microbench/mma_rate.cu) against 16-64 cycles of tensor-pipe time.

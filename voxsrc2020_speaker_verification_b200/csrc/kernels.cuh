@@ -46,6 +46,26 @@ cudaError_t launch_topk_stats(const float* scores, int ld, long long n_rows, int
                               float* vals_out, int vals_ld, cudaStream_t st);
 cudaError_t launch_trial_scores(const float* emb, int d, const int32_t* idx1, const int32_t* idx2, long long t, const float* mean,
                                 const float* stdv, float* cos_out, float* snorm_out, cudaStream_t st);
+// fused cohort statistics (asnorm_fused.cu)
+struct AsnormFusedParams {
+  int n_rows, c;               // valid test rows / cohort rows
+  int n_row_blocks, n_tiles;   // 128-row blocks of the test matrix, 128-row tiles of the cohort (both zero padded)
+  int dp, kboxes;              // padded embedding dimension (multiple of 64, <= 256) and dp / 64
+  int topk;                    // k (< c)
+  float z_lo, z_hi;            // histogram range: sample mean + [z_lo, z_hi) sample standard deviations
+  int nb, cap;                 // bins (even) and candidate list capacity per row and epilogue group
+  int stages;                  // cohort ring depth
+  int knock;                   // timing experiments (debug build, SVX_ASNORM_KNOCK): 1 skip the epilogue's TMEM reads, 2 skip its arithmetic, 4 skip the MMAs
+  float* mean; float* stdv;    // [n_rows] (may be null when vals is wanted only)
+  float* vals; int vals_ld;    // optional: the selected scores of every row, unordered, padded with -1e30 to vals_ld
+  int* flag_count; int* flag_rows;   // rows handed back to the unfused path (threshold bin outside the range / overfull)
+};
+cudaError_t asnorm_fused_init();
+size_t asnorm_fused_smem_bytes(const AsnormFusedParams& p);
+cudaError_t launch_asnorm_fused(const AsnormFusedParams& p, const CUtensorMap& map_a, const CUtensorMap& map_b, int sms, cudaStream_t st);
+cudaError_t launch_split2(const float* in, __nv_bfloat16* out, long long n, long long n_pad, int d, int dp, cudaStream_t st);
+cudaError_t launch_gather_rows(const float* in, const int* rows, int n, int d, float* out, cudaStream_t st);
+cudaError_t launch_scatter_rows(const float* in, const int* rows, int n, int d, float* out, int out_ld, cudaStream_t st);
 cudaError_t launch_group_mean(const float* unit_rows, int d, const int32_t* member_rows, const int32_t* group_off, float* out, int n_groups,
                               cudaStream_t st);
 

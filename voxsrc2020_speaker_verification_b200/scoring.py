@@ -39,6 +39,16 @@ class Scorer:
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def set_option(self, key: str, value: int) -> None:
+        """"fused" = 0: cohort statistics through the unfused kernels (the fused kernel is the default)."""
+        lib.check(self._lib.svx_scorer_set_option(self._h, key.encode(), int(value)))
+
+    def last_path(self) -> Tuple[int, int]:
+        """(rows finished by the fused kernel, rows handed to the unfused kernels) of the last statistics call."""
+        a, b = ctypes.c_longlong(), ctypes.c_longlong()
+        lib.check(self._lib.svx_scorer_last_path(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
     def l2norm(self, x: torch.Tensor) -> torch.Tensor:
         """snorm.l2norm per row (snorm.py:23-25,32)."""
         x = x.contiguous()
