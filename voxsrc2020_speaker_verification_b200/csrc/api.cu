@@ -344,42 +344,39 @@ static int cohort_pass(svx_scorer* h, const float* test_dev, int64_t n, const fl
   // cohort (k <= c/3) and a cohort large enough for the first 128 scores to be a sample (c >= 1024).  Everything else — and any
   // row the fused kernel hands back — goes through the unfused kernels.
   static const bool env_unfused = dbg_env("SVX_SCORE_UNFUSED") != nullptr;   // debug switch
-  const bool fused_ok = h->use_fused && !env_unfused && d <= 256 && c >= 1024 && static_cast<long long>(topk) * 3 <= c && n <= (1LL << 30);
+  const bool fused_ok = h->use_fused && !env_unfused && d <= 256 && d % 4 == 0 && c >= 1024 && static_cast<long long>(topk) * 3 <= c && n <= (1LL << 30);
   if (!fused_ok) return cohort_pass_unfused(h, test_dev, n, cohort_dev, c, d, topk, mean_dev, std_dev, vals_dev, topk, st);
 
   const int dp = (d + 63) / 64 * 64;
   const long long n_pad = (n + 127) / 128 * 128;
   const int c_pad = (c + 127) / 128 * 128;
-  if (grow_buf(&h->d_a2, &h->a2_bytes, static_cast<size_t>(n_pad) * 2 * dp * 2)) return 1;
   if (grow_buf(&h->d_b2, &h->b2_bytes, static_cast<size_t>(c_pad) * 2 * dp * 2)) return 1;
   if (grow_buf(&h->d_flag, &h->flag_bytes, (static_cast<size_t>(n) + 1) * 4)) return 1;
-  API_CUDA(launch_split2(test_dev, h->d_a2, n, n_pad, d, dp, st));
   API_CUDA(launch_split2(cohort_dev, h->d_b2, c, c_pad, d, dp, st));
   API_CUDA(cudaMemsetAsync(h->d_flag, 0, 4, st));
   AsnormFusedParams fp;
   memset(&fp, 0, sizeof fp);
+  fp.x = test_dev; fp.d = d;
   fp.n_rows = static_cast<int>(n); fp.c = c; fp.n_row_blocks = static_cast<int>(n_pad / 128); fp.n_tiles = c_pad / 128;
   fp.dp = dp; fp.kboxes = dp / 64; fp.topk = topk;
   const double zq = normal_upper_quantile(static_cast<double>(topk) / c);
   fp.z_lo = static_cast<float>(zq - 1.0); fp.z_hi = static_cast<float>(zq + 2.2);
-  fp.nb = 96; fp.cap = 28;                    // candidates per epilogue group: the shared-memory plan is then exactly 227 KB at d = 256
+  fp.nb = 96; fp.cap = 28;                    // candidates per epilogue group
   fp.mean = mean_dev; fp.stdv = std_dev; fp.vals = vals_dev; fp.vals_ld = topk;
   fp.flag_count = h->d_flag; fp.flag_rows = h->d_flag + 1;
-  fp.stages = 8;
+  fp.stages = 12;
   { static const char* kn = dbg_env("SVX_ASNORM_KNOCK"); fp.knock = kn ? atoi(kn) : 0; }
   while (fp.stages > 2 && asnorm_fused_smem_bytes(fp) > 227 * 1024) --fp.stages;
   if (asnorm_fused_smem_bytes(fp) > 227 * 1024) { set_last_error("fused cohort statistics: shared-memory plan does not fit"); return 1; }
-  CUtensorMap ma, mb;
+  CUtensorMap mb;
   {
-    const uint64_t adims[2] = {static_cast<uint64_t>(2 * dp), static_cast<uint64_t>(n_pad)};
     const uint64_t bdims[2] = {static_cast<uint64_t>(2 * dp), static_cast<uint64_t>(c_pad)};
     const uint64_t str[1] = {static_cast<uint64_t>(2 * dp) * 2};
     const uint32_t box[2] = {64u, 128u};
-    if (encode_tmap(&ma, 1, h->d_a2, 2, adims, str, box, 128)) return 1;
     if (encode_tmap(&mb, 1, h->d_b2, 2, bdims, str, box, 128)) return 1;
   }
-  API_CUDA(launch_asnorm_fused(fp, ma, mb, h->sms, st));
-  h->launches += 3;
+  API_CUDA(launch_asnorm_fused(fp, mb, h->sms, st));
+  h->launches += 2;
   // rows the fused kernel could not finish (threshold bin outside its histogram, or overfull): usually none
   int n_flag = 0;
   API_CUDA(cudaMemcpyAsync(&n_flag, h->d_flag, 4, cudaMemcpyDeviceToHost, st));

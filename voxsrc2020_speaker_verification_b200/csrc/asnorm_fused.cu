@@ -37,7 +37,7 @@ using namespace ptx;
 namespace {
 
 constexpr int kThreads = 384;
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 12;
 constexpr uint32_t kBoxBytes = 128u * 128u;   // 128 rows x 64 bf16
 constexpr float kPad = -1e30f;
 
@@ -61,25 +61,24 @@ __device__ __forceinline__ void red_add_u32(uint32_t addr, uint32_t v) { asm vol
 
 template <bool VALS>
 __global__ void __launch_bounds__(kThreads, 1)
-asnorm_fused_kernel(const __grid_constant__ AsnormFusedParams p, const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b) {
+asnorm_fused_kernel(const __grid_constant__ AsnormFusedParams p, const __grid_constant__ CUtensorMap map_b) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   Bars& B = *reinterpret_cast<Bars*>(smem);
   const int kb_n = p.kboxes;                                   // 64-element K boxes per operand half (hi or lo)
-  uint8_t* a_smem = smem + 1024;                               // [2 * kb_n] boxes: hi[0..kb_n), lo[0..kb_n)
-  uint8_t* b_smem = a_smem + static_cast<size_t>(2 * kb_n) * kBoxBytes;
+  uint8_t* b_smem = smem + 1024;
   uint8_t* aux = b_smem + static_cast<size_t>(p.stages) * kBoxBytes;   // per-row histogram (pass 0) / candidate list (pass 1), [word][128 rows]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int items = 2 * kb_n;                                   // ring items per cohort tile: hi[0], lo[0], hi[1], lo[1], ...
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&map_a); prefetch_tmap(&map_b);
-    mbar_init(&B.a_full, 1); mbar_init(&B.a_empty, 1);
+    prefetch_tmap(&map_b);
+    mbar_init(&B.a_full, 4); mbar_init(&B.a_empty, 1);          // a_full: the 4 warps of epilogue group 0 have written the operand
     for (int s = 0; s < kMaxStages; ++s) { mbar_init(&B.b_full[s], 1); mbar_init(&B.b_empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&B.t_full[b], 1); mbar_init(&B.t_empty[b], 4); }      // the 4 warps of the group that owns the buffer
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(&B.tmem_slot, 256); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc(&B.tmem_slot, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -87,21 +86,16 @@ asnorm_fused_kernel(const __grid_constant__ AsnormFusedParams p, const __grid_co
 
   if (warp == 0) {
     if (lane == 0) {
-      uint32_t it = 0;
-      int lb = 0;
-      for (int rb = blockIdx.x; rb < p.n_row_blocks; rb += gridDim.x, ++lb) {
-        mbar_wait(&B.a_empty, (lb & 1) ^ 1);                   // the MMAs of the previous row block have read the resident operand
-        mbar_expect_tx(&B.a_full, static_cast<uint32_t>(2 * kb_n) * kBoxBytes);
-        for (int h = 0; h < 2; ++h)
-          for (int kb = 0; kb < kb_n; ++kb)
-            tma_load_2d(a_smem + static_cast<size_t>(h * kb_n + kb) * kBoxBytes, &map_a, &B.a_full, h * p.dp + kb * 64, rb * 128);
+      int s = 0;
+      uint32_t ph = 0;                                             // ring position and its phase, kept incrementally (no division per item)
+      for (int rb = blockIdx.x; rb < p.n_row_blocks; rb += gridDim.x) {
         for (int pass = 0; pass < 2; ++pass)
           for (int t = 0; t < p.n_tiles; ++t)
-            for (int j = 0; j < items; ++j, ++it) {
-              const int s = it % p.stages;
-              mbar_wait(&B.b_empty[s], ((it / p.stages) & 1) ^ 1);
+            for (int j = 0; j < items; ++j) {
+              mbar_wait(&B.b_empty[s], ph ^ 1);
               mbar_expect_tx(&B.b_full[s], kBoxBytes);
               tma_load_2d(b_smem + static_cast<size_t>(s) * kBoxBytes, &map_b, &B.b_full[s], (j & 1) * p.dp + (j >> 1) * 64, t * 128);
+              if (++s == p.stages) { s = 0; ph ^= 1; }
             }
       }
     }
@@ -113,12 +107,16 @@ asnorm_fused_kernel(const __grid_constant__ AsnormFusedParams p, const __grid_co
     const uint32_t hi = static_cast<uint32_t>(dbase >> 32);
     const uint32_t lo0 = static_cast<uint32_t>(dbase);
     const uint32_t idesc = make_idesc_f16(1u, 128u, 128u);      // bf16 operands, fp32 accumulate, M = N = 128
-    const uint32_t a_lo0 = lo0 + (smem_u32(a_smem) >> 4), b_lo0 = lo0 + (smem_u32(b_smem) >> 4);
+    const uint32_t b_lo0 = lo0 + (smem_u32(b_smem) >> 4);
+    const uint32_t a_t0 = tmem_base + 256u;                      // the test operand: lane = row, hi in columns [256, 256 + dp/2), lo right after
     constexpr uint32_t kBox16 = kBoxBytes >> 4;
-    uint32_t it = 0, tt = 0;
+    uint32_t tt = 0;
     int lb = 0;
+    int s = 0;
+    uint32_t ph = 0;
     for (int rb = blockIdx.x; rb < p.n_row_blocks; rb += gridDim.x, ++lb) {
       mbar_wait(&B.a_full, lb & 1);
+      tc_fence_after();
       for (int pass = 0; pass < 2; ++pass)
         for (int t = 0; t < p.n_tiles; ++t, ++tt) {
           const int buf = tt & 1;
@@ -127,40 +125,38 @@ asnorm_fused_kernel(const __grid_constant__ AsnormFusedParams p, const __grid_co
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * 128);
 #pragma unroll 1
           for (int kb = 0; kb < kb_n; ++kb) {
-            const uint32_t ah = a_lo0 + static_cast<uint32_t>(kb) * kBox16, al = a_lo0 + static_cast<uint32_t>(kb_n + kb) * kBox16;
+            const uint32_t ah = a_t0 + static_cast<uint32_t>(kb) * 32u, al = a_t0 + static_cast<uint32_t>(kb_n + kb) * 32u;   // 64 elements = 32 columns
             {                                                     // cohort hi box: xh.ch then xl.ch
-              const int s = it % p.stages;
-              mbar_wait(&B.b_full[s], (it / p.stages) & 1);
+              mbar_wait(&B.b_full[s], ph);
               tc_fence_after();
               const uint32_t bd = b_lo0 + static_cast<uint32_t>(s) * kBox16;
               const uint32_t first = kb != 0 ? 1u : 0u;
               if (elect_one()) {
                 if (!(p.knock & 4)) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_lo(d_tmem, ah + 2 * k, bd + 2 * k, hi, idesc, k == 0 ? first : 1u);
+                for (int k = 0; k < 4; ++k) umma_ts_lo(d_tmem, ah + 8 * k, bd + 2 * k, hi, idesc, k == 0 ? first : 1u);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_lo(d_tmem, al + 2 * k, bd + 2 * k, hi, idesc, 1u);
+                for (int k = 0; k < 4; ++k) umma_ts_lo(d_tmem, al + 8 * k, bd + 2 * k, hi, idesc, 1u);
                 }
                 umma_commit(&B.b_empty[s]);
               }
               __syncwarp();
-              ++it;
+              if (++s == p.stages) { s = 0; ph ^= 1; }
             }
             {                                                     // cohort lo box: xh.cl
-              const int s = it % p.stages;
-              mbar_wait(&B.b_full[s], (it / p.stages) & 1);
+              mbar_wait(&B.b_full[s], ph);
               tc_fence_after();
               const uint32_t bd = b_lo0 + static_cast<uint32_t>(s) * kBox16;
               if (elect_one()) {
                 if (!(p.knock & 4)) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_lo(d_tmem, ah + 2 * k, bd + 2 * k, hi, idesc, 1u);
+                for (int k = 0; k < 4; ++k) umma_ts_lo(d_tmem, ah + 8 * k, bd + 2 * k, hi, idesc, 1u);
                 }
                 umma_commit(&B.b_empty[s]);
                 if (kb == kb_n - 1) umma_commit(&B.t_full[buf]);
               }
               __syncwarp();
-              ++it;
+              if (++s == p.stages) { s = 0; ph ^= 1; }
             }
           }
         }
@@ -181,6 +177,7 @@ asnorm_fused_kernel(const __grid_constant__ AsnormFusedParams p, const __grid_co
     const uint32_t trash_row = part_row + 8u * 512u + static_cast<uint32_t>(g) * 512u;   // where the unconditional stores of unselected scores go
     const int k = p.topk;
     uint32_t tt = 0;
+    int lbe = 0;
     for (int rb = blockIdx.x; rb < p.n_row_blocks; rb += gridDim.x) {
       const long long grow = static_cast<long long>(rb) * 128 + row;
       float off = 0.f, scale = 0.f;
@@ -189,6 +186,37 @@ asnorm_fused_kernel(const __grid_constant__ AsnormFusedParams p, const __grid_co
       double dsum = 0.0, dsq = 0.0;
       int cnt = 0, pos = 0;
       float* vo = (VALS && p.vals && grow < p.n_rows) ? p.vals + grow * p.vals_ld : nullptr;
+      if (g == 0) {
+        // this row's operand into tensor memory: x = hi + lo in bf16, two elements per 32-bit column (what tcgen05.mma reads as a
+        // K-major A row).  The MMAs of the previous row block must have retired first.
+        mbar_wait(&B.a_empty, (lbe & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t a_t = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + 256u;
+        const float* xr = p.x + grow * p.d;
+        const bool live = grow < p.n_rows;
+        for (int c0 = 0; c0 < p.dp; c0 += 32) {
+          uint32_t wh[16], wl[16];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live && c0 + 4 * q < p.d) f = __ldg(reinterpret_cast<const float4*>(xr + c0 + 4 * q));
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(f.x), h1 = __float2bfloat16_rn(f.y), h2 = __float2bfloat16_rn(f.z), h3 = __float2bfloat16_rn(f.w);
+            const __nv_bfloat16 l0 = __float2bfloat16_rn(f.x - __bfloat162float(h0)), l1 = __float2bfloat16_rn(f.y - __bfloat162float(h1));
+            const __nv_bfloat16 l2 = __float2bfloat16_rn(f.z - __bfloat162float(h2)), l3 = __float2bfloat16_rn(f.w - __bfloat162float(h3));
+            wh[2 * q] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+            wh[2 * q + 1] = static_cast<uint32_t>(__bfloat16_as_ushort(h2)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h3)) << 16);
+            wl[2 * q] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
+            wl[2 * q + 1] = static_cast<uint32_t>(__bfloat16_as_ushort(l2)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l3)) << 16);
+          }
+          tmem_st16(a_t + static_cast<uint32_t>(c0 >> 1), wh);
+          tmem_st16(a_t + static_cast<uint32_t>((p.dp + c0) >> 1), wl);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&B.a_full);
+      }
+      ++lbe;
       for (int pass = 0; pass < 2; ++pass) {
         for (int t = 0; t < p.n_tiles; ++t, ++tt) {
           const int buf = tt & 1;
@@ -332,7 +360,7 @@ asnorm_fused_kernel(const __grid_constant__ AsnormFusedParams p, const __grid_co
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 256);
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
 // fp32 -> split bf16 rows [hi(dp) | lo(dp)], zero padded to dp columns and n_pad rows.
@@ -359,7 +387,7 @@ cudaError_t launch_split2(const float* in, __nv_bfloat16* out, long long n, long
 size_t asnorm_fused_smem_bytes(const AsnormFusedParams& p) {
   const size_t list_words = static_cast<size_t>(2 * p.cap + 10);       // two candidate lists + the partial-result words + two trash words
   const size_t aux_words = list_words > static_cast<size_t>(p.nb / 2) ? list_words : static_cast<size_t>(p.nb / 2);
-  return 1024 + 1024 + static_cast<size_t>(2 * p.kboxes + p.stages) * kBoxBytes + aux_words * 512;
+  return 1024 + 1024 + static_cast<size_t>(p.stages) * kBoxBytes + aux_words * 512;
 }
 
 cudaError_t asnorm_fused_init() {
@@ -368,11 +396,11 @@ cudaError_t asnorm_fused_init() {
   return cudaFuncSetAttribute(asnorm_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 
-cudaError_t launch_asnorm_fused(const AsnormFusedParams& p, const CUtensorMap& map_a, const CUtensorMap& map_b, int sms, cudaStream_t st) {
+cudaError_t launch_asnorm_fused(const AsnormFusedParams& p, const CUtensorMap& map_b, int sms, cudaStream_t st) {
   if (p.n_row_blocks <= 0) return cudaSuccess;
   const int grid = p.n_row_blocks < sms ? p.n_row_blocks : sms;
-  if (p.vals) asnorm_fused_kernel<true><<<grid, kThreads, asnorm_fused_smem_bytes(p), st>>>(p, map_a, map_b);
-  else asnorm_fused_kernel<false><<<grid, kThreads, asnorm_fused_smem_bytes(p), st>>>(p, map_a, map_b);
+  if (p.vals) asnorm_fused_kernel<true><<<grid, kThreads, asnorm_fused_smem_bytes(p), st>>>(p, map_b);
+  else asnorm_fused_kernel<false><<<grid, kThreads, asnorm_fused_smem_bytes(p), st>>>(p, map_b);
   return cudaGetLastError();
 }
 

@@ -48,6 +48,7 @@ cudaError_t launch_trial_scores(const float* emb, int d, const int32_t* idx1, co
                                 const float* stdv, float* cos_out, float* snorm_out, cudaStream_t st);
 // fused cohort statistics (asnorm_fused.cu)
 struct AsnormFusedParams {
+  const float* x; int d;       // test rows [n_rows, d] fp32 (split into bf16 hi + lo by the kernel itself, into tensor memory)
   int n_rows, c;               // valid test rows / cohort rows
   int n_row_blocks, n_tiles;   // 128-row blocks of the test matrix, 128-row tiles of the cohort (both zero padded)
   int dp, kboxes;              // padded embedding dimension (multiple of 64, <= 256) and dp / 64
@@ -62,7 +63,7 @@ struct AsnormFusedParams {
 };
 cudaError_t asnorm_fused_init();
 size_t asnorm_fused_smem_bytes(const AsnormFusedParams& p);
-cudaError_t launch_asnorm_fused(const AsnormFusedParams& p, const CUtensorMap& map_a, const CUtensorMap& map_b, int sms, cudaStream_t st);
+cudaError_t launch_asnorm_fused(const AsnormFusedParams& p, const CUtensorMap& map_b, int sms, cudaStream_t st);
 cudaError_t launch_split2(const float* in, __nv_bfloat16* out, long long n, long long n_pad, int d, int dp, cudaStream_t st);
 cudaError_t launch_gather_rows(const float* in, const int* rows, int n, int d, float* out, cudaStream_t st);
 cudaError_t launch_scatter_rows(const float* in, const int* rows, int n, int d, float* out, int out_ld, cudaStream_t st);
