@@ -36,6 +36,13 @@ class _Ctx:
         self.dtype = dtype
         self.root = arch._Namer()
         self.quant = quant  # optional callable emulating bf16 storage (numerics study only)
+        self.trace = None   # optional list: one record per block (input, output, a replay closure), see trace_blocks()
+
+    def record(self, name, x_in, x_out, fn):
+        """Block-level tap for the per-block parity tests: ``fn(x)`` re-runs exactly this block (same variables) on another
+        input.  The namer state at block entry is captured so that the replay resolves the same TF variable names."""
+        if self.trace is not None:
+            self.trace.append({"name": name, "in": x_in, "out": x_out, "replay": fn})
 
     def tensor(self, name: str) -> torch.Tensor:
         return torch.from_numpy(np.asarray(self.params[name])).to(self.dtype)
@@ -162,11 +169,13 @@ def _tail(ctx: _Ctx, x, cfg=None):
 # ---------------------------------------------------------------- TDNN
 def tdnn_forward(ctx: _Ctx, cfg: ModelConfig, x):
     """reference tdnn_model.py:24-30,128-155: five conv(SAME,dilated) → ReLU → BN blocks."""
-    for f, k, d in zip(cfg.tdnn_filters, cfg.tdnn_kernels, cfg.tdnn_dilations):
-        x = conv2d(ctx, ctx.root, x, f, (k, 1), 1, "same", (d, 1))
-        x = F.relu(x)
-        x = _q(ctx, batch_norm(ctx, ctx.root, x))
-    return _tail(ctx, x)
+    for li, (f, k, d) in enumerate(zip(cfg.tdnn_filters, cfg.tdnn_kernels, cfg.tdnn_dilations)):
+        def layer(ctx_, t, f=f, k=k, d=d):
+            t = conv2d(ctx_, ctx_.root, t, f, (k, 1), 1, "same", (d, 1))
+            t = F.relu(t)
+            return _q(ctx_, batch_norm(ctx_, ctx_.root, t))
+        x = _traced(ctx, "tdnn%d" % (li + 1), layer, x)
+    return _traced(ctx, "tail", lambda c_, t: _tail(c_, t), x)
 
 
 # ---------------------------------------------------------------- Res2Net
@@ -209,13 +218,16 @@ def bottleneck_block_v1(ctx: _Ctx, x, filters, project, strides, split, width):
 
 def res2net_forward(ctx: _Ctx, cfg: ModelConfig, x):
     """reference res2net_model.py:185-243."""
-    x = conv2d_fixed_padding(ctx, ctx.root, x, cfg.num_filters[0], 3, 1)               # :192-194
-    x = _q(ctx, F.relu(batch_norm(ctx, ctx.root, x)))                                  # :201-203
+    def stem(ctx_, t):
+        t = conv2d_fixed_padding(ctx_, ctx_.root, t, cfg.num_filters[0], 3, 1)         # :192-194
+        return _q(ctx_, F.relu(batch_norm(ctx_, ctx_.root, t)))                        # :201-203
+    x = _traced(ctx, "stem", stem, x)
     for li, nblocks in enumerate(cfg.block_sizes):                                     # :212-221
         for b in range(nblocks):
-            x = bottleneck_block_v1(ctx, x, cfg.num_filters[li], b == 0,
-                                    cfg.block_strides[li] if b == 0 else 1, cfg.split, cfg.width[li])
-    return _tail(ctx, x, cfg)
+            x = _traced(ctx, "layer%d/block%d" % (li + 1, b),
+                        lambda c_, t, li=li, b=b: bottleneck_block_v1(c_, t, cfg.num_filters[li], b == 0,
+                                                                      cfg.block_strides[li] if b == 0 else 1, cfg.split, cfg.width[li]), x)
+    return _traced(ctx, "tail", lambda c_, t: _tail(c_, t, cfg), x)
 
 
 # ---------------------------------------------------------------- DPN
@@ -243,16 +255,37 @@ def dual_path_block(ctx: _Ctx, inputs, r, bw, inc, projection_type, cardinality)
 
 def dpn_forward(ctx: _Ctx, cfg: ModelConfig, x):
     """reference dpn_model.py:111-168."""
-    x = conv2d(ctx, ctx.root, x, cfg.init_features, 3, 1, "same")             # :33-34
-    x = _q(ctx, F.relu(batch_norm(ctx, ctx.root, x)))                         # :35-36
+    def stem(ctx_, t):
+        t = conv2d(ctx_, ctx_.root, t, cfg.init_features, 3, 1, "same")       # :33-34
+        return _q(ctx_, F.relu(batch_norm(ctx_, ctx_.root, t)))               # :35-36
+    x = _traced(ctx, "stem", stem, x)
     types = ["projected", "downsampled", "downsampled", "downsampled"]        # :92
+    # between blocks the two paths travel as one tensor [res | dense] (dpn_model.py:77,84: the first bw channels are the residual path)
     for si, (_, _, r, bw, inc) in enumerate(arch.dpn_stage_channels(cfg)):
-        x = dual_path_block(ctx, x, r, bw, inc, types[si], cfg.cardinality)
-        for _ in range(1, cfg.k_sec[si]):
-            x = dual_path_block(ctx, x, r, bw, inc, "normal", cfg.cardinality)
-    x = torch.cat(x, dim=1)                                                    # :24-29
-    x = _q(ctx, F.relu(batch_norm(ctx, ctx.root, x)))
-    return _tail(ctx, x)
+        for b in range(cfg.k_sec[si]):
+            def block(ctx_, t, r=r, bw=bw, inc=inc, kind=(types[si] if b == 0 else "normal")):
+                inp = t if kind != "normal" else [t[:, :bw], t[:, bw:]]
+                return torch.cat(dual_path_block(ctx_, inp, r, bw, inc, kind, cfg.cardinality), dim=1)
+            x = _traced(ctx, "stage%d/block%d" % (si + 1, b), block, x)
+
+    def tail(ctx_, t):
+        t = _q(ctx_, F.relu(batch_norm(ctx_, ctx_.root, t)))                  # :24-29
+        return _tail(ctx_, t)
+    return _traced(ctx, "tail", tail, x)
+
+
+def _traced(ctx: _Ctx, name: str, fn, x):
+    """Run one block; when tracing, keep its input / output and a closure that replays the block on another input."""
+    counts = dict(ctx.root.counts)
+    y = fn(ctx, x)
+    if ctx.trace is not None:
+        def replay(x_new, counts=counts):
+            c2 = _Ctx(ctx.params, False, ctx.dtype, ctx.quant)
+            c2.root.counts = dict(counts)
+            with torch.no_grad():
+                return fn(c2, x_new)
+        ctx.record(name, x, y, replay)
+    return y
 
 
 _FORWARD = {FAMILY_TDNN: tdnn_forward, FAMILY_RES2NET: res2net_forward, FAMILY_DPN: dpn_forward}
@@ -272,6 +305,18 @@ def forward(cfg: ModelConfig, params: Dict[str, np.ndarray], feats: np.ndarray, 
     with torch.no_grad():
         y = _FORWARD[cfg.family](ctx, cfg, x)
     return y.float().numpy()
+
+
+def trace_blocks(cfg: ModelConfig, params: Dict[str, np.ndarray], feats: np.ndarray):
+    """Forward pass of ONE segment [T,F] that also returns the block-level trace: a list of records
+    {"name", "in", "out" (NCHW float32 tensors; [N,E] for the tail), "replay": f(x) -> y} in execution order."""
+    x = torch.from_numpy(np.ascontiguousarray(feats[None])).float()
+    x = x.permute(0, 2, 1).unsqueeze(3) if cfg.expand_dim == 2 else x.unsqueeze(1)
+    ctx = _Ctx(params)
+    ctx.trace = []
+    with torch.no_grad():
+        y = _FORWARD[cfg.family](ctx, cfg, x)
+    return y.float().numpy()[0], ctx.trace
 
 
 def extract_utterance(cfg: ModelConfig, params, feats_tf: np.ndarray, dtype=torch.float32) -> np.ndarray:

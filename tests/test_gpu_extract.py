@@ -13,10 +13,23 @@ from voxsrc2020_speaker_verification_b200 import arch
 pytestmark = pytest.mark.gpu
 
 COS_TOL = 0.9999
+# Cosine is blind to a gain error, and the chunk rule averages UN-normalised chunk embeddings, so magnitude is bounded too:
+# relative L2 (cos >= 0.9999 alone allows 1.41e-2) and the ratio of the norms.
+REL_L2_TOL = 1.6e-2
+NORM_TOL = 5e-3
 
 
 def cosines(a, b):
     return (a * b).sum(1) / np.linalg.norm(a, axis=1) / np.linalg.norm(b, axis=1)
+
+
+def check_close(got, want, cos_tol=COS_TOL, rel_tol=REL_L2_TOL, norm_tol=NORM_TOL):
+    cos = cosines(got, want)
+    rel = np.linalg.norm(got - want, axis=1) / np.linalg.norm(want, axis=1)
+    ratio = np.linalg.norm(got, axis=1) / np.linalg.norm(want, axis=1)
+    assert cos.min() >= cos_tol, (cos, rel, ratio)
+    assert rel.max() <= rel_tol, (cos, rel, ratio)
+    assert np.abs(ratio - 1).max() <= norm_tol, (cos, rel, ratio)
 
 
 _cache = {}
@@ -76,8 +89,7 @@ def test_segments_match_oracle(model_id, feat_dim, lens, path):
     ex.set_option("no_flat", 0)
     want = oracle_segments(cfg, params, utts)
     assert np.isfinite(got).all()
-    cos = cosines(got, want)
-    assert cos.min() >= COS_TOL, (cos, np.abs(got - want).max())
+    check_close(got, want)
     assert ex.last_launches > 0
 
 
@@ -99,8 +111,7 @@ def test_chunk_rule(model_id, feat_dim):
     utts = [net_oracle.synth_feats(rng, 1, t, feat_dim)[0] for t in (1024, 1025, 300, 2030)]
     got = ex.extract(utts)
     want = np.stack([net_oracle.extract_utterance(cfg, params, u) for u in utts])
-    cos = cosines(got, want)
-    assert cos.min() >= COS_TOL, cos
+    check_close(got, want)
     # the 24-frame tail of the 1024-frame utterance is dropped: identical to its first 1000 frames
     first = ex.extract([utts[0][:1000]])
     np.testing.assert_allclose(got[0], first[0], atol=1e-5)
@@ -113,12 +124,44 @@ def test_short_utterance_fails_loudly():
         ex.extract([np.zeros((24, 40), np.float32)])
 
 
-def test_bf16_precision_mode():
-    cfg, params, ex = model("tdnn", 40, "bf16")
+# bf16 operands (the dtype the north star names; fp16 is the default because it meets cosine >= 0.9999): bounds from the measured
+# values of profiles/r02_parity_probe.txt — TDNN 0.9998, Res2Net-50 0.9994-0.9997, DPN-68 0.9975-0.9983 on the damped synthetic
+# weights.  Every BLOCK is at the bf16 rounding floor (tests/test_gpu_blocks.py); the whole-network figure is that floor amplified
+# by a random network's conditioning.
+@pytest.mark.parametrize("model_id,feat_dim,lens,cos_tol,rel_tol,norm_tol",
+                         [("tdnn", 40, [80, 200], 0.9995, 3.5e-2, 1e-2),
+                          ("res2net50_w24_s4_c32", 80, [200, 57], 0.999, 5e-2, 1e-2),
+                          ("dpn68", 80, [200, 57], 0.996, 1e-1, 2e-2)])
+def test_bf16_precision_mode(model_id, feat_dim, lens, cos_tol, rel_tol, norm_tol):
+    cfg, params, ex = model(model_id, feat_dim, "bf16")
     rng = np.random.default_rng(5)
-    utts = [net_oracle.synth_feats(rng, 1, t, 40)[0] for t in (80, 200)]
-    cos = cosines(run_segments(ex, utts), oracle_segments(cfg, params, utts))
-    assert cos.min() >= 0.9995, cos
+    utts = [net_oracle.synth_feats(rng, 1, t, feat_dim)[0] for t in lens]
+    check_close(run_segments(ex, utts), oracle_segments(cfg, params, utts), cos_tol, rel_tol, norm_tol)
+
+
+def test_res2net200_full_utterances_with_chunk_rule():
+    """BASELINE configs[3]: res2net200_w8_s6_c16 (66 bottleneck blocks, 8-channel splits) on 300 / 1025 / 3000-frame utterances
+    through the chunk rule.  Every block is at the fp16 rounding floor (~5e-4 relative, test_gpu_blocks.py); 66 of them on random
+    weights amplify it to cosine 0.9988-0.9998 (profiles/r02_parity_probe.txt) — the bound here is that measured figure, not the
+    0.9999 the 16-block networks meet."""
+    cfg, params, ex = model("res2net200_w8_s6_c16", 80)
+    rng = np.random.default_rng(77)
+    utts = [net_oracle.synth_feats(rng, 1, t, 80)[0] for t in (300, 1025, 3000)]
+    got = ex.extract(utts)
+    want = np.stack([net_oracle.extract_utterance(cfg, params, u) for u in utts])
+    check_close(got, want, 0.998, 7e-2, 1e-2)
+
+
+def test_full_depth_attentive_model_and_long_dpn():
+    """res2net101_w24_s4_c32_att (33 blocks + attentive statistics pooling, res2net_model.py:264-268) and dpn68 at 599 / 600 frames
+    (odd / even lengths through three TF-SAME stride-2 stages)."""
+    cfg, params, ex = model("res2net101_w24_s4_c32_att", 80)
+    rng = np.random.default_rng(78)
+    utts = [net_oracle.synth_feats(rng, 1, t, 80)[0] for t in (200, 57)]
+    check_close(run_segments(ex, utts), oracle_segments(cfg, params, utts))
+    cfg, params, ex = model("dpn68", 80)
+    utts = [net_oracle.synth_feats(rng, 1, t, 80)[0] for t in (599, 600)]
+    check_close(run_segments(ex, utts), oracle_segments(cfg, params, utts))
 
 
 def test_extract_bucketed_order():
@@ -138,7 +181,7 @@ def test_many_spans_per_cta():
     utts = [feats[i] for i in range(40)]
     a = run_segments(ex, utts)
     want = oracle_segments(cfg, params, utts[-3:])
-    assert cosines(a[-3:], want).min() >= COS_TOL
+    check_close(a[-3:], want)
     b = run_segments(ex, utts[-3:])
     np.testing.assert_allclose(a[-3:], b, atol=1e-5)
 

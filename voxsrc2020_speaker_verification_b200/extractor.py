@@ -102,6 +102,11 @@ class Extractor:
     def set_option(self, key: str, value: int) -> None:
         lib.check(self._lib.svx_extractor_set_option(self._h, key.encode(), int(value)))
 
+    def set_dump_dir(self, path: Optional[str]) -> None:
+        """Parity tooling: every op of the following runs writes its destination tensor (raw 16-bit NHWC tall image) into
+        ``path``; None switches it off."""
+        lib.check(self._lib.svx_extractor_set_dump_dir(self._h, path.encode() if path else None))
+
     @property
     def last_launches(self) -> int:
         return int(self._lib.svx_extractor_last_launches(self._h))
