@@ -141,6 +141,11 @@ int svx_topk_stats(const float* vals_dev, int ld, int64_t n, int m, int topk, fl
 int svx_trial_scores(const float* emb_dev, int d, const int32_t* idx1_dev, const int32_t* idx2_dev, int64_t n_trials,
                      const float* mean_dev, const float* std_dev, float* cos_dev, float* snorm_dev, void* cuda_stream);
 long long svx_scorer_last_launches(svx_scorer* h);
+/* compute_eer_and_min_dcf (eer_minDCF.py:41-64): scores / labels (1 = target) of n trials on the device -> out_host[4] =
+ * {eer, eer_threshold, min_dcf, min_dcf_threshold}, on the ROC sklearn.metrics.roc_curve builds (descending distinct thresholds,
+ * intermediate collinear points dropped, origin with threshold +inf), ties broken like np.nanargmin / the reference's `<` scan. */
+int svx_eer_min_dcf(const float* scores_dev, const int32_t* labels_dev, int64_t n, double c_miss, double c_fa, double p_target,
+                    double* out_host, void* cuda_stream);
 /* "fused" = 0 routes svx_asnorm_stats / svx_cohort_topk_values through the unfused kernels (GEMM → score block → per-row select);
  * the default (1) is the fused kernel, which never writes the scores (shapes it does not take fall back on their own). */
 int svx_scorer_set_option(svx_scorer* h, const char* key, int value);

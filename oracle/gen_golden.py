@@ -8,6 +8,7 @@ Fixtures:
   score/ref_cosine.txt, ref_snorm_topk400.txt   score files exactly as reference snorm.py __main__ writes them
   score/ref_spk_*.{txt,npz}        same with --test_spk2utt speaker-level enrolment
   io/feats_cm.ark, feats_fm.ark, ref_feats.npz    matrices as decoded by reference kaldi_io.read_mat_ark
+  eer/trials.txt, scores.txt, ref_eer.npy, ref_stdout.txt   what the reference's eer_minDCF.py computes / prints for them
   net/<model>.npz                  oracle (NOT reference: TensorFlow is absent) embeddings on seeded inputs —
                                    a regression pin for the restatement only
 """
@@ -104,6 +105,37 @@ def gen_score(out):
                           cwd=REF, stderr=subprocess.DEVNULL)
 
 
+def gen_eer(out):
+    """Trial / score files with realistic class overlap, ties and repeated pairs, and what the REFERENCE's eer_minDCF.py prints for
+    them (three operating points).  eer_minDCF.py:68-94."""
+    os.makedirs(out, exist_ok=True)
+    import eer_minDCF  # noqa: E402  (the reference's)
+    rng = np.random.default_rng(31337)
+    n = 2500
+    label = (rng.random(n) < 0.12).astype(int)
+    score = np.where(label == 1, rng.normal(0.55, 0.18, n), rng.normal(0.12, 0.16, n)).astype(np.float32)
+    score[rng.integers(0, n, 200)] = np.float32(0.25)            # a block of tied scores across both classes
+    score[:50] = np.round(score[:50], 1)                         # more ties
+    keys = ["u%03d" % i for i in range(400)]
+    pairs = [(keys[rng.integers(0, 400)], keys[rng.integers(0, 400)]) for _ in range(n)]
+    with open(os.path.join(out, "trials.txt"), "w") as ft, open(os.path.join(out, "scores.txt"), "w") as fs:
+        for (a, b), l, s_ in zip(pairs, label, score):
+            ft.write("%d %s %s\n" % (l, a, b))
+            fs.write("%s %s %s\n" % (a, b, str(np.float32(s_))))
+    # the reference keys both files by (utt1, utt2): repeated pairs keep the LAST line (eer_minDCF.py:25-40)
+    pair_label = eer_minDCF.read_trial_file(os.path.join(out, "trials.txt"))
+    pair_score = eer_minDCF.read_score_file(os.path.join(out, "scores.txt"))
+    y = [pair_label[p] for p in pair_label]
+    y_pred = [pair_score[p] for p in pair_label]
+    rows = []
+    for c_miss, c_fa, p_target in ((1, 1, 0.01), (1, 1, 0.05), (10, 1, 0.001)):
+        rows.append([c_miss, c_fa, p_target] + [float(v) for v in eer_minDCF.compute_eer_and_min_dcf(y, y_pred, c_miss, c_fa, p_target)])
+    np.save(os.path.join(out, "ref_eer.npy"), np.array(rows, np.float64))
+    with open(os.path.join(out, "ref_stdout.txt"), "w") as f:
+        f.write(subprocess.check_output([sys.executable, os.path.join(REF, "eer_minDCF.py"), "--trial", os.path.join(out, "trials.txt"),
+                                         "--score", os.path.join(out, "scores.txt")], cwd=REF, stderr=subprocess.DEVNULL).decode())
+
+
 def compress_cm(m):
     """Minimal Kaldi 'CM ' (kSpeechFeature) writer used only to make a fixture the reference decodes."""
     rows, cols = m.shape
@@ -165,4 +197,5 @@ if __name__ == "__main__":
     gen_score(os.path.join(g, "score"))
     gen_io(os.path.join(g, "io"))
     gen_net(os.path.join(g, "net"))
+    gen_eer(os.path.join(g, "eer"))
     print("golden fixtures written under", g)

@@ -486,4 +486,22 @@ int svx_trial_scores(const float* emb_dev, int d, const int32_t* idx1_dev, const
 
 long long svx_scorer_last_launches(svx_scorer* h) { return h ? h->launches : -1; }
 
+int svx_eer_min_dcf(const float* scores_dev, const int32_t* labels_dev, int64_t n, double c_miss, double c_fa, double p_target,
+                    double* out_host, void* cuda_stream) {
+  if (!scores_dev || !labels_dev || !out_host) { set_last_error("null argument"); return 1; }
+  if (n < 2 || n > 0x7fffffff) { set_last_error("EER needs between 2 and 2^31-1 trials"); return 1; }
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  size_t bytes = 0;
+  API_CUDA(eer_min_dcf(scores_dev, labels_dev, n, c_miss, c_fa, p_target, nullptr, nullptr, &bytes, st));
+  void* ws = nullptr; double* d_out = nullptr;
+  API_CUDA(cudaMallocAsync(&ws, bytes, st));
+  API_CUDA(cudaMallocAsync(&d_out, 4 * sizeof(double), st));
+  cudaError_t e = eer_min_dcf(scores_dev, labels_dev, n, c_miss, c_fa, p_target, d_out, ws, &bytes, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, d_out, 4 * sizeof(double), cudaMemcpyDeviceToHost, st);
+  cudaFreeAsync(ws, st); cudaFreeAsync(d_out, st);
+  API_CUDA(e);
+  API_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
 }  // extern "C"

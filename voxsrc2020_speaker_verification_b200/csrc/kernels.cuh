@@ -67,6 +67,9 @@ cudaError_t launch_asnorm_fused(const AsnormFusedParams& p, const CUtensorMap& m
 cudaError_t launch_split2(const float* in, __nv_bfloat16* out, long long n, long long n_pad, int d, int dp, cudaStream_t st);
 cudaError_t launch_gather_rows(const float* in, const int* rows, int n, int d, float* out, cudaStream_t st);
 cudaError_t launch_scatter_rows(const float* in, const int* rows, int n, int d, float* out, int out_ld, cudaStream_t st);
+// EER / minDCF (metrics.cu): ws == nullptr -> *ws_bytes = workspace size; out_dev = {eer, eer_threshold, min_dcf, min_dcf_threshold}
+cudaError_t eer_min_dcf(const float* scores, const int32_t* labels, long long n, double c_miss, double c_fa, double p_target, double* out_dev,
+                        void* ws, size_t* ws_bytes, cudaStream_t st);
 cudaError_t launch_group_mean(const float* unit_rows, int d, const int32_t* member_rows, const int32_t* group_off, float* out, int n_groups,
                               cudaStream_t st);
 

@@ -58,6 +58,7 @@ SYMBOLS = {
     "svx_topk_stats": (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "svx_trial_scores": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "svx_scorer_last_launches": (c_longlong, [c_void_p]),
+    "svx_eer_min_dcf": (c_int, [c_void_p, c_void_p, c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_double, c_void_p, c_void_p]),
     "svx_scorer_set_option": (c_int, [c_void_p, c_char_p, c_int]),
     "svx_scorer_last_path": (c_int, [c_void_p, POINTER(c_longlong), POINTER(c_longlong)]),
 }
