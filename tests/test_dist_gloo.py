@@ -47,6 +47,9 @@ def _worker(rank, world, port, q):
     mine = svdist.balance_by_frames(lengths, world)[rank]
     local = torch.tensor([[float(i), float(lengths[i])] for i in mine])
     allv = svdist.gather_embeddings(local, torch.tensor(mine), len(lengths))
+    # the same through extract_sharded: one all-gather, the partition derived on every rank
+    allv2 = svdist.extract_sharded(lambda idx: torch.tensor([[float(i), float(lengths[i])] for i in idx]).reshape(len(idx), 2), lengths)
+    assert torch.equal(allv, allv2)
     if rank == 0:
         q.put((mean.numpy(), std.numpy(), allv.numpy()))
     dist.destroy_process_group()

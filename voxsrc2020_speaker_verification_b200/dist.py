@@ -41,6 +41,36 @@ def balance_by_frames(lengths: Sequence[int], world: int) -> List[List[int]]:
     return parts
 
 
+def gather_sharded(local: torch.Tensor, parts: Sequence[Sequence[int]], group=None) -> torch.Tensor:
+    """Embeddings of a ``balance_by_frames`` partition back in the caller's order on every rank: ONE all-gather of the ranks'
+    [n_max, E] blocks (every rank derives the same partition, so neither counts nor indices travel)."""
+    world = dist.get_world_size(group)
+    n_total = sum(len(p) for p in parts)
+    n_max = max(1, max(len(p) for p in parts))
+    e = local.shape[1]
+    pad = torch.zeros((n_max, e), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    allb = torch.empty((world * n_max, e), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(allb, pad, group=group)
+    out = torch.empty((n_total, e), dtype=local.dtype, device=local.device)
+    for r, p in enumerate(parts):
+        if len(p):
+            out[torch.as_tensor(list(p), dtype=torch.int64, device=local.device)] = allb[r * n_max: r * n_max + len(p)]
+    return out
+
+
+def extract_sharded(extract_local, lengths: Sequence[int], group=None) -> torch.Tensor:
+    """The extraction stage over the ranks of ``group`` (reference layout: eval_inference_model.sh:29-39, one process per GPU,
+    static scp shards, no communication — here the shards are balanced by frame count and the result is gathered).
+
+    ``extract_local(indices)`` → CUDA tensor [len(indices), E]: the embeddings of this rank's utterances, in that order.
+    Returns [len(lengths), E] in the caller's order on every rank."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    parts = balance_by_frames(lengths, world)
+    local = extract_local(parts[rank])
+    return gather_sharded(local, parts, group)
+
+
 def gather_embeddings(local: torch.Tensor, local_index: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
     """All-gather per-rank embeddings [n_r, E] with their global utterance indices → [n_total, E] on every rank."""
     world = dist.get_world_size(group)

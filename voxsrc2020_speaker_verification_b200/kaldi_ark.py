@@ -13,7 +13,7 @@ from __future__ import annotations
 import io
 import os
 import struct
-from typing import BinaryIO, Dict, Iterator, List, Optional, Tuple
+from typing import BinaryIO, Dict, Iterator, List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -129,6 +129,43 @@ def read_mat_raw(fd: BinaryIO):
     return "dense", m, m.shape[0], m.shape[1]
 
 
+def peek_mat_shape(fd: BinaryIO) -> Tuple[int, int]:
+    """(rows, cols) of the binary matrix at the current position, reading only its header (the position is restored)."""
+    pos = fd.tell()
+    try:
+        if _read_exact(fd, 2) != b"\0B":
+            raise UnknownMatrixHeader("only binary Kaldi matrices are supported")
+        header = _read_exact(fd, 3).decode("latin1")
+        if header == "CM ":
+            _, _, rows, cols = struct.unpack("<ffii", _read_exact(fd, 16))
+        elif header in ("FM ", "DM "):
+            s1, rows, s2, cols = struct.unpack("<bibi", _read_exact(fd, 10))
+        else:
+            raise UnknownMatrixHeader("The header contained %r" % header)
+        return rows, cols
+    finally:
+        fd.seek(pos)
+
+
+def scp_shapes(path: str) -> List[Tuple[str, int, int]]:
+    """(key, rows, cols) of every record a script file addresses — headers only (what a rank needs to balance the work)."""
+    out, cur_path, cur_fd = [], None, None
+    try:
+        for key, rx, off in read_scp(path):
+            if rx != cur_path:
+                if cur_fd is not None:
+                    cur_fd.close()
+                cur_fd, cur_path = open(rx, "rb"), rx
+            if off is None:
+                raise ValueError("scp entry %s has no byte offset" % key)
+            cur_fd.seek(off)
+            out.append((key,) + peek_mat_shape(cur_fd))
+    finally:
+        if cur_fd is not None:
+            cur_fd.close()
+    return out
+
+
 def read_mat_ark_raw(path_or_fd):
     """(key, kind, payload, rows, cols) for every record of a matrix ark (see ``read_mat_raw``)."""
     fd, own = _open(path_or_fd)
@@ -191,11 +228,15 @@ def read_mat_scp(path: str) -> Iterator[Tuple[str, np.ndarray]]:
             cur_fd.close()
 
 
-def read_mat_scp_raw(path: str):
-    """(key, kind, payload, rows, cols) addressed by a script file; 'CM ' records stay compressed (see ``read_mat_raw``)."""
+def read_mat_scp_raw(path: str, only: Optional[Sequence[int]] = None):
+    """(key, kind, payload, rows, cols) addressed by a script file; 'CM ' records stay compressed (see ``read_mat_raw``).
+    ``only``: line indices to read (a rank's share), in that order."""
     cur_path, cur_fd = None, None
     try:
-        for key, rx, off in read_scp(path):
+        entries = read_scp(path)
+        if only is not None:
+            entries = [entries[i] for i in only]
+        for key, rx, off in entries:
             if rx != cur_path:
                 if cur_fd is not None:
                     cur_fd.close()

@@ -21,6 +21,61 @@ from . import kaldi_ark
 from .extractor import Extractor
 
 
+def run_distributed(pb_file: str, expand_dim: int, rspec: str, wspec: str, precision: str = "fp16", max_frames: int = 60000,
+                    cmvn: bool = True, model_id=None, feat_dim=None) -> int:
+    """One scp, all GPUs of the node (launched by torchrun, one rank per GPU): every rank reads the record HEADERS, takes a
+    frame-balanced share of the utterances (dist.balance_by_frames), extracts it on its own GPU and the embeddings are
+    all-gathered over NCCL; rank 0 writes ``wspec.ark/.scp`` in the scp's order.  Replaces the reference's static N-way scp split
+    + N processes + ``cat`` (eval_inference_model.sh:29-39) when the utterance lengths are uneven."""
+    import os
+    import torch.distributed as tdist
+    from . import dist as svdist
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    own_group = not tdist.is_initialized()
+    if own_group:
+        tdist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    try:
+        ex = Extractor.from_pb(pb_file, expand_dim, device=local, precision=precision, model_id=model_id, feat_dim=feat_dim)
+        shapes = kaldi_ark.scp_shapes(rspec + ".scp")
+        for key, rows, cols in shapes:
+            if rows < 25:
+                raise ZeroDivisionError("utterance %s has %d frames (< 25)" % (key, rows))
+            if cols != ex.feat_dim:
+                raise ValueError("utterance %s has %d-dim features, the model takes %d" % (key, cols, ex.feat_dim))
+
+        def extract_local(indices):
+            out = torch.empty((len(indices), ex.embed_dim), dtype=torch.float32, device=torch.device("cuda", local))
+            recs = [(kind, payload, rows) for _, kind, payload, rows, _ in kaldi_ark.read_mat_scp_raw(rspec + ".scp", only=indices)]
+            pos = 0
+            while pos < len(recs):                      # launch sequences of <= 4 * max_frames frames, like run()
+                end, frames = pos, 0
+                while end < len(recs) and (end == pos or frames + recs[end][2] <= 4 * max_frames):
+                    frames += recs[end][2]
+                    end += 1
+                chunk = recs[pos:end]
+                if all(kind == "CM " for kind, _, _ in chunk):
+                    emb = extract_compressed(ex, chunk, max_frames, cmvn)
+                else:
+                    mats = [kaldi_ark._decode_compressed(io.BytesIO(p), "CM ") if kind == "CM " else np.asarray(p, np.float32) for kind, p, _ in chunk]
+                    emb = ex.extract_bucketed(mats, max_frames=max_frames, cmvn=cmvn)
+                out[pos:end] = torch.from_numpy(emb).to(out.device)
+                pos = end
+            return out
+
+        emb = svdist.extract_sharded(extract_local, [r for _, r, _ in shapes])
+        if tdist.get_rank() == 0:
+            host = emb.cpu().numpy()
+            with kaldi_ark.VectorArkScpWriter(wspec) as writer:
+                for (key, _, _), e in zip(shapes, host):
+                    writer.write(key, e)
+        tdist.barrier()
+        return len(shapes)
+    finally:
+        if own_group:
+            tdist.destroy_process_group()
+
+
 def run(pb_file: str, expand_dim: int, rspec: str, wspec: str, precision: str = "fp16", device: int = 0,
         max_frames: int = 60000, cmvn: bool = True, model_id=None, feat_dim=None) -> int:
     ex = Extractor.from_pb(pb_file, expand_dim, device=device, precision=precision, model_id=model_id, feat_dim=feat_dim)
@@ -95,7 +150,12 @@ def main(argv=None) -> int:
     p.add_argument("--max-frames", type=int, default=60000, help="frames per GPU launch sequence")
     p.add_argument("--model-id", default=None)
     p.add_argument("--feat-dim", type=int, default=None)
+    p.add_argument("--distributed", action="store_true",
+                   help="under torchrun: all ranks share ONE scp (frame-balanced), NCCL all-gather of the embeddings, rank 0 writes")
     a = p.parse_args(argv)
+    if a.distributed:
+        n = run_distributed(a.pb_file, a.expand_dim, a.rspec, a.wspec, a.precision, a.max_frames, a.cmvn, a.model_id, a.feat_dim)
+        return 0
     n = run(a.pb_file, a.expand_dim, a.rspec, a.wspec, a.precision, 0, a.max_frames, a.cmvn, a.model_id, a.feat_dim)
     print("extracted %d embeddings → %s.ark" % (n, a.wspec), file=sys.stderr)
     return 0
