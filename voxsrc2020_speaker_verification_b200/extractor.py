@@ -99,6 +99,16 @@ class Extractor:
             raise ValueError("--expand-dim %d does not fit model %s (needs %d)" % (expand_dim, model_id, ex.cfg.expand_dim))
         return ex.load_params(consts)
 
+    @classmethod
+    def from_checkpoint(cls, prefix: str, model_id: str, feat_dim: int, device: int = 0, precision: str = "fp16") -> "Extractor":
+        """Build straight from a training checkpoint ``model.ckpt-N`` (tensor bundle: ``.index`` + ``.data-*``) instead of the
+        frozen ``.pb`` the reference exports from it (export_inference_graph.py:61-66, export_inference_model.sh:36-44).  A
+        checkpoint does not say which architecture it holds, so ``model_id`` and ``feat_dim`` are required; every variable is
+        validated by shape."""
+        from . import ckpt_loader
+        ex = cls(model_id, feat_dim, device, precision)
+        return ex.load_params(ckpt_loader.load_model_params(prefix, ex.cfg, ex.feat_dim))
+
     def set_option(self, key: str, value: int) -> None:
         lib.check(self._lib.svx_extractor_set_option(self._h, key.encode(), int(value)))
 

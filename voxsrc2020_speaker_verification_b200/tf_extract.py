@@ -21,6 +21,20 @@ from . import kaldi_ark
 from .extractor import Extractor
 
 
+def _load_model(pb_file: str, expand_dim: int, device: int, precision: str, model_id, feat_dim) -> Extractor:
+    """``--pb-file`` names a frozen graph (the reference's contract) or, as an addition, a checkpoint prefix ``…/model.ckpt-N``
+    (then --model-id and --feat-dim are required: a checkpoint does not describe its graph)."""
+    import os
+    if not pb_file.endswith(".pb") and os.path.exists(pb_file + ".index"):
+        if model_id is None or feat_dim is None:
+            raise ValueError("a checkpoint prefix needs --model-id and --feat-dim")
+        ex = Extractor.from_checkpoint(pb_file, model_id, feat_dim, device=device, precision=precision)
+        if expand_dim is not None and expand_dim != ex.cfg.expand_dim:
+            raise ValueError("--expand-dim %d does not fit model %s (needs %d)" % (expand_dim, model_id, ex.cfg.expand_dim))
+        return ex
+    return Extractor.from_pb(pb_file, expand_dim, device=device, precision=precision, model_id=model_id, feat_dim=feat_dim)
+
+
 def run_distributed(pb_file: str, expand_dim: int, rspec: str, wspec: str, precision: str = "fp16", max_frames: int = 60000,
                     cmvn: bool = True, model_id=None, feat_dim=None) -> int:
     """One scp, all GPUs of the node (launched by torchrun, one rank per GPU): every rank reads the record HEADERS, takes a
@@ -36,7 +50,7 @@ def run_distributed(pb_file: str, expand_dim: int, rspec: str, wspec: str, preci
     if own_group:
         tdist.init_process_group("nccl", device_id=torch.device("cuda", local))
     try:
-        ex = Extractor.from_pb(pb_file, expand_dim, device=local, precision=precision, model_id=model_id, feat_dim=feat_dim)
+        ex = _load_model(pb_file, expand_dim, local, precision, model_id, feat_dim)
         shapes = kaldi_ark.scp_shapes(rspec + ".scp")
         for key, rows, cols in shapes:
             if rows < 25:
@@ -78,7 +92,7 @@ def run_distributed(pb_file: str, expand_dim: int, rspec: str, wspec: str, preci
 
 def run(pb_file: str, expand_dim: int, rspec: str, wspec: str, precision: str = "fp16", device: int = 0,
         max_frames: int = 60000, cmvn: bool = True, model_id=None, feat_dim=None) -> int:
-    ex = Extractor.from_pb(pb_file, expand_dim, device=device, precision=precision, model_id=model_id, feat_dim=feat_dim)
+    ex = _load_model(pb_file, expand_dim, device, precision, model_id, feat_dim)
     n_done = 0
     with kaldi_ark.VectorArkScpWriter(wspec) as writer:
         keys, recs, frames = [], [], 0
