@@ -28,4 +28,9 @@ torch.cuda.synchronize(); dt1 = (time.perf_counter() - t0) / 5
 if rank == 0:
     print("world %d: max |sharded - single| = %.2e; sharded %.2f ms, single GPU %.2f ms" % (world, err, dt * 1e3, dt1 * 1e3))
 assert err < 2e-6, err
+m2, s2 = svdist.rows_sharded_cohort_mean_std(sc, x, cohort, K)
+err2 = max(float((m0 - m2).abs().max()), float((s0 - s2).abs().max()))
+assert err2 < 2e-6, err2
+if rank == 0:
+    print("OK rows-sharded max |diff| = %.2e" % err2)
 dist.destroy_process_group()
