@@ -724,8 +724,11 @@ static int g_flat_sms = 0;
 template <typename T, int AUX, bool PRE, bool POST>
 static cudaError_t set_attr() {
   cudaError_t e = cudaFuncSetAttribute(conv_flat_kernel<T, AUX, PRE, POST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+#ifdef SVX_DEBUG_SWITCHES      // the multicast-cluster instantiation exists in the debug build only (measured slower)
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(conv_flat_kernel<T, AUX, PRE, POST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  e = cudaFuncSetAttribute(conv_flat_kernel<T, AUX, PRE, POST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+#endif
+  return e;
 }
 
 template <typename T>
@@ -767,7 +770,12 @@ static int max_clusters(int cs, size_t smem) {
   attr[0].val.clusterDim.x = static_cast<unsigned>(cs); attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, conv_flat_kernel<T, 0, false, true, true>, &cfg) != cudaSuccess || n <= 0) {
+#ifdef SVX_DEBUG_SWITCHES
+  const cudaError_t qe = cudaOccupancyMaxActiveClusters(&n, conv_flat_kernel<T, 0, false, true, true>, &cfg);
+#else
+  const cudaError_t qe = cudaErrorNotSupported;
+#endif
+  if (qe != cudaSuccess || n <= 0) {
     cudaGetLastError();
     n = (g_flat_sms > 0 ? g_flat_sms : 148) / cs * 3 / 4;      // conservative guess
   }
@@ -802,9 +810,14 @@ static cudaError_t launch_typed(const FlatConvParams& p, const FlatMaps& maps, d
   if (launch_log)
     fprintf(stderr, "conv_flat launch: grid %u smem %zu cluster %dx%d n_tiles %d n_tile %d mt %d P %lld aux %d\n", grid.x, smem, p.cm, p.cn, p.n_tiles,
             p.n_tile, p.mt, p.P, p.aux_mode);
+#ifdef SVX_DEBUG_SWITCHES
 #define SVX_FLAT(AUX, PRE, POST)                                                                       \
   le = mc ? cudaLaunchKernelEx(&cfg, conv_flat_kernel<T, AUX, PRE, POST, true>, p, maps)              \
           : cudaLaunchKernelEx(&cfg, conv_flat_kernel<T, AUX, PRE, POST, false>, p, maps)
+#else
+  if (mc) return cudaErrorNotSupported;
+#define SVX_FLAT(AUX, PRE, POST) le = cudaLaunchKernelEx(&cfg, conv_flat_kernel<T, AUX, PRE, POST, false>, p, maps)
+#endif
   if (p.aux_mode == 0) {
     if (p.pre_relu && !p.post_relu) SVX_FLAT(0, true, false);
     else if (!p.pre_relu && p.post_relu) SVX_FLAT(0, false, true);

@@ -812,7 +812,21 @@ int Model::plan_flat(ConvDesc& c) {
   }
   bool found = false;
   double best = 1e30;
+  // debug build: SVX_FORCE_PLAN="taps,cin,cout,n_tile,mt,bres[;...]" pins the tile shape of one layer class (-1 = free)
+  int f_ntile = -1, f_mt = -1, f_bres = -1;
+  if (const char* fpl = dbg_env("SVX_FORCE_PLAN")) {
+    const char* q = fpl;
+    while (q && *q) {
+      int a[6];
+      if (sscanf(q, "%d,%d,%d,%d,%d,%d", &a[0], &a[1], &a[2], &a[3], &a[4], &a[5]) == 6 && a[0] == taps && a[1] == c.cin && a[2] == c.cout) {
+        f_ntile = a[3]; f_mt = a[4]; f_bres = a[5];
+      }
+      q = strchr(q, ';');
+      if (q) ++q;
+    }
+  }
   for (int n_tile : cands) {
+    if (f_ntile > 0 && n_tile != f_ntile) continue;
     const int n_tiles = (N + n_tile - 1) / n_tile;
     for (int box_ch : {64, 32}) {
       if (split && box_ch != c.split_box) continue;
@@ -863,7 +877,9 @@ int Model::plan_flat(ConvDesc& c) {
           static const long long bres_max = dbg_env("SVX_BRES_MAX") ? atoll(dbg_env("SVX_BRES_MAX")) : 64 * 1024;   // tuning knobs; resident weights above 64 KB starve the A ring (measured +1.2 % against 96 KB)
           static const double lat_cyc = dbg_env("SVX_LAT_CYC") ? atof(dbg_env("SVX_LAT_CYC")) : 3000.0;
           static const double slot_scale = dbg_env("SVX_SLOT_SCALE") ? atof(dbg_env("SVX_SLOT_SCALE")) : 1.0;
-          if (b_res && b_total > bres_max) continue;
+          if (b_res && b_total > bres_max && f_bres != 1) continue;
+          if (f_bres >= 0 && b_res != f_bres) continue;
+          if (f_mt > 0 && mt != f_mt) continue;
           if (!b_res && items < 2) continue;
           static const int slots0 = dbg_env("SVX_SLOTS0") ? atoi(dbg_env("SVX_SLOTS0")) : 2;
           int a_stages = 2, b_stages = b_res ? 0 : 2, slots = slots0;               // slots: per warpgroup (2: convert j+1 while j is stored)
