@@ -226,3 +226,22 @@ def test_cmvn_sliding_on_device_matches_host_restatement():
     a = ex.extract(utts[1:], cmvn=True)
     b = ex.extract([cmn_oracle.apply_cmvn_sliding(u) for u in utts[1:]])
     np.testing.assert_allclose(a, b, atol=2e-4)
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+@pytest.mark.parametrize("n_utt,frames", [(3, 57), (40, 120), (256, 200)])
+def test_fused_chain_equals_separate_convs(precision, n_utt, frames):
+    """res2_chain.cu (the three hierarchical 3x3 convs of a stride-1 Res2Net block in one launch, running sums in shared memory)
+    against the same convs as separate flat-kernel launches: same MMA order and rounding points, so the embeddings are
+    bit-identical — from 3 short utterances (bands shorter than the pipeline) to the full BASELINE batch (225 tiles per CTA)."""
+    cfg, params, ex = model("res2net50_w24_s4_c32", 80, precision)
+    rng = np.random.default_rng(31)
+    feats = net_oracle.synth_feats(rng, n_utt, frames, 80)
+    utts = [feats[i] for i in range(n_utt)]
+    ex.set_option("no_chain", 1)
+    sep = run_segments(ex, utts)
+    n_sep = ex.last_launches
+    ex.set_option("no_chain", 0)
+    fused = run_segments(ex, utts)
+    assert ex.last_launches == n_sep - 2 * 3            # the three 24-channel blocks of stage 1: one launch instead of three, each
+    np.testing.assert_array_equal(fused, sep)

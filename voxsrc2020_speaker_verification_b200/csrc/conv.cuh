@@ -222,6 +222,24 @@ int conv_flat_max_clusters(int cluster_size);   // resident clusters of that man
 size_t conv_flat_smem_bytes(const FlatConvParams& p);
 cudaError_t launch_conv_flat(const FlatConvParams& p, const FlatMaps& maps, int is_bf16, cudaStream_t stream);
 
+// ------------------------------------------------------------------------------------------------------------
+// Fused hierarchical 3x3 chain of a stride-1 Res2Net block with 4 splits of <= 32 channels (res2_chain.cu): three dependent
+// 3x3 convs, the running sums x_{i+1} + y_i kept in shared memory.  Same flat pixel sequence as FlatConvParams.
+struct ChainParams {
+  long long P;                 // pixels to cover (rows_used * Wp)
+  long long P_cap;             // pixels allocated
+  int tap_shift[kMaxTaps];     // dh*Wp + dw of the 9 taps
+  uint32_t idesc;              // M = 128, N = 32
+  const float* scale[3]; const float* shift[3];   // folded BN of the three convs, 32 entries each (pad channels: 0)
+  const uint8_t* pix_valid;
+  uint8_t* y; uint32_t y_pitch;                   // concat: slice k of a pixel at y + pixel*y_pitch + k*64 bytes
+  unsigned long long* dbg;
+};
+struct ChainMaps { CUtensorMap x[3], w[3]; };   // planar splits x_0..x_2 ({32 ch, 128 px} boxes) and the three weight matrices ({32 k, 32 n} per tap)
+cudaError_t res2_chain_init();
+size_t res2_chain_smem_bytes();
+cudaError_t launch_res2_chain(const ChainParams& p, const ChainMaps& maps, int is_bf16, cudaStream_t stream);
+
 cudaError_t launch_conv_simple(const SimpleConvParams& p, int is_bf16, cudaStream_t stream);
 cudaError_t launch_conv_umma(const UmmaConvParams& p, const AMaps& amaps, const CUtensorMap& bmap, const CUtensorMap& auxmap,
                              const OMaps& omaps, int is_bf16, cudaStream_t stream);

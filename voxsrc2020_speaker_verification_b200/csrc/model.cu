@@ -237,6 +237,7 @@ void Model::build_res2net() {
             c.out_store = wp; c.out2_store = wpp;
             c.in = {i == 0 ? ms[0] : zs[i], 0};
             if (i < S - 2) { c.out2 = {zs[i + 1], 0}; c.add2 = {ms[i + 1], 0}; }       // x_{i+1} + o_i (:65-66)
+            if (S == 4 && wpp == 32 && wp == 32) c.chain_pos = i;                      // candidates for the fused chain (res2_chain.cu)
           } else {
             c.in = {mp, i * w};                                                        // no cross-split add when strided
           }
@@ -523,6 +524,7 @@ int Model::finalize() {
     if (!host_.count(v.name) || !host_[v.name].set) { set_last_error("tensor not set: " + v.name); return 1; }
   SVX_CUDA(conv_umma_init());
   SVX_CUDA(conv_flat_init());
+  SVX_CUDA(res2_chain_init());
   for (Op& op : ops_) {
     if (op.kind == OP_CONV) {
       if (upload_conv_weights(op.conv)) return 1;
@@ -579,6 +581,7 @@ int Model::set_option(const char* key, int value) {
   if (!strcmp(key, "force_simple")) { force_simple_ = value; return 0; }
   if (!strcmp(key, "time_convs")) { time_convs_ = value; return 0; }
   if (!strcmp(key, "no_flat")) { force_no_flat_ = value; return 0; }
+  if (!strcmp(key, "no_chain")) { no_chain_ = value; return 0; }
   set_last_error(std::string("unknown option: ") + key);
   return 1;
 }
@@ -1075,6 +1078,8 @@ int Model::plan_flat(ConvDesc& c) {
   return 0;
 }
 
+static unsigned long long* flat_dbg_words();
+
 int Model::ensure_capacity(int rows0) {
   if (!rows_cap_.empty() && rows0 <= rows_cap_[0]) return 0;
   SVX_CUDA(cudaDeviceSynchronize());
@@ -1101,7 +1106,99 @@ int Model::ensure_capacity(int rows0) {
   }
   for (Op& op : ops_)
     if (op.kind == OP_CONV && plan_conv(op.conv)) return 1;
+  for (size_t i = 0; i < ops_.size(); ++i)
+    if (ops_[i].kind == OP_CONV && ops_[i].conv.chain_pos == 0 && plan_chain(i)) return 1;
   if (has_att_ && (plan_conv(att_a_) || plan_conv(att_b_))) return 1;
+  return 0;
+}
+
+// Fused hierarchical chain (res2_chain.cu): ops i, i+1, i+2 are the three 3x3 convs of a stride-1 Res2Net block.  Leaves
+// chain_ok = false when the shapes do not qualify; the convs then run one by one on the flat kernel.
+int Model::plan_chain(size_t i0) {
+  Op& op0 = ops_[i0];
+  op0.chain_ok = false;
+  static const bool disabled = dbg_env("SVX_NO_CHAIN") != nullptr;   // debug switch
+  if (disabled || i0 + 2 >= ops_.size()) return 0;
+  ConvDesc* cv[3];
+  for (int k = 0; k < 3; ++k) {
+    Op& o = ops_[i0 + k];
+    if (o.kind != OP_CONV || o.conv.chain_pos != k) return 0;
+    cv[k] = &o.conv;
+  }
+  const ActTensor& ty = tensors_[cv[0]->out.id];
+  const int stage = ty.stage;
+  const int Wp = stage_Wp_[stage], W = stage_W_[stage];
+  if (Wp <= W || Wp + 1 >= 128) return 0;                      // one zero column; the halo must be shorter than a tile
+  if ((ty.C * 2) % 32 != 0 || (cv[0]->out.coff * 2) % 32 != 0) return 0;
+  for (int k = 0; k < 3; ++k) {
+    const ConvDesc& c = *cv[k];
+    if (c.kh != 3 || c.kw != 3 || c.stride != 1 || c.dil != 1 || c.groups != 1 || c.ph != 1 || c.pw != 1) return 0;
+    if (c.kpad != 32 || c.n_pad != 32 || c.cin != c.cout || c.cout > 32 || !c.post_relu || c.pre_relu || c.res.id >= 0 || c.outb.id >= 0) return 0;
+    if (c.out.id != cv[0]->out.id || c.out.coff != cv[0]->out.coff + 32 * k) return 0;
+    if (!c.d_scale || !c.d_shift || !c.use_flat) return 0;
+    const ActTensor& tin = tensors_[c.in.id];
+    if (tin.C != 32 || c.in.coff != 0 || tin.stage != stage) return 0;
+    if (k < 2) {
+      // conv k writes x_{k+1} + y_k to the tensor conv k+1 reads, from the planar split add2
+      if (c.out2.id < 0 || c.add2.id < 0 || c.out2.id != cv[k + 1]->in.id || c.out2.coff != 0 || c.add2.coff != 0) return 0;
+      if (tensors_[c.add2.id].C != 32 || tensors_[c.add2.id].stage != stage) return 0;
+    } else if (c.out2.id >= 0) return 0;
+  }
+  ChainParams cp;
+  memset(&cp, 0, sizeof cp);
+  for (int t = 0; t < 9; ++t) cp.tap_shift[t] = (t / 3 - 1) * Wp + (t % 3 - 1);
+  cp.idesc = ptx::make_idesc_f16(is_bf16_ ? 1u : 0u, 128u, 32u);
+  for (int k = 0; k < 3; ++k) { cp.scale[k] = cv[k]->d_scale; cp.shift[k] = cv[k]->d_shift; }
+  cp.pix_valid = d_pix_valid_[stage];
+  cp.y = static_cast<uint8_t*>(ty.ptr) + static_cast<size_t>(cv[0]->out.coff) * 2;
+  cp.y_pitch = static_cast<uint32_t>(ty.C * 2);
+  const uint64_t P_cap = static_cast<uint64_t>(rows_cap_[stage]) * Wp;
+  cp.P_cap = static_cast<long long>(P_cap);
+  ChainMaps& cm = op0.cmaps;
+  memset(&cm, 0, sizeof cm);
+  const int src[3] = {cv[0]->in.id, cv[0]->add2.id, cv[1]->add2.id};      // the planar splits x_0, x_1, x_2
+  for (int k = 0; k < 3; ++k) {
+    const uint64_t dims[2] = {32, P_cap};
+    const uint64_t str[1] = {64};
+    const uint32_t box[2] = {32, 128};
+    if (encode_tmap(&cm.x[k], is_bf16_, tensors_[src[k]].ptr, 2, dims, str, box, 64, 128)) return 1;
+    const uint64_t wd[2] = {9 * 32, 32};
+    const uint64_t ws[1] = {9 * 32 * 2};
+    const uint32_t wb[2] = {32, 32};
+    if (encode_tmap(&cm.w[k], is_bf16_, cv[k]->d_wgt, 2, wd, ws, wb, 64)) return 1;
+  }
+  op0.cp = cp;
+  op0.chain_ok = true;
+  return 0;
+}
+
+int Model::launch_chain(size_t i0, cudaStream_t st) {
+  Op& op0 = ops_[i0];
+  const ConvDesc& c0 = op0.conv;
+  const int stage = tensors_[c0.out.id].stage;
+  if (time_convs_) {
+    while (events_.size() < ev_used_ + 2) { cudaEvent_t e; SVX_CUDA(cudaEventCreate(&e)); events_.push_back(e); }
+    SVX_CUDA(cudaEventRecord(events_[ev_used_], st));
+  }
+  op0.cp.P = static_cast<long long>(rows_used_[stage]) * stage_Wp_[stage];
+  op0.cp.dbg = flat_dbg_words();
+  if (tensor_dir_.size() != tensors_.size()) tensor_dir_.assign(tensors_.size(), 0);
+  tensor_dir_[c0.out.id] = 0;                        // the chain walks the pixels forwards
+  SVX_CUDA(launch_res2_chain(op0.cp, op0.cmaps, is_bf16_, st));
+  if (time_convs_) {
+    SVX_CUDA(cudaEventRecord(events_[ev_used_ + 1], st));
+    ev_used_ += 2;
+    double pix = 0.0;
+    for (int h : seg_h_host_[stage]) pix += static_cast<double>(h) * stage_W_[stage];
+    const double fl = 3.0 * 2.0 * pix * 9.0 * c0.cin * c0.cout;
+    conv_flops_ += fl;
+    if (conv_labels_.size() < ev_used_ / 2) {
+      char lb[256];
+      snprintf(lb, sizeof lb, "stage %d fused 3x3 chain x3 cin %4d cout %4d  %.1f GFLOP", stage, c0.cin, c0.cout, fl * 1e-9);
+      conv_labels_.push_back(lb);
+    }
+  }
+  ++launches_;
   return 0;
 }
 
@@ -1324,7 +1421,7 @@ int Model::run_segments_sl(const float* d_feats, const std::vector<int>& starts,
         grow(&d_fc_partial_, &fc_partial_bytes_, static_cast<size_t>(fc_splits(flat_dim_)) * nb * cfg_.embed_dim * 4)) {
       set_last_error("allocation failed"); return 1;
     }
-    int op_index = 0;
+    int op_index = 0, chain_skip = 0;
     const char* dump_dir = dump_dir_.empty() ? nullptr : dump_dir_.c_str();   // svx_extractor_set_dump_dir: raw dump of every op's destination tensor
     for (Op& op : ops_) {
       struct Dump {
@@ -1361,6 +1458,12 @@ int Model::run_segments_sl(const float* d_feats, const std::vector<int>& starts,
           break;
         }
         case OP_CONV:
+          if (op.conv.chain_pos > 0 && chain_skip > 0) { --chain_skip; break; }     // ran inside the fused chain launch
+          if (op.conv.chain_pos == 0 && op.chain_ok && !no_chain_ && !force_simple_ && !force_no_flat_) {
+            if (launch_chain(static_cast<size_t>(op_index - 1), st)) return 1;
+            chain_skip = 2;
+            break;
+          }
           if (launch_conv(op.conv, st)) return 1;
           break;
         case OP_BN_RELU: {

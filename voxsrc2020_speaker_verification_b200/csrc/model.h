@@ -64,6 +64,7 @@ struct ConvDesc {
   int n_gemm = 0;                     // GEMM N: cout, or n_splits * split_wp
   FlatConvParams fp; FlatMaps fmaps;
   SimpleConvParams sp;
+  int chain_pos = -1;                 // position in the hierarchical 3x3 chain of a stride-1 Res2Net block (res2_chain.cu), -1: none
 };
 
 struct Op {
@@ -73,6 +74,8 @@ struct Op {
   // OP_BN_RELU / OP_AVGPOOL:
   TensorRef in, out; int C = 0; int stride = 1; std::string bn_name;
   float* d_scale = nullptr; float* d_shift = nullptr; float* d_w9 = nullptr;
+  // OP_CONV with conv.chain_pos == 0: this conv and the next two run as ONE fused launch when chain_ok
+  bool chain_ok = false; ChainParams cp; ChainMaps cmaps;
 };
 
 struct ActTensor {
@@ -113,6 +116,8 @@ class Model {
   int ensure_capacity(int rows0);
   int plan_conv(ConvDesc& c);
   int plan_flat(ConvDesc& c);
+  int plan_chain(size_t op_index);
+  int launch_chain(size_t op_index, cudaStream_t st);
   int fold_bn(const std::string& bn, int C, bool four_d, std::vector<float>& scale, std::vector<float>& shift);
   int upload_conv_weights(ConvDesc& c);
   int launch_conv(ConvDesc& c, cudaStream_t st);
@@ -135,6 +140,7 @@ class Model {
   std::vector<int> stage_Wp_;        // pixels per row in memory: W + 1 zero column for the 2-D networks, W for the TDNN
   std::vector<uint8_t*> d_pix_valid_;
   int force_no_flat_ = 0;
+  int no_chain_ = 0;                  // option "no_chain": run the hierarchical 3x3 convs as separate launches
   std::vector<int> tensor_dir_;       // per activation tensor: 1 if its last writer walked the pixels backwards
   std::vector<int> rows_cap_, rows_used_;
   int seg_cap_ = 0;
