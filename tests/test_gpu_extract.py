@@ -245,3 +245,21 @@ def test_fused_chain_equals_separate_convs(precision, n_utt, frames):
     fused = run_segments(ex, utts)
     assert ex.last_launches == n_sep - 2 * 3            # the three 24-channel blocks of stage 1: one launch instead of three, each
     np.testing.assert_array_equal(fused, sep)
+
+
+@pytest.mark.parametrize("model_id,feat_dim,precision,n_utt,frames", [
+    ("res2net50_w24_s4_c32", 80, "fp16", 5, 57), ("res2net50_w24_s4_c32", 80, "bf16", 64, 200), ("res2net50_w24_s4_c32", 80, "fp16", 256, 200),
+    ("res2net50_w24_s4_c64", 40, "fp16", 9, 48), ("dpn68", 80, "fp16", 12, 120), ("tdnn", 40, "fp16", 33, 320)])
+def test_pair_gemm_equals_flat_kernel(model_id, feat_dim, precision, n_utt, frames):
+    """conv_pair.cu (deep 1x1 convs as a cta_group::2 GEMM, one M = 256 x N <= 256 tile per CTA pair) against the same convs on the
+    flat kernel: same K order and epilogue expression, so the embeddings are bit-identical; from a handful of pixel blocks (fewer
+    tiles than CTA pairs) to the full BASELINE batch.  The networks cover residual, planar-split and two-destination epilogues."""
+    cfg, params, ex = model(model_id, feat_dim, precision)
+    rng = np.random.default_rng(37)
+    feats = net_oracle.synth_feats(rng, n_utt, frames, feat_dim)
+    utts = [feats[i] for i in range(n_utt)]
+    ex.set_option("no_pair", 1)
+    flat = run_segments(ex, utts)
+    ex.set_option("no_pair", 0)
+    paired = run_segments(ex, utts)
+    np.testing.assert_array_equal(paired, flat)

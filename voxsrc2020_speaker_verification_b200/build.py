@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libsvx.so")
 DBG_LIB_PATH = os.path.join(HERE, "libsvx_dbg.so")   # debug build: SVX_* environment switches, CTA-pair instantiation, 2 s watchdog
-SOURCES = ["conv_flat.cu", "res2_chain.cu", "conv_umma.cu", "conv_simple.cu", "elementwise.cu", "frontend.cu", "scoring.cu", "asnorm_fused.cu", "metrics.cu", "model.cu", "api.cu"]
+SOURCES = ["conv_flat.cu", "res2_chain.cu", "conv_pair.cu", "conv_umma.cu", "conv_simple.cu", "elementwise.cu", "frontend.cu", "scoring.cu", "asnorm_fused.cu", "metrics.cu", "model.cu", "api.cu"]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
           "--expt-relaxed-constexpr", "-Xptxas", "-v"]

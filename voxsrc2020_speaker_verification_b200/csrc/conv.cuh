@@ -240,6 +240,35 @@ cudaError_t res2_chain_init();
 size_t res2_chain_smem_bytes();
 cudaError_t launch_res2_chain(const ChainParams& p, const ChainMaps& maps, int is_bf16, cudaStream_t stream);
 
+// ------------------------------------------------------------------------------------------------------------
+// CTA-pair GEMM for the deep 1x1 stride-1 convs (conv_pair.cu): one M = 256 x n_tile tile per pair of CTAs (cta_group::2),
+// every CTA loads its own 128 pixels and half of the weight rows.  Output leaves in 16-channel groups (32 bytes) through a
+// routing table, so dense outputs, planar splits and a second destination are the same code.
+struct PairConvParams {
+  long long P, P_cap;          // pixels to cover / allocated
+  int nkb;                     // K boxes of 64 elements
+  int n_tile, n_tiles;         // 128, 192 or 256 output channels per pair tile
+  int n_gemm;                  // GEMM N (n_tile * n_tiles, <= 1024)
+  int stages; uint32_t stage_bytes;
+  uint32_t idesc;              // M = 256, N = n_tile
+  const float* scale; const float* shift; int n_valid;
+  const uint8_t* pix_valid;
+  int aux_mode;                // 0 none, 1 residual added before post-ReLU
+  int n_res;                   // residual applies to GEMM columns < n_res (multiple of 16)
+  const uint8_t* res; uint32_t res_pitch;     // residual slice: column c of pixel p at res + p*res_pitch + 2c
+  int pre_relu, post_relu;
+  int reverse;                 // walk the pixel blocks from the last to the first (see FlatConvParams::reverse)
+  uint8_t route[64];           // per 16-column group: index into dst_base / dst_pitch, 0xff = not stored
+  uint16_t goff[64];           //   and the byte offset of the group inside a pixel of that destination
+  uint8_t* dst_base[10]; uint32_t dst_pitch[10];
+  int knock;                   // debug timing experiments only (SVX_PAIR_KNOCK)
+  unsigned long long* dbg;
+};
+struct PairMaps { CUtensorMap a, b; };   // a: {64 ch, 128 px} boxes of the input, b: {64 k, n_tile/2 rows} boxes of the weights, SWIZZLE_128B
+cudaError_t conv_pair_init();
+size_t conv_pair_smem_bytes(const PairConvParams& p);
+cudaError_t launch_conv_pair(const PairConvParams& p, const PairMaps& maps, int is_bf16, cudaStream_t stream);
+
 cudaError_t launch_conv_simple(const SimpleConvParams& p, int is_bf16, cudaStream_t stream);
 cudaError_t launch_conv_umma(const UmmaConvParams& p, const AMaps& amaps, const CUtensorMap& bmap, const CUtensorMap& auxmap,
                              const OMaps& omaps, int is_bf16, cudaStream_t stream);

@@ -525,6 +525,7 @@ int Model::finalize() {
   SVX_CUDA(conv_umma_init());
   SVX_CUDA(conv_flat_init());
   SVX_CUDA(res2_chain_init());
+  SVX_CUDA(conv_pair_init());
   for (Op& op : ops_) {
     if (op.kind == OP_CONV) {
       if (upload_conv_weights(op.conv)) return 1;
@@ -582,6 +583,7 @@ int Model::set_option(const char* key, int value) {
   if (!strcmp(key, "time_convs")) { time_convs_ = value; return 0; }
   if (!strcmp(key, "no_flat")) { force_no_flat_ = value; return 0; }
   if (!strcmp(key, "no_chain")) { no_chain_ = value; return 0; }
+  if (!strcmp(key, "no_pair")) { no_pair_ = value; return 0; }
   set_last_error(std::string("unknown option: ") + key);
   return 1;
 }
@@ -619,6 +621,8 @@ int Model::plan_conv(ConvDesc& c) {
   sp.out_rows = 0; sp.out_W = out_W; sp.out_Wp = out_Wp; sp.epi = e;
   c.use_flat = false;
   if (plan_flat(c)) return 1;
+  c.use_pair = false;
+  if (c.use_flat && plan_pair(c)) return 1;
   // ---- tcgen05 form
   c.use_umma = false;
   const int taps = c.kh * c.kw;
@@ -1080,6 +1084,114 @@ int Model::plan_flat(ConvDesc& c) {
 
 static unsigned long long* flat_dbg_words();
 
+// CTA-pair GEMM (conv_pair.cu) for 1x1 stride-1 convs with K >= 192: a pair of SMs per M = 256 x N <= 256 tile halves the weight
+// bytes every SM receives.  Leaves use_pair = false when the shape does not qualify (the flat plan then runs).
+int Model::plan_pair(ConvDesc& c) {
+  static const bool disabled = dbg_env("SVX_NO_PAIR") != nullptr;   // debug switch
+  static const int min_k = dbg_env("SVX_PAIR_MIN_K") ? atoi(dbg_env("SVX_PAIR_MIN_K")) : 384;   // K = 192 / 256 (stage 2 of Res2Net-50): HBM-bound, the flat kernel is as fast
+  if (disabled) return 0;
+  const ActTensor& tin = tensors_[c.in.id];
+  const ActTensor& tout = tensors_[c.out.id];
+  if (c.kh != 1 || c.kw != 1 || c.stride != 1 || c.groups != 1 || tin.stage != tout.stage) return 0;
+  if (c.kbox != 64 || c.kpad % 64 != 0 || c.kpad < min_k) return 0;
+  if (c.out2.id >= 0 || c.add2.id >= 0) return 0;
+  const int N = c.n_gemm;
+  if (N % 32 != 0 || N > 1024 || N < 128) return 0;
+  const int n_tile = N % 256 == 0 ? 256 : N % 192 == 0 ? 192 : N % 128 == 0 ? 128 : 0;
+  if (n_tile == 0 || c.n_pad < N) return 0;
+  const int n_split = c.n_split < 0 ? c.cout : c.n_split;
+  const bool split = c.split_w > 0;
+  const int aux_mode = c.res.id >= 0 ? 1 : 0;
+  if (split && aux_mode) return 0;
+  PairConvParams pp;
+  memset(&pp, 0, sizeof pp);
+  memset(pp.route, 0xff, sizeof pp.route);
+  const size_t esz = 2;
+  int n_dst = 0;
+  auto add_dst = [&](const TensorRef& r) -> int {
+    const ActTensor& t = tensors_[r.id];
+    if (t.stage != tout.stage || (t.C * esz) % 32 != 0 || n_dst >= 10) return -1;
+    pp.dst_base[n_dst] = static_cast<uint8_t*>(t.ptr);
+    pp.dst_pitch[n_dst] = static_cast<uint32_t>(t.C * esz);
+    return n_dst++;
+  };
+  if (split) {
+    if (c.split_wp % 16 != 0 || c.split_w % 16 != 0 || c.split_out.size() > 8) return 0;
+    const int split_store = (c.split_store > c.split_w && c.split_store <= c.split_wp) ? c.split_store : c.split_w;
+    if (split_store % 16 != 0) return 0;
+    std::vector<int> di;
+    for (const TensorRef& r : c.split_out) {
+      if (r.coff % 16 != 0) return 0;
+      const int d = add_dst(r);
+      if (d < 0) return 0;
+      di.push_back(d);
+    }
+    for (int g = 0; g < N / 16; ++g) {
+      const int ch = g * 16, s = ch / c.split_wp, j = ch - s * c.split_wp;
+      if (s >= static_cast<int>(di.size()) || j >= split_store) continue;
+      pp.route[g] = static_cast<uint8_t>(di[s]);
+      pp.goff[g] = static_cast<uint16_t>((c.split_out[s].coff + j) * esz);
+    }
+  } else {
+    if (N != c.cout || n_split % 16 != 0 || c.out.coff % 16 != 0) return 0;
+    const int d0 = add_dst(c.out);
+    if (d0 < 0) return 0;
+    int d1 = -1;
+    if (n_split < c.cout) {
+      if (c.outb.id < 0 || c.outb.coff % 16 != 0) return 0;
+      d1 = add_dst(c.outb);
+      if (d1 < 0) return 0;
+    }
+    for (int g = 0; g < N / 16; ++g) {
+      const int ch = g * 16;
+      if (ch < n_split) { pp.route[g] = static_cast<uint8_t>(d0); pp.goff[g] = static_cast<uint16_t>((c.out.coff + ch) * esz); }
+      else { pp.route[g] = static_cast<uint8_t>(d1); pp.goff[g] = static_cast<uint16_t>((c.outb.coff + ch - n_split) * esz); }
+    }
+  }
+  if (aux_mode) {
+    const ActTensor& tr = tensors_[c.res.id];
+    if (tr.stage != tout.stage || (tr.C * esz) % 32 != 0 || c.res.coff % 16 != 0 || n_split % 16 != 0) return 0;
+    pp.res = static_cast<const uint8_t*>(tr.ptr) + static_cast<size_t>(c.res.coff) * esz;
+    pp.res_pitch = static_cast<uint32_t>(tr.C * esz);
+    pp.n_res = n_split;
+  }
+  pp.aux_mode = aux_mode;
+  pp.nkb = c.kpad / 64;
+  pp.n_tile = n_tile; pp.n_tiles = N / n_tile; pp.n_gemm = N; pp.n_valid = N;
+  pp.stage_bytes = 128u * 128u + static_cast<uint32_t>(round_up((n_tile / 2) * 128, 1024));
+  pp.stages = static_cast<int>((227 * 1024 - 1024 - (1024 + 8192 + 1024) - 8 * 4096) / pp.stage_bytes);
+  if (pp.stages > 8) pp.stages = 8;
+  if (pp.stages < 3) return 0;
+  pp.idesc = ptx::make_idesc_f16(is_bf16_ ? 1u : 0u, 256u, static_cast<uint32_t>(n_tile));
+  pp.scale = c.d_scale; pp.shift = c.d_shift;
+  pp.pix_valid = d_pix_valid_[tout.stage];
+  pp.pre_relu = c.pre_relu; pp.post_relu = c.post_relu;
+  const int Wp = stage_Wp_[tout.stage];
+  const uint64_t P_cap = static_cast<uint64_t>(rows_cap_[tout.stage]) * Wp;
+  pp.P_cap = static_cast<long long>(P_cap);
+  PairMaps& pm = c.pmaps;
+  memset(&pm, 0, sizeof pm);
+  {
+    const int a_width = (c.in.coff == 0 && tin.C > c.cin && tin.C <= c.kpad) ? tin.C : c.cin;
+    const uint64_t dims[2] = {static_cast<uint64_t>(a_width), P_cap};
+    const uint64_t str[1] = {static_cast<uint64_t>(tin.C) * esz};
+    const uint32_t box[2] = {64u, 128u};
+    const int pitch = tin.C * 2, off = c.in.coff * 2, wb = c.cin * 2;
+    const int promo = (a_width == tin.C || (pitch % 128 == 0 && off % 128 == 0 && wb % 128 == 0)) ? 128 : 64;
+    if (encode_tmap(&pm.a, is_bf16_, static_cast<uint8_t*>(tin.ptr) + static_cast<size_t>(c.in.coff) * esz, 2, dims, str, box, 128, promo)) return 1;
+  }
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(c.kpad), static_cast<uint64_t>(c.n_pad)};
+    const uint64_t str[1] = {static_cast<uint64_t>(c.kpad) * esz};
+    const uint32_t box[2] = {64u, static_cast<uint32_t>(n_tile / 2)};
+    if (encode_tmap(&pm.b, is_bf16_, c.d_wgt, 2, dims, str, box, 128)) return 1;
+  }
+  if (conv_pair_smem_bytes(pp) > 227 * 1024) return 0;
+  c.pp = pp;
+  c.use_pair = true;
+  return 0;
+}
+
 int Model::ensure_capacity(int rows0) {
   if (!rows_cap_.empty() && rows0 <= rows_cap_[0]) return 0;
   SVX_CUDA(cudaDeviceSynchronize());
@@ -1265,6 +1377,7 @@ int Model::launch_conv(ConvDesc& c, cudaStream_t st) {
   const int out_stage = tensors_[c.out.id].stage;
   const int out_rows = rows_used_[out_stage];
   const bool flat = c.use_flat && !force_simple_ && !force_no_flat_;
+  const bool pair = flat && c.use_pair && !no_pair_;
   const bool umma = !flat && c.use_umma && !force_simple_;
   if (flat || umma) {
     static const char* trace_dir = dbg_env("SVX_TRACE_DIR");   // debug: per-launch event timeline of CTA 0
@@ -1278,7 +1391,17 @@ int Model::launch_conv(ConvDesc& c, cudaStream_t st) {
       while (events_.size() < ev_used_ + 2) { cudaEvent_t e; SVX_CUDA(cudaEventCreate(&e)); events_.push_back(e); }
       SVX_CUDA(cudaEventRecord(events_[ev_used_], st));
     }
-    if (flat) {
+    if (pair) {
+      c.pp.P = static_cast<long long>(out_rows) * stage_Wp_[out_stage];
+      c.pp.dbg = flat_dbg_words();
+      { static const char* kn = dbg_env("SVX_PAIR_KNOCK"); c.pp.knock = kn ? atoi(kn) : 0; }
+      if (tensor_dir_.size() != tensors_.size()) tensor_dir_.assign(tensors_.size(), 0);
+      c.pp.reverse = 1 - tensor_dir_[c.in.id];
+      auto mark = [&](const TensorRef& r) { if (r.id >= 0) tensor_dir_[r.id] = c.pp.reverse; };
+      mark(c.out); mark(c.outb);
+      for (const TensorRef& r : c.split_out) mark(r);
+      SVX_CUDA(launch_conv_pair(c.pp, c.pmaps, is_bf16_, st));
+    } else if (flat) {
       c.fp.P = static_cast<long long>(out_rows) * stage_Wp_[out_stage];
       c.fp.trace = trace_dir ? d_trace : nullptr;
       c.fp.dbg = flat_dbg_words();
@@ -1321,8 +1444,8 @@ int Model::launch_conv(ConvDesc& c, cudaStream_t st) {
       if (conv_labels_.size() < ev_used_ / 2) {
         char lb[256];
         snprintf(lb, sizeof lb, "stage %d %dx%d s%d g%d cin %4d cout %4d aux %d %s n_tile %3d x%d mt %d bres %d a_st %d b_st %d slots %d direct %d  %.1f GFLOP", out_stage,
-                 c.kh, c.kw, c.stride, c.groups, c.cin, c.cout, flat ? c.fp.aux_mode : c.up.aux_mode, flat ? "flat" : "umma", flat ? c.fp.n_tile : c.up.n_tile,
-                 flat ? c.fp.n_tiles : c.up.n_tiles, flat ? c.fp.mt : 1, flat ? c.fp.b_resident : (c.up.bres_bytes != 0), flat ? c.fp.a_stages : c.up.stages,
+                 c.kh, c.kw, c.stride, c.groups, c.cin, c.cout, flat ? c.fp.aux_mode : c.up.aux_mode, pair ? "pair" : flat ? "flat" : "umma", pair ? c.pp.n_tile : flat ? c.fp.n_tile : c.up.n_tile,
+                 pair ? c.pp.n_tiles : flat ? c.fp.n_tiles : c.up.n_tiles, flat ? c.fp.mt : 1, flat ? c.fp.b_resident : (c.up.bres_bytes != 0), flat ? c.fp.a_stages : c.up.stages,
                  flat ? c.fp.b_stages : 0, flat ? c.fp.slots : 0, flat ? c.fp.direct : 0, fl * 1e-9);
         conv_labels_.push_back(lb);
       }

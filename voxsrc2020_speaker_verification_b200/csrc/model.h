@@ -63,6 +63,7 @@ struct ConvDesc {
   std::vector<TensorRef> split_out; int split_w = 0, split_wp = 0, split_box = 0;
   int n_gemm = 0;                     // GEMM N: cout, or n_splits * split_wp
   FlatConvParams fp; FlatMaps fmaps;
+  bool use_pair = false; PairConvParams pp; PairMaps pmaps;   // CTA-pair GEMM (conv_pair.cu) instead of the flat kernel
   SimpleConvParams sp;
   int chain_pos = -1;                 // position in the hierarchical 3x3 chain of a stride-1 Res2Net block (res2_chain.cu), -1: none
 };
@@ -116,6 +117,7 @@ class Model {
   int ensure_capacity(int rows0);
   int plan_conv(ConvDesc& c);
   int plan_flat(ConvDesc& c);
+  int plan_pair(ConvDesc& c);
   int plan_chain(size_t op_index);
   int launch_chain(size_t op_index, cudaStream_t st);
   int fold_bn(const std::string& bn, int C, bool four_d, std::vector<float>& scale, std::vector<float>& shift);
@@ -140,6 +142,7 @@ class Model {
   std::vector<int> stage_Wp_;        // pixels per row in memory: W + 1 zero column for the 2-D networks, W for the TDNN
   std::vector<uint8_t*> d_pix_valid_;
   int force_no_flat_ = 0;
+  int no_pair_ = 0;                   // option "no_pair": deep 1x1 convs on the flat kernel instead of the CTA-pair GEMM
   int no_chain_ = 0;                  // option "no_chain": run the hierarchical 3x3 convs as separate launches
   std::vector<int> tensor_dir_;       // per activation tensor: 1 if its last writer walked the pixels backwards
   std::vector<int> rows_cap_, rows_used_;
