@@ -233,9 +233,10 @@ struct ChainParams {
   const float* scale[3]; const float* shift[3];   // folded BN of the three convs, 32 entries each (pad channels: 0)
   const uint8_t* pix_valid;
   uint8_t* y; uint32_t y_pitch;                   // concat: slice k of a pixel at y + pixel*y_pitch + k*64 bytes
+  const uint8_t* xs[2];                           // planar splits x_1, x_2 (64 bytes per pixel): read by the epilogue thread that owns the pixel
   unsigned long long* dbg;
 };
-struct ChainMaps { CUtensorMap x[3], w[3]; };   // planar splits x_0..x_2 ({32 ch, 128 px} boxes) and the three weight matrices ({32 k, 32 n} per tap)
+struct ChainMaps { CUtensorMap x[3], w[3]; };   // x[0]: planar split x_0 ({32 ch, 128 px} boxes; x[1], x[2] unused), w: the three weight matrices ({32 k, 32 n} per tap)
 cudaError_t res2_chain_init();
 size_t res2_chain_smem_bytes();
 cudaError_t launch_res2_chain(const ChainParams& p, const ChainMaps& maps, int is_bf16, cudaStream_t stream);
@@ -246,16 +247,23 @@ cudaError_t launch_res2_chain(const ChainParams& p, const ChainMaps& maps, int i
 // routing table, so dense outputs, planar splits and a second destination are the same code.
 struct PairConvParams {
   long long P, P_cap;          // pixels to cover / allocated
-  int nkb;                     // K boxes of 64 elements
+  int nkb;                     // K boxes of 64 elements (per tap)
+  int ks_last;                 // K = 16 steps of the last box that hold real channels (1..4); the other boxes have 4
+  int kpad;                    // weight columns per tap (nkb * 64)
+  int taps, halo;              // 1x1: 1 / 0.  3x3: 9 taps as shifts of the flat pixel sequence, halo = max |shift|
+  int tap_shift[kMaxTaps];
+  int a_rows; uint32_t a_bytes;         // pixel rows of one A box (128 + 2 halo, multiple of 8) and its bytes rounded up to 1 KB
+  int b_resident; uint32_t b_item_bytes;   // weights resident in shared memory (taps * nkb items of n_tile/2 rows) instead of streamed with A (1x1 only)
   int n_tile, n_tiles;         // 128, 192 or 256 output channels per pair tile
   int n_gemm;                  // GEMM N (n_tile * n_tiles, <= 1024)
   int stages; uint32_t stage_bytes;
   uint32_t idesc;              // M = 256, N = n_tile
   const float* scale; const float* shift; int n_valid;
   const uint8_t* pix_valid;
-  int aux_mode;                // 0 none, 1 residual added before post-ReLU
+  int aux_mode;                // 0 none, 1 residual added before post-ReLU, 2 second output out2 = y + res (hierarchical 3x3, res = next split)
   int n_res;                   // residual applies to GEMM columns < n_res (multiple of 16)
-  const uint8_t* res; uint32_t res_pitch;     // residual slice: column c of pixel p at res + p*res_pitch + 2c
+  const uint8_t* res; uint32_t res_pitch;     // residual / add2 slice: column c of pixel p at res + p*res_pitch + 2c
+  uint8_t* out2; uint32_t out2_pitch;         // aux mode 2: second output slice, same addressing
   int pre_relu, post_relu;
   int reverse;                 // walk the pixel blocks from the last to the first (see FlatConvParams::reverse)
   uint8_t route[64];           // per 16-column group: index into dst_base / dst_pitch, 0xff = not stored

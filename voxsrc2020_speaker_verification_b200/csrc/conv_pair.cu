@@ -20,6 +20,13 @@
 //               lane through a per-group routing table (dense output, planar splits, second destination); the peer's
 //               epilogue warps hand the accumulator buffer back with a remote arrive on the leader's barrier
 //
+// The same kernel runs the 3x3 stride-1 convs whose half of the weights fits in shared memory (the 48- and 96-channel hierarchical
+// convs of Res2Net stages 2-3): the image is the flat pixel sequence of conv_flat.cu, every CTA loads ONE haloed span
+// (128 + 2 halo pixels) per K box and the nine taps are shared-memory descriptors displaced by the tap shift — the same
+// displacement in both CTAs of the pair — against RESIDENT weights (9 taps x K boxes x n_tile/2 rows per CTA, loaded once).
+// The flat kernel has to stream those weights through a 2-4 deep ring for every span (they do not fit beside its slots), which
+// left it at 2.5x its MMA time.  Aux mode 2 writes the hierarchical second output s = x_next + y beside y.
+//
 // Arithmetic and rounding points are those of conv_flat.cu (same K order, same epilogue expression).
 #include <cstdio>
 #include <cstring>
@@ -34,13 +41,14 @@ using namespace ptx;
 namespace {
 
 constexpr int kPairThreads = 384;
-constexpr uint32_t kPairABytes = 128u * 128u;        // 128 pixels x 64 channels x 2 bytes
 constexpr uint32_t kPairHeader = 1024u + 8192u + 1024u;   // barriers | scale[1024], shift[1024] | routing table
 
 struct PairSmem {
   uint64_t full[8], empty[8];
   uint64_t tmem_full[2], tmem_empty[2];
+  uint64_t bres_bar;
   uint32_t tmem_slot;
+  uint32_t tapoff16[12];        // ((halo + tap_shift[tap]) * 128) >> 4: descriptor displacement of each filter tap
 };
 static_assert(sizeof(PairSmem) <= 1024, "barrier block");
 
@@ -165,6 +173,23 @@ __device__ __forceinline__ uint4 pair_epi8(const uint32_t* r, uint32_t sc, uint3
   return o;
 }
 
+// Aux mode 2 (hierarchical 3x3): y = relu(scale * acc + shift) and the second output s = y + x_next, y taken BEFORE its rounding
+// to 16 bits (conv_flat.cu epi8, AUX >= 2).
+template <typename T>
+__device__ __forceinline__ void pair_epi8_two(const uint32_t* r, uint32_t sc, uint32_t sh, const uint4& ax, uint32_t vmask, uint4& o, uint4& o2) {
+  const float4 s0 = lds_f4(sc), s1 = lds_f4(sc + 16), b0 = lds_f4(sh), b1 = lds_f4(sh + 16);
+  float v[8];
+  v[0] = fmaxf(fmaf(__uint_as_float(r[0]), s0.x, b0.x), 0.f); v[1] = fmaxf(fmaf(__uint_as_float(r[1]), s0.y, b0.y), 0.f);
+  v[2] = fmaxf(fmaf(__uint_as_float(r[2]), s0.z, b0.z), 0.f); v[3] = fmaxf(fmaf(__uint_as_float(r[3]), s0.w, b0.w), 0.f);
+  v[4] = fmaxf(fmaf(__uint_as_float(r[4]), s1.x, b1.x), 0.f); v[5] = fmaxf(fmaf(__uint_as_float(r[5]), s1.y, b1.y), 0.f);
+  v[6] = fmaxf(fmaf(__uint_as_float(r[6]), s1.z, b1.z), 0.f); v[7] = fmaxf(fmaf(__uint_as_float(r[7]), s1.w, b1.w), 0.f);
+  const float2 a0 = TypeOps<T>::unpack2(ax.x), a1 = TypeOps<T>::unpack2(ax.y), a2 = TypeOps<T>::unpack2(ax.z), a3 = TypeOps<T>::unpack2(ax.w);
+  o.x = PackSat<T, false>::f(v[0], v[1]) & vmask; o.y = PackSat<T, false>::f(v[2], v[3]) & vmask;
+  o.z = PackSat<T, false>::f(v[4], v[5]) & vmask; o.w = PackSat<T, false>::f(v[6], v[7]) & vmask;
+  o2.x = PackSat<T, false>::f(v[0] + a0.x, v[1] + a0.y) & vmask; o2.y = PackSat<T, false>::f(v[2] + a1.x, v[3] + a1.y) & vmask;
+  o2.z = PackSat<T, false>::f(v[4] + a2.x, v[5] + a2.y) & vmask; o2.w = PackSat<T, false>::f(v[6] + a3.x, v[7] + a3.y) & vmask;
+}
+
 }  // namespace
 
 template <typename T, int AUX, int RELU>
@@ -177,7 +202,9 @@ conv_pair_kernel(const __grid_constant__ PairConvParams p, const __grid_constant
   float* s_shift = s_scale + 1024;
   unsigned long long* s_dst = reinterpret_cast<unsigned long long*>(smem + 1024 + 8192);     // [64] destination of each 16-channel group (0: none)
   uint32_t* s_pitch = reinterpret_cast<uint32_t*>(smem + 1024 + 8192 + 512);                 // [64] its bytes per pixel
-  uint8_t* stage_smem = smem + kPairHeader;
+  uint8_t* bres_smem = smem + kPairHeader;                                   // resident weights (taps * nkb items), if any
+  const uint32_t bres_bytes = p.b_resident ? static_cast<uint32_t>(p.taps * p.nkb) * p.b_item_bytes : 0u;
+  uint8_t* stage_smem = bres_smem + bres_bytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -188,12 +215,13 @@ conv_pair_kernel(const __grid_constant__ PairConvParams p, const __grid_constant
   const int n_total = n_mb * p.n_tiles;
   const int half_rows = p.n_tile >> 1;
   const int ng = p.n_tile >> 4;            // 16-channel groups per tile
-  const int ngh = ng >> 1;                 // ... per epilogue warpgroup
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&maps.a); prefetch_tmap(&maps.b);
     for (int i = 0; i < 8; ++i) { mbar_init(&S.full[i], 1); mbar_init(&S.empty[i], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&S.tmem_full[b], 1); mbar_init(&S.tmem_empty[b], 16); }   // 8 epilogue warps of each CTA
+    mbar_init(&S.bres_bar, 1);
+    for (int t = 0; t < 12; ++t) S.tapoff16[t] = t < p.taps ? static_cast<uint32_t>(p.halo + p.tap_shift[t]) * 8u : 0u;
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -215,6 +243,15 @@ conv_pair_kernel(const __grid_constant__ PairConvParams p, const __grid_constant
   cluster_sync_all();            // the peer's barriers are initialised before anything arrives on them remotely
   tc_fence_after();
   const uint32_t tmem_base = S.tmem_slot;
+  if (p.b_resident && warp == 0 && lane == 0) {      // weights are static: fetched before the dependency wait; both halves complete on the leader's barrier
+    const uint32_t bres_leader = mapa_u32(smem_u32(&S.bres_bar), 0);
+    const uint32_t item_tx = static_cast<uint32_t>(half_rows) * 128u;
+    if (rank == 0) mbar_expect_tx(&S.bres_bar, 2u * item_tx * static_cast<uint32_t>(p.taps * p.nkb));
+    for (int kb = 0; kb < p.nkb; ++kb)
+      for (int tap = 0; tap < p.taps; ++tap)
+        tma_load_2d_pair(bres_smem + static_cast<size_t>(kb * p.taps + tap) * p.b_item_bytes, &maps.b, bres_leader, tap * p.kpad + kb * 64,
+                         static_cast<int>(rank) * half_rows);
+  }
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
@@ -222,7 +259,7 @@ conv_pair_kernel(const __grid_constant__ PairConvParams p, const __grid_constant
     // ------------------------------------------------------------------ producer (both CTAs)
     if (lane == 0) {
       const uint32_t full_leader = mapa_u32(smem_u32(&S.full[0]), 0);
-      const uint32_t tx = kPairABytes + static_cast<uint32_t>(half_rows) * 128u;
+      const uint32_t tx = static_cast<uint32_t>(p.a_rows) * 128u + (p.b_resident ? 0u : static_cast<uint32_t>(half_rows) * 128u);
       uint32_t it = 0;
       for (int t = pair; t < n_total; t += n_pairs) {
         const int mb = t / p.n_tiles, nb = t - mb * p.n_tiles;
@@ -233,8 +270,8 @@ conv_pair_kernel(const __grid_constant__ PairConvParams p, const __grid_constant
           wait_pair(&S.empty[s], ((it / static_cast<uint32_t>(p.stages)) & 1u) ^ 1u, p.dbg, 0x01, it);
           if (rank == 0) mbar_expect_tx(&S.full[s], 2u * tx);          // the leader's barrier collects the bytes of both CTAs
           uint8_t* dst = stage_smem + static_cast<size_t>(s) * p.stage_bytes;
-          tma_load_2d_pair(dst, &maps.a, full_leader + s * 8u, kb * 64, px);
-          tma_load_2d_pair(dst + kPairABytes, &maps.b, full_leader + s * 8u, kb * 64, nrow);
+          tma_load_2d_pair(dst, &maps.a, full_leader + s * 8u, kb * 64, px - p.halo);        // haloed span: rows before the image / past its end are zero-filled
+          if (!p.b_resident) tma_load_2d_pair(dst + p.a_bytes, &maps.b, full_leader + s * 8u, kb * 64, nrow);
         }
       }
     }
@@ -247,6 +284,10 @@ conv_pair_kernel(const __grid_constant__ PairConvParams p, const __grid_constant
       const uint32_t stage16 = p.stage_bytes >> 4;
       const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t idesc = p.idesc;
+      const uint32_t bres_lo = static_cast<uint32_t>(desc_base) + (smem_u32(bres_smem) >> 4);
+      const uint32_t a16 = p.a_bytes >> 4, item16 = p.b_item_bytes >> 4;
+      const int taps = p.taps;
+      if (p.b_resident) wait_pair(&S.bres_bar, 0, p.dbg, 0x10, 0);
       uint32_t it = 0;
       int lt = 0;
       for (int t = pair; t < n_total; t += n_pairs, ++lt) {
@@ -256,16 +297,28 @@ conv_pair_kernel(const __grid_constant__ PairConvParams p, const __grid_constant
         const uint32_t d_tmem = tb + buf * 256u;
         for (int kb = 0; kb < p.nkb; ++kb, ++it) {
           const uint32_t s = it % static_cast<uint32_t>(p.stages);
+          const int ks = kb == p.nkb - 1 ? p.ks_last : 4;                 // K = 16 steps of this box that hold real channels
+          uint32_t toff = S.tapoff16[0];
           wait_pair(&S.full[s], (it / static_cast<uint32_t>(p.stages)) & 1u, p.dbg, 0x12, it);
           tc_fence_after();
-          const uint32_t a_lo = lo0 + s * stage16, b_lo = a_lo + (kPairABytes >> 4);
-          const uint32_t first = kb == 0 ? 0u : 1u;
+          const uint32_t a_lo = lo0 + s * stage16;
+          uint32_t b_lo = p.b_resident ? bres_lo + static_cast<uint32_t>(kb * taps) * item16 : a_lo + a16;
+#pragma unroll 1
+          for (int tap = 0; tap < taps; ++tap) {
+            const uint32_t toff_next = S.tapoff16[tap + 1];              // next tap's displacement loads while this tap issues
+            const uint32_t at = a_lo + toff;
+            const uint32_t first = (kb | tap) == 0 ? 0u : 1u;
+            if (elect_one()) {
+              umma2_lo(d_tmem, at, b_lo, hi, idesc, first);
+              if (ks > 1) umma2_lo(d_tmem, at + 2u, b_lo + 2u, hi, idesc, 1u);
+              if (ks > 2) umma2_lo(d_tmem, at + 4u, b_lo + 4u, hi, idesc, 1u);
+              if (ks > 3) umma2_lo(d_tmem, at + 6u, b_lo + 6u, hi, idesc, 1u);
+            }
+            b_lo += item16;
+            toff = toff_next;
+          }
           if (elect_one()) {
-            umma2_lo(d_tmem, a_lo, b_lo, hi, idesc, first);
-            umma2_lo(d_tmem, a_lo + 2u, b_lo + 2u, hi, idesc, 1u);
-            umma2_lo(d_tmem, a_lo + 4u, b_lo + 4u, hi, idesc, 1u);
-            umma2_lo(d_tmem, a_lo + 6u, b_lo + 6u, hi, idesc, 1u);
-            umma2_commit_mc(&S.empty[s], 3);                           // stage s is free in BOTH CTAs once these MMAs have read it
+            umma2_commit_mc(&S.empty[s], 3);                             // stage s is free in BOTH CTAs once these MMAs have read it
             if (kb == p.nkb - 1) umma2_commit_mc(&S.tmem_full[buf], 3);
           }
         }
@@ -288,6 +341,8 @@ conv_pair_kernel(const __grid_constant__ PairConvParams p, const __grid_constant
     const int cpx = lane >> 2, c32 = lane & 3;
     const uint32_t co_off0 = static_cast<uint32_t>(cpx) * 128u + ((static_cast<uint32_t>(2 * c32) ^ static_cast<uint32_t>(cpx)) << 4);       // row 8 i + cpx: + i * 1024
     const uint32_t co_off1 = static_cast<uint32_t>(cpx) * 128u + ((static_cast<uint32_t>(2 * c32 + 1) ^ static_cast<uint32_t>(cpx)) << 4);
+    const int g_first = wg ? (ng + 1) >> 1 : 0;          // this warpgroup's 16-channel groups of the tile: the first or the second half
+    const int ngh = wg ? ng >> 1 : (ng + 1) >> 1;
     const int nchunk = (ngh + 3) >> 2;
     // Residual values of chunk c of tile t, in the coalesced mapping.  They are loaded ONE TILE AHEAD: as soon as chunk c of the
     // current tile has been copied into the staging tile, its registers take the same chunk of the pair's next tile, so the
@@ -296,7 +351,7 @@ conv_pair_kernel(const __grid_constant__ PairConvParams p, const __grid_constant
     auto load_res = [&](int t, int c) {
       const int mb = t / p.n_tiles, nb = t - mb * p.n_tiles;
       const long long px0 = static_cast<long long>(p.reverse ? n_mb - 1 - mb : mb) * 256 + static_cast<int>(rank) * 128 + q4 * 32;
-      const int gl = c * 4 + c32, G = nb * ng + wg * ngh + gl;
+      const int gl = c * 4 + c32, G = nb * ng + g_first + gl;
       const bool here = t < n_total && gl < ngh && G < n_res_grp && !PKNOCK(4);
       const uint8_t* rsrc = p.res + static_cast<size_t>(G) * 32u;
 #pragma unroll
@@ -306,18 +361,18 @@ conv_pair_kernel(const __grid_constant__ PairConvParams p, const __grid_constant
         else rx[c][2 * i] = rx[c][2 * i + 1] = make_uint4(0, 0, 0, 0);
       }
     };
-    if (AUX == 1) { load_res(pair, 0); load_res(pair, 1); }
+    if (AUX != 0) { load_res(pair, 0); load_res(pair, 1); }
     int lt = 0;
     for (int t = pair; t < n_total; t += n_pairs, ++lt) {
       const int mb = t / p.n_tiles, nb = t - mb * p.n_tiles;
       const long long px0 = static_cast<long long>(p.reverse ? n_mb - 1 - mb : mb) * 256 + static_cast<int>(rank) * 128 + q4 * 32;   // first pixel of this warp
       const long long pp = px0 + lane;
       const uint32_t vmask = (pp < p.P && p.pix_valid[pp]) ? 0xffffffffu : 0u;
-      const int G0 = nb * ng + wg * ngh;                 // first global 16-channel group of this warpgroup
+      const int G0 = nb * ng + g_first;                  // first global 16-channel group of this warpgroup
       const uint32_t buf = static_cast<uint32_t>(lt) & 1u;
       wait_pair(&S.tmem_full[buf], (static_cast<uint32_t>(lt) >> 1) & 1u, p.dbg, 0x41, lt);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + buf * 256u + static_cast<uint32_t>(wg * ngh) * 16u;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + buf * 256u + static_cast<uint32_t>(g_first) * 16u;
       if (PKNOCK(1)) {
         tc_fence_before();
         __syncwarp();
@@ -330,7 +385,7 @@ conv_pair_kernel(const __grid_constant__ PairConvParams p, const __grid_constant
           const int gvalid = min(4, ngh - 4 * c);
           uint32_t acc[2][16];
           tmem_ld16(taddr + static_cast<uint32_t>(c * 64), acc[0]);
-          if (AUX == 1) {
+          if (AUX != 0) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               sts_u4(st_base + static_cast<uint32_t>(i) * 1024u + co_off0, rx[c][2 * i]);
@@ -339,6 +394,7 @@ conv_pair_kernel(const __grid_constant__ PairConvParams p, const __grid_constant
             __syncwarp();
             load_res(t + n_pairs, c);
           }
+          uint4 s2[8];                                       // aux mode 2: the second output of this chunk, stored after y has left the staging tile
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             if (g < gvalid) {
@@ -349,9 +405,15 @@ conv_pair_kernel(const __grid_constant__ PairConvParams p, const __grid_constant
               const bool res_here = AUX == 1 && G < n_res_grp;
               const uint32_t a0 = my_row + ((static_cast<uint32_t>(2 * g) ^ my_x) << 4), a1 = my_row + ((static_cast<uint32_t>(2 * g + 1) ^ my_x) << 4);
               uint4 ax0 = make_uint4(0, 0, 0, 0), ax1 = ax0;
-              if (AUX == 1) { ax0 = lds_u4(a0); ax1 = lds_u4(a1); }
-              const uint4 o0 = pair_epi8<T, AUX, RELU>(acc[g & 1], sc, sh, ax0, res_here, vmask);
-              const uint4 o1 = pair_epi8<T, AUX, RELU>(acc[g & 1] + 8, sc + 32, sh + 32, ax1, res_here, vmask);
+              if (AUX != 0) { ax0 = lds_u4(a0); ax1 = lds_u4(a1); }
+              uint4 o0, o1;
+              if (AUX == 2) {
+                pair_epi8_two<T>(acc[g & 1], sc, sh, ax0, vmask, o0, s2[2 * g]);
+                pair_epi8_two<T>(acc[g & 1] + 8, sc + 32, sh + 32, ax1, vmask, o1, s2[2 * g + 1]);
+              } else {
+                o0 = pair_epi8<T, AUX, RELU>(acc[g & 1], sc, sh, ax0, res_here, vmask);
+                o1 = pair_epi8<T, AUX, RELU>(acc[g & 1] + 8, sc + 32, sh + 32, ax1, res_here, vmask);
+              }
               sts_u4(a0, o0);
               sts_u4(a1, o1);
             }
@@ -372,6 +434,27 @@ conv_pair_kernel(const __grid_constant__ PairConvParams p, const __grid_constant
             }
           }
           __syncwarp();                                      // the staging tile is reused by the next chunk / tile
+          if (AUX == 2) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (g < gvalid) {
+                sts_u4(my_row + ((static_cast<uint32_t>(2 * g) ^ my_x) << 4), s2[2 * g]);
+                sts_u4(my_row + ((static_cast<uint32_t>(2 * g + 1) ^ my_x) << 4), s2[2 * g + 1]);
+              }
+            }
+            __syncwarp();
+            if (c32 < gvalid) {
+              uint8_t* d2 = p.out2 + static_cast<size_t>(G0 + c * 4 + c32) * 32u;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const long long px = px0 + 8 * i + cpx;
+                const uint4 v0 = lds_u4(st_base + static_cast<uint32_t>(i) * 1024u + co_off0);
+                const uint4 v1 = lds_u4(st_base + static_cast<uint32_t>(i) * 1024u + co_off1);
+                if (px < p.P_cap && !PKNOCK(2)) stg256(d2 + static_cast<size_t>(px) * p.out2_pitch, v0, v1);
+              }
+            }
+            __syncwarp();
+          }
         }
       }
     }
@@ -382,7 +465,10 @@ conv_pair_kernel(const __grid_constant__ PairConvParams p, const __grid_constant
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
-size_t conv_pair_smem_bytes(const PairConvParams& p) { return 1024 + kPairHeader + static_cast<size_t>(p.stages) * p.stage_bytes + 8 * 4096; }   // + one 4 KB staging tile per epilogue warp
+size_t conv_pair_smem_bytes(const PairConvParams& p) {
+  const size_t bres = p.b_resident ? static_cast<size_t>(p.taps) * p.nkb * p.b_item_bytes : 0;
+  return 1024 + kPairHeader + bres + static_cast<size_t>(p.stages) * p.stage_bytes + 8 * 4096;
+}   // + one 4 KB staging tile per epilogue warp
 
 static int g_pair_clusters = 0;
 
@@ -395,7 +481,8 @@ static cudaError_t pair_attr_type() {
   if ((e = pair_attr<T, 0, 1>()) != cudaSuccess) return e;
   if ((e = pair_attr<T, 0, 2>()) != cudaSuccess) return e;
   if ((e = pair_attr<T, 1, 0>()) != cudaSuccess) return e;
-  return pair_attr<T, 1, 1>();
+  if ((e = pair_attr<T, 1, 1>()) != cudaSuccess) return e;
+  return pair_attr<T, 2, 1>();
 }
 
 cudaError_t conv_pair_init() {
@@ -434,11 +521,13 @@ cudaError_t launch_conv_pair(const PairConvParams& p, const PairMaps& maps, int 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   if (p.pre_relu && (p.post_relu || p.aux_mode)) return cudaErrorInvalidValue;
+  if (p.aux_mode == 2 && !p.post_relu) return cudaErrorInvalidValue;
   const int relu = p.pre_relu ? 2 : p.post_relu ? 1 : 0;
   cudaError_t le = cudaErrorInvalidValue;
 #define SVX_PAIR(T)                                                                                     \
   do {                                                                                                  \
-    if (p.aux_mode) le = relu == 1 ? cudaLaunchKernelEx(&cfg, conv_pair_kernel<T, 1, 1>, p, maps)       \
+    if (p.aux_mode == 2) le = cudaLaunchKernelEx(&cfg, conv_pair_kernel<T, 2, 1>, p, maps);             \
+    else if (p.aux_mode) le = relu == 1 ? cudaLaunchKernelEx(&cfg, conv_pair_kernel<T, 1, 1>, p, maps)       \
                                    : cudaLaunchKernelEx(&cfg, conv_pair_kernel<T, 1, 0>, p, maps);      \
     else le = relu == 1 ? cudaLaunchKernelEx(&cfg, conv_pair_kernel<T, 0, 1>, p, maps)                  \
             : relu == 2 ? cudaLaunchKernelEx(&cfg, conv_pair_kernel<T, 0, 2>, p, maps)                  \

@@ -1084,24 +1084,39 @@ int Model::plan_flat(ConvDesc& c) {
 
 static unsigned long long* flat_dbg_words();
 
-// CTA-pair GEMM (conv_pair.cu) for 1x1 stride-1 convs with K >= 192: a pair of SMs per M = 256 x N <= 256 tile halves the weight
-// bytes every SM receives.  Leaves use_pair = false when the shape does not qualify (the flat plan then runs).
+// CTA-pair kernel (conv_pair.cu): 1x1 stride-1 convs with K >= 384 (a pair of SMs per M = 256 x N <= 256 tile halves the weight bytes
+// every SM receives) and the 3x3 stride-1 convs whose half of the weights fits in shared memory beside the pixel ring (resident
+// weights instead of a 2-4 deep weight ring per span).  Leaves use_pair = false when the shape does not qualify (the flat plan runs).
 int Model::plan_pair(ConvDesc& c) {
   static const bool disabled = dbg_env("SVX_NO_PAIR") != nullptr;   // debug switch
   static const int min_k = dbg_env("SVX_PAIR_MIN_K") ? atoi(dbg_env("SVX_PAIR_MIN_K")) : 384;   // K = 192 / 256 (stage 2 of Res2Net-50): HBM-bound, the flat kernel is as fast
+  static const bool no_3x3 = dbg_env("SVX_NO_PAIR3") != nullptr;
+  // 3x3: measured faster from 96 channels (97/93/86 -> 78/80/56 us per hierarchical chain of stage 3); at 48 channels the two
+  // epilogue passes of aux mode 2 on three 16-channel groups cost more than the weight ring saves (120 -> 195 us)
+  static const int min_c3 = dbg_env("SVX_PAIR3_MIN_C") ? atoi(dbg_env("SVX_PAIR3_MIN_C")) : 96;
   if (disabled) return 0;
   const ActTensor& tin = tensors_[c.in.id];
   const ActTensor& tout = tensors_[c.out.id];
-  if (c.kh != 1 || c.kw != 1 || c.stride != 1 || c.groups != 1 || tin.stage != tout.stage) return 0;
-  if (c.kbox != 64 || c.kpad % 64 != 0 || c.kpad < min_k) return 0;
-  if (c.out2.id >= 0 || c.add2.id >= 0) return 0;
+  const int taps = c.kh * c.kw;
+  if (c.stride != 1 || c.groups != 1 || tin.stage != tout.stage || taps > kMaxTaps) return 0;
+  if (c.kbox != 64 || c.kpad % 64 != 0) return 0;
+  const int Wp = stage_Wp_[tout.stage], W = stage_W_[tout.stage];
+  if (taps == 1) {
+    if (c.kpad < min_k) return 0;
+  } else {
+    if (no_3x3 || c.cin < min_c3) return 0;
+    if (c.kw > 1 && (Wp <= W || c.pw > 1 || c.kw - 1 - c.pw > 1)) return 0;   // one zero column covers |dw| <= 1 only
+  }
+  const int aux_mode = c.res.id >= 0 ? 1 : (c.out2.id >= 0 ? 2 : 0);
+  if (c.res.id >= 0 && c.out2.id >= 0) return 0;
+  if (aux_mode == 2 && (c.add2.id < 0 || !c.post_relu || c.pre_relu)) return 0;
   const int N = c.n_gemm;
-  if (N % 32 != 0 || N > 1024 || N < 128) return 0;
-  const int n_tile = N % 256 == 0 ? 256 : N % 192 == 0 ? 192 : N % 128 == 0 ? 128 : 0;
-  if (n_tile == 0 || c.n_pad < N) return 0;
+  if (N % 16 != 0 || N > 1024 || N < 32) return 0;
+  int n_tile = N % 256 == 0 ? 256 : N % 192 == 0 ? 192 : N % 128 == 0 ? 128 : 0;
+  if (n_tile == 0 && N <= 256) n_tile = N;            // one tile: any multiple of 16
+  if (n_tile == 0 || c.n_pad < N || (n_tile / 2) % 8 != 0) return 0;
   const int n_split = c.n_split < 0 ? c.cout : c.n_split;
   const bool split = c.split_w > 0;
-  const int aux_mode = c.res.id >= 0 ? 1 : 0;
   if (split && aux_mode) return 0;
   PairConvParams pp;
   memset(&pp, 0, sizeof pp);
@@ -1148,25 +1163,55 @@ int Model::plan_pair(ConvDesc& c) {
       else { pp.route[g] = static_cast<uint8_t>(d1); pp.goff[g] = static_cast<uint16_t>((c.outb.coff + ch - n_split) * esz); }
     }
   }
-  if (aux_mode) {
+  if (aux_mode == 1) {
     const ActTensor& tr = tensors_[c.res.id];
     if (tr.stage != tout.stage || (tr.C * esz) % 32 != 0 || c.res.coff % 16 != 0 || n_split % 16 != 0) return 0;
     pp.res = static_cast<const uint8_t*>(tr.ptr) + static_cast<size_t>(c.res.coff) * esz;
     pp.res_pitch = static_cast<uint32_t>(tr.C * esz);
     pp.n_res = n_split;
+  } else if (aux_mode == 2) {
+    const ActTensor& ta = tensors_[c.add2.id];
+    const ActTensor& t2 = tensors_[c.out2.id];
+    if (ta.stage != tout.stage || t2.stage != tout.stage || (ta.C * esz) % 32 != 0 || (t2.C * esz) % 32 != 0 || c.add2.coff % 16 != 0 || c.out2.coff % 16 != 0) return 0;
+    if (n_split != c.cout || N != c.cout || N > 128 || ta.C - c.add2.coff < N || t2.C - c.out2.coff < N) return 0;
+    pp.res = static_cast<const uint8_t*>(ta.ptr) + static_cast<size_t>(c.add2.coff) * esz;
+    pp.res_pitch = static_cast<uint32_t>(ta.C * esz);
+    pp.n_res = N;
+    pp.out2 = static_cast<uint8_t*>(t2.ptr) + static_cast<size_t>(c.out2.coff) * esz;
+    pp.out2_pitch = static_cast<uint32_t>(t2.C * esz);
   }
   pp.aux_mode = aux_mode;
   pp.nkb = c.kpad / 64;
+  pp.kpad = c.kpad;
+  {
+    const int last = c.cin - (pp.nkb - 1) * 64;                 // real channels of the last K box (the rest is zero-filled / zero weights)
+    pp.ks_last = std::min(4, std::max(1, (last + 15) / 16));
+  }
+  pp.taps = taps;
+  int halo = 0;
+  for (int t = 0; t < taps; ++t) {
+    const int r = t / c.kw, s = t % c.kw;
+    pp.tap_shift[t] = (r * c.dil - c.ph) * Wp + (s - c.pw);
+    halo = std::max(halo, std::abs(pp.tap_shift[t]));
+  }
+  pp.halo = halo;
+  pp.a_rows = round_up(128 + 2 * halo, 8);
+  if (pp.a_rows > 256) return 0;
+  pp.a_bytes = static_cast<uint32_t>(round_up(pp.a_rows * 128, 1024));
   pp.n_tile = n_tile; pp.n_tiles = N / n_tile; pp.n_gemm = N; pp.n_valid = N;
-  pp.stage_bytes = 128u * 128u + static_cast<uint32_t>(round_up((n_tile / 2) * 128, 1024));
-  pp.stages = static_cast<int>((227 * 1024 - 1024 - (1024 + 8192 + 1024) - 8 * 4096) / pp.stage_bytes);
+  pp.b_item_bytes = static_cast<uint32_t>(round_up((n_tile / 2) * 128, 1024));
+  pp.b_resident = taps > 1 ? 1 : 0;
+  if (pp.b_resident && (pp.n_tiles != 1 || (n_tile / 2) % 8 != 0)) return 0;
+  const long long bres = pp.b_resident ? static_cast<long long>(taps) * pp.nkb * pp.b_item_bytes : 0;
+  pp.stage_bytes = pp.a_bytes + (pp.b_resident ? 0u : pp.b_item_bytes);
+  const long long room = 227 * 1024 - 1024 - (1024 + 8192 + 1024) - 8 * 4096 - bres;
+  if (room < 3LL * pp.stage_bytes) return 0;
+  pp.stages = static_cast<int>(room / pp.stage_bytes);
   if (pp.stages > 8) pp.stages = 8;
-  if (pp.stages < 3) return 0;
   pp.idesc = ptx::make_idesc_f16(is_bf16_ ? 1u : 0u, 256u, static_cast<uint32_t>(n_tile));
   pp.scale = c.d_scale; pp.shift = c.d_shift;
   pp.pix_valid = d_pix_valid_[tout.stage];
   pp.pre_relu = c.pre_relu; pp.post_relu = c.post_relu;
-  const int Wp = stage_Wp_[tout.stage];
   const uint64_t P_cap = static_cast<uint64_t>(rows_cap_[tout.stage]) * Wp;
   pp.P_cap = static_cast<long long>(P_cap);
   PairMaps& pm = c.pmaps;
@@ -1175,14 +1220,14 @@ int Model::plan_pair(ConvDesc& c) {
     const int a_width = (c.in.coff == 0 && tin.C > c.cin && tin.C <= c.kpad) ? tin.C : c.cin;
     const uint64_t dims[2] = {static_cast<uint64_t>(a_width), P_cap};
     const uint64_t str[1] = {static_cast<uint64_t>(tin.C) * esz};
-    const uint32_t box[2] = {64u, 128u};
+    const uint32_t box[2] = {64u, static_cast<uint32_t>(pp.a_rows)};
     const int pitch = tin.C * 2, off = c.in.coff * 2, wb = c.cin * 2;
     const int promo = (a_width == tin.C || (pitch % 128 == 0 && off % 128 == 0 && wb % 128 == 0)) ? 128 : 64;
     if (encode_tmap(&pm.a, is_bf16_, static_cast<uint8_t*>(tin.ptr) + static_cast<size_t>(c.in.coff) * esz, 2, dims, str, box, 128, promo)) return 1;
   }
   {
-    const uint64_t dims[2] = {static_cast<uint64_t>(c.kpad), static_cast<uint64_t>(c.n_pad)};
-    const uint64_t str[1] = {static_cast<uint64_t>(c.kpad) * esz};
+    const uint64_t dims[2] = {static_cast<uint64_t>(taps) * c.kpad, static_cast<uint64_t>(c.n_pad)};
+    const uint64_t str[1] = {static_cast<uint64_t>(taps) * c.kpad * esz};
     const uint32_t box[2] = {64u, static_cast<uint32_t>(n_tile / 2)};
     if (encode_tmap(&pm.b, is_bf16_, c.d_wgt, 2, dims, str, box, 128)) return 1;
   }
@@ -1269,6 +1314,7 @@ int Model::plan_chain(size_t i0) {
   ChainMaps& cm = op0.cmaps;
   memset(&cm, 0, sizeof cm);
   const int src[3] = {cv[0]->in.id, cv[0]->add2.id, cv[1]->add2.id};      // the planar splits x_0, x_1, x_2
+  cp.xs[0] = static_cast<const uint8_t*>(tensors_[src[1]].ptr); cp.xs[1] = static_cast<const uint8_t*>(tensors_[src[2]].ptr);
   for (int k = 0; k < 3; ++k) {
     const uint64_t dims[2] = {32, P_cap};
     const uint64_t str[1] = {64};
