@@ -233,10 +233,9 @@ struct ChainParams {
   const float* scale[3]; const float* shift[3];   // folded BN of the three convs, 32 entries each (pad channels: 0)
   const uint8_t* pix_valid;
   uint8_t* y; uint32_t y_pitch;                   // concat: slice k of a pixel at y + pixel*y_pitch + k*64 bytes
-  const uint8_t* xs[2];                           // planar splits x_1, x_2 (64 bytes per pixel): read by the epilogue thread that owns the pixel
   unsigned long long* dbg;
 };
-struct ChainMaps { CUtensorMap x[3], w[3]; };   // x[0]: planar split x_0 ({32 ch, 128 px} boxes; x[1], x[2] unused), w: the three weight matrices ({32 k, 32 n} per tap)
+struct ChainMaps { CUtensorMap x[3], w[3]; };   // planar splits x_0..x_2 ({32 ch, 128 px} boxes) and the three weight matrices ({32 k, 32 n} per tap)
 cudaError_t res2_chain_init();
 size_t res2_chain_smem_bytes();
 cudaError_t launch_res2_chain(const ChainParams& p, const ChainMaps& maps, int is_bf16, cudaStream_t stream);

@@ -1089,7 +1089,9 @@ static unsigned long long* flat_dbg_words();
 // weights instead of a 2-4 deep weight ring per span).  Leaves use_pair = false when the shape does not qualify (the flat plan runs).
 int Model::plan_pair(ConvDesc& c) {
   static const bool disabled = dbg_env("SVX_NO_PAIR") != nullptr;   // debug switch
-  static const int min_k = dbg_env("SVX_PAIR_MIN_K") ? atoi(dbg_env("SVX_PAIR_MIN_K")) : 384;   // K = 192 / 256 (stage 2 of Res2Net-50): HBM-bound, the flat kernel is as fast
+  // 1x1: measured faster from K = 192 (Res2Net-50 stage 2: 192->256 + residual 348 -> 317 us, 256->192 275 -> 196 us); at K = 128 (stage 1,
+  // HBM-bound at 4.1 M pixels) the flat kernel's TMA-store epilogue wins (495 vs 725 us)
+  static const int min_k = dbg_env("SVX_PAIR_MIN_K") ? atoi(dbg_env("SVX_PAIR_MIN_K")) : 192;
   static const bool no_3x3 = dbg_env("SVX_NO_PAIR3") != nullptr;
   // 3x3: measured faster from 96 channels (97/93/86 -> 78/80/56 us per hierarchical chain of stage 3); at 48 channels the two
   // epilogue passes of aux mode 2 on three 16-channel groups cost more than the weight ring saves (120 -> 195 us)
@@ -1314,7 +1316,6 @@ int Model::plan_chain(size_t i0) {
   ChainMaps& cm = op0.cmaps;
   memset(&cm, 0, sizeof cm);
   const int src[3] = {cv[0]->in.id, cv[0]->add2.id, cv[1]->add2.id};      // the planar splits x_0, x_1, x_2
-  cp.xs[0] = static_cast<const uint8_t*>(tensors_[src[1]].ptr); cp.xs[1] = static_cast<const uint8_t*>(tensors_[src[2]].ptr);
   for (int k = 0; k < 3; ++k) {
     const uint64_t dims[2] = {32, P_cap};
     const uint64_t str[1] = {64};

@@ -10,17 +10,15 @@
 //
 // The image is the flat pixel sequence of conv_flat.cu (p = row*Wp + col, one zero column per row), so filter tap (dh, dw) is
 // the constant shift dh*Wp + dw, and a CTA STREAMS through a contiguous band of 128-pixel tiles.  The three convs run as a
-// software pipeline kD = 4 tiles apart (the halo Wp + 1 is less than a tile, so one tile would do for the data; the other
-// three are SLACK): conv k+1 may start tile U once the epilogue of conv k has finished tile U+1, which it was handed kD - 1
-// iterations earlier — with a skew of 2 every iteration waited for the full MMA -> commit -> epilogue -> arrive round trip
-// (2.4 us against 1.1 us of MMAs).  Each conv's epilogue warpgroup turns accumulators (TMEM, four buffers per conv) into y
-// (written straight to the concat with 256-bit stores) and into the next conv's operand s = x + y, x read by the thread that owns
-// the pixel one iteration ahead.  Operands live in three shared-memory rings of 128-pixel tiles in the canonical K-major
-// SWIZZLE_64B layout (64-byte pixel rows = 32 padded channels); a tap is a shared-memory descriptor displaced by its shift.
-// A ring of L tiles carries one extra slot that mirrors slot 0, so that a 128-row operand window that starts anywhere in the
-// ring is contiguous (a UMMA operand cannot wrap).
+// software pipeline two tiles apart (the halo Wp + 1 is less than a tile): in iteration i the MMA warp issues conv 0 on tile
+// T, conv 1 on tile T-2 and conv 2 on tile T-4; each conv's epilogue warpgroup has the other two convs' MMAs (~1.7 us) to
+// turn its accumulators into y (written straight to the concat with 256-bit stores) and into the next conv's operand
+// (s = x + y, added IN PLACE over the x tile that TMA put in the next ring).  Operands live in three shared-memory rings of
+// 128-pixel tiles in the canonical K-major SWIZZLE_64B layout (64-byte pixel rows = 32 padded channels); a tap is a
+// shared-memory descriptor displaced by its shift.  A ring of L tiles carries one extra slot that mirrors slot 0, so that a
+// 128-row operand window that starts anywhere in the ring is contiguous (a UMMA operand cannot wrap).
 //
-//   warp 0      producer: weights (resident, 54 KB), then one tile of x_0 per iteration (TMA, 2 iterations ahead)
+//   warp 0      producer: weights (resident, 54 KB), then per iteration one tile of x_0, x_1, x_2 (TMA, 2 iterations ahead)
 //   warp 1      TMEM allocator + tcgen05.mma issuer: 3 convs x 9 taps x 2 K-steps of M=128, N=32, K=16 per iteration
 //   warps 4-15  three epilogue warpgroups, one per conv
 //
@@ -40,8 +38,7 @@ using namespace ptx;
 namespace {
 
 constexpr int kChainThreads = 512;
-constexpr int kD = 4;                               // pipeline skew between consecutive convs, in tiles
-constexpr int kL0 = 5, kL1 = kD + 2, kL2 = kD + 2;   // ring depths in tiles (each ring has one more slot: the mirror of slot 0)
+constexpr int kL0 = 5, kL1 = 6, kL2 = 6;           // ring depths in tiles (each ring has one more slot: the mirror of slot 0)
 constexpr uint32_t kTileBytes = 128u * 64u;        // 128 pixels x 32 channels x 2 bytes
 constexpr uint32_t kTapBytes = 2048u;              // one tap's weights: [32 n][32 k] 16-bit, SWIZZLE_64B
 constexpr uint32_t kConvWBytes = 9u * kTapBytes;
@@ -53,9 +50,9 @@ constexpr uint32_t kRingBytes = kRing2 + (kL2 + 1) * kTileBytes;
 
 struct ChainSmem {
   uint64_t w_bar;
-  uint64_t x_full[8];          // ring 0, slot: tile of split 0 landed (tx bytes)
-  uint64_t mma_done[3][4];     // conv k, its tile counter & 3: the MMAs have completed (accumulators ready, operand tiles read)
-  uint64_t epi_done[3][4];     // conv k, its tile counter & 3: accumulators drained, s tile of the next ring written (128 arrivals)
+  uint64_t x_full[3][8];       // ring k, slot: tile of split k landed (tx bytes)
+  uint64_t mma_done[3][4];     // conv k, iteration & 3: its MMAs have completed (accumulators ready, operand tiles read)
+  uint64_t epi_done[3][4];     // conv k, iteration & 3: accumulators drained, s tile of the next ring written (128 arrivals)
   uint32_t tmem_slot;
   int32_t tap16[12];           // tap shift in 16-byte units of a 64-byte pixel row
   alignas(16) float scale[3][32];   // read as float4
@@ -75,10 +72,6 @@ __device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
 }
 __device__ __forceinline__ void sts_u4(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {
-  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
 }
 __device__ __forceinline__ void stg256(void* p, const uint4& a, const uint4& b) {
   asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
@@ -137,32 +130,28 @@ res2_chain_kernel(const __grid_constant__ ChainParams p, const __grid_constant__
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // band of tiles of this CTA.  Conv 0 covers tiles tA .. t1+1 (n0 of them), conv 1 tiles t0-1 .. t1 (n1), conv 2 the band itself (n2);
-  // conv k starts f_k iterations into the loop, and every barrier / ring / TMEM index below is the conv's OWN tile counter.
+  // band of tiles of this CTA
   const long long n_tiles = (p.P + 127) / 128;
   const long long band = (n_tiles + gridDim.x - 1) / gridDim.x;
   const long long t0 = static_cast<long long>(blockIdx.x) * band;
   const long long t1 = t0 + band < n_tiles ? t0 + band : n_tiles;
-  const int nb = t1 > t0 ? static_cast<int>(t1 - t0) : 0;
-  const int n0 = nb + 4, n1 = nb + 2, n2 = nb;
-  constexpr int f1 = kD + 1, f2 = 2 * kD + 2;
-  const int n_it = nb > 0 ? f2 + n2 : 0;
-  const long long tA = t0 - 2;            // conv 0's first tile
+  const int n_it = t1 > t0 ? static_cast<int>(t1 - t0) + 6 : 0;
+  const long long tA = t0 - 2;            // conv 0's tile in iteration 0
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&maps.x[0]);
-    for (int k = 0; k < 3; ++k) prefetch_tmap(&maps.w[k]);
+    for (int k = 0; k < 3; ++k) { prefetch_tmap(&maps.x[k]); prefetch_tmap(&maps.w[k]); }
     mbar_init(&S.w_bar, 1);
-    for (int i = 0; i < 8; ++i) mbar_init(&S.x_full[i], 1);
-    for (int k = 0; k < 3; ++k)
+    for (int k = 0; k < 3; ++k) {
+      for (int i = 0; i < 8; ++i) mbar_init(&S.x_full[k][i], 1);
       for (int i = 0; i < 4; ++i) { mbar_init(&S.mma_done[k][i], 1); mbar_init(&S.epi_done[k][i], 128); }
+    }
     for (int t = 0; t < 12; ++t) S.tap16[t] = t < 9 ? p.tap_shift[t] * 4 : 0;
     fence_barrier_init();
     mbar_expect_tx(&S.w_bar, 3 * kConvWBytes);     // weights are static: fetched before the dependency wait
     for (int k = 0; k < 3; ++k)
       for (int tap = 0; tap < 9; ++tap) tma_load_2d(w_smem + k * kConvWBytes + tap * kTapBytes, &maps.w[k], &S.w_bar, tap * 32, 0);
   }
-  if (warp == 1) { tmem_alloc(&S.tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc(&S.tmem_slot, 256); tmem_relinquish(); }
   if (threadIdx.x < 96) {
     const int k = threadIdx.x >> 5, c = threadIdx.x & 31;
     S.scale[k][c] = p.scale[k] ? p.scale[k][c] : 1.f;
@@ -176,26 +165,36 @@ res2_chain_kernel(const __grid_constant__ ChainParams p, const __grid_constant__
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ producer: x_0 tiles tA-1 .. t1+2, tile tA-1+r in slot r % kL0 (slot 0 also in the mirror)
-    if (lane == 0 && nb > 0) {
-      auto load = [&](int rel) {
-        const int slot = rel % kL0;
-        const bool mirror = slot == 0;
-        uint64_t* bar = &S.x_full[slot];
+    // ------------------------------------------------------------------ producer
+    if (lane == 0 && n_it > 0) {
+      // ring k receives the tiles of split k in order; tile number `rel` of a ring goes to slot rel % L (slot 0 also to the mirror)
+      auto load = [&](int k, int rel, long long tile) {
+        const int L = k == 0 ? kL0 : k == 1 ? kL1 : kL2;
+        const uint32_t rb = k == 0 ? kRing0 : k == 1 ? kRing1 : kRing2;
+        const int slot = rel % L;
+        const bool mirror = k == 0 && slot == 0;       // rings 1 and 2 are mirrored by the epilogue that writes s
+        uint64_t* bar = &S.x_full[k][slot];
         mbar_expect_tx(bar, mirror ? 2 * kTileBytes : kTileBytes);
-        const int px = static_cast<int>((tA - 1 + rel) * 128);
-        tma_load_2d(ring_smem + kRing0 + static_cast<uint32_t>(slot) * kTileBytes, &maps.x[0], bar, 0, px);
-        if (mirror) tma_load_2d(ring_smem + kRing0 + static_cast<uint32_t>(kL0) * kTileBytes, &maps.x[0], bar, 0, px);
+        const int px = static_cast<int>(tile * 128);
+        tma_load_2d(ring_smem + rb + static_cast<uint32_t>(slot) * kTileBytes, &maps.x[k], bar, 0, px);
+        if (mirror) tma_load_2d(ring_smem + rb + static_cast<uint32_t>(L) * kTileBytes, &maps.x[k], bar, 0, px);
       };
-      for (int r = 0; r < 4; ++r) load(r);
-      for (int i = 0; i + 4 <= n0 + 1; ++i) {       // conv 0's tile i reads ring numbers i, i+1, i+2; number i+4 replaces i-1
-        if (i >= 1) wait_chain(&S.mma_done[0][(i - 1) & 3], static_cast<uint32_t>((i - 1) >> 2) & 1u, p.dbg, 0x01, i);
-        load(i + 4);
+      // prologue: x_0 tiles tA-1 .. tA+2, x_1 tiles tA, tA+1, x_2 tiles tA-2, tA-1
+      for (int r = 0; r < 4; ++r) load(0, r, tA - 1 + r);
+      for (int r = 0; r < 2; ++r) load(1, r, tA + r);
+      for (int r = 0; r < 2; ++r) load(2, r, tA - 2 + r);
+      for (int it = 0; it < n_it; ++it) {
+        if (it >= 1) {      // the slots refilled below were last read by the MMAs of iteration it-1
+          const uint32_t par = static_cast<uint32_t>((it - 1) >> 2) & 1u;
+          for (int k = 0; k < 3; ++k) wait_chain(&S.mma_done[k][(it - 1) & 3], par, p.dbg, 0x01 + k, it);
+        }
+        if (it + 4 <= n_it + 1) load(0, it + 4, tA + it + 3);
+        if (it + 2 <= n_it - 1) { load(1, it + 2, tA + it + 2); load(2, it + 2, tA + it); }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (converged warp, elected lane issues)
-    if (nb > 0) {
+    if (n_it > 0) {
       wait_chain(&S.w_bar, 0, p.dbg, 0x10, 0);
       const uint64_t desc_base = make_kmajor_desc(0, 512u, 4u);        // SWIZZLE_64B, 8-row groups 512 bytes apart
       const uint32_t hi = static_cast<uint32_t>(desc_base >> 32);
@@ -206,37 +205,30 @@ res2_chain_kernel(const __grid_constant__ ChainParams p, const __grid_constant__
       const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t idesc = p.idesc;
       for (int it = 0; it < n_it; ++it) {
-        // ---- conv 0, its tile i: x_0 ring numbers i, i+1, i+2
-        if (it < n0) {
-          const int i = it;
-          if (i == 0) {
-            wait_chain(&S.x_full[0], 0, p.dbg, 0x11, i);
-            wait_chain(&S.x_full[1], 0, p.dbg, 0x11, i);
-          }
-          wait_chain(&S.x_full[(i + 2) % kL0], static_cast<uint32_t>((i + 2) / kL0) & 1u, p.dbg, 0x12, i);
-          if (i >= 4) wait_chain(&S.epi_done[0][i & 3], static_cast<uint32_t>((i - 4) >> 2) & 1u, p.dbg, 0x13, i);      // accumulator buffer drained
-          tc_fence_after();
-          issue_conv<kL0>(r0_lo, (i + 1) % kL0, S.tap16, w_lo, hi, tb + (0u * 4u + static_cast<uint32_t>(i & 3)) * 32u, idesc);
-          if (elect_one()) umma_commit(&S.mma_done[0][i & 3]);
+        const uint32_t buf = static_cast<uint32_t>(it & 1);
+        const uint32_t par_m2 = static_cast<uint32_t>((it - 2) >> 2) & 1u, par_m1 = static_cast<uint32_t>((it - 1) >> 2) & 1u;
+        // ---- conv 0 on tile tA + it: x_0 tiles (ring numbers) it, it+1, it+2
+        if (it == 0) {
+          wait_chain(&S.x_full[0][0], 0, p.dbg, 0x11, it);
+          wait_chain(&S.x_full[0][1], 0, p.dbg, 0x11, it);
         }
-        // ---- conv 1, its tile i (image tile tA+1+i): s_1 ring numbers i, i+1, i+2, the last one written by conv 0's epilogue of ITS tile i+2
-        if (it >= f1 && it - f1 < n1) {
-          const int i = it - f1;
-          wait_chain(&S.epi_done[0][(i + 2) & 3], static_cast<uint32_t>((i + 2) >> 2) & 1u, p.dbg, 0x14, i);
-          if (i >= 4) wait_chain(&S.epi_done[1][i & 3], static_cast<uint32_t>((i - 4) >> 2) & 1u, p.dbg, 0x15, i);
-          tc_fence_after();
-          issue_conv<kL1>(r1_lo, (i + 1) % kL1, S.tap16, w_lo + (kConvWBytes >> 4), hi, tb + (1u * 4u + static_cast<uint32_t>(i & 3)) * 32u, idesc);
-          if (elect_one()) umma_commit(&S.mma_done[1][i & 3]);
-        }
-        // ---- conv 2, its tile i (image tile tA+2+i): s_2 ring numbers i, i+1, i+2
-        if (it >= f2) {
-          const int i = it - f2;
-          wait_chain(&S.epi_done[1][(i + 2) & 3], static_cast<uint32_t>((i + 2) >> 2) & 1u, p.dbg, 0x16, i);
-          if (i >= 4) wait_chain(&S.epi_done[2][i & 3], static_cast<uint32_t>((i - 4) >> 2) & 1u, p.dbg, 0x17, i);
-          tc_fence_after();
-          issue_conv<kL2>(r2_lo, (i + 1) % kL2, S.tap16, w_lo + 2u * (kConvWBytes >> 4), hi, tb + (2u * 4u + static_cast<uint32_t>(i & 3)) * 32u, idesc);
-          if (elect_one()) umma_commit(&S.mma_done[2][i & 3]);
-        }
+        wait_chain(&S.x_full[0][(it + 2) % kL0], static_cast<uint32_t>((it + 2) / kL0) & 1u, p.dbg, 0x12, it);
+        if (it >= 2) wait_chain(&S.epi_done[0][(it - 2) & 3], par_m2, p.dbg, 0x13, it);      // accumulator buffer drained
+        tc_fence_after();
+        issue_conv<kL0>(r0_lo, (it + 1) % kL0, S.tap16, w_lo, hi, tb + (0u * 2u + buf) * 32u, idesc);
+        if (elect_one()) umma_commit(&S.mma_done[0][it & 3]);
+        // ---- conv 1 on tile tA + it - 2: s_1 tiles written by conv 0's epilogue up to iteration it-1
+        if (it >= 1) wait_chain(&S.epi_done[0][(it - 1) & 3], par_m1, p.dbg, 0x14, it);
+        if (it >= 2) wait_chain(&S.epi_done[1][(it - 2) & 3], par_m2, p.dbg, 0x15, it);
+        tc_fence_after();
+        issue_conv<kL1>(r1_lo, pmod(it - 2, kL1), S.tap16, w_lo + (kConvWBytes >> 4), hi, tb + (1u * 2u + buf) * 32u, idesc);
+        if (elect_one()) umma_commit(&S.mma_done[1][it & 3]);
+        // ---- conv 2 on tile tA + it - 4: s_2 tiles written by conv 1's epilogue up to iteration it-1
+        if (it >= 1) wait_chain(&S.epi_done[1][(it - 1) & 3], par_m1, p.dbg, 0x16, it);
+        if (it >= 2) wait_chain(&S.epi_done[2][(it - 2) & 3], par_m2, p.dbg, 0x17, it);
+        tc_fence_after();
+        issue_conv<kL2>(r2_lo, pmod(it - 2, kL2), S.tap16, w_lo + 2u * (kConvWBytes >> 4), hi, tb + (2u * 2u + buf) * 32u, idesc);
+        if (elect_one()) umma_commit(&S.mma_done[2][it & 3]);
       }
     }
   } else if (warp >= 4) {
@@ -250,27 +242,15 @@ res2_chain_kernel(const __grid_constant__ ChainParams p, const __grid_constant__
     const uint32_t row_xor = static_cast<uint32_t>((m >> 1) & 3) << 4;
     const uint32_t sc_base = smem_u32(&S.scale[k][0]), sh_base = smem_u32(&S.shift[k][0]);
     uint8_t* y_base = p.y + static_cast<size_t>(k) * 64u;
-    const uint8_t* xn = k < 2 ? p.xs[k] : nullptr;                        // planar split x_{k+1}: 64 bytes per pixel
-    const int nk = nb > 0 ? (k == 0 ? n0 : k == 1 ? n1 : n2) : 0;
-    const long long tile0 = tA + k;                                       // image tile of this conv's tile 0
-    uint4 xa[4], xb[4];
-    auto load_x = [&](long long pp, uint4 (&d)[4]) {
-      if (pp >= 0 && pp < p.P_cap) {
-        ldg256(xn + static_cast<size_t>(pp) * 64u, d[0], d[1]);
-        ldg256(xn + static_cast<size_t>(pp) * 64u + 32u, d[2], d[3]);
-      } else d[0] = d[1] = d[2] = d[3] = make_uint4(0, 0, 0, 0);
-    };
-    if (k < 2 && nk > 0) load_x(tile0 * 128 + m, xa);
-    for (int i = 0; i < nk; ++i) {
-      const long long tile = tile0 + i;
+    for (int it = 0; it < n_it; ++it) {
+      const long long tile = tA + it - 2 * k;
       const long long pp = tile * 128 + m;
       const bool valid = pp >= 0 && pp < p.P && p.pix_valid[pp] != 0;
       const uint32_t vmask = valid ? 0xffffffffu : 0u;
       const bool store_y = tile >= t0 && tile < t1 && pp < p.P_cap;
-      if (k < 2 && i + 1 < nk) load_x(pp + 128, xb);                      // next tile's x values: in flight under this tile's arithmetic
-      wait_chain(&S.mma_done[k][i & 3], static_cast<uint32_t>(i >> 2) & 1u, p.dbg, 0x20 + k, i);
+      wait_chain(&S.mma_done[k][it & 3], static_cast<uint32_t>(it >> 2) & 1u, p.dbg, 0x20 + k, it);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>(k * 4 + (i & 3)) * 32u;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>(k * 2 + (it & 1)) * 32u;
       uint32_t ra[16], rb[16];
       tmem_ld16(taddr, ra);
       tmem_ld16(taddr + 16, rb);
@@ -285,25 +265,6 @@ res2_chain_kernel(const __grid_constant__ ChainParams p, const __grid_constant__
         v[g * 4 + 2] = fmaxf(fmaf(__uint_as_float(r[2]), s4.z, b4.z), 0.f);
         v[g * 4 + 3] = fmaxf(fmaf(__uint_as_float(r[3]), s4.w, b4.w), 0.f);
       }
-      if (k < 2) {
-        // s = x_{k+1} + y_k -> ring number i of the next ring (slot 0 also into the mirror), before y leaves: the next conv waits for it
-        const int slot = i % Ln;
-        const uint32_t base = ring_next + static_cast<uint32_t>(slot) * kTileBytes + row_off;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const uint32_t addr = base + ((static_cast<uint32_t>(c) << 4) ^ row_xor);
-          const uint4 ax = xa[c];
-          const float2 a0 = TypeOps<T>::unpack2(ax.x), a1 = TypeOps<T>::unpack2(ax.y), a2 = TypeOps<T>::unpack2(ax.z), a3 = TypeOps<T>::unpack2(ax.w);
-          uint4 s;
-          s.x = TypeOps<T>::pack2(v[c * 8 + 0] + a0.x, v[c * 8 + 1] + a0.y) & vmask; s.y = TypeOps<T>::pack2(v[c * 8 + 2] + a1.x, v[c * 8 + 3] + a1.y) & vmask;
-          s.z = TypeOps<T>::pack2(v[c * 8 + 4] + a2.x, v[c * 8 + 5] + a2.y) & vmask; s.w = TypeOps<T>::pack2(v[c * 8 + 6] + a3.x, v[c * 8 + 7] + a3.y) & vmask;
-          sts_u4(addr, s);
-          if (slot == 0) sts_u4(addr + static_cast<uint32_t>(Ln) * kTileBytes, s);
-        }
-        fence_proxy_async();            // generic-proxy writes of this thread -> visible to the tensor core's operand reads
-      }
-      tc_fence_before();
-      mbar_arrive(&S.epi_done[k][i & 3]);
       if (store_y) {
         uint4 o[4];
 #pragma unroll
@@ -316,14 +277,30 @@ res2_chain_kernel(const __grid_constant__ ChainParams p, const __grid_constant__
         stg256(dst + 32, o[2], o[3]);
       }
       if (k < 2) {
+        // s = x_{k+1} + y_k in place over the x tile (ring number `it` of the next ring), slot 0 also into the mirror
+        const int slot = it % Ln;
+        wait_chain(&S.x_full[k + 1][slot], static_cast<uint32_t>(it / Ln) & 1u, p.dbg, 0x28 + k, it);
+        const uint32_t base = ring_next + static_cast<uint32_t>(slot) * kTileBytes + row_off;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) xa[c] = xb[c];
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t addr = base + ((static_cast<uint32_t>(c) << 4) ^ row_xor);
+          const uint4 ax = lds_u4(addr);
+          const float2 a0 = TypeOps<T>::unpack2(ax.x), a1 = TypeOps<T>::unpack2(ax.y), a2 = TypeOps<T>::unpack2(ax.z), a3 = TypeOps<T>::unpack2(ax.w);
+          uint4 s;
+          s.x = TypeOps<T>::pack2(v[c * 8 + 0] + a0.x, v[c * 8 + 1] + a0.y) & vmask; s.y = TypeOps<T>::pack2(v[c * 8 + 2] + a1.x, v[c * 8 + 3] + a1.y) & vmask;
+          s.z = TypeOps<T>::pack2(v[c * 8 + 4] + a2.x, v[c * 8 + 5] + a2.y) & vmask; s.w = TypeOps<T>::pack2(v[c * 8 + 6] + a3.x, v[c * 8 + 7] + a3.y) & vmask;
+          sts_u4(addr, s);
+          if (slot == 0) sts_u4(addr + static_cast<uint32_t>(Ln) * kTileBytes, s);
+        }
+        fence_proxy_async();            // generic-proxy writes of this thread -> visible to the tensor core's operand reads
       }
+      tc_fence_before();
+      mbar_arrive(&S.epi_done[k][it & 3]);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
 }
 
 size_t res2_chain_smem_bytes() { return 1024 + kHeaderBytes + 3 * kConvWBytes + kRingBytes; }
