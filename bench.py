@@ -454,7 +454,7 @@ def main():
             "e2e": {"value": world * BATCH / (e2e_ms * 1e-3), "unit": "embeddings/s",
                     "h2d_bytes_per_step": BATCH * FRAMES * FEAT_DIM * 4 + (BATCH + 1) * 4, "d2h_bytes_per_step": BATCH * ex.embed_dim * 4},
             "gpu_launches": int(launches_per_step) * args.steps,
-            "roofline": {"bound": "tensor", "kernel": "conv_flat_kernel + conv_umma_kernel (all tcgen05 conv launches of one step)",
+            "roofline": {"bound": "tensor", "kernel": "conv_flat_kernel + conv_pair_kernel + res2_chain_kernel + conv_umma_kernel (all tcgen05 conv launches of one step)",
                          "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                          "frac": achieved / pk["bf16_tflops_sustained"], "traffic": traffic,
                          "peak_source": pk["source"] + " sustained (kernels timed inside a long step)",
