@@ -246,13 +246,23 @@ cudaError_t launch_res2_chain(const ChainParams& p, const ChainMaps& maps, int i
 // routing table, so dense outputs, planar splits and a second destination are the same code.
 struct PairConvParams {
   long long P, P_cap;          // pixels to cover / allocated
-  int nkb;                     // K boxes of 64 elements (per tap)
-  int ks_last;                 // K = 16 steps of the last box that hold real channels (1..4); the other boxes have 4
-  int kpad;                    // weight columns per tap (nkb * 64)
-  int taps, halo;              // 1x1: 1 / 0.  3x3: 9 taps as shifts of the flat pixel sequence, halo = max |shift|
-  int tap_shift[kMaxTaps];
-  int a_rows; uint32_t a_bytes;         // pixel rows of one A box (128 + 2 halo, multiple of 8) and its bytes rounded up to 1 KB
-  int b_resident; uint32_t b_item_bytes;   // weights resident in shared memory (taps * nkb items of n_tile/2 rows) instead of streamed with A (1x1 only)
+  // A tile's main loop is a list of K BOXES (one A load each) and every box carries ITEMS (tap displacement, weight column, K steps):
+  //   1x1: one box per 64 input channels, one item each;  3x3 stride 1: the same boxes, nine items each (shifts of the flat pixel
+  //   sequence);  stride 2 (2-D tile mode): one box per parity phase and 64 channels, 1 / 2 / 2 / 4 items per phase for a 3x3.
+  int n_boxes;                 // <= 16
+  uint8_t box_map[16];         // A tensor map of the box: 0 = PairMaps::a, 1..3 = PairMaps::a2[box_map - 1] (parity phases)
+  int16_t box_c[16];           // channel coordinate of the box
+  uint8_t box_item0[17];       // items of box b: [box_item0[b], box_item0[b + 1])
+  uint16_t item_off16[24];     // (row displacement of the item's tap inside the box) * 128 bytes >> 4
+  uint16_t item_wcol[24];      // weight column of the item (coordinate 0 of the B tensor map)
+  uint8_t item_ks[24];         // K = 16 steps of the item that hold real channels (1..4)
+  int halo;                    // flat modes: the A box starts halo pixels before the tile
+  int a_rows; uint32_t a_bytes;         // rows of one A box (flat: 128 + 2 halo; 2-D: tile_bw * box_h) and its bytes rounded up to 1 KB
+  int b_resident; uint32_t b_item_bytes;   // weights resident in shared memory (one item of n_tile/2 rows each) instead of streamed with A (one item per box)
+  // 2-D tile mode (tile_bw != 0): a CTA tile is tile_h output rows; box = [box_h][tile_bw][64 ch] starting at (a_col0, first output row + a_row0)
+  int tile_bw, tile_h, box_h, a_col0, a_row0;
+  int out_wp;                  // pixels per output row in memory
+  int rows;                    // output rows to cover (2-D tile mode; set per launch)
   int n_tile, n_tiles;         // 128, 192 or 256 output channels per pair tile
   int n_gemm;                  // GEMM N (n_tile * n_tiles, <= 1024)
   int stages; uint32_t stage_bytes;
@@ -271,7 +281,7 @@ struct PairConvParams {
   int knock;                   // debug timing experiments only (SVX_PAIR_KNOCK)
   unsigned long long* dbg;
 };
-struct PairMaps { CUtensorMap a, b; };   // a: {64 ch, 128 px} boxes of the input, b: {64 k, n_tile/2 rows} boxes of the weights, SWIZZLE_128B
+struct PairMaps { CUtensorMap a, b, a2[3]; };   // a: {64 ch, a_rows px} boxes of the input (2-D tile mode: parity phase 0, 3-D), b: {64 k, n_tile/2 rows} boxes of the weights, a2: parity phases 1..3; SWIZZLE_128B
 cudaError_t conv_pair_init();
 size_t conv_pair_smem_bytes(const PairConvParams& p);
 cudaError_t launch_conv_pair(const PairConvParams& p, const PairMaps& maps, int is_bf16, cudaStream_t stream);

@@ -27,6 +27,15 @@
 // The flat kernel has to stream those weights through a 2-4 deep ring for every span (they do not fit beside its slots), which
 // left it at 2.5x its MMA time.  Aux mode 2 writes the hierarchical second output s = x_next + y beside y.
 //
+// Stride-2 convs of the Res2Net down-sampling blocks (2-D tile mode): a CTA's tile is tile_h output rows; the input is seen through
+// four PARITY-PHASE views of the high-resolution tensor (3-D tensor maps with strides of two pixels / two rows: in_row = 2 out_row +
+// dh - 1 lands in phase (dh - 1) & 1 at row out_row + floor((dh - 1) / 2), the same for columns), one haloed box per phase and K
+// box, laid out [box_h][tile_bw][64 channels] so that box rows are again a flat pixel sequence of pitch tile_bw and every tap is a
+// descriptor displaced by (dr + 1) * tile_bw + dc + 1.  conv_umma.cu reloaded one box per TAP (nine per tile).
+//
+// All three forms share one main loop: a tile is a list of K BOXES (A loads) and every box carries a list of ITEMS (tap
+// displacement, weight column, K steps) — 1x1: one item per box; 3x3: nine per box; stride-2 3x3: 1 / 2 / 2 / 4 per phase.
+//
 // Arithmetic and rounding points are those of conv_flat.cu (same K order, same epilogue expression).
 #include <cstdio>
 #include <cstring>
@@ -48,7 +57,7 @@ struct PairSmem {
   uint64_t tmem_full[2], tmem_empty[2];
   uint64_t bres_bar;
   uint32_t tmem_slot;
-  uint32_t tapoff16[12];        // ((halo + tap_shift[tap]) * 128) >> 4: descriptor displacement of each filter tap
+  uint32_t item_off16[24];      // descriptor displacement of each item (its tap's row displacement inside the box * 128 bytes >> 4)
 };
 static_assert(sizeof(PairSmem) <= 1024, "barrier block");
 
@@ -68,6 +77,12 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void umma2_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
@@ -203,7 +218,8 @@ conv_pair_kernel(const __grid_constant__ PairConvParams p, const __grid_constant
   unsigned long long* s_dst = reinterpret_cast<unsigned long long*>(smem + 1024 + 8192);     // [64] destination of each 16-channel group (0: none)
   uint32_t* s_pitch = reinterpret_cast<uint32_t*>(smem + 1024 + 8192 + 512);                 // [64] its bytes per pixel
   uint8_t* bres_smem = smem + kPairHeader;                                   // resident weights (taps * nkb items), if any
-  const uint32_t bres_bytes = p.b_resident ? static_cast<uint32_t>(p.taps * p.nkb) * p.b_item_bytes : 0u;
+  const int n_items = p.box_item0[p.n_boxes];
+  const uint32_t bres_bytes = p.b_resident ? static_cast<uint32_t>(n_items) * p.b_item_bytes : 0u;
   uint8_t* stage_smem = bres_smem + bres_bytes;
 
   const int warp = threadIdx.x >> 5;
@@ -211,17 +227,19 @@ conv_pair_kernel(const __grid_constant__ PairConvParams p, const __grid_constant
   const uint32_t rank = cluster_ctarank();
   const int pair = static_cast<int>(blockIdx.x >> 1);
   const int n_pairs = static_cast<int>(gridDim.x >> 1);
-  const int n_mb = static_cast<int>((p.P + 255) / 256);
+  const bool tile2d = p.tile_bw != 0;
+  const int n_mb = tile2d ? (p.rows + 2 * p.tile_h - 1) / (2 * p.tile_h) : static_cast<int>((p.P + 255) / 256);     // pair tiles along the pixels
   const int n_total = n_mb * p.n_tiles;
   const int half_rows = p.n_tile >> 1;
   const int ng = p.n_tile >> 4;            // 16-channel groups per tile
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&maps.a); prefetch_tmap(&maps.b);
+    prefetch_tmap(&maps.a2[0]); prefetch_tmap(&maps.a2[1]); prefetch_tmap(&maps.a2[2]);
     for (int i = 0; i < 8; ++i) { mbar_init(&S.full[i], 1); mbar_init(&S.empty[i], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&S.tmem_full[b], 1); mbar_init(&S.tmem_empty[b], 16); }   // 8 epilogue warps of each CTA
     mbar_init(&S.bres_bar, 1);
-    for (int t = 0; t < 12; ++t) S.tapoff16[t] = t < p.taps ? static_cast<uint32_t>(p.halo + p.tap_shift[t]) * 8u : 0u;
+    for (int j = 0; j < 24; ++j) S.item_off16[j] = j < n_items ? p.item_off16[j] : 0u;
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -246,11 +264,9 @@ conv_pair_kernel(const __grid_constant__ PairConvParams p, const __grid_constant
   if (p.b_resident && warp == 0 && lane == 0) {      // weights are static: fetched before the dependency wait; both halves complete on the leader's barrier
     const uint32_t bres_leader = mapa_u32(smem_u32(&S.bres_bar), 0);
     const uint32_t item_tx = static_cast<uint32_t>(half_rows) * 128u;
-    if (rank == 0) mbar_expect_tx(&S.bres_bar, 2u * item_tx * static_cast<uint32_t>(p.taps * p.nkb));
-    for (int kb = 0; kb < p.nkb; ++kb)
-      for (int tap = 0; tap < p.taps; ++tap)
-        tma_load_2d_pair(bres_smem + static_cast<size_t>(kb * p.taps + tap) * p.b_item_bytes, &maps.b, bres_leader, tap * p.kpad + kb * 64,
-                         static_cast<int>(rank) * half_rows);
+    if (rank == 0) mbar_expect_tx(&S.bres_bar, 2u * item_tx * static_cast<uint32_t>(n_items));
+    for (int j = 0; j < n_items; ++j)
+      tma_load_2d_pair(bres_smem + static_cast<size_t>(j) * p.b_item_bytes, &maps.b, bres_leader, p.item_wcol[j], static_cast<int>(rank) * half_rows);
   }
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -259,19 +275,21 @@ conv_pair_kernel(const __grid_constant__ PairConvParams p, const __grid_constant
     // ------------------------------------------------------------------ producer (both CTAs)
     if (lane == 0) {
       const uint32_t full_leader = mapa_u32(smem_u32(&S.full[0]), 0);
-      const uint32_t tx = static_cast<uint32_t>(p.a_rows) * 128u + (p.b_resident ? 0u : static_cast<uint32_t>(half_rows) * 128u);
+      const uint32_t tx = static_cast<uint32_t>(p.a_rows) * 128u + (p.b_resident ? 0u : static_cast<uint32_t>(half_rows) * 128u);   // a_rows = box rows in either mode
       uint32_t it = 0;
       for (int t = pair; t < n_total; t += n_pairs) {
         const int mb = t / p.n_tiles, nb = t - mb * p.n_tiles;
-        const int px = (p.reverse ? n_mb - 1 - mb : mb) * 256 + static_cast<int>(rank) * 128;
+        const int ti = (p.reverse ? n_mb - 1 - mb : mb) * 2 + static_cast<int>(rank);         // this CTA's tile along the pixels
         const int nrow = nb * p.n_tile + static_cast<int>(rank) * half_rows;
-        for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+        for (int b = 0; b < p.n_boxes; ++b, ++it) {
           const uint32_t s = it % static_cast<uint32_t>(p.stages);
           wait_pair(&S.empty[s], ((it / static_cast<uint32_t>(p.stages)) & 1u) ^ 1u, p.dbg, 0x01, it);
           if (rank == 0) mbar_expect_tx(&S.full[s], 2u * tx);          // the leader's barrier collects the bytes of both CTAs
           uint8_t* dst = stage_smem + static_cast<size_t>(s) * p.stage_bytes;
-          tma_load_2d_pair(dst, &maps.a, full_leader + s * 8u, kb * 64, px - p.halo);        // haloed span: rows before the image / past its end are zero-filled
-          if (!p.b_resident) tma_load_2d_pair(dst + p.a_bytes, &maps.b, full_leader + s * 8u, kb * 64, nrow);
+          // haloed span / box: rows before the image or past its end are zero-filled
+          if (tile2d) tma_load_3d_pair(dst, p.box_map[b] == 0 ? &maps.a : &maps.a2[p.box_map[b] - 1], full_leader + s * 8u, p.box_c[b], p.a_col0, ti * p.tile_h + p.a_row0);
+          else tma_load_2d_pair(dst, &maps.a, full_leader + s * 8u, p.box_c[b], ti * 128 - p.halo);
+          if (!p.b_resident) tma_load_2d_pair(dst + p.a_bytes, &maps.b, full_leader + s * 8u, p.item_wcol[p.box_item0[b]], nrow);
         }
       }
     }
@@ -286,7 +304,6 @@ conv_pair_kernel(const __grid_constant__ PairConvParams p, const __grid_constant
       const uint32_t idesc = p.idesc;
       const uint32_t bres_lo = static_cast<uint32_t>(desc_base) + (smem_u32(bres_smem) >> 4);
       const uint32_t a16 = p.a_bytes >> 4, item16 = p.b_item_bytes >> 4;
-      const int taps = p.taps;
       if (p.b_resident) wait_pair(&S.bres_bar, 0, p.dbg, 0x10, 0);
       uint32_t it = 0;
       int lt = 0;
@@ -295,19 +312,22 @@ conv_pair_kernel(const __grid_constant__ PairConvParams p, const __grid_constant
         wait_pair(&S.tmem_empty[buf], ((static_cast<uint32_t>(lt) >> 1) & 1u) ^ 1u, p.dbg, 0x11, lt);
         tc_fence_after();
         const uint32_t d_tmem = tb + buf * 256u;
-        for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+        int j = 0;
+        for (int b = 0; b < p.n_boxes; ++b, ++it) {
           const uint32_t s = it % static_cast<uint32_t>(p.stages);
-          const int ks = kb == p.nkb - 1 ? p.ks_last : 4;                 // K = 16 steps of this box that hold real channels
-          uint32_t toff = S.tapoff16[0];
+          const int j_end = p.box_item0[b + 1];
+          uint32_t toff = S.item_off16[j];
+          int ks = p.item_ks[j];                                         // K = 16 steps of this item that hold real channels
           wait_pair(&S.full[s], (it / static_cast<uint32_t>(p.stages)) & 1u, p.dbg, 0x12, it);
           tc_fence_after();
           const uint32_t a_lo = lo0 + s * stage16;
-          uint32_t b_lo = p.b_resident ? bres_lo + static_cast<uint32_t>(kb * taps) * item16 : a_lo + a16;
+          uint32_t b_lo = p.b_resident ? bres_lo + static_cast<uint32_t>(j) * item16 : a_lo + a16;
 #pragma unroll 1
-          for (int tap = 0; tap < taps; ++tap) {
-            const uint32_t toff_next = S.tapoff16[tap + 1];              // next tap's displacement loads while this tap issues
+          for (; j < j_end; ++j) {
+            const uint32_t toff_next = S.item_off16[j + 1];              // next item's displacement loads while this one issues
+            const int ks_next = p.item_ks[j + 1];
             const uint32_t at = a_lo + toff;
-            const uint32_t first = (kb | tap) == 0 ? 0u : 1u;
+            const uint32_t first = j == 0 ? 0u : 1u;
             if (elect_one()) {
               umma2_lo(d_tmem, at, b_lo, hi, idesc, first);
               if (ks > 1) umma2_lo(d_tmem, at + 2u, b_lo + 2u, hi, idesc, 1u);
@@ -316,10 +336,11 @@ conv_pair_kernel(const __grid_constant__ PairConvParams p, const __grid_constant
             }
             b_lo += item16;
             toff = toff_next;
+            ks = ks_next;
           }
           if (elect_one()) {
             umma2_commit_mc(&S.empty[s], 3);                             // stage s is free in BOTH CTAs once these MMAs have read it
-            if (kb == p.nkb - 1) umma2_commit_mc(&S.tmem_full[buf], 3);
+            if (b == p.n_boxes - 1) umma2_commit_mc(&S.tmem_full[buf], 3);
           }
         }
       }
@@ -350,7 +371,7 @@ conv_pair_kernel(const __grid_constant__ PairConvParams p, const __grid_constant
     uint4 rx[2][8];
     auto load_res = [&](int t, int c) {
       const int mb = t / p.n_tiles, nb = t - mb * p.n_tiles;
-      const long long px0 = static_cast<long long>(p.reverse ? n_mb - 1 - mb : mb) * 256 + static_cast<int>(rank) * 128 + q4 * 32;
+      const long long px0 = static_cast<long long>(p.reverse ? n_mb - 1 - mb : mb) * 256 + static_cast<int>(rank) * 128 + q4 * 32;   // flat mode only (no aux tile in 2-D tile mode)
       const int gl = c * 4 + c32, G = nb * ng + g_first + gl;
       const bool here = t < n_total && gl < ngh && G < n_res_grp && !PKNOCK(4);
       const uint8_t* rsrc = p.res + static_cast<size_t>(G) * 32u;
@@ -365,9 +386,22 @@ conv_pair_kernel(const __grid_constant__ PairConvParams p, const __grid_constant
     int lt = 0;
     for (int t = pair; t < n_total; t += n_pairs, ++lt) {
       const int mb = t / p.n_tiles, nb = t - mb * p.n_tiles;
-      const long long px0 = static_cast<long long>(p.reverse ? n_mb - 1 - mb : mb) * 256 + static_cast<int>(rank) * 128 + q4 * 32;   // first pixel of this warp
-      const long long pp = px0 + lane;
-      const uint32_t vmask = (pp < p.P && p.pix_valid[pp]) ? 0xffffffffu : 0u;
+      const int ti = (p.reverse ? n_mb - 1 - mb : mb) * 2 + static_cast<int>(rank);           // this CTA's tile along the pixels
+      // accumulator row m of the tile -> output pixel (flat mode: consecutive pixels; 2-D tile mode: tile_h output rows laid out with
+      // the box pitch tile_bw, the columns past the output row pitch and the rows past tile_h are not output pixels)
+      auto pix_of = [&](int m, long long& q) -> bool {
+        if (!tile2d) { q = static_cast<long long>(ti) * 128 + m; return true; }
+        const int r = m / p.tile_bw, c = m - r * p.tile_bw;
+        q = static_cast<long long>(ti * p.tile_h + r) * p.out_wp + c;
+        return r < p.tile_h && c < p.out_wp;
+      };
+      long long pp;
+      const bool own = pix_of(q4 * 32 + lane, pp);
+      const uint32_t vmask = (own && pp < p.P && p.pix_valid[pp]) ? 0xffffffffu : 0u;
+      long long cq[4];                                     // output pixels of the four rows this lane stores in the coalesced mapping
+      bool cok[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { cok[i] = pix_of(q4 * 32 + 8 * i + cpx, cq[i]); cok[i] = cok[i] && cq[i] < p.P_cap; }
       const int G0 = nb * ng + g_first;                  // first global 16-channel group of this warpgroup
       const uint32_t buf = static_cast<uint32_t>(lt) & 1u;
       wait_pair(&S.tmem_full[buf], (static_cast<uint32_t>(lt) >> 1) & 1u, p.dbg, 0x41, lt);
@@ -427,10 +461,9 @@ conv_pair_kernel(const __grid_constant__ PairConvParams p, const __grid_constant
             const unsigned long long pitch = s_pitch[G];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const long long px = px0 + 8 * i + cpx;
               const uint4 v0 = lds_u4(st_base + static_cast<uint32_t>(i) * 1024u + co_off0);
               const uint4 v1 = lds_u4(st_base + static_cast<uint32_t>(i) * 1024u + co_off1);
-              if (d != 0ull && px < p.P_cap && !PKNOCK(2)) stg256(reinterpret_cast<void*>(d + static_cast<unsigned long long>(px) * pitch), v0, v1);
+              if (d != 0ull && cok[i] && !PKNOCK(2)) stg256(reinterpret_cast<void*>(d + static_cast<unsigned long long>(cq[i]) * pitch), v0, v1);
             }
           }
           __syncwarp();                                      // the staging tile is reused by the next chunk / tile
@@ -447,10 +480,9 @@ conv_pair_kernel(const __grid_constant__ PairConvParams p, const __grid_constant
               uint8_t* d2 = p.out2 + static_cast<size_t>(G0 + c * 4 + c32) * 32u;
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const long long px = px0 + 8 * i + cpx;
                 const uint4 v0 = lds_u4(st_base + static_cast<uint32_t>(i) * 1024u + co_off0);
                 const uint4 v1 = lds_u4(st_base + static_cast<uint32_t>(i) * 1024u + co_off1);
-                if (px < p.P_cap && !PKNOCK(2)) stg256(d2 + static_cast<size_t>(px) * p.out2_pitch, v0, v1);
+                if (cok[i] && !PKNOCK(2)) stg256(d2 + static_cast<size_t>(cq[i]) * p.out2_pitch, v0, v1);
               }
             }
             __syncwarp();
@@ -466,7 +498,7 @@ conv_pair_kernel(const __grid_constant__ PairConvParams p, const __grid_constant
 }
 
 size_t conv_pair_smem_bytes(const PairConvParams& p) {
-  const size_t bres = p.b_resident ? static_cast<size_t>(p.taps) * p.nkb * p.b_item_bytes : 0;
+  const size_t bres = p.b_resident ? static_cast<size_t>(p.box_item0[p.n_boxes]) * p.b_item_bytes : 0;
   return 1024 + kPairHeader + bres + static_cast<size_t>(p.stages) * p.stage_bytes + 8 * 4096;
 }   // + one 4 KB staging tile per epilogue warp
 
@@ -507,7 +539,8 @@ cudaError_t conv_pair_init() {
 
 cudaError_t launch_conv_pair(const PairConvParams& p, const PairMaps& maps, int is_bf16, cudaStream_t st) {
   if (p.P <= 0) return cudaSuccess;
-  const long long n_total = ((p.P + 255) / 256) * p.n_tiles;
+  const long long n_mb = p.tile_bw ? (p.rows + 2 * p.tile_h - 1) / (2 * p.tile_h) : (p.P + 255) / 256;
+  const long long n_total = n_mb * p.n_tiles;
   long long pairs = g_pair_clusters > 0 ? g_pair_clusters : 74;
   if (pairs > n_total) pairs = n_total;
   cudaLaunchConfig_t cfg;
@@ -536,7 +569,7 @@ cudaError_t launch_conv_pair(const PairConvParams& p, const PairMaps& maps, int 
   if (is_bf16) SVX_PAIR(__nv_bfloat16); else SVX_PAIR(__half);
 #undef SVX_PAIR
   if (le != cudaSuccess) {
-    fprintf(stderr, "conv_pair launch failed: grid %u smem %zu n_tile %d x%d nkb %d stages %d\n", cfg.gridDim.x, cfg.dynamicSmemBytes, p.n_tile, p.n_tiles, p.nkb, p.stages);
+    fprintf(stderr, "conv_pair launch failed: grid %u smem %zu n_tile %d x%d boxes %d stages %d\n", cfg.gridDim.x, cfg.dynamicSmemBytes, p.n_tile, p.n_tiles, p.n_boxes, p.stages);
     return le;
   }
   return cudaGetLastError();

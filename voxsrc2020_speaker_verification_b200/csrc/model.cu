@@ -584,6 +584,7 @@ int Model::set_option(const char* key, int value) {
   if (!strcmp(key, "no_flat")) { force_no_flat_ = value; return 0; }
   if (!strcmp(key, "no_chain")) { no_chain_ = value; return 0; }
   if (!strcmp(key, "no_pair")) { no_pair_ = value; return 0; }
+  if (!strcmp(key, "no_pair_s2")) { no_pair_s2_ = value; return 0; }
   set_last_error(std::string("unknown option: ") + key);
   return 1;
 }
@@ -622,7 +623,7 @@ int Model::plan_conv(ConvDesc& c) {
   c.use_flat = false;
   if (plan_flat(c)) return 1;
   c.use_pair = false;
-  if (c.use_flat && plan_pair(c)) return 1;
+  if ((c.use_flat || c.stride == 2) && plan_pair(c)) return 1;
   // ---- tcgen05 form
   c.use_umma = false;
   const int taps = c.kh * c.kw;
@@ -1100,10 +1101,19 @@ int Model::plan_pair(ConvDesc& c) {
   const ActTensor& tin = tensors_[c.in.id];
   const ActTensor& tout = tensors_[c.out.id];
   const int taps = c.kh * c.kw;
-  if (c.stride != 1 || c.groups != 1 || tin.stage != tout.stage || taps > kMaxTaps) return 0;
+  static const bool no_s2 = dbg_env("SVX_NO_PAIR_S2") != nullptr;
+  const bool s2 = c.stride == 2;          // Res2Net down-sampling convs: 2-D tile mode over four parity-phase views of the input
+  if (c.groups != 1 || taps > kMaxTaps || c.dil != 1) return 0;
+  if (!s2 && (c.stride != 1 || tin.stage != tout.stage)) return 0;
   if (c.kbox != 64 || c.kpad % 64 != 0) return 0;
   const int Wp = stage_Wp_[tout.stage], W = stage_W_[tout.stage];
-  if (taps == 1) {
+  if (s2) {
+    // explicit (k-1)/2 padding on both sides (models.py:121-134): in = 2 out + d - pad; the segment layout gives row offsets off[s] = 2 off[s+1]
+    if (no_s2 || cfg_.family != SVX_FAMILY_RES2NET || tin.stage + 1 != tout.stage) return 0;
+    if (!((c.kh == 1 && c.kw == 1 && c.ph == 0 && c.pw == 0) || (c.kh == 3 && c.kw == 3 && c.ph == 1 && c.pw == 1))) return 0;
+    if (c.res.id >= 0 || c.out2.id >= 0 || c.split_w > 0 || c.pre_relu) return 0;
+    if (Wp <= W || stage_Wp_[tin.stage] != 2 * W + 1) return 0;
+  } else if (taps == 1) {
     if (c.kpad < min_k) return 0;
   } else {
     if (no_3x3 || c.cin < min_c3) return 0;
@@ -1183,28 +1193,66 @@ int Model::plan_pair(ConvDesc& c) {
     pp.out2_pitch = static_cast<uint32_t>(t2.C * esz);
   }
   pp.aux_mode = aux_mode;
-  pp.nkb = c.kpad / 64;
-  pp.kpad = c.kpad;
-  {
-    const int last = c.cin - (pp.nkb - 1) * 64;                 // real channels of the last K box (the rest is zero-filled / zero weights)
-    pp.ks_last = std::min(4, std::max(1, (last + 15) / 16));
-  }
-  pp.taps = taps;
-  int halo = 0;
-  for (int t = 0; t < taps; ++t) {
-    const int r = t / c.kw, s = t % c.kw;
-    pp.tap_shift[t] = (r * c.dil - c.ph) * Wp + (s - c.pw);
-    halo = std::max(halo, std::abs(pp.tap_shift[t]));
-  }
-  pp.halo = halo;
-  pp.a_rows = round_up(128 + 2 * halo, 8);
-  if (pp.a_rows > 256) return 0;
-  pp.a_bytes = static_cast<uint32_t>(round_up(pp.a_rows * 128, 1024));
+  const int nkb = c.kpad / 64;
+  const int ks_last = std::min(4, std::max(1, (c.cin - (nkb - 1) * 64 + 15) / 16));   // real channels of the last K box (the rest is zero-filled / zero weights)
   pp.n_tile = n_tile; pp.n_tiles = N / n_tile; pp.n_gemm = N; pp.n_valid = N;
   pp.b_item_bytes = static_cast<uint32_t>(round_up((n_tile / 2) * 128, 1024));
   pp.b_resident = taps > 1 ? 1 : 0;
+  pp.out_wp = Wp;
+  int n_items = 0;
+  auto add_item = [&](int row_shift, int wcol, int ks) {
+    pp.item_off16[n_items] = static_cast<uint16_t>(row_shift * 8); pp.item_wcol[n_items] = static_cast<uint16_t>(wcol); pp.item_ks[n_items] = static_cast<uint8_t>(ks);
+    ++n_items;
+  };
+  if (!s2) {
+    int halo = 0;
+    int shift[kMaxTaps];
+    for (int t = 0; t < taps; ++t) {
+      const int r = t / c.kw, s = t % c.kw;
+      shift[t] = (r * c.dil - c.ph) * Wp + (s - c.pw);
+      halo = std::max(halo, std::abs(shift[t]));
+    }
+    pp.halo = halo;
+    pp.a_rows = round_up(128 + 2 * halo, 8);
+    if (nkb > 16 || nkb * taps > 24) return 0;
+    pp.n_boxes = nkb;
+    for (int kb = 0; kb < nkb; ++kb) {
+      pp.box_map[kb] = 0; pp.box_c[kb] = static_cast<int16_t>(kb * 64); pp.box_item0[kb] = static_cast<uint8_t>(n_items);
+      for (int t = 0; t < taps; ++t) add_item(halo + shift[t], t * c.kpad + kb * 64, kb == nkb - 1 ? ks_last : 4);
+    }
+    pp.box_item0[nkb] = static_cast<uint8_t>(n_items);
+  } else {
+    // 2-D tile mode: tile = tile_h output rows; phase (pr, pc) holds the input pixels (2 k + pr, 2 j + pc).  Tap (dh, dw) of output (R, c) reads
+    // input (2 R + dh - ph, 2 c + dw - pw) = phase ((dh - ph) & 1, (dw - pw) & 1) at (R + dr, c + dc), dr / dc = floor((d - pad) / 2) in {-1, 0}.
+    // 3x3: the box starts one row / one column early, tap displacement (dr + 1) * bw + (dc + 1); 1x1: phase (0, 0), no halo.
+    const bool k3 = c.kh == 3;
+    pp.tile_bw = k3 ? Wp + 1 : Wp;
+    if (pp.tile_bw > 128) return 0;
+    pp.tile_h = 128 / pp.tile_bw;                       // as many output rows as fit the 128 accumulator rows
+    pp.box_h = k3 ? pp.tile_h + 1 : pp.tile_h;
+    pp.a_col0 = k3 ? -1 : 0; pp.a_row0 = k3 ? -1 : 0;
+    if (pp.box_h > 256 || pp.tile_bw * pp.box_h > 224) return 0;
+    pp.a_rows = pp.tile_bw * pp.box_h;
+    const int n_phase = k3 ? 4 : 1;
+    if (n_phase * nkb > 16 || taps * nkb > 24) return 0;
+    pp.n_boxes = 0;
+    for (int ph = 0; ph < n_phase; ++ph)
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int b = pp.n_boxes++;
+        pp.box_map[b] = static_cast<uint8_t>(ph); pp.box_c[b] = static_cast<int16_t>(kb * 64); pp.box_item0[b] = static_cast<uint8_t>(n_items);
+        for (int t = 0; t < taps; ++t) {
+          const int dh = t / c.kw - c.ph, dw = t % c.kw - c.pw;                  // input offset relative to (2 R, 2 c)
+          const int pr = dh & 1, pc = dw & 1, dr = (dh - pr) / 2, dc = (dw - pc) / 2;
+          if (pr * 2 + pc != ph) continue;
+          add_item(k3 ? (dr + 1) * pp.tile_bw + (dc + 1) : 0, t * c.kpad + kb * 64, kb == nkb - 1 ? ks_last : 4);
+        }
+      }
+    pp.box_item0[pp.n_boxes] = static_cast<uint8_t>(n_items);
+  }
+  if (pp.a_rows > 256 && !s2) return 0;
+  pp.a_bytes = static_cast<uint32_t>(round_up((pp.a_rows + (s2 ? 48 : 0)) * 128, 1024));   // 2-D tiles: the unused accumulator rows 126 / 127 read past the box
   if (pp.b_resident && (pp.n_tiles != 1 || (n_tile / 2) % 8 != 0)) return 0;
-  const long long bres = pp.b_resident ? static_cast<long long>(taps) * pp.nkb * pp.b_item_bytes : 0;
+  const long long bres = pp.b_resident ? static_cast<long long>(n_items) * pp.b_item_bytes : 0;
   pp.stage_bytes = pp.a_bytes + (pp.b_resident ? 0u : pp.b_item_bytes);
   const long long room = 227 * 1024 - 1024 - (1024 + 8192 + 1024) - 8 * 4096 - bres;
   if (room < 3LL * pp.stage_bytes) return 0;
@@ -1218,7 +1266,7 @@ int Model::plan_pair(ConvDesc& c) {
   pp.P_cap = static_cast<long long>(P_cap);
   PairMaps& pm = c.pmaps;
   memset(&pm, 0, sizeof pm);
-  {
+  if (!s2) {
     const int a_width = (c.in.coff == 0 && tin.C > c.cin && tin.C <= c.kpad) ? tin.C : c.cin;
     const uint64_t dims[2] = {static_cast<uint64_t>(a_width), P_cap};
     const uint64_t str[1] = {static_cast<uint64_t>(tin.C) * esz};
@@ -1226,6 +1274,20 @@ int Model::plan_pair(ConvDesc& c) {
     const int pitch = tin.C * 2, off = c.in.coff * 2, wb = c.cin * 2;
     const int promo = (a_width == tin.C || (pitch % 128 == 0 && off % 128 == 0 && wb % 128 == 0)) ? 128 : 64;
     if (encode_tmap(&pm.a, is_bf16_, static_cast<uint8_t*>(tin.ptr) + static_cast<size_t>(c.in.coff) * esz, 2, dims, str, box, 128, promo)) return 1;
+  } else {
+    // parity-phase views of the high-resolution input: pixel (k, j) of phase (pr, pc) = input pixel (2 k + pr, 2 j + pc)
+    const int Wp_in = stage_Wp_[tin.stage], rows_in = rows_cap_[tin.stage];
+    const int n_phase = c.kh == 3 ? 4 : 1;
+    // channels past cin meet zero weight rows; they only have to exist and be finite: the rest of the tensor's row, at most the K pad
+    const int a_width = std::min(tin.C - c.in.coff, c.kpad);
+    for (int ph = 0; ph < n_phase; ++ph) {
+      const int pr = ph >> 1, pc = ph & 1;
+      const uint64_t dims[3] = {static_cast<uint64_t>(a_width), static_cast<uint64_t>((Wp_in - pc + 1) / 2), static_cast<uint64_t>((rows_in - pr + 1) / 2)};
+      const uint64_t str[2] = {2ull * tin.C * esz, 2ull * Wp_in * tin.C * esz};
+      const uint32_t box[3] = {64u, static_cast<uint32_t>(pp.tile_bw), static_cast<uint32_t>(pp.box_h)};
+      uint8_t* base = static_cast<uint8_t*>(tin.ptr) + (static_cast<size_t>(pr) * Wp_in + pc) * tin.C * esz + static_cast<size_t>(c.in.coff) * esz;
+      if (encode_tmap(ph == 0 ? &pm.a : &pm.a2[ph - 1], is_bf16_, base, 3, dims, str, box, 128, 64)) return 1;
+    }
   }
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(taps) * c.kpad, static_cast<uint64_t>(c.n_pad)};
@@ -1424,9 +1486,9 @@ int Model::launch_conv(ConvDesc& c, cudaStream_t st) {
   const int out_stage = tensors_[c.out.id].stage;
   const int out_rows = rows_used_[out_stage];
   const bool flat = c.use_flat && !force_simple_ && !force_no_flat_;
-  const bool pair = flat && c.use_pair && !no_pair_;
-  const bool umma = !flat && c.use_umma && !force_simple_;
-  if (flat || umma) {
+  const bool pair = c.use_pair && !no_pair_ && !force_simple_ && (flat || (c.stride == 2 && !force_no_flat_ && !no_pair_s2_));
+  const bool umma = !flat && !pair && c.use_umma && !force_simple_;
+  if (pair || flat || umma) {
     static const char* trace_dir = dbg_env("SVX_TRACE_DIR");   // debug: per-launch event timeline of CTA 0
     static unsigned long long* d_trace = nullptr;
     static int trace_idx = 0;
@@ -1440,6 +1502,7 @@ int Model::launch_conv(ConvDesc& c, cudaStream_t st) {
     }
     if (pair) {
       c.pp.P = static_cast<long long>(out_rows) * stage_Wp_[out_stage];
+      c.pp.rows = out_rows;
       c.pp.dbg = flat_dbg_words();
       { static const char* kn = dbg_env("SVX_PAIR_KNOCK"); c.pp.knock = kn ? atoi(kn) : 0; }
       if (tensor_dir_.size() != tensors_.size()) tensor_dir_.assign(tensors_.size(), 0);

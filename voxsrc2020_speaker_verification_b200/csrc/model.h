@@ -142,6 +142,7 @@ class Model {
   std::vector<int> stage_Wp_;        // pixels per row in memory: W + 1 zero column for the 2-D networks, W for the TDNN
   std::vector<uint8_t*> d_pix_valid_;
   int force_no_flat_ = 0;
+  int no_pair_s2_ = 0;                // option "no_pair_s2": stride-2 convs on conv_umma.cu instead of the pair kernel's 2-D tile mode
   int no_pair_ = 0;                   // option "no_pair": deep 1x1 convs on the flat kernel instead of the CTA-pair GEMM
   int no_chain_ = 0;                  // option "no_chain": run the hierarchical 3x3 convs as separate launches
   std::vector<int> tensor_dir_;       // per activation tensor: 1 if its last writer walked the pixels backwards
