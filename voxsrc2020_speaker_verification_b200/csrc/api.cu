@@ -344,7 +344,7 @@ static int cohort_pass(svx_scorer* h, const float* test_dev, int64_t n, const fl
   // cohort (k <= c/3) and a cohort large enough for the first 128 scores to be a sample (c >= 1024).  Everything else — and any
   // row the fused kernel hands back — goes through the unfused kernels.
   static const bool env_unfused = dbg_env("SVX_SCORE_UNFUSED") != nullptr;   // debug switch
-  const bool fused_ok = h->use_fused && !env_unfused && d <= 256 && d % 4 == 0 && c >= 1024 && static_cast<long long>(topk) * 3 <= c && n <= (1LL << 30);
+  const bool fused_ok = h->use_fused && !env_unfused && d <= 256 && d % 4 == 0 && c >= 1024 && c <= 65535 && static_cast<long long>(topk) * 3 <= c && n <= (1LL << 30);
   if (!fused_ok) return cohort_pass_unfused(h, test_dev, n, cohort_dev, c, d, topk, mean_dev, std_dev, vals_dev, topk, st);
 
   const int dp = (d + 63) / 64 * 64;
@@ -361,7 +361,7 @@ static int cohort_pass(svx_scorer* h, const float* test_dev, int64_t n, const fl
   fp.dp = dp; fp.kboxes = dp / 64; fp.topk = topk;
   const double zq = normal_upper_quantile(static_cast<double>(topk) / c);
   fp.z_lo = static_cast<float>(zq - 1.0); fp.z_hi = static_cast<float>(zq + 2.2);
-  fp.nb = 96; fp.cap = 28;                    // candidates per epilogue group
+  fp.nb = 96; fp.cap = 48;                    // histogram bins (16-bit counts: c <= 65535); candidates per epilogue group
   fp.mean = mean_dev; fp.stdv = std_dev; fp.vals = vals_dev; fp.vals_ld = topk;
   fp.flag_count = h->d_flag; fp.flag_rows = h->d_flag + 1;
   fp.stages = 12;

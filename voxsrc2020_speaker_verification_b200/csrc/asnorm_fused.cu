@@ -53,9 +53,42 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(static_cast<uint16_t>(v)) : "memory"); }
 __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
-__device__ __forceinline__ void red_add_u32(uint32_t addr, uint32_t v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+
+constexpr int kListSlack = 4;                  // spare words behind a candidate list: its write pointer is clamped once per four scores
+
+// bytes of the area that holds the two private histograms (pass 0) and then the two candidate lists (pass 1), a multiple of 512
+__host__ __device__ inline uint32_t asnorm_main_bytes(int nb, int cap) {
+  const uint32_t h = (2u * static_cast<uint32_t>(nb + 1) * 256u + 511u) & ~511u;
+  const uint32_t l = 2u * static_cast<uint32_t>(cap + kListSlack) * 512u;
+  return h > l ? h : l;
+}
+
+// stored bin of a score: 0 below the range, 1 + floor((v - lo) * scale) inside, nb at and above its top.  Monotone in v.
+__device__ __forceinline__ int asnorm_bin(float v, float scale, float off1, float top) {
+  return __float2int_rz(fminf(fmaxf(fmaf(v, scale, off1), 0.f), top));
+}
+
+// smallest float whose stored bin is >= target (+inf when there is none): bisection over the order-preserving integer key of a float
+__device__ __forceinline__ float asnorm_bin_threshold(int target, float scale, float off1, float top) {
+  auto unkey = [](uint32_t kk) { return __uint_as_float((kk & 0x80000000u) ? (kk & 0x7fffffffu) : ~kk); };
+  uint32_t lo = ~0xff7fffffu;                  // key(-FLT_MAX)
+  uint32_t hi = 0x7f800000u | 0x80000000u;     // key(+inf)
+  if (asnorm_bin(unkey(hi), scale, off1, top) < target) return unkey(hi);
+  if (asnorm_bin(unkey(lo), scale, off1, top) >= target) return unkey(lo);
+  while (hi - lo > 1u) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    if (asnorm_bin(unkey(mid), scale, off1, top) >= target) hi = mid; else lo = mid;
+  }
+  return unkey(hi);
+}
 
 }  // namespace
 
@@ -165,26 +198,34 @@ asnorm_fused_kernel(const __grid_constant__ AsnormFusedParams p, const __grid_co
     }
   } else if (warp >= 4) {
     // Two epilogue warpgroups: group g takes the tiles whose accumulator buffer is g (even / odd tiles), so every test row has two
-    // threads that share its histogram (shared-memory atomics) and keep private partial sums and candidate lists; group 0
-    // computes the bin range from the row block's first tile and finishes the row.  Three named barriers per row block.
+    // threads, each with a private histogram, private partial sums and a private candidate list; group 0 computes the bin range
+    // from the row block's first tile and finishes the row.  Three named barriers per row block.
     const int g = (warp - 4) >> 2;
     const int q4 = warp & 3;
     const int row = q4 * 32 + lane;
-    const uint32_t aux_row = smem_u32(aux) + static_cast<uint32_t>(row) * 4u;     // word w of this row: aux_row + w * 512
-    const int nb = p.nb, cap = p.cap;                            // cap: candidates per GROUP; list words [g * cap, g * cap + cap)
-    const uint32_t list_row = aux_row + static_cast<uint32_t>(g * cap) * 512u;
-    const uint32_t part_row = aux_row + static_cast<uint32_t>(2 * cap) * 512u;   // 8 words: range (pass 0), then group 1's partial results
+    const int nb = p.nb, cap = p.cap;                            // cap: candidates per GROUP
+    const uint32_t aux_u32 = smem_u32(aux);
+    const uint32_t aux_row = aux_u32 + static_cast<uint32_t>(row) * 4u;           // list word w of this row: aux_row + w * 512
+    const uint32_t hist_bytes = static_cast<uint32_t>(nb + 1) * 256u;             // one group's histogram: 16-bit counts, bin b of row r at b * 256 + r * 2
+    const uint32_t hist_row0 = aux_u32 + static_cast<uint32_t>(row) * 2u, hist_row1 = hist_row0 + hist_bytes;
+    const uint32_t hist_row = g ? hist_row1 : hist_row0;                         // this group's PRIVATE histogram (pass 0)
+    const uint32_t list_row = aux_row + static_cast<uint32_t>(g * (cap + kListSlack)) * 512u;   // this group's candidate list (pass 1)
+    const uint32_t list_end = list_row + static_cast<uint32_t>(cap) * 512u;
+    const uint32_t part_row = aux_row + asnorm_main_bytes(nb, cap);              // 8 words: range (pass 0), then group 1's partial results
     const uint32_t trash_row = part_row + 8u * 512u + static_cast<uint32_t>(g) * 512u;   // where the unconditional stores of unselected scores go
+    const float top = static_cast<float>(nb) + 0.5f;
     const int k = p.topk;
     uint32_t tt = 0;
     int lbe = 0;
     for (int rb = blockIdx.x; rb < p.n_row_blocks; rb += gridDim.x) {
       const long long grow = static_cast<long long>(rb) * 128 + row;
-      float off = 0.f, scale = 0.f;
+      float off1 = 0.f, scale = 0.f;
       int bstar = -2, need = 0, above = 0;
       bool bad = false;
       double dsum = 0.0, dsq = 0.0;
-      int cnt = 0, pos = 0;
+      int pos = 0;
+      uint32_t lptr = list_row;                                   // next free word of this group's candidate list
+      float thr_gt = __int_as_float(0x7f800000), thr_ge = __int_as_float(0x7f800000);
       float* vo = (VALS && p.vals && grow < p.n_rows) ? p.vals + grow * p.vals_ld : nullptr;
       if (g == 0) {
         // this row's operand into tensor memory: x = hi + lo in bf16, two elements per 32-bit column (what tcgen05.mma reads as a
@@ -220,18 +261,18 @@ asnorm_fused_kernel(const __grid_constant__ AsnormFusedParams p, const __grid_co
       for (int pass = 0; pass < 2; ++pass) {
         for (int t = 0; t < p.n_tiles; ++t, ++tt) {
           const int buf = tt & 1;
-          if (pass == 0 && t == 1 && g == 1) {                    // group 1's first tile: the range is published, the histogram zeroed
+          if (pass == 0 && t == 1 && g == 1) {                    // group 1's first tile: the range is published, the histograms zeroed
             named_bar_sync(1, 256);
-            off = __uint_as_float(lds_u32(part_row)); scale = __uint_as_float(lds_u32(part_row + 512u));
+            off1 = __uint_as_float(lds_u32(part_row)); scale = __uint_as_float(lds_u32(part_row + 512u));
           }
           if (buf != g) continue;
           mbar_wait(&B.t_full[buf], (tt >> 1) & 1);
           tc_fence_after();
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>(buf * 128);
           const int nvalid = min(128, p.c - t * 128);            // cohort rows past c are zero padding
-          uint32_t r[16];
           if (pass == 0 && t == 0) {
             // bin range from the statistics of the first tile's scores (a 128-score sample of this row)
+            uint32_t r[16];
             float s1 = 0.f, s2 = 0.f;
             for (int c0 = 0; c0 < 128; c0 += 16) {
               tmem_ld16(taddr + c0, r);
@@ -245,74 +286,110 @@ asnorm_fused_kernel(const __grid_constant__ AsnormFusedParams p, const __grid_co
             const float sd = sqrtf(fmaxf(s2 * inv - mu * mu, 1e-30f));
             const float lo = mu + p.z_lo * sd;
             scale = static_cast<float>(nb) / ((p.z_hi - p.z_lo) * sd);
-            off = -lo * scale;
-            for (int w = 0; w < (nb >> 1); ++w) sts_u32(aux_row + w * 512, 0u);
-            sts_u32(part_row, __float_as_uint(off)); sts_u32(part_row + 512u, __float_as_uint(scale));
+            off1 = 1.f - lo * scale;                               // stored bin = 1 + range bin; stored bin 0 = below the range
+            for (int b = 0; b <= nb; ++b) { sts_u16(hist_row0 + static_cast<uint32_t>(b) * 256u, 0u); sts_u16(hist_row1 + static_cast<uint32_t>(b) * 256u, 0u); }
+            sts_u32(part_row, __float_as_uint(off1)); sts_u32(part_row + 512u, __float_as_uint(scale));
             named_bar_sync(1, 256);
           }
-          // Branch-free over the 16 scores of a TMEM load: with few epilogue warps per scheduler nothing hides the latency of a
-          // per-score branch chain (compare -> convert -> address -> atomic), which cost ~85-160 cycles per score in the first
-          // build; here the 16 chains are independent instruction streams and the atomics / list stores are predicated.
-          for (int c0 = 0; c0 < 128; c0 += 16) {
-            if (c0 >= nvalid || (p.knock & 1)) break;
-            tmem_ld16(taddr + c0, r);
-            tmem_ld_wait();
-            if ((p.knock & 2) || ((p.knock & 8) && pass == 0) || ((p.knock & 16) && pass == 1)) continue;
-            int bin[16];
+          if (!(p.knock & 1)) {
+            // The tile's 128 scores of this row in four loads of 32 columns; load c+1 is in flight while the scores of load c are
+            // processed, and the accumulator buffer goes back to the MMA warp as soon as the last load has landed.
+            const bool partial = nvalid < 128;                   // last cohort tile: zero-padded columns score 0 and must not count
+            const bool skip = (p.knock & 2) || ((p.knock & 8) && pass == 0) || ((p.knock & 16) && pass == 1);
+            uint32_t ra[32], rbuf[32];
+            tmem_ld32(taddr, ra);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float tb = fmaf(__uint_as_float(r[i]), scale, off);
-              const int b = min(nb - 1, __float2int_rz(tb));
-              bin[i] = (tb >= 0.f && c0 + i < nvalid) ? b : -1;
-            }
-            if (pass == 0) {
-              // no predication at all (ptxas turns a predicated atomic into a branch region, ~40 cycles of convergence-barrier
-              // latency per score with nothing to hide it): scores outside the range add to a trash word of this row instead
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                red_add_u32(bin[i] >= 0 ? aux_row + static_cast<uint32_t>(bin[i] >> 1) * 512u : trash_row, (bin[i] & 1) ? 65536u : 1u);
-            } else {
-              float s16 = 0.f, q16 = 0.f;
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float v = __uint_as_float(r[i]);
-                const bool gt = bin[i] > bstar;
-                const float vs = gt ? v : 0.f;
-                s16 += vs;
-                q16 = fmaf(vs, vs, q16);
-                // (cohort-sharded layout only) the selected scores themselves: group 0 fills the row from the front, group 1 from
-                // position above-1 backwards — together they write exactly `above` scores
-                if constexpr (VALS) { if (vo != nullptr && gt && pos < above) vo[g == 0 ? pos : above - 1 - pos] = v; }
-                pos += gt ? 1 : 0;
-                const bool eq = bin[i] == bstar;
-                sts_u32((eq && cnt < cap) ? list_row + static_cast<uint32_t>(cnt) * 512u : trash_row, r[i]);   // unconditional store, see above
-                cnt += eq ? 1 : 0;
+            for (int ch = 0; ch < 4; ++ch) {
+              uint32_t (&r)[32] = (ch & 1) ? rbuf : ra;
+              tmem_ld_wait_dep(r);
+              if (ch < 3) tmem_ld32(taddr + static_cast<uint32_t>(ch + 1) * 32u, (ch & 1) ? ra : rbuf);
+              else {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&B.t_empty[buf]);
               }
-              dsum += static_cast<double>(s16);                            // <= 16 fp32 terms per partial sum, the running sums in double
-              dsq += static_cast<double>(q16);
+              if (skip) continue;
+              if (partial) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) r[i] = (ch * 32 + i < nvalid) ? r[i] : 0xff800000u;     // -inf: below every range
+              }
+              if (pass == 0) {
+                // No shared-memory atomics (ATOMS costs ~2 cycles per LANE, and a predicated one becomes a branch region): every
+                // group has a PRIVATE histogram, so a count is a plain 16-bit load / add / store of a word only this thread
+                // touches.  Four scores at a time: their loads are in flight together, and a score whose bin an earlier score of
+                // the same four also hits carries that score's increment (the later store wins).  Stored bin 0 collects the
+                // scores below the range and is never read.
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                  int b[4];
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) b[j] = asnorm_bin(__uint_as_float(r[i + j]), scale, off1, top);
+                  const uint32_t a0 = hist_row + static_cast<uint32_t>(b[0]) * 256u, a1 = hist_row + static_cast<uint32_t>(b[1]) * 256u;
+                  const uint32_t a2 = hist_row + static_cast<uint32_t>(b[2]) * 256u, a3 = hist_row + static_cast<uint32_t>(b[3]) * 256u;
+                  const uint32_t i1 = 1u + (b[1] == b[0] ? 1u : 0u);
+                  const uint32_t i2 = 1u + (b[2] == b[0] ? 1u : 0u) + (b[2] == b[1] ? 1u : 0u);
+                  const uint32_t i3 = 1u + (b[3] == b[0] ? 1u : 0u) + (b[3] == b[1] ? 1u : 0u) + (b[3] == b[2] ? 1u : 0u);
+                  const uint32_t h0 = lds_u16(a0), h1 = lds_u16(a1), h2 = lds_u16(a2), h3 = lds_u16(a3);
+                  sts_u16(a0, h0 + 1u); sts_u16(a1, h1 + i1); sts_u16(a2, h2 + i2); sts_u16(a3, h3 + i3);
+                }
+              } else {
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                  float s16 = 0.f, q16 = 0.f;
+#pragma unroll
+                  for (int i4 = 0; i4 < 16; i4 += 4) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      const uint32_t rv = r[hh * 16 + i4 + j];
+                      const float v = __uint_as_float(rv);
+                      const bool gt = v >= thr_gt;                // bin above b*: in the top-k for certain
+                      const bool ge = v >= thr_ge;                // bin b* or above
+                      const float vs = gt ? v : 0.f;
+                      s16 += vs;
+                      q16 = fmaf(vs, vs, q16);
+                      // (cohort-sharded layout only) the selected scores themselves: group 0 fills the row from the front, group 1
+                      // from position above-1 backwards — together they write exactly `above` scores
+                      if constexpr (VALS) { if (vo != nullptr && gt && pos < above) vo[g == 0 ? pos : above - 1 - pos] = v; }
+                      pos += gt ? 1 : 0;
+                      const bool eq = ge && !gt;
+                      sts_u32(eq ? lptr : trash_row, rv);         // unconditional store (a predicated one becomes a branch region)
+                      lptr += eq ? 512u : 0u;
+                    }
+                    lptr = min(lptr, list_end);                   // an overfull list stays inside its kListSlack spare words; the row is handed back
+                  }
+                  dsum += static_cast<double>(s16);               // <= 16 fp32 terms per partial sum, the running sums in double
+                  dsq += static_cast<double>(q16);
+                }
+              }
             }
+          } else {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&B.t_empty[buf]);
           }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&B.t_empty[buf]);
         }
         if (pass == 0) {
           __threadfence_block();
-          named_bar_sync(1, 256);                                 // both groups' atomics have landed
+          named_bar_sync(1, 256);                                 // both groups' histograms are complete
           // walk the bins from the top: b* holds the k-th largest score (both threads of a row find the same one)
           int cum = 0;
           bstar = -1;
-          for (int b = nb - 1; b >= 0; --b) {
-            const uint32_t w = lds_u32(aux_row + static_cast<uint32_t>(b >> 1) * 512u);
-            const int h = static_cast<int>((b & 1) ? (w >> 16) : (w & 0xffffu));
-            if (cum + h >= k) { bstar = b; need = k - cum; above = cum; bad = h > 2 * cap; break; }
+          for (int b = nb; b >= 1; --b) {
+            const int h = static_cast<int>(lds_u16(hist_row0 + static_cast<uint32_t>(b) * 256u) + lds_u16(hist_row1 + static_cast<uint32_t>(b) * 256u));
+            if (cum + h >= k) { bstar = b; need = k - cum; above = cum; bad = h > 2 * cap - 2; break; }
             cum += h;
           }
           if (bstar < 0) bad = true;                              // fewer than k scores inside the bin range
-          if (bad) bstar = 1 << 30;                               // pass 1 then selects nothing for this row
-          named_bar_sync(1, 256);                                 // everybody has read the histogram: its words become the lists
+          if (!bad) {
+            // the binning is monotone in the score, so "bin >= b" is "score >= the smallest float whose bin is b": two compares
+            // per score in pass 1 instead of the binning arithmetic
+            thr_ge = asnorm_bin_threshold(bstar, scale, off1, top);
+            thr_gt = asnorm_bin_threshold(bstar + 1, scale, off1, top);
+          }                                                       // bad: both stay +inf, pass 1 selects nothing for this row
+          named_bar_sync(1, 256);                                 // everybody has read the histograms: their words become the lists
         }
       }
+      const int cnt = static_cast<int>((lptr - list_row) >> 9);
       if (g == 1) {                                               // hand this group's part to group 0
         sts_u32(part_row + 2 * 512u, static_cast<uint32_t>(cnt)); sts_u32(part_row + 3 * 512u, static_cast<uint32_t>(pos));
         const unsigned long long a = __double_as_longlong(dsum), b = __double_as_longlong(dsq);
@@ -324,7 +401,7 @@ asnorm_fused_kernel(const __grid_constant__ AsnormFusedParams p, const __grid_co
         const int cnt1 = static_cast<int>(lds_u32(part_row + 2 * 512u)), pos1 = static_cast<int>(lds_u32(part_row + 3 * 512u));
         dsum += __longlong_as_double(static_cast<long long>(lds_u32(part_row + 4 * 512u)) | (static_cast<long long>(lds_u32(part_row + 5 * 512u)) << 32));
         dsq += __longlong_as_double(static_cast<long long>(lds_u32(part_row + 6 * 512u)) | (static_cast<long long>(lds_u32(part_row + 7 * 512u)) << 32));
-        if (!bad && (cnt > cap || cnt1 > cap || pos + pos1 != above || cnt + cnt1 < need)) bad = true;
+        if (!bad && (cnt >= cap || cnt1 >= cap || pos + pos1 != above || cnt + cnt1 < need)) bad = true;
         if (grow < p.n_rows) {
           if (bad) {
             const int slot = atomicAdd(p.flag_count, 1);
@@ -332,7 +409,8 @@ asnorm_fused_kernel(const __grid_constant__ AsnormFusedParams p, const __grid_co
           } else {
             // the `need` largest members of the threshold bin: group 1's candidates are appended to group 0's, then a partial
             // selection sort over this row's list words
-            for (int j = 0; j < cnt1; ++j) sts_u32(aux_row + static_cast<uint32_t>(cnt + j) * 512u, lds_u32(aux_row + static_cast<uint32_t>(cap + j) * 512u));
+            const uint32_t list1 = aux_row + static_cast<uint32_t>(cap + kListSlack) * 512u;
+            for (int j = 0; j < cnt1; ++j) sts_u32(aux_row + static_cast<uint32_t>(cnt + j) * 512u, lds_u32(list1 + static_cast<uint32_t>(j) * 512u));
             const int total = cnt + cnt1;
             for (int i = 0; i < need; ++i) {
               int best = i;
@@ -385,8 +463,8 @@ cudaError_t launch_split2(const float* in, __nv_bfloat16* out, long long n, long
 }
 
 size_t asnorm_fused_smem_bytes(const AsnormFusedParams& p) {
-  const size_t list_words = static_cast<size_t>(2 * p.cap + 10);       // two candidate lists + the partial-result words + two trash words
-  const size_t aux_words = list_words > static_cast<size_t>(p.nb / 2) ? list_words : static_cast<size_t>(p.nb / 2);
+  // the histogram / list area, then the 8 partial-result words and two trash words of every row
+  const size_t aux_words = asnorm_main_bytes(p.nb, p.cap) / 512 + 10;
   return 1024 + 1024 + static_cast<size_t>(p.stages) * kBoxBytes + aux_words * 512;
 }
 
