@@ -360,8 +360,10 @@ static int cohort_pass(svx_scorer* h, const float* test_dev, int64_t n, const fl
   fp.n_rows = static_cast<int>(n); fp.c = c; fp.n_row_blocks = static_cast<int>(n_pad / 128); fp.n_tiles = c_pad / 128;
   fp.dp = dp; fp.kboxes = dp / 64; fp.topk = topk;
   const double zq = normal_upper_quantile(static_cast<double>(topk) / c);
-  fp.z_lo = static_cast<float>(zq - 1.0); fp.z_hi = static_cast<float>(zq + 2.2);
-  fp.nb = 96; fp.cap = 48;                    // histogram bins (16-bit counts: c <= 65535); candidates per epilogue group
+  // statistics only: one-term pass 0, candidates = three bins around the threshold bin -> narrower bins over a narrower range
+  if (vals_dev) { fp.z_lo = static_cast<float>(zq - 1.0); fp.z_hi = static_cast<float>(zq + 2.2); fp.nb = 96; }
+  else { fp.z_lo = static_cast<float>(zq - 0.9); fp.z_hi = static_cast<float>(zq + 1.3); fp.nb = 112; }
+  fp.cap = 48;                                // candidates per epilogue group; histogram counts are 16-bit (c <= 65535)
   fp.mean = mean_dev; fp.stdv = std_dev; fp.vals = vals_dev; fp.vals_ld = topk;
   fp.flag_count = h->d_flag; fp.flag_rows = h->d_flag + 1;
   fp.stages = 12;

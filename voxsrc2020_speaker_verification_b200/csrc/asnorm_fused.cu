@@ -65,15 +65,21 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volati
 constexpr int kListSlack = 4;                  // spare words behind a candidate list: its write pointer is clamped once per four scores
 
 // bytes of the area that holds the two private histograms (pass 0) and then the two candidate lists (pass 1), a multiple of 512
+__host__ __device__ inline uint32_t asnorm_hist_bytes(int nb) { return static_cast<uint32_t>((nb + 2) >> 1) * 512u; }   // stored bins 0 .. nb
+__device__ __forceinline__ uint32_t hist_addr(uint32_t hist_row, int b) {
+  return hist_row + static_cast<uint32_t>(b) * 256u - static_cast<uint32_t>(b & 1) * 254u;
+}
 __host__ __device__ inline uint32_t asnorm_main_bytes(int nb, int cap) {
-  const uint32_t h = (2u * static_cast<uint32_t>(nb + 1) * 256u + 511u) & ~511u;
+  const uint32_t h = 2u * asnorm_hist_bytes(nb);
   const uint32_t l = 2u * static_cast<uint32_t>(cap + kListSlack) * 512u;
   return h > l ? h : l;
 }
 
-// stored bin of a score: 0 below the range, 1 + floor((v - lo) * scale) inside, nb at and above its top.  Monotone in v.
-__device__ __forceinline__ int asnorm_bin(float v, float scale, float off1, float top) {
-  return __float2int_rz(fminf(fmaxf(fmaf(v, scale, off1), 0.f), top));
+// Stored bin of a score, three instructions: u = sat((v - lo) / range) in [0, 1] (FFMA.SAT, NaN -> 0), then 2^23 + floor(u * K) by a
+// round-toward-zero FMA onto 2^23 (K just below nb + 1, so u = 1 lands in bin nb), whose mantissa is the bin.  Bin 0 = below the
+// range (and its lowest sliver), bin nb = its top sliver and everything above.  Monotone in v.
+__device__ __forceinline__ int asnorm_bin(float v, float scale, float off, float kf) {
+  return __float_as_int(__fmaf_rz(__saturatef(fmaf(v, scale, off)), kf, 8388608.f)) - 0x4B000000;
 }
 
 // smallest float whose stored bin is >= target (+inf when there is none): bisection over the order-preserving integer key of a float
@@ -103,6 +109,11 @@ asnorm_fused_kernel(const __grid_constant__ AsnormFusedParams p, const __grid_co
   uint8_t* aux = b_smem + static_cast<size_t>(p.stages) * kBoxBytes;   // per-row histogram (pass 0) / candidate list (pass 1), [word][128 rows]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int items = 2 * kb_n;                                   // ring items per cohort tile: hi[0], lo[0], hi[1], lo[1], ...
+  // One-term pass 0 (statistics only): the histogram pass runs on xh.ch alone — half of the cohort bytes, a third of the MMAs.  Its
+  // scores are off by ~2^-8 of a score's standard deviation, a small fraction of a bin, so the k-th largest EXACT score lies in
+  // the bins b*-1 .. b*+1 around the approximate threshold bin; pass 1 (exact scores) sums what lies above that band, lists the
+  // band, and the row is exact whenever 0 <= k - |above| <= |band| — which pass 1 itself verifies (otherwise the row is handed back).
+  constexpr bool kOneTerm = !VALS;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_b);
@@ -122,14 +133,16 @@ asnorm_fused_kernel(const __grid_constant__ AsnormFusedParams p, const __grid_co
       int s = 0;
       uint32_t ph = 0;                                             // ring position and its phase, kept incrementally (no division per item)
       for (int rb = blockIdx.x; rb < p.n_row_blocks; rb += gridDim.x) {
-        for (int pass = 0; pass < 2; ++pass)
+        for (int pass = 0; pass < 2; ++pass) {
+          const bool one = kOneTerm && pass == 0;                    // pass 0 of the one-term form reads the cohort's hi half only
           for (int t = 0; t < p.n_tiles; ++t)
-            for (int j = 0; j < items; ++j) {
+            for (int j = 0; j < (one ? kb_n : items); ++j) {
               mbar_wait(&B.b_empty[s], ph ^ 1);
               mbar_expect_tx(&B.b_full[s], kBoxBytes);
-              tma_load_2d(b_smem + static_cast<size_t>(s) * kBoxBytes, &map_b, &B.b_full[s], (j & 1) * p.dp + (j >> 1) * 64, t * 128);
+              tma_load_2d(b_smem + static_cast<size_t>(s) * kBoxBytes, &map_b, &B.b_full[s], one ? j * 64 : (j & 1) * p.dp + (j >> 1) * 64, t * 128);
               if (++s == p.stages) { s = 0; ph ^= 1; }
             }
+        }
       }
     }
   } else if (warp == 1) {
@@ -164,17 +177,22 @@ asnorm_fused_kernel(const __grid_constant__ AsnormFusedParams p, const __grid_co
               tc_fence_after();
               const uint32_t bd = b_lo0 + static_cast<uint32_t>(s) * kBox16;
               const uint32_t first = kb != 0 ? 1u : 0u;
+              const bool one = kOneTerm && pass == 0;
               if (elect_one()) {
                 if (!(p.knock & 4)) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) umma_ts_lo(d_tmem, ah + 8 * k, bd + 2 * k, hi, idesc, k == 0 ? first : 1u);
+                if (!one) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) umma_ts_lo(d_tmem, al + 8 * k, bd + 2 * k, hi, idesc, 1u);
                 }
+                }
                 umma_commit(&B.b_empty[s]);
+                if (one && kb == kb_n - 1) umma_commit(&B.t_full[buf]);
               }
               __syncwarp();
               if (++s == p.stages) { s = 0; ph ^= 1; }
+              if (one) continue;
             }
             {                                                     // cohort lo box: xh.cl
               mbar_wait(&B.b_full[s], ph);
@@ -206,14 +224,16 @@ asnorm_fused_kernel(const __grid_constant__ AsnormFusedParams p, const __grid_co
     const int nb = p.nb, cap = p.cap;                            // cap: candidates per GROUP
     const uint32_t aux_u32 = smem_u32(aux);
     const uint32_t aux_row = aux_u32 + static_cast<uint32_t>(row) * 4u;           // list word w of this row: aux_row + w * 512
-    const uint32_t hist_bytes = static_cast<uint32_t>(nb + 1) * 256u;             // one group's histogram: 16-bit counts, bin b of row r at b * 256 + r * 2
-    const uint32_t hist_row0 = aux_u32 + static_cast<uint32_t>(row) * 2u, hist_row1 = hist_row0 + hist_bytes;
+    // one group's histogram: 16-bit counts, two bins per 32-bit word, word index == row (mod 128) -> bank = lane, no conflicts:
+    // bin b of row r at (b >> 1) * 512 + r * 4 + (b & 1) * 2  ==  b * 256 + r * 4 - (b & 1) * 254
+    const uint32_t hist_bytes = asnorm_hist_bytes(nb);
+    const uint32_t hist_row0 = aux_row, hist_row1 = hist_row0 + hist_bytes;
     const uint32_t hist_row = g ? hist_row1 : hist_row0;                         // this group's PRIVATE histogram (pass 0)
     const uint32_t list_row = aux_row + static_cast<uint32_t>(g * (cap + kListSlack)) * 512u;   // this group's candidate list (pass 1)
     const uint32_t list_end = list_row + static_cast<uint32_t>(cap) * 512u;
     const uint32_t part_row = aux_row + asnorm_main_bytes(nb, cap);              // 8 words: range (pass 0), then group 1's partial results
     const uint32_t trash_row = part_row + 8u * 512u + static_cast<uint32_t>(g) * 512u;   // where the unconditional stores of unselected scores go
-    const float top = static_cast<float>(nb) + 0.5f;
+    const float top = __int_as_float(__float_as_int(static_cast<float>(nb + 1)) - 1);   // the float just below nb + 1
     const int k = p.topk;
     uint32_t tt = 0;
     int lbe = 0;
@@ -258,137 +278,154 @@ asnorm_fused_kernel(const __grid_constant__ AsnormFusedParams p, const __grid_co
         if (lane == 0) mbar_arrive(&B.a_full);
       }
       ++lbe;
-      for (int pass = 0; pass < 2; ++pass) {
-        for (int t = 0; t < p.n_tiles; ++t, ++tt) {
-          const int buf = tt & 1;
-          if (pass == 0 && t == 1 && g == 1) {                    // group 1's first tile: the range is published, the histograms zeroed
-            named_bar_sync(1, 256);
-            off1 = __uint_as_float(lds_u32(part_row)); scale = __uint_as_float(lds_u32(part_row + 512u));
-          }
-          if (buf != g) continue;
-          mbar_wait(&B.t_full[buf], (tt >> 1) & 1);
-          tc_fence_after();
-          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>(buf * 128);
-          const int nvalid = min(128, p.c - t * 128);            // cohort rows past c are zero padding
-          if (pass == 0 && t == 0) {
-            // bin range from the statistics of the first tile's scores (a 128-score sample of this row)
-            uint32_t r[16];
-            float s1 = 0.f, s2 = 0.f;
-            for (int c0 = 0; c0 < 128; c0 += 16) {
-              tmem_ld16(taddr + c0, r);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (c0 + i < nvalid) { const float v = __uint_as_float(r[i]); s1 += v; s2 = fmaf(v, v, s2); }
-            }
-            const float inv = 1.f / static_cast<float>(nvalid);
-            const float mu = s1 * inv;
-            const float sd = sqrtf(fmaxf(s2 * inv - mu * mu, 1e-30f));
-            const float lo = mu + p.z_lo * sd;
-            scale = static_cast<float>(nb) / ((p.z_hi - p.z_lo) * sd);
-            off1 = 1.f - lo * scale;                               // stored bin = 1 + range bin; stored bin 0 = below the range
-            for (int b = 0; b <= nb; ++b) { sts_u16(hist_row0 + static_cast<uint32_t>(b) * 256u, 0u); sts_u16(hist_row1 + static_cast<uint32_t>(b) * 256u, 0u); }
-            sts_u32(part_row, __float_as_uint(off1)); sts_u32(part_row + 512u, __float_as_uint(scale));
-            named_bar_sync(1, 256);
-          }
-          if (!(p.knock & 1)) {
-            // The tile's 128 scores of this row in four loads of 32 columns; load c+1 is in flight while the scores of load c are
-            // processed, and the accumulator buffer goes back to the MMA warp as soon as the last load has landed.
-            const bool partial = nvalid < 128;                   // last cohort tile: zero-padded columns score 0 and must not count
-            const bool skip = (p.knock & 2) || ((p.knock & 8) && pass == 0) || ((p.knock & 16) && pass == 1);
-            uint32_t ra[32], rbuf[32];
-            tmem_ld32(taddr, ra);
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-              uint32_t (&r)[32] = (ch & 1) ? rbuf : ra;
-              tmem_ld_wait_dep(r);
-              if (ch < 3) tmem_ld32(taddr + static_cast<uint32_t>(ch + 1) * 32u, (ch & 1) ? ra : rbuf);
-              else {
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&B.t_empty[buf]);
-              }
-              if (skip) continue;
-              if (partial) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) r[i] = (ch * 32 + i < nvalid) ? r[i] : 0xff800000u;     // -inf: below every range
-              }
-              if (pass == 0) {
-                // No shared-memory atomics (ATOMS costs ~2 cycles per LANE, and a predicated one becomes a branch region): every
-                // group has a PRIVATE histogram, so a count is a plain 16-bit load / add / store of a word only this thread
-                // touches.  Four scores at a time: their loads are in flight together, and a score whose bin an earlier score of
-                // the same four also hits carries that score's increment (the later store wins).  Stored bin 0 collects the
-                // scores below the range and is never read.
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                  int b[4];
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) b[j] = asnorm_bin(__uint_as_float(r[i + j]), scale, off1, top);
-                  const uint32_t a0 = hist_row + static_cast<uint32_t>(b[0]) * 256u, a1 = hist_row + static_cast<uint32_t>(b[1]) * 256u;
-                  const uint32_t a2 = hist_row + static_cast<uint32_t>(b[2]) * 256u, a3 = hist_row + static_cast<uint32_t>(b[3]) * 256u;
-                  const uint32_t i1 = 1u + (b[1] == b[0] ? 1u : 0u);
-                  const uint32_t i2 = 1u + (b[2] == b[0] ? 1u : 0u) + (b[2] == b[1] ? 1u : 0u);
-                  const uint32_t i3 = 1u + (b[3] == b[0] ? 1u : 0u) + (b[3] == b[1] ? 1u : 0u) + (b[3] == b[2] ? 1u : 0u);
-                  const uint32_t h0 = lds_u16(a0), h1 = lds_u16(a1), h2 = lds_u16(a2), h3 = lds_u16(a3);
-                  sts_u16(a0, h0 + 1u); sts_u16(a1, h1 + i1); sts_u16(a2, h2 + i2); sts_u16(a3, h3 + i3);
-                }
-              } else {
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                  float s16 = 0.f, q16 = 0.f;
-#pragma unroll
-                  for (int i4 = 0; i4 < 16; i4 += 4) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                      const uint32_t rv = r[hh * 16 + i4 + j];
-                      const float v = __uint_as_float(rv);
-                      const bool gt = v >= thr_gt;                // bin above b*: in the top-k for certain
-                      const bool ge = v >= thr_ge;                // bin b* or above
-                      const float vs = gt ? v : 0.f;
-                      s16 += vs;
-                      q16 = fmaf(vs, vs, q16);
-                      // (cohort-sharded layout only) the selected scores themselves: group 0 fills the row from the front, group 1
-                      // from position above-1 backwards — together they write exactly `above` scores
-                      if constexpr (VALS) { if (vo != nullptr && gt && pos < above) vo[g == 0 ? pos : above - 1 - pos] = v; }
-                      pos += gt ? 1 : 0;
-                      const bool eq = ge && !gt;
-                      sts_u32(eq ? lptr : trash_row, rv);         // unconditional store (a predicated one becomes a branch region)
-                      lptr += eq ? 512u : 0u;
-                    }
-                    lptr = min(lptr, list_end);                   // an overfull list stays inside its kListSlack spare words; the row is handed back
-                  }
-                  dsum += static_cast<double>(s16);               // <= 16 fp32 terms per partial sum, the running sums in double
-                  dsq += static_cast<double>(q16);
-                }
-              }
-            }
-          } else {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&B.t_empty[buf]);
-          }
-        }
-        if (pass == 0) {
-          __threadfence_block();
-          named_bar_sync(1, 256);                                 // both groups' histograms are complete
-          // walk the bins from the top: b* holds the k-th largest score (both threads of a row find the same one)
-          int cum = 0;
-          bstar = -1;
-          for (int b = nb; b >= 1; --b) {
-            const int h = static_cast<int>(lds_u16(hist_row0 + static_cast<uint32_t>(b) * 256u) + lds_u16(hist_row1 + static_cast<uint32_t>(b) * 256u));
-            if (cum + h >= k) { bstar = b; need = k - cum; above = cum; bad = h > 2 * cap - 2; break; }
-            cum += h;
-          }
-          if (bstar < 0) bad = true;                              // fewer than k scores inside the bin range
-          if (!bad) {
-            // the binning is monotone in the score, so "bin >= b" is "score >= the smallest float whose bin is b": two compares
-            // per score in pass 1 instead of the binning arithmetic
-            thr_ge = asnorm_bin_threshold(bstar, scale, off1, top);
-            thr_gt = asnorm_bin_threshold(bstar + 1, scale, off1, top);
-          }                                                       // bad: both stay +inf, pass 1 selects nothing for this row
-          named_bar_sync(1, 256);                                 // everybody has read the histograms: their words become the lists
-        }
+      // Both passes walk the tile through eight TMEM loads of 16 columns, load c+1 in flight while the scores of load c are
+      // processed; the accumulator buffer goes back to the MMA warp as soon as the last load has landed.  The loop bodies are kept
+      // SMALL on purpose (two 16-score blocks, not unrolled further): an earlier build with the whole tile unrolled for both
+      // passes was 150 KB of code and ran 20 % slower than the same arithmetic in 40 KB — four roles in different code regions
+      // share one instruction cache.
+      const int npad = p.n_tiles * 128 - p.c;                      // zero cohort rows behind the last tile: each scores exactly 0
+#define SVX_TILE_CHUNKS(PROCESS)                                                              \
+      {                                                                                       \
+        uint32_t ra[16], rq[16];                                                              \
+        tmem_ld16(taddr, ra);                                                                 \
+        _Pragma("unroll 1")                                                                   \
+        for (uint32_t c0 = 0; c0 < 128u; c0 += 32u) {                                         \
+          tmem_ld_wait_dep16(ra);                                                             \
+          tmem_ld16(taddr + c0 + 16u, rq);                                                    \
+          PROCESS(ra);                                                                        \
+          tmem_ld_wait_dep16(rq);                                                             \
+          if (c0 + 32u < 128u) tmem_ld16(taddr + c0 + 32u, ra);                               \
+          else { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&B.t_empty[buf]); } \
+          PROCESS(rq);                                                                        \
+        }                                                                                     \
       }
+      // ------------------------------------------------------------------ pass 0: histogram
+      for (int t = 0; t < p.n_tiles; ++t, ++tt) {
+        const int buf = tt & 1;
+        if (t == 1 && g == 1) {                                   // group 1's first tile: the range is published, the histograms zeroed
+          named_bar_sync(1, 256);
+          off1 = __uint_as_float(lds_u32(part_row)); scale = __uint_as_float(lds_u32(part_row + 512u));
+        }
+        if (buf != g) continue;
+        mbar_wait(&B.t_full[buf], (tt >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>(buf * 128);
+        if (t == 0) {
+          // bin range from the statistics of the first tile's scores (a 128-score sample of this row; c >= 1024: a full tile)
+          uint32_t r[16];
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+          for (int c0 = 0; c0 < 128; c0 += 16) {
+            tmem_ld16(taddr + c0, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { const float v = __uint_as_float(r[i]); s1 += v; s2 = fmaf(v, v, s2); }
+          }
+          const float mu = s1 * (1.f / 128.f);
+          const float sd = sqrtf(fmaxf(s2 * (1.f / 128.f) - mu * mu, 1e-30f));
+          const float lo = mu + p.z_lo * sd;
+          scale = 1.f / ((p.z_hi - p.z_lo) * sd);                 // (v - lo) / range: [0, 1] over the bin range
+          off1 = -lo * scale;
+          for (uint32_t w = 0; w < 2u * hist_bytes; w += 512u) sts_u32(hist_row0 + w, 0u);
+          sts_u32(part_row, __float_as_uint(off1)); sts_u32(part_row + 512u, __float_as_uint(scale));
+          named_bar_sync(1, 256);
+        }
+        if (p.knock & 1) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&B.t_empty[buf]); continue; }
+        // No shared-memory atomics (ATOMS costs ~2 cycles per LANE, and a predicated one becomes a branch region): every group has
+        // a PRIVATE histogram, so a count is a plain 16-bit load / add / store of a word only this thread touches.  Four scores at
+        // a time: their loads are in flight together, and a score whose bin an earlier score of the same four also hits carries
+        // that score's increment (the later store wins).  Stored bin 0 collects the scores below the range and is never read.
+        const bool skip0 = (p.knock & (2 | 8)) != 0;
+        auto process0 = [&](uint32_t (&r)[16]) {
+          if (skip0) return;
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            int b[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = asnorm_bin(__uint_as_float(r[i + j]), scale, off1, top);
+            const uint32_t a0 = hist_addr(hist_row, b[0]), a1 = hist_addr(hist_row, b[1]), a2 = hist_addr(hist_row, b[2]), a3 = hist_addr(hist_row, b[3]);
+            const uint32_t i1 = 1u + (b[1] == b[0] ? 1u : 0u);
+            const uint32_t i2 = 1u + (b[2] == b[0] ? 1u : 0u) + (b[2] == b[1] ? 1u : 0u);
+            const uint32_t i3 = 1u + (b[3] == b[0] ? 1u : 0u) + (b[3] == b[1] ? 1u : 0u) + (b[3] == b[2] ? 1u : 0u);
+            const uint32_t h0 = lds_u16(a0), h1 = lds_u16(a1), h2 = lds_u16(a2), h3 = lds_u16(a3);
+            sts_u16(a0, h0 + 1u); sts_u16(a1, h1 + i1); sts_u16(a2, h2 + i2); sts_u16(a3, h3 + i3);
+          }
+        };
+        SVX_TILE_CHUNKS(process0)
+      }
+      {
+        __threadfence_block();
+        named_bar_sync(1, 256);                                   // both groups' histograms are complete
+        // walk the bins from the top: b* holds the k-th largest score (both threads of a row find the same one); the zero
+        // padding's scores are taken out of the bin of 0.0
+        const int bin0 = asnorm_bin(0.f, scale, off1, top);
+        int cum = 0;
+        bstar = -1;
+        for (int b = nb; b >= 1; --b) {
+          int h = static_cast<int>(lds_u16(hist_addr(hist_row0, b)) + lds_u16(hist_addr(hist_row1, b)));
+          if (b == bin0) h -= npad;
+          if (cum + h >= k) { bstar = b; need = k - cum; above = cum; bad = h > 2 * cap - 2; break; }
+          cum += h;
+        }
+        if (bstar < 0) bad = true;                                // fewer than k scores inside the bin range
+        // the binning is monotone in the score, so "bin >= b" is "score >= the smallest float whose bin is b": two compares per
+        // score in pass 1 instead of the binning arithmetic
+        if (kOneTerm) {
+          bad = bstar < 2 || bstar + 2 > nb;                      // the band needs a real edge on both sides
+          if (!bad) {
+            thr_ge = asnorm_bin_threshold(bstar - 1, scale, off1, top);
+            thr_gt = asnorm_bin_threshold(bstar + 2, scale, off1, top);
+          }
+        } else if (!bad) {
+          thr_ge = asnorm_bin_threshold(bstar, scale, off1, top);
+          thr_gt = asnorm_bin_threshold(bstar + 1, scale, off1, top);
+        }                                                         // bad: both stay +inf, pass 1 selects nothing for this row
+        // the zero padding scores 0.0 in pass 1 too: above the band it only inflates the count (0 adds nothing to the sums);
+        // inside the band it would sit in the list — such a row (its k-th largest score is ~0) is handed back
+        // (with the selected scores written out the padding must not be selected at all)
+        if (npad > 0 && !bad && thr_ge <= 0.f && (VALS || !(thr_gt <= 0.f))) { bad = true; thr_ge = thr_gt = __int_as_float(0x7f800000); }
+        named_bar_sync(1, 256);                                   // everybody has read the histograms: their words become the lists
+      }
+      // ------------------------------------------------------------------ pass 1: sums above the threshold, candidates around it
+      for (int t = 0; t < p.n_tiles; ++t, ++tt) {
+        const int buf = tt & 1;
+        if (buf != g) continue;
+        mbar_wait(&B.t_full[buf], (tt >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>(buf * 128);
+        if (p.knock & 1) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&B.t_empty[buf]); continue; }
+        const bool skip1 = (p.knock & (2 | 16)) != 0;
+        auto process1 = [&](uint32_t (&r)[16]) {
+          if (skip1) return;
+          float s16 = 0.f, q16 = 0.f;
+#pragma unroll
+          for (int i4 = 0; i4 < 16; i4 += 4) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t rv = r[i4 + j];
+              const float v = __uint_as_float(rv);
+              const bool gt = v >= thr_gt;                        // above the threshold bin(s): in the top-k for certain
+              const bool ge = v >= thr_ge;                        // in or above them
+              const float vs = gt ? v : 0.f;
+              s16 += vs;
+              q16 = fmaf(vs, vs, q16);
+              // (cohort-sharded layout only) the selected scores themselves: group 0 fills the row from the front, group 1 from
+              // position above-1 backwards — together they write exactly `above` scores
+              if constexpr (VALS) { if (vo != nullptr && gt && pos < above) vo[g == 0 ? pos : above - 1 - pos] = v; }
+              pos += gt ? 1 : 0;
+              const bool eq = ge && !gt;
+              sts_u32(eq ? lptr : trash_row, rv);                 // unconditional store (a predicated one becomes a branch region)
+              lptr += eq ? 512u : 0u;
+            }
+            lptr = min(lptr, list_end);                           // an overfull list stays inside its kListSlack spare words; the row is handed back
+          }
+          dsum += static_cast<double>(s16);                       // 16 fp32 terms per partial sum, the running sums in double
+          dsq += static_cast<double>(q16);
+        };
+        SVX_TILE_CHUNKS(process1)
+      }
+#undef SVX_TILE_CHUNKS
+      if (thr_gt <= 0.f) pos -= (g == ((p.n_tiles - 1 + p.n_tiles) & 1)) ? npad : 0;     // the padding counted by the group that took the last tile
       const int cnt = static_cast<int>((lptr - list_row) >> 9);
       if (g == 1) {                                               // hand this group's part to group 0
         sts_u32(part_row + 2 * 512u, static_cast<uint32_t>(cnt)); sts_u32(part_row + 3 * 512u, static_cast<uint32_t>(pos));
@@ -401,7 +438,8 @@ asnorm_fused_kernel(const __grid_constant__ AsnormFusedParams p, const __grid_co
         const int cnt1 = static_cast<int>(lds_u32(part_row + 2 * 512u)), pos1 = static_cast<int>(lds_u32(part_row + 3 * 512u));
         dsum += __longlong_as_double(static_cast<long long>(lds_u32(part_row + 4 * 512u)) | (static_cast<long long>(lds_u32(part_row + 5 * 512u)) << 32));
         dsq += __longlong_as_double(static_cast<long long>(lds_u32(part_row + 6 * 512u)) | (static_cast<long long>(lds_u32(part_row + 7 * 512u)) << 32));
-        if (!bad && (cnt >= cap || cnt1 >= cap || pos + pos1 != above || cnt + cnt1 < need)) bad = true;
+        if (kOneTerm) { above = pos + pos1; need = k - above; }     // counted on the exact scores
+        if (!bad && (cnt >= cap || cnt1 >= cap || pos + pos1 != above || need < 0 || cnt + cnt1 < need)) bad = true;
         if (grow < p.n_rows) {
           if (bad) {
             const int slot = atomicAdd(p.flag_count, 1);
@@ -412,7 +450,21 @@ asnorm_fused_kernel(const __grid_constant__ AsnormFusedParams p, const __grid_co
             const uint32_t list1 = aux_row + static_cast<uint32_t>(cap + kListSlack) * 512u;
             for (int j = 0; j < cnt1; ++j) sts_u32(aux_row + static_cast<uint32_t>(cnt + j) * 512u, lds_u32(list1 + static_cast<uint32_t>(j) * 512u));
             const int total = cnt + cnt1;
-            for (int i = 0; i < need; ++i) {
+            int n_sel = need;
+            double sgn = 1.0;
+            if (!vo && 2 * need > total) {
+              // more than half of the list is wanted: add all of it, then take the total - need LARGEST OF THE NEGATED values out again
+              for (int j = 0; j < total; ++j) {
+                const uint32_t a = aux_row + static_cast<uint32_t>(j) * 512u;
+                const float v = __uint_as_float(lds_u32(a));
+                dsum += static_cast<double>(v);
+                dsq = fma(static_cast<double>(v), static_cast<double>(v), dsq);
+                sts_u32(a, __float_as_uint(-v));
+              }
+              n_sel = total - need;
+              sgn = -1.0;
+            }
+            for (int i = 0; i < n_sel; ++i) {
               int best = i;
               float bv = __uint_as_float(lds_u32(aux_row + static_cast<uint32_t>(i) * 512u));
               const float first_v = bv;
@@ -421,8 +473,8 @@ asnorm_fused_kernel(const __grid_constant__ AsnormFusedParams p, const __grid_co
                 if (v > bv) { bv = v; best = j; }
               }
               if (best != i) sts_u32(aux_row + static_cast<uint32_t>(best) * 512u, __float_as_uint(first_v));
-              dsum += static_cast<double>(bv);
-              dsq = fma(static_cast<double>(bv), static_cast<double>(bv), dsq);
+              dsum += static_cast<double>(bv);                    // (negated list: bv = -v removes v)
+              dsq = fma(sgn * static_cast<double>(bv), static_cast<double>(bv), dsq);
               if (vo) vo[above + i] = bv;
             }
             if (vo)
