@@ -39,7 +39,10 @@ def _block_out_ops(cfg):
         for li, nblocks in enumerate(cfg.block_sizes):
             for b in range(nblocks):
                 stride = cfg.block_strides[li] if b == 0 else 1
-                idx += (1 if b == 0 else 0) + 1 + (cfg.split - 1) + (1 if stride == 2 else 0)
+                # projection shortcut of a first block: its own op, except in the first stage at stride 1, where it is folded into
+                # conv3 as extra K (model.cu build_res2net)
+                own_shortcut = b == 0 and not (li == 0 and stride == 1)
+                idx += (1 if own_shortcut else 0) + 1 + (cfg.split - 1) + (1 if stride == 2 else 0)
                 out.append(idx)                                 # conv3
                 idx += 1
     else:
@@ -54,8 +57,8 @@ def _block_out_ops(cfg):
 def _load_dump(path, dtype):
     m = re.search(r"op(\d+)_k(\d+)_t(\d+)_r(\d+)_w(\d+)_c(\d+)_off(\d+)_n(\d+)\.bin$", path)
     idx, kind, tid, rows, wp, C, off, n = (int(g) for g in m.groups())
-    raw = np.fromfile(path, dtype=np.uint16).reshape(rows, wp, C)
-    t = torch.from_numpy(raw.astype(np.int32)).to(torch.int16).view(torch.float16 if dtype == "fp16" else torch.bfloat16)
+    raw = np.fromfile(path, dtype=np.uint16).reshape(rows, wp, C)[:, :, off:]      # the op's slice of its destination tensor
+    t = torch.from_numpy(np.ascontiguousarray(raw).astype(np.int32)).to(torch.int16).view(torch.float16 if dtype == "fp16" else torch.bfloat16)
     return idx, t.float().numpy()
 
 

@@ -11,7 +11,7 @@ cudaError_t launch_pack_input(const float* feats, const int32_t* seg_frame_off, 
                               const int32_t* seg_of_row, void* out, int rows, int F, int Cpad, int is_bf16, cudaStream_t st);
 cudaError_t launch_stem_conv(const float* feats, const int32_t* seg_frame_off, const int32_t* seg_row_off, const int32_t* seg_h,
                              const int32_t* seg_of_row, const float* w9, const float* scale, const float* shift, void* out,
-                             int rows, int F, int Wp, int C, int Cpad, int is_bf16, cudaStream_t st);
+                             int rows, int F, int Wp, int C, int Cpad, int pitch, int is_bf16, cudaStream_t st);   // pitch: channels per pixel of the destination tensor (>= Cpad)
 cudaError_t launch_bn_relu(const void* in, int in_C, int in_coff, int in_Wp, const float* scale, const float* shift, void* out,
                            int out_C, int out_rows, int out_W, int out_Wp, int C, int stride, const int32_t* out_seg_of_row,
                            const int32_t* out_seg_row_off, const int32_t* in_seg_row_off, int is_bf16, cudaStream_t st);

@@ -193,28 +193,39 @@ void Model::build_res2net() {
     // conv3 then reads S*wp channels; the weight rows of the pad positions are zero.
     static const bool no_ypad = dbg_env("SVX_NO_YPAD") != nullptr;   // debug switch
     const int wp = (!no_ypad && w % 16 != 0) ? round_up(w, 16) : w;
-    const int y = new_tensor(stage, S * wp);
+    // First stage, stride 1: the projection shortcut of the first block is folded into its conv3 as extra K (ConvDesc::fold_*).
+    // The block input — the stem's output — then lives in the channels behind the concat slices of y (y is 64 channels wider),
+    // written there by the stem and read from there by conv1: no shortcut launch, no shortcut tensor, no residual read.
+    static const bool no_fold = dbg_env("SVX_NO_FOLD") != nullptr;   // debug switch
+    const bool fold = li == 0 && st == 1 && !no_fold && cin % 8 == 0 && cin <= 64 && ops_.size() == 1 && ops_[0].kind == OP_STEM;
+    const int y_all = new_tensor(stage, S * wp);
+    const int y_first = fold ? new_tensor(stage, S * wp + 64) : y_all;   // the first block's own concat (the other blocks keep the dense pitch)
+    if (fold) { ops_[0].out = {y_first, S * wp}; cur = y_first; }
     const int mp = st == 2 ? new_tensor(in_stage, mid) : -1;
     int out_t = xa;
     for (int b = 0; b < cfg_.block_sizes[li]; ++b) {
       const bool first = b == 0;
       const int bstride = first ? st : 1;
       int shortcut = cur;
+      const bool folded = first && fold;
+      const int y = folded ? y_first : y_all;
+      const int in_off = folded ? S * wp : 0;                    // where the block input sits in its tensor
+      std::string fold_kernel, fold_bn;
       if (first) {   // projection shortcut: 1x1 conv stride s + BN (res2net_model.py:85-87,119-127)
         Op op; op.kind = OP_CONV; ConvDesc& c = op.conv;
         c.kernel_name = next_name(root, "", "conv2d") + "/kernel"; add_var(c.kernel_name, {1, 1, cin, cout});
         c.bn_name = next_name(root, "", "batch_normalization");
         add_var(c.bn_name + "/moving_mean", {cout}); add_var(c.bn_name + "/moving_variance", {cout});
         c.in = {cur, 0}; c.cin = cin; c.stride = bstride; c.cout = cout; c.out = {sc, 0};
-        ops_.push_back(op);
-        shortcut = sc;
+        if (folded) { fold_kernel = c.kernel_name; fold_bn = c.bn_name; shortcut = -1; }
+        else { ops_.push_back(op); shortcut = sc; }
       }
       {   // conv1 1x1 + BN + ReLU (res2net_model.py:89-91)
         Op op; op.kind = OP_CONV; ConvDesc& c = op.conv;
         c.kernel_name = next_name(root, "", "conv2d") + "/kernel"; add_var(c.kernel_name, {1, 1, cin, mid});
         c.bn_name = next_name(root, "", "batch_normalization");
         add_var(c.bn_name + "/moving_mean", {mid}); add_var(c.bn_name + "/moving_variance", {mid});
-        c.in = {cur, 0}; c.cin = cin; c.cout = mid; c.post_relu = 1;
+        c.in = {cur, in_off}; c.cin = cin; c.cout = mid; c.post_relu = 1;
         if (bstride == 1) {   // x_0..x_{S-2} to their planar tensors, the last split passes straight into the concat (:74-75)
           c.out = {y, 0}; c.split_w = w; c.split_store = wpp;
           for (int i = 0; i + 1 < S; ++i) c.split_out.push_back({ms[i], 0});
@@ -253,7 +264,9 @@ void Model::build_res2net() {
         c.kernel_name = next_name(root, "", "conv2d") + "/kernel"; add_var(c.kernel_name, {1, 1, mid, cout});
         c.bn_name = next_name(root, "", "batch_normalization");
         add_var(c.bn_name + "/moving_mean", {cout}); add_var(c.bn_name + "/moving_variance", {cout});
-        c.in = {y, 0}; c.cin = S * wp; c.cout = cout; c.res = {shortcut, 0}; c.post_relu = 1; c.out = {out_t, 0};
+        c.in = {y, 0}; c.cin = S * wp; c.cout = cout; c.post_relu = 1; c.out = {out_t, 0};
+        if (folded) { c.fold_kernel_name = fold_kernel; c.fold_bn_name = fold_bn; c.fold_cin = cin; c.fold_off = S * wp; c.cin = S * wp + cin; }
+        else c.res = {shortcut, 0};
         if (wp != w) { c.in_gw = w; c.in_gwp = wp; }
         ops_.push_back(op);
       }
@@ -433,7 +446,8 @@ static int pick_ntile(int cout, int max_multi) {
 int Model::upload_conv_weights(ConvDesc& c) {
   const HostTensor& k = host_[c.kernel_name];   // [kh,kw,cin_g,cout_total]
   const int taps = c.kh * c.kw;
-  const int cin_tf = c.in_gw > 0 ? (c.cin / c.in_gwp) * c.in_gw : c.cin;   // input channels of the TF variable (padded concat: fewer than cin)
+  const int cin_main = c.fold_cin > 0 ? c.fold_off : c.cin;               // channels of the conv's own input (a folded shortcut's follow)
+  const int cin_tf = c.in_gw > 0 ? (cin_main / c.in_gwp) * c.in_gw : cin_main;   // input channels of the TF variable (padded concat: fewer than cin)
   const int cin_g = cin_tf / c.groups, cout_g = c.cout / c.groups;
   const int cout_total = static_cast<int>(k.shape[3]);
   const bool grouped = c.groups > 1;
@@ -476,6 +490,18 @@ int Model::upload_conv_weights(ConvDesc& c) {
             k.data[(static_cast<size_t>(t) * cin_g + ci) * cout_total + c.kernel_out_off + n];
       }
   }
+  std::vector<float> fold_shift;
+  if (c.fold_cin > 0) {   // the folded shortcut: rows fold_off .. fold_off + fold_cin, scaled by s_shortcut / s_conv per output channel
+    if (taps != 1 || grouped || c.split_w > 0 || c.bn_name.empty()) { set_last_error("folded shortcut on an unsupported conv"); return 1; }
+    const HostTensor& kf = host_[c.fold_kernel_name];   // [1,1,fold_cin,cout]
+    std::vector<float> s3, b3, ss, bs;
+    fold_bn(c.bn_name, c.cout, true, s3, b3);
+    fold_bn(c.fold_bn_name, c.cout, true, ss, bs);
+    for (int n = 0; n < c.cout; ++n)
+      for (int ci = 0; ci < c.fold_cin; ++ci)
+        w[static_cast<size_t>(n) * K + c.fold_off + ci] = kf.data[static_cast<size_t>(ci) * c.cout + n] * (ss[n] / s3[n]);
+    fold_shift = bs;
+  }
   void* d = nullptr;
   SVX_CUDA(cudaMalloc(&d, w.size() * 2));
   owned_.push_back(d);
@@ -493,6 +519,7 @@ int Model::upload_conv_weights(ConvDesc& c) {
   if (!c.bn_name.empty()) {
     std::vector<float> sc, sh;
     fold_bn(c.bn_name, c.cout, true, sc, sh);
+    for (size_t n = 0; n < fold_shift.size(); ++n) sh[n] += fold_shift[n];
     if (c.split_w > 0) {
       std::vector<float> sc2(c.n_pad, 0.f), sh2(c.n_pad, 0.f);
       for (int n = 0; n < c.cout; ++n) { sc2[gemm_row(n)] = sc[n]; sh2[gemm_row(n)] = sh[n]; }
@@ -1114,7 +1141,9 @@ int Model::plan_pair(ConvDesc& c) {
     if (c.res.id >= 0 || c.out2.id >= 0 || c.split_w > 0 || c.pre_relu) return 0;
     if (Wp <= W || stage_Wp_[tin.stage] != 2 * W + 1) return 0;
   } else if (taps == 1) {
-    if (c.kpad < min_k) return 0;
+    // (K padded up to 192 from fewer channels stays on the flat kernel — except conv3 with the shortcut folded in, K = 160 on
+    // 200 x 80 pixels: 490 us here, 576-672 us on every flat plan, profiles/r02_experiments.md)
+    if (c.kpad < min_k || (c.cin < min_k && c.fold_cin == 0)) return 0;
   } else {
     if (no_3x3 || c.cin < min_c3) return 0;
     if (c.kw > 1 && (Wp <= W || c.pw > 1 || c.kw - 1 - c.pw > 1)) return 0;   // one zero column covers |dw| <= 1 only
@@ -1549,7 +1578,8 @@ int Model::launch_conv(ConvDesc& c, cudaStream_t st) {
       // algorithmic FLOPs: 2 * valid output pixels * taps * cin * cout (no padding waste counted)
       double pix = 0.0;
       for (int h : seg_h_host_[out_stage]) pix += static_cast<double>(h) * stage_W_[out_stage];
-      const double fl = 2.0 * pix * c.kh * c.kw * ((c.in_gw > 0 ? (c.cin / c.in_gwp) * c.in_gw : c.cin) / c.groups) * c.cout;
+      const int cin_own = c.fold_cin > 0 ? c.fold_off : c.cin;      // (a folded shortcut's channels are real input channels too)
+      const double fl = 2.0 * pix * c.kh * c.kw * (((c.in_gw > 0 ? (cin_own / c.in_gwp) * c.in_gw : cin_own) + c.fold_cin) / c.groups) * c.cout;
       conv_flops_ += fl;
       if (conv_labels_.size() < ev_used_ / 2) {
         char lb[256];
@@ -1686,7 +1716,8 @@ int Model::run_segments_sl(const float* d_feats, const std::vector<int>& starts,
         case OP_STEM: {
           const ActTensor& t = tensors_[op.out.id];
           SVX_CUDA(launch_stem_conv(d_feats, d_seg_frame_off_, d_seg_row_off_[0], d_seg_h_[0], d_seg_of_row_[0], op.d_w9, op.d_scale,
-                                    op.d_shift, t.ptr, rows_used_[0], cfg_.feat_dim, stage_Wp_[0], op.C, t.C, is_bf16_, st));
+                                    op.d_shift, static_cast<uint8_t*>(t.ptr) + static_cast<size_t>(op.out.coff) * 2, rows_used_[0], cfg_.feat_dim,
+                                    stage_Wp_[0], op.C, round_up(op.C, 8), t.C, is_bf16_, st));
           ++launches_;
           break;
         }

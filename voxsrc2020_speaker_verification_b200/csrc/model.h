@@ -43,6 +43,11 @@ struct ConvDesc {
   // input read from a concat whose slices are padded (in_gw real channels in every in_gwp): cin is the PADDED count, the weight
   // rows of the pad positions are zero and the pad channels of the tensor hold zeros
   int in_gw = 0, in_gwp = 0;
+  // a second bias-free 1x1 conv + BN folded in as extra K (the projection shortcut of a stride-1 block, res2net_model.py:85-87 /
+  // :98-101: relu(bn3(W3 y) + bn_s(Ws x)) = relu(s3 * ([W3 ; Ws * s_s / s3] [y ; x]) + b3 + b_s)): its fold_cin input channels sit
+  // in the input tensor from channel fold_off on, its weight rows are scaled per output channel by s_s / s3 in fp32 before the
+  // one rounding to 16 bits
+  std::string fold_kernel_name, fold_bn_name; int fold_cin = 0, fold_off = 0;
   int split_store = 0;                // planar-split conv: channels stored per split (> split_w: destination tensors padded, pad written as zeros)
   int out2_store = 0;                 // same for the second output / aux tile of the direct epilogue (padded planar tensors)
   int out_store = 0;                  // channels the direct epilogue writes (>= cout: the pad of a padded concat slice is written as zeros)
