@@ -199,7 +199,11 @@ void Model::build_res2net() {
     static const bool no_fold = dbg_env("SVX_NO_FOLD") != nullptr;   // debug switch
     const bool fold = li == 0 && st == 1 && !no_fold && cin % 8 == 0 && cin <= 64 && ops_.size() == 1 && ops_[0].kind == OP_STEM;
     const int y_all = new_tensor(stage, S * wp);
-    const int y_first = fold ? new_tensor(stage, S * wp + 64) : y_all;   // the first block's own concat (the other blocks keep the dense pitch)
+    // the first block's own concat, block input behind the slices (the other blocks keep the dense pitch).  64 spare channel slots
+    // (pitch 384 B for 320 B of data): the dense form (pitch 320 B, SVX_FOLD_PAD=32) reads 0.3 GB less in conv3 but measured
+    // 0.06-0.13 ms slower per step in a three-way A/B on one box (rows that straddle 128-byte lines)
+    static const int fold_pad = dbg_env("SVX_FOLD_PAD") ? atoi(dbg_env("SVX_FOLD_PAD")) : 64;   // debug switch
+    const int y_first = fold ? new_tensor(stage, S * wp + std::max(fold_pad, round_up(cin, 16))) : y_all;
     if (fold) { ops_[0].out = {y_first, S * wp}; cur = y_first; }
     const int mp = st == 2 ? new_tensor(in_stage, mid) : -1;
     int out_t = xa;
