@@ -6,43 +6,30 @@
 namespace svx {
 
 // ---------------------------------------------------------------------------------------------------------
-// seg_of_row: mark which tall-image rows belong to which segment (-1 = zero padding row).
-__global__ void fill_seg_of_row_kernel(int32_t* seg_of_row, int rows_cap, const int32_t* seg_row_off, const int32_t* seg_h,
-                                       int n_seg) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows_cap) return;
-  // binary search: last segment whose offset <= i
-  int lo = 0, hi = n_seg - 1, ans = -1;
+// Row map of one stage in ONE launch, one warp per tall-image row: seg_of_row[row] = the segment the row belongs to (-1 = zero
+// padding row; binary search over the segment offsets, the same in every lane), and pix_valid[p] for the flat pixel sequence
+// p = row*Wp + col: 1 when the row belongs to a segment and col < W (0 on gap rows and on the zero column).
+__global__ void __launch_bounds__(256) fill_row_map_kernel(int32_t* seg_of_row, uint8_t* pix_valid, int rows, const int32_t* seg_row_off,
+                                                           const int32_t* seg_h, int n_seg, int W, int Wp) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  int lo = 0, hi = n_seg - 1, ans = -1;     // last segment whose offset <= row
   while (lo <= hi) {
     const int mid = (lo + hi) >> 1;
-    if (seg_row_off[mid] <= i) { ans = mid; lo = mid + 1; } else { hi = mid - 1; }
+    if (seg_row_off[mid] <= row) { ans = mid; lo = mid + 1; } else { hi = mid - 1; }
   }
   int v = -1;
-  if (ans >= 0 && i < seg_row_off[ans] + seg_h[ans]) v = ans;
-  seg_of_row[i] = v;
+  if (ans >= 0 && row < seg_row_off[ans] + seg_h[ans]) v = ans;
+  if (lane == 0) seg_of_row[row] = v;
+  uint8_t* pr = pix_valid + static_cast<size_t>(row) * Wp;
+  for (int col = lane; col < Wp; col += 32) pr[col] = (col < W && v >= 0) ? 1 : 0;
 }
 
-cudaError_t launch_fill_seg_of_row(int32_t* seg_of_row, int rows, const int32_t* seg_row_off, const int32_t* seg_h, int n_seg,
-                                   cudaStream_t st) {
+cudaError_t launch_fill_row_map(int32_t* seg_of_row, uint8_t* pix_valid, int rows, const int32_t* seg_row_off, const int32_t* seg_h, int n_seg,
+                                int W, int Wp, cudaStream_t st) {
   if (rows <= 0) return cudaSuccess;
-  fill_seg_of_row_kernel<<<(rows + 255) / 256, 256, 0, st>>>(seg_of_row, rows, seg_row_off, seg_h, n_seg);
-  return cudaGetLastError();
-}
-
-// pix_valid[p] for the flat pixel sequence p = row*Wp + col: 1 when the row belongs to a segment and col < W
-// (0 on gap rows and on the zero column).
-__global__ void fill_pix_valid_kernel(uint8_t* pix_valid, long long n, const int32_t* seg_of_row, int W, int Wp) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int row = static_cast<int>(i / Wp);
-  const int col = static_cast<int>(i - static_cast<long long>(row) * Wp);
-  pix_valid[i] = (col < W && seg_of_row[row] >= 0) ? 1 : 0;
-}
-
-cudaError_t launch_fill_pix_valid(uint8_t* pix_valid, int rows, const int32_t* seg_of_row, int W, int Wp, cudaStream_t st) {
-  const long long n = static_cast<long long>(rows) * Wp;
-  if (n <= 0) return cudaSuccess;
-  fill_pix_valid_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(pix_valid, n, seg_of_row, W, Wp);
+  fill_row_map_kernel<<<(rows + 7) / 8, 256, 0, st>>>(seg_of_row, pix_valid, rows, seg_row_off, seg_h, n_seg, W, Wp);
   return cudaGetLastError();
 }
 

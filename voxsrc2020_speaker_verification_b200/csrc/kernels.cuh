@@ -4,9 +4,8 @@
 
 namespace svx {
 
-cudaError_t launch_fill_seg_of_row(int32_t* seg_of_row, int rows, const int32_t* seg_row_off, const int32_t* seg_h, int n_seg,
-                                   cudaStream_t st);
-cudaError_t launch_fill_pix_valid(uint8_t* pix_valid, int rows, const int32_t* seg_of_row, int W, int Wp, cudaStream_t st);
+cudaError_t launch_fill_row_map(int32_t* seg_of_row, uint8_t* pix_valid, int rows, const int32_t* seg_row_off, const int32_t* seg_h, int n_seg,
+                                int W, int Wp, cudaStream_t st);
 cudaError_t launch_pack_input(const float* feats, const int32_t* seg_frame_off, const int32_t* seg_row_off,
                               const int32_t* seg_of_row, void* out, int rows, int F, int Cpad, int is_bf16, cudaStream_t st);
 cudaError_t launch_stem_conv(const float* feats, const int32_t* seg_frame_off, const int32_t* seg_row_off, const int32_t* seg_h,

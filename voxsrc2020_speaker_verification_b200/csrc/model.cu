@@ -1680,9 +1680,8 @@ int Model::run_segments_sl(const float* d_feats, const std::vector<int>& starts,
     for (int i = 0; i < nb; ++i) hp[i] = starts[i0 + i];
     SVX_CUDA(cudaMemcpyAsync(d_seg_frame_off_, hp, nb * 4, cudaMemcpyHostToDevice, st));
     for (int s = 0; s < n_stages_; ++s) {
-      SVX_CUDA(launch_fill_seg_of_row(d_seg_of_row_[s], rows_used_[s], d_seg_row_off_[s], d_seg_h_[s], nb, st));
-      SVX_CUDA(launch_fill_pix_valid(d_pix_valid_[s], rows_used_[s], d_seg_of_row_[s], stage_W_[s], stage_Wp_[s], st));
-      launches_ += 2;
+      SVX_CUDA(launch_fill_row_map(d_seg_of_row_[s], d_pix_valid_[s], rows_used_[s], d_seg_row_off_[s], d_seg_h_[s], nb, stage_W_[s], stage_Wp_[s], st));
+      launches_ += 1;
     }
     if (grow(&d_pooled_, &pooled_bytes_, static_cast<size_t>(nb) * flat_dim_ * 4) ||
         grow(&d_fc_partial_, &fc_partial_bytes_, static_cast<size_t>(fc_splits(flat_dim_)) * nb * cfg_.embed_dim * 4)) {
