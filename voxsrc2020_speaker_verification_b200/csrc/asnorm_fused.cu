@@ -5,25 +5,36 @@
 //             xh.ch + xl.ch + xh.cl  (fp32 accumulation in TMEM, ~2^-16 relative error per product — the same three terms, in the
 //             same order, as the unfused path, which is pinned to the reference's golden vectors)
 //
-// One persistent CTA per SM owns 128 test rows at a time.  Their split operand ([hi | lo], 2 x Dp bf16 per row, <= 128 KB) stays
-// RESIDENT in shared memory while the cohort streams through a TMA ring in tiles of 128 cohort rows, TWICE:
-//   pass 0  epilogue thread r (one per test row, reading its accumulator row from TMEM) bins every score into a per-row histogram
-//           in shared memory; the bin range is centred on where the k-th largest is expected: mean + z * std of the row's first 128
-//           scores, z from the normal quantile of k/c.  After the pass the thread walks its bins from the top and finds the bin b*
-//           that holds the k-th largest, the count above it and how many of b*'s members are needed.
-//   pass 1  the GEMM runs again (same instruction sequence -> bit-identical scores); scores above b* are accumulated (sum and sum
-//           of squares in double), the members of b* are collected in a short per-row list, and the thread finally picks the
-//           largest `need` of them.  Exact for ties: only the VALUES of the top-k multiset matter.
-// A row whose threshold bin falls outside the histogram range or holds more than `cap` scores is reported through flag_rows and
-// finished by the unfused kernels (api.cu) — correctness never depends on the score distribution, only the speed does.
+// One persistent CTA per SM owns 128 test rows at a time.  Their split operand ([hi | lo], 2 x Dp bf16 per row) is written by the
+// epilogue threads into TENSOR MEMORY (tcgen05.mma with A from TMEM), the cohort streams through a TMA ring in tiles of 128 cohort
+// rows, TWICE:
+//   pass 0  (statistics only: on the xh.ch term alone — half of the cohort bytes, a third of the MMAs; its scores are off by ~2^-8 of
+//           a score's standard deviation, a small fraction of a bin)  epilogue thread r (one per test row and epilogue group,
+//           reading its accumulator row from TMEM) bins every score into a PRIVATE 16-bit histogram in shared memory: plain load /
+//           add / store in batches of four with duplicate folding — no atomics (ATOMS costs ~2 cycles per lane, a predicated one
+//           becomes a branch region).  The bin range is centred on where the k-th largest is expected: mean + z * std of the row's
+//           first 128 scores, z from the normal quantile of k/c.  After the pass the thread walks the bins of both groups from the
+//           top and finds the bin b* that holds the k-th largest.
+//   pass 1  the exact three-term GEMM.  Binning is monotone in the score, so "bin >= b" is "score >= t_b" for a threshold found by
+//           bisection once per row: scores at or above t_{b*+2} are accumulated (sum and sum of squares in double), the scores of the
+//           band [t_{b*-1}, t_{b*+2}) are collected in a short per-row list, and the thread finally picks the largest
+//           k - |above| of them.  Exact whenever 0 <= k - |above| <= |band|, whatever the error of pass 0 — pass 1 verifies it.
+//           (When the selected scores themselves are wanted — cohort-sharded layout — pass 0 runs on all three terms and the band
+//           is the bin b* alone.)  Exact for ties: only the VALUES of the top-k multiset matter.
+// A row whose threshold bin falls outside the histogram range, whose band overflows its list or fails the check above is reported
+// through flag_rows and finished by the unfused kernels (api.cu) — correctness never depends on the score distribution, only the
+// speed does.
 //
 // Roles (384 threads): warp 0 TMA producer, warp 1 tcgen05.mma issuer (two 128-column accumulator buffers in TMEM, so the MMAs of
-// tile t+1 overlap the epilogue of tile t), warps 4-7 / 8-11 two epilogue warpgroups on alternating tiles (warp & 3 = TMEM lane quarter).  All histogram / list words of a row
-// live at word index == row (mod 128): every epilogue thread touches only its own words, bank = lane, no synchronisation.
+// tile t+1 overlap the epilogue of tile t), warps 4-7 / 8-11 two epilogue warpgroups on alternating tiles (warp & 3 = TMEM lane
+// quarter).  All histogram / list words of a row live at word index == row (mod 128): every epilogue thread touches only its own
+// words, bank = lane, no synchronisation inside a pass.
 //
-// Bounds: per tile of 128 cohort rows the CTA ingests 2 * Dp * 128 * 2 B (128 KB at D = 256) for 12 * Dp/64 MMAs of
-// 128x128x16 (48 at D = 256, 3072 tensor cycles): with ~45-50 GB/s of TMA ingest per SM when every SM pulls from L2 the kernel is
-// ingest-bound at ~2.7 us per tile and pass.
+// Bounds (profiles/r02_ncu_final.md): per tile of 128 cohort rows the CTA ingests 2 * Dp * 128 * 2 B (128 KB at D = 256;
+// half of it in pass 0) at ~50 GB/s per SM when every SM pulls the same cohort from L2: 1.35 ms for the two passes of the
+// BASELINE job, plus the part of the epilogues that two accumulator buffers cannot hide (0.65 ms).  A third accumulator buffer for
+// pass 0 (over the lo half of the operand, written between the passes) was built and measured: no gain — the two epilogue groups'
+// own throughput is the bound of pass 0, not the number of buffers (profiles/r02_experiments.md).
 #include <cstdio>
 #include <cstring>
 
@@ -395,9 +406,11 @@ asnorm_fused_kernel(const __grid_constant__ AsnormFusedParams p, const __grid_co
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>(buf * 128);
         if (p.knock & 1) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&B.t_empty[buf]); continue; }
         const bool skip1 = (p.knock & (2 | 16)) != 0;
+        // fp32 partial sums over ONE tile (only the scores above the threshold are non-zero: a handful per tile), the running sums in
+        // double once per tile: per 16 scores the two F2F.F64 + DADD pairs were 12 % of the epilogue warps' stall samples (FP64 pipe)
+        float s16 = 0.f, q16 = 0.f;
         auto process1 = [&](uint32_t (&r)[16]) {
           if (skip1) return;
-          float s16 = 0.f, q16 = 0.f;
 #pragma unroll
           for (int i4 = 0; i4 < 16; i4 += 4) {
 #pragma unroll
@@ -419,10 +432,10 @@ asnorm_fused_kernel(const __grid_constant__ AsnormFusedParams p, const __grid_co
             }
             lptr = min(lptr, list_end);                           // an overfull list stays inside its kListSlack spare words; the row is handed back
           }
-          dsum += static_cast<double>(s16);                       // 16 fp32 terms per partial sum, the running sums in double
-          dsq += static_cast<double>(q16);
         };
         SVX_TILE_CHUNKS(process1)
+        dsum += static_cast<double>(s16);
+        dsq += static_cast<double>(q16);
       }
 #undef SVX_TILE_CHUNKS
       if (thr_gt <= 0.f) pos -= (g == ((p.n_tiles - 1 + p.n_tiles) & 1)) ? npad : 0;     // the padding counted by the group that took the last tile
