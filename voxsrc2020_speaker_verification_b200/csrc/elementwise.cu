@@ -68,8 +68,10 @@ cudaError_t launch_pack_input(const float* feats, const int32_t* seg_frame_off, 
 // Stem: 3x3 conv, Cin = 1, stride 1, zero padding (1,1) in time and feature, then BN and ReLU
 // (res2net_model.py:192-203, dpn_model.py:32-37).  Reads the fp32 features directly ([N,T,F,1] with expand_dim=3),
 // writes the stage-0 tall image [rows, F, Cpad].
+constexpr int kStemPix = 8;   // feature columns per thread
+
 template <typename T>
-__global__ void __launch_bounds__(256, 3) stem_conv_kernel(const float* feats, const int32_t* seg_frame_off, const int32_t* seg_row_off,
+__global__ void __launch_bounds__(256, 2) stem_conv_kernel(const float* feats, const int32_t* seg_frame_off, const int32_t* seg_row_off,
                                                         const int32_t* seg_h, const int32_t* seg_of_row, const float* w9,
                                                         const float* scale, const float* shift, T* out, int rows, int F,
                                                         int Wp, int C, int Cpad, int pitch) {
@@ -84,45 +86,45 @@ __global__ void __launch_bounds__(256, 3) stem_conv_kernel(const float* feats, c
   }
   __syncthreads();
   const int groups = Cpad >> 3;
-  // One thread = 4 consecutive feature columns x 8 output channels, taps outermost: the 32 accumulators and the 3 x 6 input window
-  // live in registers, the 8 weights of a tap are fetched from shared memory (one 2 x 128-bit broadcast read per 32 FMAs).  The
+  // One thread = kStemPix (8) consecutive feature columns x 8 output channels, taps outermost: the 64 accumulators and the 3 x 10 input window
+  // live in registers, the 8 weights of a tap are fetched from shared memory (one 2 x 128-bit broadcast read per 64 FMAs).  The
   // first form of this kernel kept all 72 weights of the thread in registers (141 registers: 8 warps per SM, every one of them
   // waiting on its own input loads half of the time: 199 us for a 215 MB write).  32-bit index arithmetic (the launcher
   // guarantees the count fits).
-  const int nch = (F + 3) >> 2;
+  const int nch = (F + kStemPix - 1) / kStemPix;
   const unsigned total = static_cast<unsigned>(rows) * nch * groups;
   // grid-stride: a block stages the weights once and then works through many chunks (one chunk per block made the staging round
   // trip — two dependent global loads and a barrier — longer than the block's arithmetic)
   for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
   const int g = static_cast<int>(idx % groups);
   const unsigned chunk = idx / groups;
-  const int f0 = static_cast<int>(chunk % nch) * 4;
+  const int f0 = static_cast<int>(chunk % nch) * kStemPix;
   const int row = static_cast<int>(chunk / nch);
   const int seg = seg_of_row[row];
   T* orow = out + (static_cast<size_t>(row) * Wp + f0) * pitch + g * 8;
   if (seg < 0) {
 #pragma unroll
-    for (int p = 0; p < 4; ++p)
+    for (int p = 0; p < kStemPix; ++p)
       if (f0 + p < F) *reinterpret_cast<uint4*>(orow + static_cast<size_t>(p) * pitch) = make_uint4(0, 0, 0, 0);
     continue;
   }
   const int t = row - seg_row_off[seg];
   const int T_ = seg_h[seg];
   const float* base = feats + static_cast<size_t>(seg_frame_off[seg]) * F;
-  float x[3][6];
+  float x[3][kStemPix + 2];
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
     const int tt = t + r - 1;
     const bool rok = tt >= 0 && tt < T_;
 #pragma unroll
-    for (int q = 0; q < 6; ++q) {
+    for (int q = 0; q < kStemPix + 2; ++q) {
       const int ff = f0 + q - 1;
       x[r][q] = (rok && ff >= 0 && ff < F) ? __ldg(base + static_cast<size_t>(tt) * F + ff) : 0.f;
     }
   }
-  float v[4][8];
+  float v[kStemPix][8];
 #pragma unroll
-  for (int p = 0; p < 4; ++p)
+  for (int p = 0; p < kStemPix; ++p)
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[p][j] = 0.f;
 #pragma unroll
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(256, 3) stem_conv_kernel(const float* feats, c
       const float4 a = *reinterpret_cast<const float4*>(sw + (r * 3 + s_) * Cpad + g * 8), b4 = *reinterpret_cast<const float4*>(sw + (r * 3 + s_) * Cpad + g * 8 + 4);
       const float w[8] = {a.x, a.y, a.z, a.w, b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-      for (int p = 0; p < 4; ++p) {
+      for (int p = 0; p < kStemPix; ++p) {
         const float xv = x[r][p + s_];
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[p][j] = fmaf(xv, w[j], v[p][j]);
@@ -142,7 +144,7 @@ __global__ void __launch_bounds__(256, 3) stem_conv_kernel(const float* feats, c
 #pragma unroll
   for (int j = 0; j < 8; ++j) { sc[j] = sw[9 * Cpad + g * 8 + j]; sh[j] = sw[10 * Cpad + g * 8 + j]; }
 #pragma unroll
-  for (int p = 0; p < 4; ++p) {
+  for (int p = 0; p < kStemPix; ++p) {
     if (f0 + p >= F) break;
     uint4 o;
     o.x = TypeOps<T>::pack2(fmaxf(fmaf(v[p][0], sc[0], sh[0]), 0.f), fmaxf(fmaf(v[p][1], sc[1], sh[1]), 0.f));
@@ -157,14 +159,14 @@ __global__ void __launch_bounds__(256, 3) stem_conv_kernel(const float* feats, c
 cudaError_t launch_stem_conv(const float* feats, const int32_t* seg_frame_off, const int32_t* seg_row_off, const int32_t* seg_h,
                              const int32_t* seg_of_row, const float* w9, const float* scale, const float* shift, void* out,
                              int rows, int F, int Wp, int C, int Cpad, int pitch, int is_bf16, cudaStream_t st) {
-  const long long total = static_cast<long long>(rows) * ((F + 3) / 4) * (Cpad / 8);
+  const long long total = static_cast<long long>(rows) * ((F + kStemPix - 1) / kStemPix) * (Cpad / 8);
   if (total <= 0) return cudaSuccess;
   if (total >= (1LL << 31)) return cudaErrorInvalidValue;   // stage-0 capacity is 2^17 rows: far below
   unsigned blocks = static_cast<unsigned>((total + 255) / 256);
   {
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const unsigned cap = static_cast<unsigned>(sms) * 12u;      // four rounds of the three resident blocks per SM
+    const unsigned cap = static_cast<unsigned>(sms) * 8u;       // four rounds of the two resident blocks per SM
     if (blocks > cap) blocks = cap;
   }
   const size_t smem = 11 * Cpad * sizeof(float);
@@ -469,67 +471,107 @@ cudaError_t launch_att_pool(const void* x, const void* logits, int C, int W, int
 // ---------------------------------------------------------------------------------------------------------
 // Embedding FC with both 2-D batch norms folded in (BN → dense → BN, res2net_model.py:240-242):
 //   out[n, e] = bias[e] + sum_d pooled[n, d] * Wf[d, e]       Wf = diag(s1) W diag(s2), fp32.
-// Split-K: grid = (E/128, n-tiles of 8, K-splits); each thread owns one output column for 8 segments and
-// streams its slice of Wf with coalesced loads into a partial-sum slab; a second kernel adds the slabs in a
-// fixed order (bit-reproducible, no atomics).
-constexpr int kFcRows = 32;     // rows per block: every weight element is used 32 times from a register
-constexpr int kFcKChunk = 256;  // 32 x 256 floats of pooled statistics = 32 KB of shared memory
+// Split-K SGEMM on the CUDA cores, fp32 throughout: one wave of CTAs (row tiles x K splits ~ the SM count), CTA tile 128 segments x
+// 256 outputs, thread tile 8 x 16 (128 accumulators: 6 x 128-bit shared-memory reads per 128 FMAs), K in slabs of 16 through two
+// shared-memory buffers with the next slab's global loads in flight; every split writes a partial-sum slab and a second kernel adds
+// the slabs in a fixed order (bit-reproducible, no atomics).  The first form (one output column x 32 segments per thread, 1 280
+// small blocks) ran at 23 TFLOP/s; this one is bound by the FMA pipe.
+constexpr int kFcTileM = 128, kFcTileN = 256, kFcSlab = 16;
 
-__global__ void __launch_bounds__(128) fc_kernel(const float* __restrict__ pooled, const float* __restrict__ Wf, float* partial, int n,
-                                                 int D, int E) {
-  __shared__ __align__(16) float sp[kFcRows][kFcKChunk];
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  const int n0 = blockIdx.y * kFcRows;
-  const int d0 = blockIdx.z * kFcKChunk;
-  const int dn = min(kFcKChunk, D - d0);
-  // stage the 32 x 256 slice of the statistics: 16 independent 128-bit loads per thread (the scalar form was 64 dependent
-  // round trips to L2 per thread before the first FMA: ~a third of the kernel's time)
-  if ((D & 3) == 0 && dn == kFcKChunk) {
-#pragma unroll 8
-    for (int i = threadIdx.x; i < kFcRows * kFcKChunk / 4; i += 128) {
-      const int r = i >> 6, q = i & 63;
+__global__ void __launch_bounds__(256, 1) fc_kernel(const float* __restrict__ pooled, const float* __restrict__ Wf, float* partial, int n,
+                                                    int D, int E, int slabs_per_split) {
+  __shared__ __align__(16) float As[2][kFcSlab][kFcTileM];     // [k][segment]
+  __shared__ __align__(16) float Bs[2][kFcSlab][kFcTileN];     // [k][output]
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;                      // outputs tx*4 + {0,64,128,192} + 0..3, segments ty*8 + 0..7
+  const int n0 = blockIdx.y * kFcTileM;
+  const int e0 = blockIdx.x * kFcTileN;
+  const int k_begin = blockIdx.z * slabs_per_split * kFcSlab;
+  const int k_end = min(D, k_begin + slabs_per_split * kFcSlab);
+  const bool vec = (D & 3) == 0 && (E & 3) == 0;
+  // global -> registers of one slab: A 128 x 16 (two float4 per thread: row tid & 127, k quads (tid >> 7) and (tid >> 7) + 2),
+  // B 16 x 256 (four float4 per thread: k = tid >> 6 (+4, +8, +12), outputs (tid & 63) * 4)
+  float4 ra[2], rb[4];
+  auto load_slab = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int r = tid & 127, kq = (tid >> 7) + 2 * i, k = k0 + kq * 4;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (n0 + r < n) v = __ldg(reinterpret_cast<const float4*>(pooled + static_cast<size_t>(n0 + r) * D + d0) + q);
-      *reinterpret_cast<float4*>(&sp[r][q * 4]) = v;
+      if (n0 + r < n) {
+        const float* src = pooled + static_cast<size_t>(n0 + r) * D + k;
+        if (vec && k + 4 <= k_end) v = __ldg(reinterpret_cast<const float4*>(src));
+        else { if (k < k_end) v.x = src[0]; if (k + 1 < k_end) v.y = src[1]; if (k + 2 < k_end) v.z = src[2]; if (k + 3 < k_end) v.w = src[3]; }
+      }
+      ra[i] = v;
     }
-  } else {
-    for (int i = threadIdx.x; i < kFcRows * kFcKChunk; i += blockDim.x) {
-      const int r = i / kFcKChunk, d = i % kFcKChunk;
-      sp[r][d] = (n0 + r < n && d < dn) ? pooled[static_cast<size_t>(n0 + r) * D + d0 + d] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int kk = (tid >> 6) + 4 * i, c = (tid & 63) * 4, k = k0 + kk;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < k_end) {
+        const float* src = Wf + static_cast<size_t>(k) * E + e0 + c;
+        if (vec && e0 + c + 4 <= E) v = __ldg(reinterpret_cast<const float4*>(src));
+        else { if (e0 + c < E) v.x = src[0]; if (e0 + c + 1 < E) v.y = src[1]; if (e0 + c + 2 < E) v.z = src[2]; if (e0 + c + 3 < E) v.w = src[3]; }
+      }
+      rb[i] = v;
     }
-  }
+  };
+  auto store_slab = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int r = tid & 127, kq = (tid >> 7) + 2 * i;
+      As[buf][kq * 4 + 0][r] = ra[i].x; As[buf][kq * 4 + 1][r] = ra[i].y; As[buf][kq * 4 + 2][r] = ra[i].z; As[buf][kq * 4 + 3][r] = ra[i].w;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int kk = (tid >> 6) + 4 * i, c = (tid & 63) * 4;
+      *reinterpret_cast<float4*>(&Bs[buf][kk][c]) = rb[i];
+    }
+  };
+  float acc[8][16];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[i][j] = 0.f;
+  int buf = 0;
+  if (k_begin < k_end) { load_slab(k_begin); store_slab(0); }
   __syncthreads();
-  if (e >= E) return;
-  float acc[kFcRows];
+  for (int k0 = k_begin; k0 < k_end; k0 += kFcSlab) {
+    const bool more = k0 + kFcSlab < k_end;
+    if (more) load_slab(k0 + kFcSlab);
 #pragma unroll
-  for (int r = 0; r < kFcRows; ++r) acc[r] = 0.f;
-  const float* wp = Wf + static_cast<size_t>(d0) * E + e;
-  int d = 0;
-  // same summation order as the scalar loop (d ascending), 4 weights per iteration, the next 4 already in flight
-  float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
-  if (dn >= 4) { w0 = __ldg(wp); w1 = __ldg(wp + E); w2 = __ldg(wp + 2 * static_cast<size_t>(E)); w3 = __ldg(wp + 3 * static_cast<size_t>(E)); }
-  for (; d + 4 <= dn; d += 4) {
-    float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
-    if (d + 8 <= dn) {
-      const float* wn = wp + static_cast<size_t>(d + 4) * E;
-      x0 = __ldg(wn); x1 = __ldg(wn + E); x2 = __ldg(wn + 2 * static_cast<size_t>(E)); x3 = __ldg(wn + 3 * static_cast<size_t>(E));
+    for (int kk = 0; kk < kFcSlab; ++kk) {                     // K ascending inside the slab, slabs ascending: a fixed summation order
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 8]), a1 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 8 + 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float b[16];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 v = *reinterpret_cast<const float4*>(&Bs[buf][kk][c * 64 + tx * 4]);
+        b[c * 4 + 0] = v.x; b[c * 4 + 1] = v.y; b[c * 4 + 2] = v.z; b[c * 4 + 3] = v.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
-#pragma unroll
-    for (int r = 0; r < kFcRows; ++r) {
-      const float4 x = *reinterpret_cast<const float4*>(&sp[r][d]);   // broadcast read
-      acc[r] = fmaf(x.w, w3, fmaf(x.z, w2, fmaf(x.y, w1, fmaf(x.x, w0, acc[r]))));
-    }
-    w0 = x0; w1 = x1; w2 = x2; w3 = x3;
-  }
-  for (; d < dn; ++d) {
-    const float w = wp[static_cast<size_t>(d) * E];
-#pragma unroll
-    for (int r = 0; r < kFcRows; ++r) acc[r] = fmaf(sp[r][d], w, acc[r]);
+    if (more) store_slab(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
   }
   float* po = partial + static_cast<size_t>(blockIdx.z) * n * E;
 #pragma unroll
-  for (int r = 0; r < kFcRows; ++r)
-    if (n0 + r < n) po[static_cast<size_t>(n0 + r) * E + e] = acc[r];
+  for (int i = 0; i < 8; ++i) {
+    const int r = n0 + ty * 8 + i;
+    if (r >= n) continue;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int e = e0 + c * 64 + tx * 4;
+      float* dst = po + static_cast<size_t>(r) * E + e;
+      if (vec && e + 4 <= E) *reinterpret_cast<float4*>(dst) = make_float4(acc[i][c * 4], acc[i][c * 4 + 1], acc[i][c * 4 + 2], acc[i][c * 4 + 3]);
+      else
+        for (int q = 0; q < 4; ++q) if (e + q < E) dst[q] = acc[i][c * 4 + q];
+    }
+  }
 }
 
 __global__ void fc_reduce_kernel(const float* partial, const float* bias, float* out, int n, int E, int splits) {
@@ -540,14 +582,33 @@ __global__ void fc_reduce_kernel(const float* partial, const float* bias, float*
   out[i] = acc;
 }
 
-int fc_splits(int D) { return (D + kFcKChunk - 1) / kFcKChunk; }
+// K splits: one wave of CTAs over the SMs (row tiles x output tiles x splits <= SM count), at least 4 slabs per split
+static void fc_plan(int n, int D, int E, int* splits, int* slabs_per_split) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles = ((n + kFcTileM - 1) / kFcTileM) * ((E + kFcTileN - 1) / kFcTileN);
+  const int slabs = (D + kFcSlab - 1) / kFcSlab;
+  int want = tiles > 0 ? sms / tiles : 1;
+  if (want < 1) want = 1;
+  int per = (slabs + want - 1) / want;
+  if (per < 4) per = 4;
+  *slabs_per_split = per;
+  *splits = (slabs + per - 1) / per;
+}
+
+int fc_splits(int D, int n, int E) {
+  int splits = 1, per = 1;
+  fc_plan(n, D, E, &splits, &per);
+  return splits;
+}
 
 cudaError_t launch_fc(const float* pooled, const float* Wf, const float* bias, float* partial, float* out, int n, int D, int E,
                       cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
-  const int splits = fc_splits(D);
-  dim3 grid((E + 127) / 128, (n + kFcRows - 1) / kFcRows, splits);
-  fc_kernel<<<grid, 128, 0, st>>>(pooled, Wf, partial, n, D, E);
+  int splits = 1, per = 1;
+  fc_plan(n, D, E, &splits, &per);
+  dim3 grid((E + kFcTileN - 1) / kFcTileN, (n + kFcTileM - 1) / kFcTileM, splits);
+  fc_kernel<<<grid, 256, 0, st>>>(pooled, Wf, partial, n, D, E, per);
   fc_reduce_kernel<<<(n * E + 255) / 256, 256, 0, st>>>(partial, bias, out, n, E, splits);
   return cudaGetLastError();
 }

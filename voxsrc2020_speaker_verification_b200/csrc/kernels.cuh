@@ -24,7 +24,7 @@ cudaError_t launch_att_tanh(void* t, int A, long long n_pix, int Wp, int W, cons
                             cudaStream_t st);
 cudaError_t launch_att_pool(const void* x, const void* logits, int C, int W, int Wp, const int32_t* seg_row_off, const int32_t* seg_h,
                             int n_seg, float* out, float eps, int is_bf16, cudaStream_t st);
-int fc_splits(int D);
+int fc_splits(int D, int n, int E);   // partial-sum slabs launch_fc writes for this shape
 cudaError_t launch_fc(const float* pooled, const float* Wf, const float* bias, float* partial, float* out, int n, int D, int E,
                       cudaStream_t st);
 cudaError_t launch_chunk_combine(const float* seg_emb, const int32_t* utt_seg_off, const int32_t* seg_len, float* out, int n_utt,

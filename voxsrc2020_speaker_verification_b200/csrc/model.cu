@@ -1684,7 +1684,7 @@ int Model::run_segments_sl(const float* d_feats, const std::vector<int>& starts,
       launches_ += 1;
     }
     if (grow(&d_pooled_, &pooled_bytes_, static_cast<size_t>(nb) * flat_dim_ * 4) ||
-        grow(&d_fc_partial_, &fc_partial_bytes_, static_cast<size_t>(fc_splits(flat_dim_)) * nb * cfg_.embed_dim * 4)) {
+        grow(&d_fc_partial_, &fc_partial_bytes_, static_cast<size_t>(fc_splits(flat_dim_, nb, cfg_.embed_dim)) * nb * cfg_.embed_dim * 4)) {
       set_last_error("allocation failed"); return 1;
     }
     int op_index = 0, chain_skip = 0;
