@@ -250,9 +250,9 @@ struct PairConvParams {
   //   1x1: one box per 64 input channels, one item each;  3x3 stride 1: the same boxes, nine items each (shifts of the flat pixel
   //   sequence);  stride 2 (2-D tile mode): one box per parity phase and 64 channels, 1 / 2 / 2 / 4 items per phase for a 3x3.
   int n_boxes;                 // <= 16
-  uint8_t box_map[16];         // A tensor map of the box: 0 = PairMaps::a, 1..3 = PairMaps::a2[box_map - 1] (parity phases)
-  int16_t box_c[16];           // channel coordinate of the box
-  uint8_t box_item0[17];       // items of box b: [box_item0[b], box_item0[b + 1])
+  uint8_t box_map[24];         // A tensor map of the box: 0 = PairMaps::a, 1..3 = PairMaps::a2[box_map - 1] (parity phases)
+  int16_t box_c[24];           // channel coordinate of the box
+  uint8_t box_item0[25];       // items of box b: [box_item0[b], box_item0[b + 1])
   uint16_t item_off16[24];     // (row displacement of the item's tap inside the box) * 128 bytes >> 4
   uint16_t item_wcol[24];      // weight column of the item (coordinate 0 of the B tensor map)
   uint8_t item_ks[24];         // K = 16 steps of the item that hold real channels (1..4)

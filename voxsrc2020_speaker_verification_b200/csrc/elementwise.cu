@@ -304,6 +304,39 @@ cudaError_t launch_avgpool3x3s2(const void* in, int in_C, int in_coff, int in_ro
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Even pixels of a tensor into (a channel slice of) a tensor of the next stage: the input of a 1x1 stride-2 projection shortcut
+// (res2net_model.py:85-87 with the explicit padding of models.py:121-134: none for a 1x1 kernel, so output (R, c) reads input
+// (2 R, 2 c)), laid behind the concat slices of the block so that conv3 reads [y | x_even] as one K axis (ConvDesc::fold_*).
+// 16-byte vectors, zero on gap rows and on the zero column.  Type-agnostic (16-bit elements).
+__global__ void __launch_bounds__(256) subsample2_kernel(const uint16_t* in, int in_C, int in_coff, int in_Wp, uint16_t* out, int out_C,
+                                                         int out_coff, int out_rows, int out_W, int out_Wp, int C,
+                                                         const int32_t* out_seg_of_row) {
+  const unsigned groups = static_cast<unsigned>(C) >> 3;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned total = static_cast<unsigned>(out_rows) * out_Wp * groups;
+  if (idx >= total) return;
+  const unsigned g = idx % groups;
+  const unsigned pix = idx / groups;
+  const int col = static_cast<int>(pix % out_Wp);
+  const int row = static_cast<int>(pix / out_Wp);
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (col < out_W && out_seg_of_row[row] >= 0)
+    v = *reinterpret_cast<const uint4*>(in + (static_cast<size_t>(2 * row) * in_Wp + 2 * col) * in_C + in_coff + g * 8);
+  *reinterpret_cast<uint4*>(out + (static_cast<size_t>(row) * out_Wp + col) * out_C + out_coff + g * 8) = v;
+}
+
+cudaError_t launch_subsample2(const void* in, int in_C, int in_coff, int in_Wp, void* out, int out_C, int out_coff, int out_rows, int out_W,
+                              int out_Wp, int C, const int32_t* out_seg_of_row, cudaStream_t st) {
+  const long long total = static_cast<long long>(out_rows) * out_Wp * (C / 8);
+  if (total <= 0) return cudaSuccess;
+  if (total >= (1LL << 31)) return cudaErrorInvalidValue;
+  subsample2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(static_cast<const uint16_t*>(in), in_C, in_coff, in_Wp,
+                                                                               static_cast<uint16_t*>(out), out_C, out_coff, out_rows, out_W,
+                                                                               out_Wp, C, out_seg_of_row);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Statistics pooling (models.py:262-269): per segment, per (w, c): mean over time and sqrt(population var + eps).
 // Two passes over the segment's rows (they sit in L2), fp32.  Optional fused pre-activation relu(x*scale+shift)
 // (DPN concat_bn_relu, dpn_model.py:24-29).  Output fp32 [n_seg, W*2C], index w*2C + {c | C + c}.

@@ -14,6 +14,9 @@ cudaError_t launch_stem_conv(const float* feats, const int32_t* seg_frame_off, c
 cudaError_t launch_bn_relu(const void* in, int in_C, int in_coff, int in_Wp, const float* scale, const float* shift, void* out,
                            int out_C, int out_rows, int out_W, int out_Wp, int C, int stride, const int32_t* out_seg_of_row,
                            const int32_t* out_seg_row_off, const int32_t* in_seg_row_off, int is_bf16, cudaStream_t st);
+// out[R, c, out_coff + ch] = in[2 R, 2 c, in_coff + ch] on the pixels of a segment, 0 elsewhere (the input of a stride-2 1x1 conv)
+cudaError_t launch_subsample2(const void* in, int in_C, int in_coff, int in_Wp, void* out, int out_C, int out_coff, int out_rows, int out_W,
+                              int out_Wp, int C, const int32_t* out_seg_of_row, cudaStream_t st);
 cudaError_t launch_avgpool3x3s2(const void* in, int in_C, int in_coff, int in_rows, int in_W, int in_Wp, void* out, int out_C, int out_coff,
                                 int out_rows, int out_W, int out_Wp, int C, const int32_t* out_seg_of_row, int is_bf16, cudaStream_t st);
 cudaError_t launch_stats_pool(const void* in, int C_tot, int C, int W, int Wp, const int32_t* seg_row_off, const int32_t* seg_h, int n_seg,

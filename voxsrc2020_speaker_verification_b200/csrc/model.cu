@@ -205,14 +205,20 @@ void Model::build_res2net() {
     static const int fold_pad = dbg_env("SVX_FOLD_PAD") ? atoi(dbg_env("SVX_FOLD_PAD")) : 64;   // debug switch
     const int y_first = fold ? new_tensor(stage, S * wp + std::max(fold_pad, round_up(cin, 16))) : y_all;
     if (fold) { ops_[0].out = {y_first, S * wp}; cur = y_first; }
+    // Stride-2 stages: the same fold with the block input's EVEN pixels (what a 1x1 stride-2 conv reads) copied behind the concat
+    // slices by a small kernel (OP_SUBSAMPLE) — a quarter of the input instead of a shortcut launch that writes a full-width
+    // tensor which conv3 then reads back as its residual.
+    static const bool no_fold2 = dbg_env("SVX_NO_FOLD2") != nullptr;   // debug switch
+    const bool fold2 = st == 2 && !no_fold && !no_fold2 && cin % 64 == 0 && (S * wp) % 64 == 0 && wp == w;
+    const int y_first2 = fold2 ? new_tensor(stage, S * wp + cin) : -1;
     const int mp = st == 2 ? new_tensor(in_stage, mid) : -1;
     int out_t = xa;
     for (int b = 0; b < cfg_.block_sizes[li]; ++b) {
       const bool first = b == 0;
       const int bstride = first ? st : 1;
       int shortcut = cur;
-      const bool folded = first && fold;
-      const int y = folded ? y_first : y_all;
+      const bool folded = first && fold, folded2 = first && fold2;
+      const int y = folded ? y_first : folded2 ? y_first2 : y_all;
       const int in_off = folded ? S * wp : 0;                    // where the block input sits in its tensor
       std::string fold_kernel, fold_bn;
       if (first) {   // projection shortcut: 1x1 conv stride s + BN (res2net_model.py:85-87,119-127)
@@ -222,7 +228,11 @@ void Model::build_res2net() {
         add_var(c.bn_name + "/moving_mean", {cout}); add_var(c.bn_name + "/moving_variance", {cout});
         c.in = {cur, 0}; c.cin = cin; c.stride = bstride; c.cout = cout; c.out = {sc, 0};
         if (folded) { fold_kernel = c.kernel_name; fold_bn = c.bn_name; shortcut = -1; }
-        else { ops_.push_back(op); shortcut = sc; }
+        else if (folded2) {
+          fold_kernel = c.kernel_name; fold_bn = c.bn_name; shortcut = -1;
+          Op sub; sub.kind = OP_SUBSAMPLE; sub.in = {cur, 0}; sub.out = {y, S * wp}; sub.C = cin;
+          ops_.push_back(sub);
+        } else { ops_.push_back(op); shortcut = sc; }
       }
       {   // conv1 1x1 + BN + ReLU (res2net_model.py:89-91)
         Op op; op.kind = OP_CONV; ConvDesc& c = op.conv;
@@ -269,7 +279,7 @@ void Model::build_res2net() {
         c.bn_name = next_name(root, "", "batch_normalization");
         add_var(c.bn_name + "/moving_mean", {cout}); add_var(c.bn_name + "/moving_variance", {cout});
         c.in = {y, 0}; c.cin = S * wp; c.cout = cout; c.post_relu = 1; c.out = {out_t, 0};
-        if (folded) { c.fold_kernel_name = fold_kernel; c.fold_bn_name = fold_bn; c.fold_cin = cin; c.fold_off = S * wp; c.cin = S * wp + cin; }
+        if (folded || folded2) { c.fold_kernel_name = fold_kernel; c.fold_bn_name = fold_bn; c.fold_cin = cin; c.fold_off = S * wp; c.cin = S * wp + cin; }
         else c.res = {shortcut, 0};
         if (wp != w) { c.in_gw = w; c.in_gwp = wp; }
         ops_.push_back(op);
@@ -1247,7 +1257,7 @@ int Model::plan_pair(ConvDesc& c) {
     }
     pp.halo = halo;
     pp.a_rows = round_up(128 + 2 * halo, 8);
-    if (nkb > 16 || nkb * taps > 24) return 0;
+    if (nkb > 24 || nkb * taps > 24) return 0;
     pp.n_boxes = nkb;
     for (int kb = 0; kb < nkb; ++kb) {
       pp.box_map[kb] = 0; pp.box_c[kb] = static_cast<int16_t>(kb * 64); pp.box_item0[kb] = static_cast<uint8_t>(n_items);
@@ -1747,6 +1757,14 @@ int Model::run_segments_sl(const float* d_feats, const std::vector<int>& starts,
           const ActTensor& to = tensors_[op.out.id];
           SVX_CUDA(launch_avgpool3x3s2(ti.ptr, ti.C, op.in.coff, rows_cap_[ti.stage], stage_W_[ti.stage], stage_Wp_[ti.stage], to.ptr, to.C,
                                        op.out.coff, rows_used_[to.stage], stage_W_[to.stage], stage_Wp_[to.stage], op.C, d_seg_of_row_[to.stage], is_bf16_, st));
+          ++launches_;
+          break;
+        }
+        case OP_SUBSAMPLE: {
+          const ActTensor& ti = tensors_[op.in.id];
+          const ActTensor& to = tensors_[op.out.id];
+          SVX_CUDA(launch_subsample2(ti.ptr, ti.C, op.in.coff, stage_Wp_[ti.stage], to.ptr, to.C, op.out.coff, rows_used_[to.stage],
+                                     stage_W_[to.stage], stage_Wp_[to.stage], op.C, d_seg_of_row_[to.stage], st));
           ++launches_;
           break;
         }

@@ -26,7 +26,7 @@ struct VarSpec {
   std::vector<int64_t> shape;
 };
 
-enum OpKind { OP_PACK_INPUT, OP_STEM, OP_CONV, OP_BN_RELU, OP_AVGPOOL, OP_POOL };
+enum OpKind { OP_PACK_INPUT, OP_STEM, OP_CONV, OP_BN_RELU, OP_AVGPOOL, OP_POOL, OP_SUBSAMPLE };
 
 struct TensorRef {
   int id = -1;      // activation tensor id
@@ -77,7 +77,7 @@ struct Op {
   OpKind kind;
   ConvDesc conv;                       // OP_CONV
   // OP_STEM: kernel_name / bn_name / out in conv
-  // OP_BN_RELU / OP_AVGPOOL:
+  // OP_BN_RELU / OP_AVGPOOL / OP_SUBSAMPLE (even pixels of `in` -> `out` of the next stage):
   TensorRef in, out; int C = 0; int stride = 1; std::string bn_name;
   float* d_scale = nullptr; float* d_shift = nullptr; float* d_w9 = nullptr;
   // OP_CONV with conv.chain_pos == 0: this conv and the next two run as ONE fused launch when chain_ok
